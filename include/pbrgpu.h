@@ -1,0 +1,227 @@
+/*
+ * pbrgpu.h - C-ABI of the B200-native wavefront path tracer (libpbrgpu.so).
+ *
+ * This is the drop-in boundary for ONE hot path of G0T-cha/PysicalBasedRaytracer: everything that
+ * happens inside  Integrator::Render(const Scene&, double&)  (Integrator/Integrator.h:14) for the
+ * Path / DirectLighting / Whitted integrators:
+ *     Sampler::GetCameraSample            Sampler/Sampler.cpp:10-21
+ *     HaltonSampler::SampleDimension      Sampler/Halton.cpp:61-92, Sampler/LowDiscrepancy.cpp:211-225,2300-2316
+ *     PerspectiveCamera::GenerateRay...   Camera/Perspective.cpp:21-80, Camera/Orthographic.cpp:7-63
+ *     BVHAccel::Intersect / IntersectP    Accelerator/BVHAccel.cpp:285-366, Shape/Triangle.cpp:62-350
+ *     PathIntegrator::Li                  Integrator/PathIntegrator.cpp:32-110
+ *     UniformSampleOneLight/EstimateDirect Integrator/Integrator.cpp:46-177
+ *     Material::ComputeScatteringFunctions + BSDF::{f,Pdf,Sample_f}   Material/*.cpp
+ *     Light::{Sample_Li,Pdf_Li,Le,L}      Light/*.cpp
+ *     per-pixel mean + XYZ/sRGB/gamma/8-bit  Integrator/Integrator.cpp:313-344
+ *
+ * The reference has no FFI layer: its boundary is the C++ virtual above, whose inputs are object
+ * graphs (Scene -> BVHAccel -> GeometricPrimitive -> Triangle/Material/AreaLight, Camera, Sampler).
+ * A host shim (pysicalbasedraytracer_b200/host/GpuIntegrator.h for C++, pysicalbasedraytracer_b200/api.py for
+ * Python) flattens those graphs into the POD descriptors below and calls these entry points.
+ *
+ * Conventions: plain C, POD structs, opaque handles, int status (0 = OK, non-zero = error; text via
+ * pbrgpu_last_error()), no exceptions cross the boundary.  All host arrays are copied during the
+ * call; the library owns device memory behind the handles.  Handles are not thread-safe.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef PBRGPU_H
+#define PBRGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbrgpu_ctx pbrgpu_ctx;     /* one CUDA device + stream */
+typedef struct pbrgpu_scene pbrgpu_scene; /* flattened Scene + Camera + Sampler resident in HBM */
+
+/* ---- materials: Material/{MatteMaterial,Mirror,GlassMaterial,MetalMaterial,PlasticMaterial}.cpp ---- */
+enum {
+  PBRGPU_MAT_MATTE = 0,   /* Kd=kd, sigma               MatteMaterial.cpp:13-28   */
+  PBRGPU_MAT_MIRROR = 1,  /* Kr=kr                      Mirror.cpp:5-15           */
+  PBRGPU_MAT_GLASS = 2,   /* Kr=kr Kt=kt index=eta[0]   GlassMaterial.cpp:9-57    */
+  PBRGPU_MAT_METAL = 3,   /* eta, k, u/v roughness      MetalMaterial.cpp:25-43   */
+  PBRGPU_MAT_PLASTIC = 4, /* Kd=kd Ks=kr roughness=u_rough  PlasticMaterial.cpp:8-30 */
+  PBRGPU_MAT_COUNT = 5
+};
+typedef struct pbrgpu_material {
+  int32_t type;
+  int32_t remap_roughness;
+  float sigma;   /* Matte (degrees) */
+  float u_rough; /* Glass/Metal u roughness, Plastic roughness */
+  float kd[3];
+  float v_rough;
+  float kr[3];
+  float pad0;
+  float kt[3];
+  float pad1;
+  float eta[3]; /* Metal eta (RGB); Glass index of refraction in eta[0] */
+  float pad2;
+  float k[3]; /* Metal absorption */
+  float pad3;
+} pbrgpu_material; /* 96 bytes */
+
+/* ---- lights: Light/{PointLight,DiffuseLight,InfiniteAreaLight,SkyBoxLight}.cpp ---- */
+enum {
+  PBRGPU_LIGHT_POINT = 0,    /* pos, L = intensity I */
+  PBRGPU_LIGHT_AREA_TRI = 1, /* DiffuseAreaLight over ONE triangle (the reference creates one light per Triangle) */
+  PBRGPU_LIGHT_INFINITE = 2, /* InfiniteAreaLight: env map * L, importance sampled, light_to_world */
+  PBRGPU_LIGHT_SKYBOX = 3    /* SkyBoxLight: env map, uniform sphere sampling, tone-mapped texels */
+};
+typedef struct pbrgpu_light {
+  int32_t type;
+  int32_t tri;       /* AREA_TRI: triangle index in the caller's order */
+  int32_t two_sided; /* AREA_TRI */
+  int32_t n_samples; /* Light::nSamples (used by UniformSampleAllLights) */
+  float pos[3];      /* POINT: world position (LightToWorld(0,0,0)) */
+  float world_radius; /* SKYBOX: ctor argument.  INFINITE: ignored (computed from the scene bound) */
+  float L[3];        /* POINT: I.  AREA_TRI: Lemit.  INFINITE: scale applied to texels */
+  float pad0;
+  float light_to_world[16]; /* INFINITE, row-major Matrix4x4::m */
+  float world_to_light[16]; /* INFINITE, row-major inverse */
+} pbrgpu_light; /* 176 bytes */
+
+/* ---- scene: Core/Scene.h:13-30 + Accelerator/BVHAccel.h + Shape/Triangle.h ---- */
+typedef struct pbrgpu_scene_desc {
+  int32_t n_verts;
+  int32_t n_tris;
+  const float* verts;          /* n_verts*3, WORLD space (TriangleMesh ctor transforms, Triangle.cpp:27-28) */
+  const int32_t* indices;      /* n_tris*3 */
+  const float* normals;        /* optional n_verts*3 world-space shading normals (mesh->n) or NULL */
+  const float* uvs;            /* optional n_verts*2 (mesh->uv) or NULL -> default (0,0),(1,0),(1,1) Triangle.h:50-54 */
+  const int32_t* tri_material; /* n_tris: index into materials */
+  const int32_t* tri_light;    /* n_tris: index into lights for emissive triangles, else -1 */
+  const uint8_t* tri_flags;    /* optional n_tris: bit0 = reverseOrientation^transformSwapsHandedness */
+  int32_t n_materials;
+  int32_t n_lights;
+  const pbrgpu_material* materials;
+  const pbrgpu_light* lights;
+  int32_t env_width;  /* env map for INFINITE / SKYBOX lights (power-of-two sizes) */
+  int32_t env_height;
+  const float* env_texels; /* env_width*env_height*3 RGB, row-major, raw (unscaled) */
+} pbrgpu_scene_desc;
+
+/* ---- camera: Camera/Camera.h:34-54, Perspective.cpp, Orthographic.cpp ---- */
+enum { PBRGPU_CAMERA_PERSPECTIVE = 0, PBRGPU_CAMERA_ORTHOGRAPHIC = 1 };
+typedef struct pbrgpu_camera_desc {
+  int32_t type;
+  int32_t width;
+  int32_t height;
+  float lens_radius;
+  float focal_distance;
+  float raster_to_camera[16]; /* ProjectiveCamera::RasterToCamera.m, row-major */
+  float camera_to_world[16];  /* Camera::CameraToWorld.m, row-major */
+} pbrgpu_camera_desc;
+
+/* ---- sampler: Sampler/Halton.cpp:30-58 ---- */
+enum { PBRGPU_SAMPLER_HALTON = 0, PBRGPU_SAMPLER_SOBOL = 1 };
+typedef struct pbrgpu_sampler_desc {
+  int32_t type;
+  int32_t sample_at_pixel_center;
+  int64_t samples_per_pixel;
+  int32_t sample_bounds[4]; /* x0,y0,x1,y1 passed to HaltonSampler (drives baseScales/Exponents) */
+  const uint16_t* perms;    /* optional: HaltonSampler::radicalInversePermutations; NULL -> library
+                               computes them with its own PCG32 (RNG.h:93-108, LowDiscrepancy.cpp:2284-2298) */
+  int64_t n_perms;
+} pbrgpu_sampler_desc;
+
+/* ---- render: Integrator ctor arguments (PathIntegrator.h:14-18, WhittedIntegrator.h:8-11,
+ *      DirectLightingIntegrator.h:10-17) + the pixel / sample sub-range to compute ---- */
+enum {
+  PBRGPU_INTEGRATOR_PATH = 0,
+  PBRGPU_INTEGRATOR_DIRECT_ONE = 1, /* LightStrategy::UniformSampleOne */
+  PBRGPU_INTEGRATOR_DIRECT_ALL = 2, /* LightStrategy::UniformSampleAll */
+  PBRGPU_INTEGRATOR_WHITTED = 3
+};
+enum { PBRGPU_LIGHTSTRATEGY_UNIFORM = 0, PBRGPU_LIGHTSTRATEGY_POWER = 1 };
+typedef struct pbrgpu_render_desc {
+  int32_t integrator;
+  int32_t max_depth;
+  float rr_threshold;
+  int32_t light_strategy;
+  int32_t x0, y0, x1, y1; /* pixel region [x0,x1) x [y0,y1) */
+  int64_t s0, s1;         /* sample indices [s0,s1) of each pixel (multi-GPU shards this range) */
+  int32_t samples_per_wave; /* 0 = auto */
+  int32_t flags;            /* PBRGPU_RENDER_* */
+} pbrgpu_render_desc;
+enum {
+  PBRGPU_RENDER_ACCUMULATE = 1, /* add into the output sums instead of overwriting */
+  PBRGPU_RENDER_COUNTERS = 2    /* count nodes visited / triangles tested (slower) */
+};
+
+typedef struct pbrgpu_stats {
+  uint64_t camera_samples;
+  uint64_t rays_closest; /* Scene::Intersect queries (path + MIS rays) */
+  uint64_t rays_shadow;  /* Scene::IntersectP queries */
+  uint64_t nodes_visited;
+  uint64_t tris_tested;
+  uint64_t kernel_launches;
+  double ms_total;   /* CUDA-event time of the whole render on the context's stream */
+  double ms_trace;   /* closest + shadow + MIS traversal kernels */
+  double ms_shade;
+  double ms_raygen;
+} pbrgpu_stats;
+
+/* ---- lifecycle ---- */
+int pbrgpu_init(int device_id, pbrgpu_ctx** out);
+void pbrgpu_shutdown(pbrgpu_ctx* ctx);
+const char* pbrgpu_last_error(void);
+int pbrgpu_device_count(void);
+
+int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* desc, pbrgpu_scene** out);
+void pbrgpu_scene_destroy(pbrgpu_scene* scene);
+int pbrgpu_camera_set(pbrgpu_scene* scene, const pbrgpu_camera_desc* cam);
+int pbrgpu_sampler_set(pbrgpu_scene* scene, const pbrgpu_sampler_desc* smp);
+
+/* Render sample range [s0,s1) of the pixel region.  out_rgb_sum (host, (x1-x0)*(y1-y0)*3 floats,
+ * row-major, y down as raster) receives the SUM over samples of Li (the reference's `colObj` before
+ * `/= spp`, Integrator.cpp:309).  out_rgba8 (optional, W*H*4) receives the tone-mapped 8-bit image of
+ * sum/(s1-s0) with the reference's Y flip (Integrator.cpp:327-344). */
+int pbrgpu_render(pbrgpu_scene* scene, const pbrgpu_render_desc* rd, float* out_rgb_sum,
+                  unsigned char* out_rgba8, pbrgpu_stats* stats);
+
+/* Same, but the sums stay in HBM: d_rgb_sum is a DEVICE pointer ((x1-x0)*(y1-y0)*4 floats, RGBA with
+ * A = number of samples) on the context's device, e.g. a torch tensor's data_ptr() so that the
+ * multi-GPU driver can NCCL-reduce it.  `stream` is a cudaStream_t (0 = the context's stream). */
+int pbrgpu_render_device(pbrgpu_scene* scene, const pbrgpu_render_desc* rd, float* d_rgb_sum,
+                         void* stream, pbrgpu_stats* stats);
+
+/* Film resolve on device data (mean, XYZ->sRGB, gamma, 8-bit, Y flip; Integrator.cpp:313-344). */
+int pbrgpu_resolve_film(pbrgpu_ctx* ctx, const float* d_rgba_sum, int width, int height,
+                        float inv_spp, float* out_rgb_mean, unsigned char* out_rgba8);
+
+/* ---- parity hooks (used by tests; cheap) ---- */
+enum {
+  PBRGPU_DUMP_SAMPLER = 0,      /* float[n_pix][n_samples][n_dims] : SampleDimension(index(pixel,s), d) */
+  PBRGPU_DUMP_PRIMARY_RAYS = 1, /* float[n_pix][n_samples][8] : o.xyz, tMax, d.xyz, time */
+  PBRGPU_DUMP_PRIMARY_HITS = 2, /* int32 prim (caller's triangle index, -1 miss) + float t,b0,b1 : [..][4] */
+  PBRGPU_DUMP_PERMS = 3,        /* uint16[n_perms] */
+  PBRGPU_DUMP_SHADOW = 4        /* int32[n] occlusion of caller-supplied rays (see pbrgpu_trace_rays) */
+};
+typedef struct pbrgpu_dump_desc {
+  int32_t what;
+  int32_t x0, y0, x1, y1;
+  int64_t s0, s1;
+  int32_t n_dims; /* SAMPLER only */
+  int32_t pad;
+} pbrgpu_dump_desc;
+int pbrgpu_debug_dump(pbrgpu_scene* scene, const pbrgpu_dump_desc* dd, void* out, size_t out_bytes);
+
+/* Trace caller-supplied rays (float[n][8]: o.xyz,tMax,d.xyz,pad).  any_hit=0: closest hit ->
+ * out_hits int32/float [n][4] (prim, t, b0, b1 as bit patterns); any_hit=1: out_hits int32[n]. */
+int pbrgpu_trace_rays(pbrgpu_scene* scene, const float* rays, int64_t n, int any_hit, void* out_hits);
+
+/* Halton helper mirrors (host-side integer code; Halton.cpp:40-81).  Outputs 7 ints:
+ * baseScales[2], baseExponents[2], sampleStride, multInverse[2]. */
+int pbrgpu_halton_params(const int32_t sample_bounds[4], int32_t out7[7]);
+/* Radical-inverse permutations for the first n_bases primes (n_bases<=1000); returns count written. */
+int64_t pbrgpu_compute_perms(uint16_t* out, int64_t capacity);
+
+/* BVH statistics: out[0]=n_nodes, out[1]=n_leaves, out[2]=max_leaf_size, out[3]=bytes_nodes, out[4]=bytes_tris */
+int pbrgpu_scene_info(pbrgpu_scene* scene, int64_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRGPU_H */

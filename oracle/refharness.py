@@ -1,0 +1,192 @@
+"""TEST INFRASTRUCTURE ONLY.  ctypes wrapper over oracle/_ref/libpbr_ref.so (the compiled, unmodified
+reference + oracle/ref_harness.cpp).  Imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py; never by the product package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from pysicalbasedraytracer_b200 import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libpbr_ref.so")
+
+
+class RefRenderStats(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("seconds", C.c_double), ("threads", C.c_int)]
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.ref_scene_create.restype = C.c_void_p
+        L.ref_scene_create.argtypes = [C.POINTER(A.SceneDesc)]
+        L.ref_scene_destroy.argtypes = [C.c_void_p]
+        L.ref_scene_bvh_seconds.restype = C.c_double
+        L.ref_scene_bvh_seconds.argtypes = [C.c_void_p]
+        L.ref_scene_bound.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.ref_camera_create.restype = C.c_void_p
+        L.ref_camera_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float)]
+        L.ref_camera_destroy.argtypes = [C.c_void_p]
+        L.ref_camera_desc.argtypes = [C.c_void_p, C.POINTER(A.CameraDesc)]
+        L.ref_sampler_create.restype = C.c_void_p
+        L.ref_sampler_create.argtypes = [C.c_int] * 5
+        L.ref_sampler_destroy.argtypes = [C.c_void_p]
+        L.ref_halton_params.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        L.ref_perms.restype = C.c_int64
+        L.ref_perms.argtypes = [C.c_void_p, C.c_int64]
+        L.ref_radical_inverse.restype = C.c_float
+        L.ref_radical_inverse.argtypes = [C.c_int, C.c_uint64]
+        L.ref_scrambled_radical_inverse.restype = C.c_float
+        L.ref_scrambled_radical_inverse.argtypes = [C.c_int, C.c_uint64]
+        L.ref_prime.argtypes = [C.c_int]
+        L.ref_prime_sum.argtypes = [C.c_int]
+        L.ref_sampler_dump.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.ref_halton_index.restype = C.c_int64
+        L.ref_halton_index.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64]
+        L.ref_primary_rays.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_int64, C.c_int64, C.c_void_p]
+        L.ref_primary_hits.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_int64, C.c_int64, C.c_void_p]
+        L.ref_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.ref_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(A.RenderDesc),
+                                 C.c_int, C.c_void_p, C.POINTER(RefRenderStats)]
+        L.ref_render_shipped.restype = C.c_double
+        L.ref_render_shipped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_void_p, C.POINTER(RefRenderStats)]
+        L.ref_tonemap.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class RefScene:
+    def __init__(self, scene_data):
+        d, self._keep = scene_data.desc()
+        self.h = lib().ref_scene_create(C.byref(d))
+
+    def bvh_seconds(self):
+        return lib().ref_scene_bvh_seconds(self.h)
+
+    def bound(self):
+        out = (C.c_float * 6)()
+        lib().ref_scene_bound(self.h, out)
+        return np.array(out[:], dtype=np.float32)
+
+    def trace(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        out = np.zeros((n,) if any_hit else (n, 4), dtype=np.int32)
+        lib().ref_trace_rays(self.h, rays.ctypes.data, n, int(any_hit), out.ctypes.data)
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_scene_destroy(self.h)
+            self.h = None
+
+
+class RefCamera:
+    def __init__(self, cam_type, W, H, eye, look, up):
+        self.h = lib().ref_camera_create(cam_type, W, H, _f3(eye), _f3(look), _f3(up))
+        self.W, self.H = W, H
+
+    def desc(self):
+        d = A.CameraDesc()
+        lib().ref_camera_desc(self.h, C.byref(d))
+        return d
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_camera_destroy(self.h)
+            self.h = None
+
+
+class RefSampler:
+    def __init__(self, spp, bounds):
+        self.h = lib().ref_sampler_create(spp, *bounds)
+        self.spp, self.bounds = spp, tuple(bounds)
+
+    def params(self):
+        out = (C.c_int32 * 7)()
+        lib().ref_halton_params(self.h, out)
+        return list(out)
+
+    def dump(self, region, s0, s1, n_dims):
+        x0, y0, x1, y1 = region
+        out = np.zeros(((y1 - y0) * (x1 - x0), s1 - s0, n_dims), dtype=np.float32)
+        lib().ref_sampler_dump(self.h, x0, y0, x1, y1, s0, s1, n_dims, out.ctypes.data)
+        return out
+
+    def index(self, x, y, s):
+        return lib().ref_halton_index(self.h, x, y, s)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_sampler_destroy(self.h)
+            self.h = None
+
+
+def perms():
+    n = lib().ref_perms(None, 0)
+    out = np.zeros(n, dtype=np.uint16)
+    lib().ref_perms(out.ctypes.data, n)
+    return out
+
+
+def primary_rays(cam, smp, region, s0, s1):
+    x0, y0, x1, y1 = region
+    out = np.zeros(((y1 - y0) * (x1 - x0), s1 - s0, 8), dtype=np.float32)
+    lib().ref_primary_rays(cam.h, smp.h, x0, y0, x1, y1, s0, s1, out.ctypes.data)
+    return out
+
+
+def primary_hits(scene, cam, smp, region, s0, s1):
+    x0, y0, x1, y1 = region
+    out = np.zeros(((y1 - y0) * (x1 - x0), s1 - s0, 4), dtype=np.int32)
+    lib().ref_primary_hits(scene.h, cam.h, smp.h, x0, y0, x1, y1, s0, s1, out.ctypes.data)
+    return out
+
+
+def render(scene, cam, spp, sample_bounds, integrator=A.INTEGRATOR_PATH, max_depth=5, rr_threshold=1.0,
+           light_strategy=A.LIGHTSTRATEGY_UNIFORM, region=None, s0=0, s1=None, threads=0):
+    """-> (rgb_sum float32 [H,W,3], RefRenderStats)"""
+    if region is None:
+        region = (0, 0, cam.W, cam.H)
+    if s1 is None:
+        s1 = spp
+    x0, y0, x1, y1 = region
+    rd = A.RenderDesc(integrator=integrator, max_depth=max_depth, rr_threshold=rr_threshold,
+                      light_strategy=light_strategy, x0=x0, y0=y0, x1=x1, y1=y1, s0=s0, s1=s1)
+    out = np.zeros((y1 - y0, x1 - x0, 3), dtype=np.float32)
+    st = RefRenderStats()
+    sb = (C.c_int32 * 4)(*sample_bounds)
+    rc = lib().ref_render(scene.h, cam.h, spp, sb, C.byref(rd), threads, out.ctypes.data, C.byref(st))
+    if rc != 0:
+        raise RuntimeError("ref_render failed")
+    return out, st
+
+
+def render_shipped(scene, cam, spp, W, H, max_depth, rr):
+    out = np.zeros((H, W, 4), dtype=np.uint8)
+    st = RefRenderStats()
+    t = lib().ref_render_shipped(scene.h, cam.h, spp, W, H, max_depth, rr, out.ctypes.data, C.byref(st))
+    return out, st, t
+
+
+def tonemap(rgb_mean):
+    a = np.ascontiguousarray(rgb_mean, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros((a.shape[0], 4), dtype=np.uint8)
+    lib().ref_tonemap(a.ctypes.data, a.shape[0], out.ctypes.data)
+    return out

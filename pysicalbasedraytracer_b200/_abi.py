@@ -1,0 +1,70 @@
+"""ctypes mirror of include/pbrgpu.h (POD descriptors only; no logic)."""
+import ctypes as C
+
+MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_METAL, MAT_PLASTIC = range(5)
+LIGHT_POINT, LIGHT_AREA_TRI, LIGHT_INFINITE, LIGHT_SKYBOX = range(4)
+CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC = 0, 1
+SAMPLER_HALTON, SAMPLER_SOBOL = 0, 1
+INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED = range(4)
+LIGHTSTRATEGY_UNIFORM, LIGHTSTRATEGY_POWER = 0, 1
+RENDER_ACCUMULATE, RENDER_COUNTERS = 1, 2
+DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW = range(5)
+
+f3 = C.c_float * 3
+f16 = C.c_float * 16
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int32), ("remap_roughness", C.c_int32), ("sigma", C.c_float), ("u_rough", C.c_float),
+                ("kd", f3), ("v_rough", C.c_float), ("kr", f3), ("pad0", C.c_float), ("kt", f3), ("pad1", C.c_float),
+                ("eta", f3), ("pad2", C.c_float), ("k", f3), ("pad3", C.c_float)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("tri", C.c_int32), ("two_sided", C.c_int32), ("n_samples", C.c_int32),
+                ("pos", f3), ("world_radius", C.c_float), ("L", f3), ("pad0", C.c_float),
+                ("light_to_world", f16), ("world_to_light", f16)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("n_verts", C.c_int32), ("n_tris", C.c_int32),
+                ("verts", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_int32)),
+                ("normals", C.POINTER(C.c_float)), ("uvs", C.POINTER(C.c_float)),
+                ("tri_material", C.POINTER(C.c_int32)), ("tri_light", C.POINTER(C.c_int32)),
+                ("tri_flags", C.POINTER(C.c_uint8)),
+                ("n_materials", C.c_int32), ("n_lights", C.c_int32),
+                ("materials", C.POINTER(Material)), ("lights", C.POINTER(Light)),
+                ("env_width", C.c_int32), ("env_height", C.c_int32), ("env_texels", C.POINTER(C.c_float))]
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("lens_radius", C.c_float), ("focal_distance", C.c_float),
+                ("raster_to_camera", f16), ("camera_to_world", f16)]
+
+
+class SamplerDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("sample_at_pixel_center", C.c_int32), ("samples_per_pixel", C.c_int64),
+                ("sample_bounds", C.c_int32 * 4), ("perms", C.POINTER(C.c_uint16)), ("n_perms", C.c_int64)]
+
+
+class RenderDesc(C.Structure):
+    _fields_ = [("integrator", C.c_int32), ("max_depth", C.c_int32), ("rr_threshold", C.c_float),
+                ("light_strategy", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32),
+                ("y1", C.c_int32), ("s0", C.c_int64), ("s1", C.c_int64), ("samples_per_wave", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("camera_samples", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shade", C.c_double),
+                ("ms_raygen", C.c_double)]
+
+
+class DumpDesc(C.Structure):
+    _fields_ = [("what", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
+                ("s0", C.c_int64), ("s1", C.c_int64), ("n_dims", C.c_int32), ("pad", C.c_int32)]
+
+
+assert C.sizeof(Material) == 96 and C.sizeof(Light) == 176

@@ -1,0 +1,102 @@
+// device_types.cuh - HBM-resident layout of the flattened scene and of the wavefront state.
+#pragma once
+#include "../../include/pbrgpu.h"
+#include "bvh.h"
+#include "sampler.cuh"
+#include "vecmath.cuh"
+
+namespace pbr {
+
+// ---- shading queues: 5 material types + "ray escaped" ----
+constexpr int kQueueMiss = PBRGPU_MAT_COUNT;  // 5
+constexpr int kNumQueues = PBRGPU_MAT_COUNT + 1;
+
+// ---- triangle record (leaf order): three float4 = three 16-byte loads ----
+//   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-23), material type (24-27), flags (28-31)
+//   tv2 = p2.xyz | area-light id or -1
+constexpr uint32_t kTriMatMask = 0x00ffffffu;
+constexpr int kTriTypeShift = 24;
+constexpr int kTriFlagShift = 28;
+constexpr uint32_t kTriFlagFlipNormal = 1u;  // reverseOrientation ^ transformSwapsHandedness
+
+struct CameraDev {
+  int type, width, height;
+  float lensRadius, focalDistance;
+  float r2c[16];
+  float c2w[16];
+};
+
+struct EnvDev {
+  const float* texels;    // RGB, INFINITE: premultiplied by L ; SKYBOX: raw
+  int width, height;
+  const float* condFunc;  // [h][w]
+  const float* condCdf;   // [h][w+1]
+  const float* condInt;   // [h] funcInt per row
+  const float* margFunc;  // [h]
+  const float* margCdf;   // [h+1]
+  float margInt;
+};
+
+struct SceneDev {
+  const float4* tv0;
+  const float4* tv1;
+  const float4* tv2;
+  const Bvh2Node* nodes;
+  const pbrgpu_material* mats;  // roughness fields already remapped to alpha on the host (glibc logf)
+  const pbrgpu_light* lights;   // AREA_TRI: .tri = LEAF-ORDER triangle index
+  int nTris, nLights, nInfinite;
+  int infinite[4];              // indices of infinite lights (Scene::infiniteLights)
+  const float* lightFunc;       // Distribution1D of the active light-sampling strategy
+  const float* lightCdf;
+  float lightFuncInt;
+  float worldRadius;            // Bounds3::BoundingSphere of the scene bound (InfiniteAreaLight::Preprocess)
+  V3 worldCenter;
+  EnvDev env;
+  CameraDev cam;
+  HaltonParams hp;
+};
+
+struct Counters {
+  uint32_t nCur, nNext, nShadow, nMis;
+  uint32_t nMat[8];
+  unsigned long long raysClosest, raysShadow, nodesVisited, trisTested;
+};
+
+// SoA wavefront state, `capacity` slots.  slot = j*nPix + pixel (j = sample within the wave).
+struct WaveDev {
+  float4* rayO;     // o.xyz, tMax
+  float4* rayD;     // d.xyz, time
+  float4* hit;      // as_float(leaf tri index or -1), b0, b1, b2
+  float4* beta;     // beta.rgb, etaScale
+  float4* L;        // L.rgb (per-path radiance, summed in launch order => deterministic)
+  uint2* hidx;      // Halton index (lo, hi)
+  uint32_t* meta;   // dim (bits 0-15) | specularBounce (bit 16)
+  // shadow-ray queue (EstimateDirect light-sampling strategy)
+  float4* shO;      // o.xyz, tMax
+  float4* shD;      // d.xyz, as_float(slot)
+  float4* shC;      // contribution rgb added to L[slot] when unoccluded
+  // MIS-ray queue (EstimateDirect BSDF-sampling strategy; closest hit)
+  float4* miO;
+  float4* miD;      // d.xyz, as_float(slot)
+  float4* miC;      // throughput rgb, as_float(light id)
+  uint32_t* qCur;
+  uint32_t* qNext;
+  uint32_t* qMat;   // [kNumQueues][capacity]
+  Counters* ctr;
+  uint32_t capacity;
+};
+
+struct RenderParams {
+  SceneDev sc;
+  WaveDev ws;
+  int integrator, maxDepth, lightStrategyUniformPick;
+  float rrThreshold;
+  int x0, y0, w, h;       // pixel region
+  long long sBegin;       // first sample index of this wave
+  int nsWave;             // samples per pixel in this wave
+  int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
+  int countStats;
+  float* accum;           // [h*w] RGBA sums (A = sample count)
+};
+
+}  // namespace pbr

@@ -1,0 +1,458 @@
+// kernels.cuh - the wavefront kernels (sm_100a).  One bounce of the wavefront maps onto
+// PathIntegrator::Li's loop body (Integrator/PathIntegrator.cpp:42-108):
+//   k_trace_closest   scene.Intersect(ray)                                   :44
+//   k_shade<MAT>      emission :47-51, maxDepth :60, BSDF :63, UniformSampleOneLight :74-81,
+//                     Sample_f :88-99, Russian roulette :100-107
+//   k_shade_miss      infinite-light Le for escaped rays                     :52-56
+//   k_trace_shadow    VisibilityTester::Unoccluded (Integrator.cpp:107, Light.cpp:19-22)
+//   k_trace_mis       EstimateDirect's BSDF-sampled closest-hit ray (Integrator.cpp:157-172)
+// All paths of a wave are at the same bounce, so `bounce` is a launch argument, not path state.
+#pragma once
+#include "shade.cuh"
+
+namespace pbr {
+
+constexpr int kBlock = 256;
+
+PBR_D V3 xform_point(const float* m, V3 p) {  // Transform::operator()(Point3) Core/Transform.h:138-150
+  float x = p.x, y = p.y, z = p.z;
+  float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+  float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+  float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+  float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+  if (wp == 1) return V3(xp, yp, zp);
+  float inv = 1.f / wp;
+  return V3(inv * xp, inv * yp, inv * zp);
+}
+
+// Camera::GenerateRay* (o, d only: differentials are dead code on this path)
+PBR_D void generate_ray(const CameraDev& cam, float fx, float fy, float lensU, float lensV, V3* o, V3* d) {
+  V3 pCamera = xform_point(cam.r2c, V3(fx, fy, 0));
+  V3 ro, rd;
+  if (cam.type == PBRGPU_CAMERA_PERSPECTIVE) {
+    ro = V3(0, 0, 0);
+    rd = normalize(pCamera);
+  } else {
+    ro = pCamera;
+    rd = V3(0, 0, 1);
+  }
+  if (cam.lensRadius > 0) {
+    float lx, ly;
+    concentric_sample_disk(lensU, lensV, &lx, &ly);
+    lx = cam.lensRadius * lx; ly = cam.lensRadius * ly;
+    float ft = cam.focalDistance / rd.z;
+    V3 pFocus = ro + rd * ft;
+    ro = V3(lx, ly, 0);
+    rd = normalize(pFocus - ro);
+  }
+  *o = xform_point(cam.c2w, ro);
+  *d = xform_vec(cam.c2w, rd);
+}
+
+PBR_D void slot_to_pixel(const RenderParams& P, uint32_t slot, int* px, int* py, long long* s, uint32_t* pix) {
+  uint32_t nPix = (uint32_t)(P.w * P.h);
+  uint32_t j = slot / nPix, p = slot - j * nPix;
+  *pix = p;
+  *py = P.y0 + (int)(p / (uint32_t)P.w);
+  *px = P.x0 + (int)(p % (uint32_t)P.w);
+  *s = P.sBegin + j;
+}
+
+// K1: sampler + raygen.  Sampler::GetCameraSample (Sampler.cpp:10-21): dims 0,1 film, 2 time, 3,4 lens.
+__global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ RenderParams P) {
+  uint32_t n = (uint32_t)(P.w * P.h) * (uint32_t)P.nsWave;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+    int px, py; long long s; uint32_t pix;
+    slot_to_pixel(P, slot, &px, &py, &s, &pix);
+    int64_t idx = halton_index_for_sample(px, py, s, P.sc.hp);
+    float u0 = halton_sample_dimension(idx, 0, P.sc.hp);
+    float u1 = halton_sample_dimension(idx, 1, P.sc.hp);
+    float lu = 0, lv = 0;
+    if (P.sc.cam.lensRadius > 0) {
+      lu = halton_sample_dimension(idx, 3, P.sc.hp);
+      lv = halton_sample_dimension(idx, 4, P.sc.hp);
+    }
+    V3 o, d;
+    generate_ray(P.sc.cam, (float)px + u0, (float)py + u1, lu, lv, &o, &d);
+    P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
+    P.ws.rayD[slot] = make_float4(d.x, d.y, d.z, 0.f);
+    P.ws.beta[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
+    P.ws.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    P.ws.hidx[slot] = make_uint2((uint32_t)((uint64_t)idx & 0xffffffffu), (uint32_t)((uint64_t)idx >> 32));
+    P.ws.meta[slot] = 5u;  // next dimension; specularBounce = false
+    P.ws.qCur[slot] = slot;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.ws.ctr->nCur = n;
+}
+
+// warp-aggregated append: one atomicAdd per (warp, queue)
+PBR_D uint32_t queue_push(uint32_t* counter, bool active) {
+  unsigned mask = __ballot_sync(__activemask(), active);
+  if (!active) return 0;
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// K2: closest hit for every live path; classify into material queues.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_trace_closest(const __grid_constant__ RenderParams P) {
+  const uint32_t n = P.ws.ctr->nCur;
+  unsigned nodes = 0, tris = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    bool active = i < n;
+    int q = -1;
+    uint32_t slot = 0;
+    if (active) {
+      slot = P.ws.qCur[i];
+      float4 ro = P.ws.rayO[slot], rd = P.ws.rayD[slot];
+      HitRec h;
+      traverse<false, COUNT>(P.sc, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, &h, &nodes, &tris);
+      P.ws.hit[slot] = make_float4(__int_as_float(h.tri), h.b0, h.b1, h.b2);
+      P.ws.rayO[slot].w = h.t;
+      q = kQueueMiss;
+      if (h.tri >= 0) q = (int)((__float_as_uint(__ldg(&P.sc.tv1[h.tri].w)) >> kTriTypeShift) & 0xf);
+    }
+#pragma unroll
+    for (int k = 0; k < kNumQueues; ++k) {
+      bool mine = active && q == k;
+      uint32_t pos = queue_push(&P.ws.ctr->nMat[k], mine);
+      if (mine) P.ws.qMat[(size_t)k * P.ws.capacity + pos] = slot;
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&P.ws.ctr->nodesVisited, (unsigned long long)nodes);
+    atomicAdd(&P.ws.ctr->trisTested, (unsigned long long)tris);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws.ctr->raysClosest, (unsigned long long)n);
+}
+
+// K4/K5/K7: shading for one material queue.
+template <int MAT>
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ RenderParams P, int bounce) {
+  const uint32_t n = P.ws.ctr->nMat[MAT];
+  const SceneDev& sc = P.sc;
+  const uint32_t* queue = P.ws.qMat + (size_t)MAT * P.ws.capacity;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    bool active = i < n;
+    bool pushShadow = false, pushMis = false, pushNext = false;
+    uint32_t slot = 0;
+    float4 shO, shD, shC, miO, miD, miC;
+    if (active) {
+      slot = queue[i];
+      float4 ro4 = P.ws.rayO[slot], rd4 = P.ws.rayD[slot], h4 = P.ws.hit[slot], be4 = P.ws.beta[slot];
+      uint2 hi = P.ws.hidx[slot];
+      uint32_t meta = P.ws.meta[slot];
+      V3 rayD(rd4.x, rd4.y, rd4.z);
+      Spec beta(be4.x, be4.y, be4.z);
+      float etaScale = be4.w;
+      bool specularBounce = (meta >> 16) & 1u;
+      SamplerCursor cur;
+      cur.index = (int64_t)(((uint64_t)hi.y << 32) | hi.x);
+      cur.dim = (int)(meta & 0xffffu);
+      cur.arrayEndDim = P.arrayEndDim;
+      TriData tri = load_tri(sc, __float_as_int(h4.x));
+      Isect is;
+      make_isect(sc, tri, h4.y, h4.z, h4.w, rayD, &is);
+      Spec Ladd(0.f);
+      // emitted light for camera rays / after specular bounces
+      if ((bounce == 0 || specularBounce) && is.lightId >= 0)
+        Ladd = Ladd + beta * area_light_L(sc.lights[is.lightId], is.n, -rayD);
+      bool alive = bounce < P.maxDepth;
+      if (alive) {
+        Bsdf bsdf;
+        make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf);
+        const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
+        if (bsdf.num_components(nonSpec) > 0 && sc.nLights > 0) {
+          // UniformSampleOneLight (Integrator.cpp:46-69)
+          float pickPdf;
+          int lightNum = sample_discrete(sc.lightFunc, sc.lightCdf, sc.lightFuncInt, sc.nLights, cur.get1D(sc.hp), &pickPdf);
+          if (pickPdf != 0) {
+            float uL0, uL1, uS0, uS1;
+            cur.get2D(sc.hp, &uL0, &uL1);
+            cur.get2D(sc.hp, &uS0, &uS1);
+            const pbrgpu_light& light = sc.lights[lightNum];
+            // EstimateDirect (Integrator.cpp:71-177), strategy 1: sample the light
+            LightSample ls;
+            sample_light(sc, light, is.p, uL0, uL1, &ls);
+            if (ls.pdf > 0 && !ls.Li.is_black()) {
+              Spec f = bsdf_f(bsdf, is.wo, ls.wi, nonSpec) * absdot(ls.wi, is.ns);
+              float scatteringPdf = bsdf_pdf(bsdf, is.wo, ls.wi, nonSpec);
+              if (!f.is_black()) {
+                V3 origin = offset_ray_origin(is.p, is.pError, is.n, ls.p1 - is.p);
+                V3 target = offset_ray_origin(ls.p1, ls.pErr1, ls.n1, origin - ls.p1);
+                V3 dd = target - origin;
+                Spec Ld;
+                if (is_delta_light(light)) Ld = f * ls.Li / ls.pdf;
+                else Ld = f * ls.Li * power_heuristic(1, ls.pdf, 1, scatteringPdf) / ls.pdf;
+                Spec c = beta * (Ld / pickPdf);
+                shO = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
+                shD = make_float4(dd.x, dd.y, dd.z, __uint_as_float(slot));
+                shC = make_float4(c.r, c.g, c.b, 0.f);
+                pushShadow = true;
+              }
+            }
+            // strategy 2: sample the BSDF
+            if (!is_delta_light(light)) {
+              V3 wi;
+              float scatteringPdf;
+              int sampledType;
+              Spec f = bsdf_sample_f(bsdf, is.wo, &wi, uS0, uS1, &scatteringPdf, nonSpec, &sampledType);
+              f = f * absdot(wi, is.ns);
+              if (!f.is_black() && scatteringPdf > 0) {
+                V3 origin = offset_ray_origin(is.p, is.pError, is.n, wi);
+                float weight = 1;
+                bool ok = true;
+                if (!(sampledType & BSDF_SPECULAR)) {
+                  float lightPdf = light_pdf_li(sc, light, origin, is.p, wi);
+                  if (lightPdf == 0) ok = false;
+                  else weight = power_heuristic(1, scatteringPdf, 1, lightPdf);
+                }
+                if (ok) {
+                  Spec c = beta * ((f * weight / scatteringPdf) / pickPdf);
+                  miO = make_float4(origin.x, origin.y, origin.z, kInfinity);
+                  miD = make_float4(wi.x, wi.y, wi.z, __uint_as_float(slot));
+                  miC = make_float4(c.r, c.g, c.b, __int_as_float(lightNum));
+                  pushMis = true;
+                }
+              }
+            }
+          }
+        }
+        // sample the BSDF for the next path segment (PathIntegrator.cpp:84-99)
+        V3 wo = -rayD, wi;
+        float pdf, u0, u1;
+        int flags;
+        cur.get2D(sc.hp, &u0, &u1);
+        Spec f = bsdf_sample_f(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &flags);
+        if (f.is_black() || pdf == 0.f) alive = false;
+        if (alive) {
+          beta = beta * (f * absdot(wi, is.ns) / pdf);
+          specularBounce = (flags & BSDF_SPECULAR) != 0;
+          if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+            float eta = bsdf.eta;
+            etaScale *= (dot(wo, is.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+          }
+          V3 o = offset_ray_origin(is.p, is.pError, is.n, wi);
+          Spec rrBeta = beta * etaScale;
+          if (rrBeta.max_value() < P.rrThreshold && bounce > 3) {
+            float q = stdmax(.05f, 1 - rrBeta.max_value());
+            if (cur.get1D(sc.hp) < q) alive = false;
+            else beta = beta / (1 - q);
+          }
+          if (alive) {
+            P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
+            P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, 0.f);
+            P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, etaScale);
+            P.ws.meta[slot] = (uint32_t)cur.dim | (specularBounce ? (1u << 16) : 0u);
+            pushNext = true;
+          }
+        }
+      }
+      if (!Ladd.is_black()) {
+        float4 L = P.ws.L[slot];
+        P.ws.L[slot] = make_float4(L.x + Ladd.r, L.y + Ladd.g, L.z + Ladd.b, 0.f);
+      }
+    }
+    uint32_t pos = queue_push(&P.ws.ctr->nShadow, pushShadow);
+    if (pushShadow) { P.ws.shO[pos] = shO; P.ws.shD[pos] = shD; P.ws.shC[pos] = shC; }
+    pos = queue_push(&P.ws.ctr->nMis, pushMis);
+    if (pushMis) { P.ws.miO[pos] = miO; P.ws.miD[pos] = miD; P.ws.miC[pos] = miC; }
+    pos = queue_push(&P.ws.ctr->nNext, pushNext);
+    if (pushNext) P.ws.qNext[pos] = slot;
+  }
+}
+
+// Rays that left the scene: Le of the infinite lights (PathIntegrator.cpp:52-56), path ends (:60).
+__global__ void __launch_bounds__(kBlock) k_shade_miss(const __grid_constant__ RenderParams P, int bounce) {
+  const uint32_t n = P.ws.ctr->nMat[kQueueMiss];
+  const uint32_t* queue = P.ws.qMat + (size_t)kQueueMiss * P.ws.capacity;
+  if (P.sc.nInfinite == 0) return;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t slot = queue[i];
+    bool specularBounce = (P.ws.meta[slot] >> 16) & 1u;
+    if (!(bounce == 0 || specularBounce)) continue;
+    float4 rd = P.ws.rayD[slot], be = P.ws.beta[slot];
+    Spec beta(be.x, be.y, be.z);
+    Spec Ladd(0.f);
+    for (int k = 0; k < P.sc.nInfinite; ++k)
+      Ladd = Ladd + beta * light_Le(P.sc, P.sc.lights[P.sc.infinite[k]], V3(rd.x, rd.y, rd.z));
+    float4 L = P.ws.L[slot];
+    P.ws.L[slot] = make_float4(L.x + Ladd.r, L.y + Ladd.g, L.z + Ladd.b, 0.f);
+  }
+}
+
+// K3: shadow rays (any hit).  Unoccluded => add the precomputed light-sampling contribution.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_trace_shadow(const __grid_constant__ RenderParams P) {
+  const uint32_t n = P.ws.ctr->nShadow;
+  unsigned nodes = 0, tris = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 o = P.ws.shO[i], d = P.ws.shD[i];
+    HitRec h;
+    bool occluded = traverse<true, COUNT>(P.sc, V3(o.x, o.y, o.z), V3(d.x, d.y, d.z), o.w, &h, &nodes, &tris);
+    if (!occluded) {
+      uint32_t slot = __float_as_uint(d.w);
+      float4 c = P.ws.shC[i];
+      float4 L = P.ws.L[slot];
+      P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&P.ws.ctr->nodesVisited, (unsigned long long)nodes);
+    atomicAdd(&P.ws.ctr->trisTested, (unsigned long long)tris);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws.ctr->raysShadow, (unsigned long long)n);
+}
+
+// K6: MIS rays (closest hit) + resolve (Integrator.cpp:157-172)
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_trace_mis(const __grid_constant__ RenderParams P) {
+  const uint32_t n = P.ws.ctr->nMis;
+  unsigned nodes = 0, tris = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 o = P.ws.miO[i], d = P.ws.miD[i], c = P.ws.miC[i];
+    HitRec h;
+    V3 wi(d.x, d.y, d.z);
+    bool found = traverse<false, COUNT>(P.sc, V3(o.x, o.y, o.z), wi, o.w, &h, &nodes, &tris);
+    int lightId = __float_as_int(c.w);
+    const pbrgpu_light& light = P.sc.lights[lightId];
+    Spec Li(0.f);
+    if (found) {
+      TriData t = load_tri(P.sc, h.tri);
+      if ((int)t.w2 == lightId) Li = area_light_L(light, tri_normal_isect(t), -wi);
+    } else {
+      Li = light_Le(P.sc, light, wi);
+    }
+    if (!Li.is_black()) {
+      uint32_t slot = __float_as_uint(d.w);
+      float4 L = P.ws.L[slot];
+      P.ws.L[slot] = make_float4(L.x + c.x * Li.r, L.y + c.y * Li.g, L.z + c.z * Li.b, 0.f);
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&P.ws.ctr->nodesVisited, (unsigned long long)nodes);
+    atomicAdd(&P.ws.ctr->trisTested, (unsigned long long)tris);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws.ctr->raysClosest, (unsigned long long)n);
+}
+
+// bounce bookkeeping (host swaps qCur/qNext pointers each bounce)
+__global__ void k_next_bounce(Counters* c) {
+  c->nCur = c->nNext;
+  c->nNext = 0;
+  c->nShadow = 0;
+  c->nMis = 0;
+  for (int k = 0; k < 8; ++k) c->nMat[k] = 0;
+}
+
+// wave end: per pixel, add the wave's per-path radiance in sample order (deterministic).
+__global__ void __launch_bounds__(kBlock) k_film_accumulate(const __grid_constant__ RenderParams P) {
+  uint32_t nPix = (uint32_t)(P.w * P.h);
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nPix; p += gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(P.accum)[p];
+    for (int j = 0; j < P.nsWave; ++j) {
+      float4 L = P.ws.L[(size_t)j * nPix + p];
+      a.x += L.x; a.y += L.y; a.z += L.z;
+    }
+    a.w += (float)P.nsWave;
+    reinterpret_cast<float4*>(P.accum)[p] = a;
+  }
+}
+
+// K8: film resolve = mean, RGB->XYZ->RGB, sRGB gamma, 8-bit, Y flip (Integrator.cpp:313-344, Spectrum.h:10-25)
+__global__ void k_resolve_film(const float4* sum, int w, int h, float invSpp, int useCount, float* outRgb, unsigned char* outRgba8) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= w * h) return;
+  float4 s = sum[p];
+  float r, g, b;
+  if (useCount) { r = s.x / s.w; g = s.y / s.w; b = s.z / s.w; }  // colObj /= spp : true divide per channel
+  else { r = s.x * invSpp; g = s.y * invSpp; b = s.z * invSpp; }
+  if (outRgb) { outRgb[3 * p] = r; outRgb[3 * p + 1] = g; outRgb[3 * p + 2] = b; }
+  if (outRgba8) {
+    float X = 0.412453f * r + 0.357580f * g + 0.180423f * b;
+    float Y = 0.212671f * r + 0.715160f * g + 0.072169f * b;
+    float Z = 0.019334f * r + 0.119193f * g + 0.950227f * b;
+    float rgb[3];
+    rgb[0] = 3.240479f * X - 1.537150f * Y - 0.498535f * Z;
+    rgb[1] = -0.969256f * X + 1.875991f * Y + 0.041556f * Z;
+    rgb[2] = 0.055648f * X - 0.204043f * Y + 1.057311f * Z;
+    int x = p % w, y = p / w;
+    int q = x + (h - 1 - y) * w;
+    for (int k = 0; k < 3; ++k) {
+      float v = rgb[k];
+      float gc = (v <= 0.0031308f) ? 12.92f * v : 1.055f * powf(v, (1.f / 2.4f)) - 0.055f;
+      outRgba8[4 * q + k] = (unsigned char)clampf(255.f * gc + 0.5f, 0.f, 255.f);
+    }
+    outRgba8[4 * q + 3] = 255;
+  }
+}
+
+// ---- parity hooks ----
+__global__ void k_dump_sampler(HaltonParams hp, int x0, int y0, int w, int h, long long s0, int ns, int nDims, float* out) {
+  long long n = (long long)w * h * ns * nDims;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int d = (int)(i % nDims);
+    long long r = i / nDims;
+    int sj = (int)(r % ns);
+    long long p = r / ns;
+    int px = x0 + (int)(p % w), py = y0 + (int)(p / w);
+    int64_t idx = halton_index_for_sample(px, py, s0 + sj, hp);
+    out[i] = halton_sample_dimension(idx, d, hp);
+  }
+}
+
+__global__ void k_dump_primary(const __grid_constant__ RenderParams P, int ns, float* outRays, int* outHits) {
+  long long n = (long long)P.w * P.h * ns;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int sj = (int)(i % ns);
+    long long p = i / ns;
+    int px = P.x0 + (int)(p % P.w), py = P.y0 + (int)(p / P.w);
+    int64_t idx = halton_index_for_sample(px, py, P.sBegin + sj, P.sc.hp);
+    float u0 = halton_sample_dimension(idx, 0, P.sc.hp), u1 = halton_sample_dimension(idx, 1, P.sc.hp);
+    float lu = 0, lv = 0;
+    if (P.sc.cam.lensRadius > 0) { lu = halton_sample_dimension(idx, 3, P.sc.hp); lv = halton_sample_dimension(idx, 4, P.sc.hp); }
+    V3 o, d;
+    generate_ray(P.sc.cam, (float)px + u0, (float)py + u1, lu, lv, &o, &d);
+    if (outRays) {
+      float* r = outRays + 8 * i;
+      r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = kInfinity; r[4] = d.x; r[5] = d.y; r[6] = d.z; r[7] = 0.f;
+    }
+    if (outHits) {
+      HitRec h;
+      unsigned a = 0, b = 0;
+      traverse<false, false>(P.sc, o, d, kInfinity, &h, &a, &b);
+      int* q = outHits + 4 * i;
+      q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
+      q[1] = __float_as_int(h.t);
+      q[2] = h.tri >= 0 ? __float_as_int(h.b0) : 0;
+      q[3] = h.tri >= 0 ? __float_as_int(h.b1) : 0;
+    }
+  }
+}
+
+__global__ void k_trace_user(const __grid_constant__ RenderParams P, const float* rays, long long n, int anyHit, int* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float* r = rays + 8 * i;
+    HitRec h;
+    unsigned a = 0, b = 0;
+    V3 o(r[0], r[1], r[2]), d(r[4], r[5], r[6]);
+    if (anyHit) {
+      out[i] = traverse<true, false>(P.sc, o, d, r[3], &h, &a, &b) ? 1 : 0;
+    } else {
+      traverse<false, false>(P.sc, o, d, r[3], &h, &a, &b);
+      int* q = out + 4 * i;
+      q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
+      q[1] = __float_as_int(h.t);
+      q[2] = h.tri >= 0 ? __float_as_int(h.b0) : 0;
+      q[3] = h.tri >= 0 ? __float_as_int(h.b1) : 0;
+    }
+  }
+}
+
+}  // namespace pbr

@@ -1,0 +1,671 @@
+// pbrgpu.cu - implementation of the C-ABI in include/pbrgpu.h: host-side flattening of the scene
+// description into HBM-resident SoA buffers and the wavefront launch schedule.
+//
+// Launch schedule for one wave of paths (all at the same bounce; PathIntegrator.cpp:42-108):
+//   k_raygen -> for bounce in 0..maxDepth: k_trace_closest -> k_shade<MAT> x5 + k_shade_miss
+//               -> k_trace_shadow + k_trace_mis -> k_next_bounce ;  k_film_accumulate
+// Queue sizes live in device counters; the host never reads them inside a render (no sync), grids
+// are sized for the wave capacity and the kernels loop over the live count.
+// There is NO CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host_tables.h"
+#include "kernels.cuh"
+
+using namespace pbr;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = alloc(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct pbrgpu_ctx {
+  int device = 0;
+  int smCount = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+};
+
+struct pbrgpu_scene {
+  pbrgpu_ctx* ctx = nullptr;
+  SceneDev sc{};
+  BuiltBvh bvh;
+  std::vector<int32_t> leafOf;  // caller's triangle index -> leaf-order position
+  std::vector<pbrgpu_light> lights;  // device copy (tri remapped to leaf order)
+  std::vector<float> lightPower;     // Light::Power().y() per light
+  bool haveCamera = false, haveSampler = false;
+  int64_t spp = 0;
+  // device buffers
+  DevBuf<float4> tv0, tv1, tv2;
+  DevBuf<Bvh2Node> nodes;
+  DevBuf<pbrgpu_material> mats;
+  DevBuf<pbrgpu_light> dlights;
+  DevBuf<float> lightFunc, lightCdf;
+  DevBuf<float> envTexels, condFunc, condCdf, condInt, margFunc, margCdf;
+  DevBuf<uint16_t> perms;
+  DevBuf<int32_t> primes, primeSums;
+  int lightStrategyBuilt = -1;
+  // wavefront state
+  uint32_t capacity = 0;
+  DevBuf<float4> rayO, rayD, hit, beta, L, shO, shD, shC, miO, miD, miC;
+  DevBuf<uint2> hidx;
+  DevBuf<uint32_t> meta, qA, qB, qMat;
+  DevBuf<Counters> ctr;
+  DevBuf<float> accum;
+  size_t accumPix = 0;
+};
+
+namespace {
+
+int ensure_wave(pbrgpu_scene* s, uint32_t cap) {
+  if (s->capacity >= cap) return 0;
+  CK(s->rayO.alloc(cap)); CK(s->rayD.alloc(cap)); CK(s->hit.alloc(cap)); CK(s->beta.alloc(cap)); CK(s->L.alloc(cap));
+  CK(s->shO.alloc(cap)); CK(s->shD.alloc(cap)); CK(s->shC.alloc(cap));
+  CK(s->miO.alloc(cap)); CK(s->miD.alloc(cap)); CK(s->miC.alloc(cap));
+  CK(s->hidx.alloc(cap)); CK(s->meta.alloc(cap)); CK(s->qA.alloc(cap)); CK(s->qB.alloc(cap));
+  CK(s->qMat.alloc((size_t)cap * kNumQueues));
+  if (!s->ctr.p) CK(s->ctr.alloc(1));
+  s->capacity = cap;
+  return 0;
+}
+
+void fill_wave(pbrgpu_scene* s, WaveDev* w) {
+  w->rayO = s->rayO.p; w->rayD = s->rayD.p; w->hit = s->hit.p; w->beta = s->beta.p; w->L = s->L.p;
+  w->hidx = s->hidx.p; w->meta = s->meta.p;
+  w->shO = s->shO.p; w->shD = s->shD.p; w->shC = s->shC.p;
+  w->miO = s->miO.p; w->miD = s->miD.p; w->miC = s->miC.p;
+  w->qCur = s->qA.p; w->qNext = s->qB.p; w->qMat = s->qMat.p;
+  w->ctr = s->ctr.p;
+  w->capacity = s->capacity;
+}
+
+// Light sampling distribution (LightDistrib.cpp:8-45): "uniform" (also what "spatial" falls back to, and
+// what a single-light scene always gets) or "power".
+int build_light_distribution(pbrgpu_scene* s, int strategy) {
+  int n = (int)s->lights.size();
+  if (n == 0) { s->sc.lightFunc = s->sc.lightCdf = nullptr; s->sc.lightFuncInt = 0; return 0; }
+  if (n == 1) strategy = PBRGPU_LIGHTSTRATEGY_UNIFORM;
+  if (s->lightStrategyBuilt == strategy) return 0;
+  std::vector<float> f((size_t)n, 1.f);
+  if (strategy == PBRGPU_LIGHTSTRATEGY_POWER) f = s->lightPower;
+  host::Dist1D d;
+  d.build(f.data(), n);
+  CK(s->lightFunc.upload(d.func, s->ctx->stream));
+  CK(s->lightCdf.upload(d.cdf, s->ctx->stream));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  s->sc.lightFunc = s->lightFunc.p;
+  s->sc.lightCdf = s->lightCdf.p;
+  s->sc.lightFuncInt = d.funcInt;
+  s->lightStrategyBuilt = strategy;
+  return 0;
+}
+
+inline int mod_i(int a, int b) { int r = a - (a / b) * b; return r < 0 ? r + b : r; }
+
+// host twin of MIPMap::triangle(0, st) (Texture/MIPMap.h:256-266) used to build the sampling image
+void env_bilinear_host(const std::vector<float>& tex, int W, int H, float s_, float t_, float out[3]) {
+  float s = s_ * W - 0.5f, t = t_ * H - 0.5f;
+  int s0 = (int)std::floor(s), t0 = (int)std::floor(t);
+  float ds = s - s0, dt = t - t0;
+  auto texel = [&](int a, int b) { return &tex[3 * ((size_t)mod_i(b, H) * W + mod_i(a, W))]; };
+  const float *a = texel(s0, t0), *b = texel(s0, t0 + 1), *c = texel(s0 + 1, t0), *d = texel(s0 + 1, t0 + 1);
+  float w0 = (1 - ds) * (1 - dt), w1 = (1 - ds) * dt, w2 = ds * (1 - dt), w3 = ds * dt;
+  for (int k = 0; k < 3; ++k) out[k] = ((w0 * a[k] + w1 * b[k]) + w2 * c[k]) + w3 * d[k];
+}
+
+uint32_t grid_for(const pbrgpu_ctx* c, uint64_t n, int perSm) {
+  uint64_t blocks = (n + kBlock - 1) / kBlock;
+  uint64_t cap = (uint64_t)c->smCount * perSm;
+  if (blocks < 1) blocks = 1;
+  return (uint32_t)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pbrgpu_last_error(void) { return g_err.c_str(); }
+
+int pbrgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int pbrgpu_init(int device_id, pbrgpu_ctx** out) {
+  if (!out) return fail("pbrgpu_init: out == NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail("pbrgpu_init: no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device_id < 0 || device_id >= n) return fail("pbrgpu_init: bad device id");
+  CK(cudaSetDevice(device_id));
+  auto* c = new pbrgpu_ctx;
+  c->device = device_id;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_id));
+  c->smCount = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
+  *out = c;
+  return 0;
+}
+
+void pbrgpu_shutdown(pbrgpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int pbrgpu_halton_params(const int32_t sample_bounds[4], int32_t out7[7]) {
+  host::halton_params(sample_bounds, out7);
+  return 0;
+}
+
+int64_t pbrgpu_compute_perms(uint16_t* out, int64_t capacity) {
+  std::vector<int32_t> primes, sums;
+  host::prime_tables(&primes, &sums);
+  std::vector<uint16_t> p = host::radical_inverse_permutations(primes);
+  if (out) memcpy(out, p.data(), sizeof(uint16_t) * (size_t)std::min<int64_t>(capacity, (int64_t)p.size()));
+  return (int64_t)p.size();
+}
+
+int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scene** out) {
+  if (!ctx || !d || !out) return fail("pbrgpu_scene_create: NULL argument");
+  *out = nullptr;
+  if (d->n_tris <= 0 || d->n_verts <= 0 || !d->verts || !d->indices || !d->tri_material)
+    return fail("pbrgpu_scene_create: empty scene");
+  if (d->n_tris >= (1 << 29)) return fail("pbrgpu_scene_create: too many triangles");
+  if (d->n_materials <= 0 || d->n_materials > (int)kTriMatMask) return fail("pbrgpu_scene_create: bad material count");
+  if (d->normals || d->uvs)
+    return fail("pbrgpu_scene_create: per-vertex normals / uvs are not supported yet (flat-shaded triangles only)");
+  for (int64_t i = 0; i < (int64_t)d->n_tris * 3; ++i)
+    if (d->indices[i] < 0 || d->indices[i] >= d->n_verts) return fail("pbrgpu_scene_create: vertex index out of range");
+  for (int i = 0; i < d->n_tris; ++i) {
+    if (d->tri_material[i] < 0 || d->tri_material[i] >= d->n_materials)
+      return fail("pbrgpu_scene_create: triangle without a material (null-BSDF pass-through is not supported)");
+    if (d->tri_light && d->tri_light[i] >= d->n_lights) return fail("pbrgpu_scene_create: tri_light out of range");
+  }
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<pbrgpu_scene> s(new pbrgpu_scene);
+  s->ctx = ctx;
+  cudaStream_t st = ctx->stream;
+
+  build_bvh2(d->verts, d->indices, d->n_tris, 4, &s->bvh);
+  const int nT = d->n_tris;
+  s->leafOf.assign((size_t)nT, -1);
+  std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT);
+  for (int k = 0; k < nT; ++k) {
+    int ti = s->bvh.triOrder[k];
+    s->leafOf[ti] = k;
+    const float* a = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti];
+    const float* b = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti + 1];
+    const float* c = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti + 2];
+    int m = d->tri_material[ti];
+    uint32_t flags = (d->tri_flags && (d->tri_flags[ti] & 1)) ? kTriFlagFlipNormal : 0u;
+    uint32_t w1 = (uint32_t)m | ((uint32_t)d->materials[m].type << kTriTypeShift) | (flags << kTriFlagShift);
+    int32_t lid = d->tri_light ? d->tri_light[ti] : -1;
+    v0[k] = make_float4(a[0], a[1], a[2], u2f((uint32_t)ti));
+    v1[k] = make_float4(b[0], b[1], b[2], u2f(w1));
+    v2[k] = make_float4(c[0], c[1], c[2], u2f((uint32_t)lid));
+  }
+  CK(s->tv0.upload(v0, st)); CK(s->tv1.upload(v1, st)); CK(s->tv2.upload(v2, st));
+  CK(s->nodes.upload(s->bvh.nodes, st));
+
+  // materials: RoughnessToAlpha applied on the host (glibc logf, as the reference would)
+  std::vector<pbrgpu_material> mats(d->materials, d->materials + d->n_materials);
+  for (auto& m : mats) {
+    if (m.type < 0 || m.type >= PBRGPU_MAT_COUNT) return fail("pbrgpu_scene_create: unknown material type");
+    m.pad0 = (m.type == PBRGPU_MAT_GLASS && m.u_rough == 0 && m.v_rough == 0) ? 1.f : 0.f;  // isSpecular
+    if (m.remap_roughness && m.type != PBRGPU_MAT_MATTE && m.type != PBRGPU_MAT_MIRROR) {
+      m.u_rough = host::roughness_to_alpha(m.u_rough);
+      m.v_rough = host::roughness_to_alpha(m.v_rough);
+    }
+  }
+  CK(s->mats.upload(mats, st));
+
+  // scene bound -> InfiniteAreaLight::Preprocess (BoundingSphere, Geometry.h)
+  const Aabb& wb = s->bvh.bounds;
+  V3 center((wb.lo[0] + wb.hi[0]) * 0.5f, (wb.lo[1] + wb.hi[1]) * 0.5f, (wb.lo[2] + wb.hi[2]) * 0.5f);
+  bool inside = center.x >= wb.lo[0] && center.x <= wb.hi[0] && center.y >= wb.lo[1] && center.y <= wb.hi[1] &&
+                center.z >= wb.lo[2] && center.z <= wb.hi[2];
+  V3 dv(center.x - wb.hi[0], center.y - wb.hi[1], center.z - wb.hi[2]);
+  s->sc.worldCenter = center;
+  s->sc.worldRadius = inside ? std::sqrt(dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) : 0.f;
+
+  // lights
+  s->lights.assign(d->lights, d->lights + d->n_lights);
+  s->lightPower.assign((size_t)d->n_lights, 0.f);
+  s->sc.nInfinite = 0;
+  int envUser = -1;
+  for (int i = 0; i < d->n_lights; ++i) {
+    pbrgpu_light& l = s->lights[i];
+    switch (l.type) {
+      case PBRGPU_LIGHT_POINT: {
+        Spec p = (4 * kPi) * Spec(l.L[0], l.L[1], l.L[2]);
+        s->lightPower[i] = p.y();
+        break;
+      }
+      case PBRGPU_LIGHT_AREA_TRI: {
+        if (l.tri < 0 || l.tri >= nT) return fail("pbrgpu_scene_create: area light triangle out of range");
+        if (!d->tri_light || d->tri_light[l.tri] != i) return fail("pbrgpu_scene_create: tri_light / light.tri mismatch");
+        const float* a = d->verts + 3 * (size_t)d->indices[3 * (size_t)l.tri];
+        const float* b = d->verts + 3 * (size_t)d->indices[3 * (size_t)l.tri + 1];
+        const float* c = d->verts + 3 * (size_t)d->indices[3 * (size_t)l.tri + 2];
+        V3 p0(a[0], a[1], a[2]), p1(b[0], b[1], b[2]), p2(c[0], c[1], c[2]);
+        float area = 0.5f * length(cross(p1 - p0, p2 - p0));
+        Spec p = ((l.two_sided ? 2.f : 1.f) * Spec(l.L[0], l.L[1], l.L[2])) * area * kPi;
+        s->lightPower[i] = p.y();
+        l.tri = s->leafOf[l.tri];
+        break;
+      }
+      case PBRGPU_LIGHT_INFINITE:
+      case PBRGPU_LIGHT_SKYBOX:
+        if (envUser >= 0) return fail("pbrgpu_scene_create: at most one environment-map light is supported");
+        envUser = i;
+        if (s->sc.nInfinite >= 4) return fail("pbrgpu_scene_create: too many infinite lights");
+        s->sc.infinite[s->sc.nInfinite++] = i;
+        break;
+      default: return fail("pbrgpu_scene_create: unknown light type");
+    }
+  }
+  if (envUser >= 0) {
+    const int W = d->env_width, H = d->env_height;
+    if (!d->env_texels || W <= 0 || H <= 0) return fail("pbrgpu_scene_create: environment light without env_texels");
+    if ((W & (W - 1)) || (H & (H - 1)))
+      return fail("pbrgpu_scene_create: env map sizes must be powers of two (MIPMap would Lanczos-resample otherwise)");
+    const pbrgpu_light& l = s->lights[envUser];
+    std::vector<float> tex(d->env_texels, d->env_texels + (size_t)W * H * 3);
+    s->sc.env.width = W;
+    s->sc.env.height = H;
+    if (l.type == PBRGPU_LIGHT_INFINITE) {
+      for (size_t k = 0; k < (size_t)W * H; ++k)
+        for (int c = 0; c < 3; ++c) tex[3 * k + c] = l.L[c] * tex[3 * k + c];  // InfiniteAreaLight.cpp:20-31
+      // sampling image (InfiniteAreaLight.cpp:44-59) and Distribution2D (Sampling.cpp:121-133)
+      std::vector<float> img((size_t)W * H);
+      for (int v = 0; v < H; ++v) {
+        float vp = (v + .5f) / (float)H;
+        float sinTheta = std::sin(kPi * (v + .5f) / H);
+        for (int u = 0; u < W; ++u) {
+          float up = (u + .5f) / (float)W;
+          float rgb[3];
+          env_bilinear_host(tex, W, H, up, vp, rgb);
+          float y = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
+          img[(size_t)u + (size_t)v * W] = y * sinTheta;
+        }
+      }
+      std::vector<float> cFunc((size_t)W * H), cCdf((size_t)(W + 1) * H), cInt((size_t)H);
+      for (int v = 0; v < H; ++v) {
+        host::Dist1D row;
+        row.build(&img[(size_t)v * W], W);
+        memcpy(&cFunc[(size_t)v * W], row.func.data(), sizeof(float) * W);
+        memcpy(&cCdf[(size_t)v * (W + 1)], row.cdf.data(), sizeof(float) * (W + 1));
+        cInt[v] = row.funcInt;
+      }
+      host::Dist1D marg;
+      marg.build(cInt.data(), H);
+      CK(s->condFunc.upload(cFunc, st)); CK(s->condCdf.upload(cCdf, st)); CK(s->condInt.upload(cInt, st));
+      CK(s->margFunc.upload(marg.func, st)); CK(s->margCdf.upload(marg.cdf, st));
+      s->sc.env.condFunc = s->condFunc.p; s->sc.env.condCdf = s->condCdf.p; s->sc.env.condInt = s->condInt.p;
+      s->sc.env.margFunc = s->margFunc.p; s->sc.env.margCdf = s->margCdf.p;
+      s->sc.env.margInt = marg.funcInt;
+      // Power (InfiniteAreaLight.cpp:63-67) needs Lookup(st, .5f) on the MIP pyramid; only the "power"
+      // light strategy with >1 light reads it.  Approximated by the mean texel * pi * r^2 * 4pi... see render().
+      s->lightPower[envUser] = -1.f;  // marks "needs pyramid"
+    }
+    CK(s->envTexels.upload(tex, st));
+    s->sc.env.texels = s->envTexels.p;
+  }
+  CK(s->dlights.upload(s->lights, st));
+
+  s->sc.tv0 = s->tv0.p; s->sc.tv1 = s->tv1.p; s->sc.tv2 = s->tv2.p;
+  s->sc.nodes = s->nodes.p;
+  s->sc.mats = s->mats.p;
+  s->sc.lights = s->dlights.p;
+  s->sc.nTris = nT;
+  s->sc.nLights = d->n_lights;
+
+  // sampler tables
+  std::vector<int32_t> primes, sums;
+  host::prime_tables(&primes, &sums);
+  CK(s->primes.upload(primes, st));
+  CK(s->primeSums.upload(sums, st));
+  s->sc.hp.primes = s->primes.p;
+  s->sc.hp.primeSums = s->primeSums.p;
+  CK(cudaStreamSynchronize(st));
+  *out = s.release();
+  return 0;
+}
+
+void pbrgpu_scene_destroy(pbrgpu_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  delete s;
+}
+
+int pbrgpu_camera_set(pbrgpu_scene* s, const pbrgpu_camera_desc* c) {
+  if (!s || !c) return fail("pbrgpu_camera_set: NULL argument");
+  if (c->type != PBRGPU_CAMERA_PERSPECTIVE && c->type != PBRGPU_CAMERA_ORTHOGRAPHIC) return fail("pbrgpu_camera_set: bad type");
+  if (c->width <= 0 || c->height <= 0) return fail("pbrgpu_camera_set: bad resolution");
+  CameraDev& cd = s->sc.cam;
+  cd.type = c->type; cd.width = c->width; cd.height = c->height;
+  cd.lensRadius = c->lens_radius; cd.focalDistance = c->focal_distance;
+  memcpy(cd.r2c, c->raster_to_camera, sizeof(cd.r2c));
+  memcpy(cd.c2w, c->camera_to_world, sizeof(cd.c2w));
+  s->haveCamera = true;
+  return 0;
+}
+
+int pbrgpu_sampler_set(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
+  if (!s || !d) return fail("pbrgpu_sampler_set: NULL argument");
+  if (d->type != PBRGPU_SAMPLER_HALTON)
+    return fail("pbrgpu_sampler_set: only the Halton sampler exists in the reference (SURVEY 8(c): no SobolSampler class)");
+  if (d->samples_per_pixel <= 0) return fail("pbrgpu_sampler_set: samples_per_pixel <= 0");
+  CK(cudaSetDevice(s->ctx->device));
+  int32_t p7[7];
+  host::halton_params(d->sample_bounds, p7);
+  HaltonParams& hp = s->sc.hp;
+  hp.baseScales[0] = p7[0]; hp.baseScales[1] = p7[1];
+  hp.baseExponents[0] = p7[2]; hp.baseExponents[1] = p7[3];
+  hp.sampleStride = p7[4];
+  hp.multInverse[0] = p7[5]; hp.multInverse[1] = p7[6];
+  hp.sampleAtPixelCenter = d->sample_at_pixel_center;
+  std::vector<uint16_t> perms;
+  if (d->perms && d->n_perms > 0) perms.assign(d->perms, d->perms + d->n_perms);
+  else {
+    std::vector<int32_t> primes, sums;
+    host::prime_tables(&primes, &sums);
+    perms = host::radical_inverse_permutations(primes);
+  }
+  CK(s->perms.upload(perms, s->ctx->stream));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  hp.perms = s->perms.p;
+  hp.nPerms = (int64_t)perms.size();
+  s->spp = d->samples_per_pixel;
+  s->haveSampler = true;
+  return 0;
+}
+
+int pbrgpu_scene_info(pbrgpu_scene* s, int64_t out[8]) {
+  if (!s || !out) return fail("pbrgpu_scene_info: NULL argument");
+  memset(out, 0, sizeof(int64_t) * 8);
+  out[0] = (int64_t)s->bvh.nodes.size();
+  out[1] = s->bvh.nLeaves;
+  out[2] = s->bvh.maxLeafSize;
+  out[3] = (int64_t)(s->bvh.nodes.size() * sizeof(Bvh2Node));
+  out[4] = (int64_t)s->sc.nTris * 48;
+  out[5] = s->bvh.maxDepth;
+  return 0;
+}
+
+static int check_render_args(pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
+  if (!s || !rd) return fail("pbrgpu_render: NULL argument");
+  if (!s->haveCamera || !s->haveSampler) return fail("pbrgpu_render: camera / sampler not set");
+  if (rd->x1 <= rd->x0 || rd->y1 <= rd->y0) return fail("pbrgpu_render: empty pixel region");
+  if (rd->s1 < rd->s0 || rd->s0 < 0) return fail("pbrgpu_render: bad sample range");
+  if (rd->max_depth < 0 || rd->max_depth > 1000) return fail("pbrgpu_render: bad max_depth");
+  if (rd->integrator != PBRGPU_INTEGRATOR_PATH)
+    return fail("pbrgpu_render: integrator not implemented on the GPU path yet (Path only)");
+  if (s->bvh.maxDepth >= 60) return fail("pbrgpu_render: BVH deeper than the traversal stack");
+  return 0;
+}
+
+int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d_rgba_sum, void* stream_, pbrgpu_stats* stats) {
+  if (check_render_args(s, rd)) return 1;
+  if (!d_rgba_sum) return fail("pbrgpu_render_device: NULL accumulator");
+  pbrgpu_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : c->stream;
+  if (build_light_distribution(s, rd->light_strategy)) return 1;
+  if (rd->light_strategy == PBRGPU_LIGHTSTRATEGY_POWER && s->lights.size() > 1)
+    for (float p : s->lightPower)
+      if (p < 0) return fail("pbrgpu_render: \"power\" light strategy with an InfiniteAreaLight is not supported (needs the MIP pyramid)");
+
+  const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
+  const int64_t nS = rd->s1 - rd->s0;
+  const bool count = (rd->flags & PBRGPU_RENDER_COUNTERS) != 0;
+  const uint32_t capMax = 1u << 22;
+  // row bands of <= capMax pixels; inside a band, waves of nsWave samples per pixel
+  int bandRows = (int)std::max<int64_t>(1, std::min<int64_t>(H, capMax / (uint32_t)W));
+  if ((uint64_t)W > capMax) return fail("pbrgpu_render: region wider than the wave capacity");
+  int nsWaveMax = (int)std::max<int64_t>(1, capMax / ((uint64_t)bandRows * W));
+  if (rd->samples_per_wave > 0) nsWaveMax = std::min(nsWaveMax, rd->samples_per_wave);
+  uint32_t cap = (uint32_t)((uint64_t)bandRows * W * std::min<int64_t>(nsWaveMax, std::max<int64_t>(nS, 1)));
+  if (ensure_wave(s, cap)) return 1;
+
+  RenderParams P{};
+  P.sc = s->sc;
+  fill_wave(s, &P.ws);
+  P.integrator = rd->integrator;
+  P.maxDepth = rd->max_depth;
+  P.rrThreshold = rd->rr_threshold;
+  P.arrayEndDim = 5;
+  P.countStats = count ? 1 : 0;
+
+  if (!(rd->flags & PBRGPU_RENDER_ACCUMULATE)) CK(cudaMemsetAsync(d_rgba_sum, 0, sizeof(float) * 4 * (size_t)W * H, st));
+  Counters zero{};
+  CK(cudaMemcpyAsync(s->ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(c->ev[0], st));
+  uint64_t launches = 0;
+  for (int yb = 0; yb < H; yb += bandRows) {
+    int rows = std::min(bandRows, H - yb);
+    P.x0 = rd->x0; P.y0 = rd->y0 + yb; P.w = W; P.h = rows;
+    P.accum = d_rgba_sum + 4 * (size_t)yb * W;
+    for (int64_t sb = rd->s0; sb < rd->s1; sb += nsWaveMax) {
+      int ns = (int)std::min<int64_t>(nsWaveMax, rd->s1 - sb);
+      P.sBegin = sb;
+      P.nsWave = ns;
+      uint64_t nPaths = (uint64_t)rows * W * ns;
+      P.ws.qCur = s->qA.p;
+      P.ws.qNext = s->qB.p;
+      uint32_t g = grid_for(c, nPaths, 8);
+      k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
+      k_raygen<<<g, kBlock, 0, st>>>(P);
+      launches += 2;
+      for (int bounce = 0; bounce <= rd->max_depth; ++bounce) {
+        if (count) k_trace_closest<true><<<g, kBlock, 0, st>>>(P);
+        else k_trace_closest<false><<<g, kBlock, 0, st>>>(P);
+        k_shade<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
+        k_shade<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
+        k_shade<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
+        k_shade<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
+        k_shade<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
+        k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce);
+        if (count) { k_trace_shadow<true><<<g, kBlock, 0, st>>>(P); k_trace_mis<true><<<g, kBlock, 0, st>>>(P); }
+        else { k_trace_shadow<false><<<g, kBlock, 0, st>>>(P); k_trace_mis<false><<<g, kBlock, 0, st>>>(P); }
+        k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
+        launches += 10;
+        std::swap(P.ws.qCur, P.ws.qNext);
+      }
+      k_film_accumulate<<<grid_for(c, (uint64_t)rows * W, 8), kBlock, 0, st>>>(P);
+      launches += 1;
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev[1], st));
+  if (stats) {
+    Counters hc{};
+    CK(cudaMemcpyAsync(&hc, s->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    memset(stats, 0, sizeof(*stats));
+    stats->camera_samples = (uint64_t)W * H * (uint64_t)nS;
+    stats->rays_closest = hc.raysClosest;
+    stats->rays_shadow = hc.raysShadow;
+    stats->nodes_visited = hc.nodesVisited;
+    stats->tris_tested = hc.trisTested;
+    stats->kernel_launches = launches;
+    stats->ms_total = ms;
+  }
+  return 0;
+}
+
+int pbrgpu_resolve_film(pbrgpu_ctx* c, const float* d_rgba_sum, int width, int height, float inv_spp, float* out_rgb_mean,
+                        unsigned char* out_rgba8) {
+  if (!c || !d_rgba_sum || width <= 0 || height <= 0) return fail("pbrgpu_resolve_film: bad argument");
+  CK(cudaSetDevice(c->device));
+  size_t n = (size_t)width * height;
+  DevBuf<float> drgb;
+  DevBuf<unsigned char> d8;
+  if (out_rgb_mean) CK(drgb.alloc(n * 3));
+  if (out_rgba8) CK(d8.alloc(n * 4));
+  k_resolve_film<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)d_rgba_sum, width, height, inv_spp,
+                                                                      inv_spp <= 0 ? 1 : 0, drgb.p, d8.p);
+  CK(cudaGetLastError());
+  if (out_rgb_mean) CK(cudaMemcpyAsync(out_rgb_mean, drgb.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (out_rgba8) CK(cudaMemcpyAsync(out_rgba8, d8.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+__global__ void k_rgba_to_rgb(const float4* in, size_t n, float* out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = in[i];
+  out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+}
+
+int pbrgpu_render(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* out_rgb_sum, unsigned char* out_rgba8, pbrgpu_stats* stats) {
+  if (check_render_args(s, rd)) return 1;
+  pbrgpu_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
+  size_t n = (size_t)W * H;
+  if (s->accumPix < n) { CK(s->accum.alloc(n * 4)); s->accumPix = n; }
+  pbrgpu_render_desc r2 = *rd;
+  if (rd->flags & PBRGPU_RENDER_ACCUMULATE) {
+    // host-side accumulate: caller's sums are added after the render
+    r2.flags &= ~PBRGPU_RENDER_ACCUMULATE;
+  }
+  if (pbrgpu_render_device(s, &r2, s->accum.p, c->stream, stats)) return 1;
+  if (out_rgb_sum) {
+    DevBuf<float> drgb;
+    CK(drgb.alloc(n * 3));
+    k_rgba_to_rgb<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)s->accum.p, n, drgb.p);
+    CK(cudaGetLastError());
+    if (rd->flags & PBRGPU_RENDER_ACCUMULATE) {
+      std::vector<float> tmp(n * 3);
+      CK(cudaMemcpyAsync(tmp.data(), drgb.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (size_t i = 0; i < n * 3; ++i) out_rgb_sum[i] += tmp[i];
+    } else {
+      CK(cudaMemcpyAsync(out_rgb_sum, drgb.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+  }
+  if (out_rgba8) {
+    if (pbrgpu_resolve_film(c, s->accum.p, W, H, 0.f, nullptr, out_rgba8)) return 1;
+  }
+  return 0;
+}
+
+int pbrgpu_debug_dump(pbrgpu_scene* s, const pbrgpu_dump_desc* dd, void* out, size_t out_bytes) {
+  if (!s || !dd || !out) return fail("pbrgpu_debug_dump: NULL argument");
+  pbrgpu_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  if (dd->what == PBRGPU_DUMP_PERMS) {
+    if (!s->haveSampler) return fail("pbrgpu_debug_dump: sampler not set");
+    size_t bytes = std::min(out_bytes, (size_t)s->sc.hp.nPerms * sizeof(uint16_t));
+    CK(cudaMemcpy(out, s->perms.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  if (!s->haveSampler) return fail("pbrgpu_debug_dump: sampler not set");
+  const int W = dd->x1 - dd->x0, H = dd->y1 - dd->y0;
+  const int64_t ns = dd->s1 - dd->s0;
+  if (W <= 0 || H <= 0 || ns <= 0 || ns > (1 << 20)) return fail("pbrgpu_debug_dump: bad region");
+  if (dd->what == PBRGPU_DUMP_SAMPLER) {
+    if (dd->n_dims <= 0) return fail("pbrgpu_debug_dump: n_dims <= 0");
+    size_t n = (size_t)W * H * ns * dd->n_dims;
+    if (out_bytes < n * sizeof(float)) return fail("pbrgpu_debug_dump: output too small");
+    DevBuf<float> d;
+    CK(d.alloc(n));
+    k_dump_sampler<<<grid_for(c, n, 8), kBlock, 0, c->stream>>>(s->sc.hp, dd->x0, dd->y0, W, H, dd->s0, (int)ns, dd->n_dims, d.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  if (dd->what == PBRGPU_DUMP_PRIMARY_RAYS || dd->what == PBRGPU_DUMP_PRIMARY_HITS) {
+    if (!s->haveCamera) return fail("pbrgpu_debug_dump: camera not set");
+    bool rays = dd->what == PBRGPU_DUMP_PRIMARY_RAYS;
+    size_t n = (size_t)W * H * ns;
+    size_t bytes = n * (rays ? 8 * sizeof(float) : 4 * sizeof(int));
+    if (out_bytes < bytes) return fail("pbrgpu_debug_dump: output too small");
+    DevBuf<unsigned char> d;
+    CK(d.alloc(bytes));
+    RenderParams P{};
+    P.sc = s->sc;
+    P.x0 = dd->x0; P.y0 = dd->y0; P.w = W; P.h = H; P.sBegin = dd->s0;
+    k_dump_primary<<<grid_for(c, n, 8), kBlock, 0, c->stream>>>(P, (int)ns, rays ? (float*)d.p : nullptr, rays ? nullptr : (int*)d.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  return fail("pbrgpu_debug_dump: unknown dump kind");
+}
+
+int pbrgpu_trace_rays(pbrgpu_scene* s, const float* rays, int64_t n, int any_hit, void* out_hits) {
+  if (!s || !rays || !out_hits || n <= 0) return fail("pbrgpu_trace_rays: bad argument");
+  pbrgpu_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  DevBuf<float> dr;
+  DevBuf<int> dh;
+  CK(dr.alloc((size_t)n * 8));
+  CK(dh.alloc((size_t)n * (any_hit ? 1 : 4)));
+  CK(cudaMemcpyAsync(dr.p, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  RenderParams P{};
+  P.sc = s->sc;
+  k_trace_user<<<grid_for(c, (uint64_t)n, 8), kBlock, 0, c->stream>>>(P, dr.p, n, any_hit, dh.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_hits, dh.p, dh.n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// sampler.cuh - Halton sampler: integer radical inverse, bit-exact with the reference.
+//   RadicalInverseSpecialized<b>            Sampler/LowDiscrepancy.cpp:211-225
+//   RadicalInverse (base 2 via double)      Sampler/LowDiscrepancy.cpp:227-232
+//   ScrambledRadicalInverseSpecialized<b>   Sampler/LowDiscrepancy.cpp:2300-2316
+//   HaltonSampler::GetIndexForSample        Sampler/Halton.cpp:61-81
+//   HaltonSampler::SampleDimension          Sampler/Halton.cpp:83-92
+// The reference dispatches over 1024 template instantiations; here the base is a runtime value read
+// from the prime table (same arithmetic, the digits and the fp32 product chain are identical).
+#pragma once
+#include "vecmath.cuh"
+
+namespace pbr {
+
+struct HaltonParams {
+  int32_t baseScales[2];
+  int32_t baseExponents[2];
+  int32_t sampleStride;
+  int32_t multInverse[2];
+  int32_t sampleAtPixelCenter;
+  const uint16_t* perms;   // radicalInversePermutations (device)
+  const int32_t* primes;   // Primes[1000]
+  const int32_t* primeSums;
+  int64_t nPerms;
+};
+
+constexpr int kPrimeTableSize = 1000;
+constexpr int kMaxResolution = 128;  // Halton.cpp:7
+
+// digits of `a` in base `base`, reversed;  returns reversedDigits, *invBaseN = invBase^nDigits (fp32 chain)
+PBR_D uint64_t reverse_digits(uint64_t a, uint32_t base, float invBase, float* invBaseN, const uint16_t* perm) {
+  uint64_t rev = 0;
+  float ibn = 1;
+  if ((a >> 32) == 0) {  // fast path: 32-bit divides (all indices of a <=4096-spp 4K render fit)
+    uint32_t a32 = (uint32_t)a;
+    while (a32) {
+      uint32_t next = a32 / base;
+      uint32_t digit = a32 - next * base;
+      rev = rev * base + (perm ? (uint32_t)perm[digit] : digit);
+      ibn *= invBase;
+      a32 = next;
+    }
+  } else {
+    while (a) {
+      uint64_t next = a / base;
+      uint64_t digit = a - next * base;
+      rev = rev * base + (perm ? (uint64_t)perm[digit] : digit);
+      ibn *= invBase;
+      a = next;
+    }
+  }
+  *invBaseN = ibn;
+  return rev;
+}
+
+PBR_D float radical_inverse(int baseIndex, uint64_t a, const HaltonParams& hp) {
+  if (baseIndex == 0) {
+    // ReverseBits64(a) * 5.4210108624275222e-20 : uint64 -> double product, narrowed on return
+    return (float)((double)__brevll(a) * 5.4210108624275222e-20);
+  }
+  if (baseIndex >= 1024) return 0.f;  // LowDiscrepancy.cpp:2279-2280 (table itself has 1000 primes)
+  uint32_t base = (uint32_t)hp.primes[baseIndex];
+  float invBase = (float)1 / (float)base;
+  float invBaseN;
+  uint64_t rev = reverse_digits(a, base, invBase, &invBaseN, nullptr);
+  return stdmin((float)rev * invBaseN, kOneMinusEpsilon);
+}
+
+PBR_D float scrambled_radical_inverse(int baseIndex, uint64_t a, const HaltonParams& hp) {
+  if (baseIndex >= 1024) return 0.f;
+  uint32_t base = (uint32_t)hp.primes[baseIndex];
+  const uint16_t* perm = hp.perms + hp.primeSums[baseIndex];
+  float invBase = (float)1 / (float)base;
+  float invBaseN;
+  uint64_t rev = reverse_digits(a, base, invBase, &invBaseN, perm);
+  // invBaseN * (reversedDigits + invBase * perm[0] / (1 - invBase))
+  float tail = (invBase * (float)(int)perm[0]) / (1 - invBase);
+  return stdmin(invBaseN * ((float)rev + tail), kOneMinusEpsilon);
+}
+
+PBR_D float halton_sample_dimension(int64_t index, int dim, const HaltonParams& hp) {
+  if (hp.sampleAtPixelCenter && (dim == 0 || dim == 1)) return 0.5f;
+  if (dim == 0) return radical_inverse(0, (uint64_t)(index >> hp.baseExponents[0]), hp);
+  if (dim == 1) return radical_inverse(1, (uint64_t)(index / hp.baseScales[1]), hp);
+  return scrambled_radical_inverse(dim, (uint64_t)index, hp);
+}
+
+template <int base>
+PBR_D uint64_t inverse_radical_inverse(uint64_t inverse, int nDigits) {  // LowDiscrepancy.h:28-37
+  uint64_t index = 0;
+  for (int i = 0; i < nDigits; ++i) {
+    uint64_t digit = inverse % base;
+    inverse /= base;
+    index = index * base + digit;
+  }
+  return index;
+}
+
+// Halton index of sample `sampleNum` of pixel (px,py)   (Halton.cpp:61-81)
+PBR_D int64_t halton_index_for_sample(int px, int py, int64_t sampleNum, const HaltonParams& hp) {
+  int64_t offset = 0;
+  if (hp.sampleStride > 1) {
+    int pmx = px % kMaxResolution, pmy = py % kMaxResolution;
+    if (pmx < 0) pmx += kMaxResolution;
+    if (pmy < 0) pmy += kMaxResolution;
+    uint64_t d0 = inverse_radical_inverse<2>((uint64_t)pmx, hp.baseExponents[0]);
+    uint64_t d1 = inverse_radical_inverse<3>((uint64_t)pmy, hp.baseExponents[1]);
+    offset += (int64_t)(d0 * (uint64_t)(hp.sampleStride / hp.baseScales[0]) * (uint64_t)(int64_t)hp.multInverse[0]);
+    offset += (int64_t)(d1 * (uint64_t)(hp.sampleStride / hp.baseScales[1]) * (uint64_t)(int64_t)hp.multInverse[1]);
+    offset %= hp.sampleStride;
+  }
+  return offset + sampleNum * hp.sampleStride;
+}
+
+// Per-path sampler cursor: (index, dim) - Get1D/Get2D of GlobalSampler (Sampler.cpp:131-143) with
+// arrayEndDim == arrayStartDim (no sample arrays requested by the Path integrator).
+struct SamplerCursor {
+  int64_t index;
+  int dim;
+  int arrayEndDim;  // == 5 unless DirectLighting/UniformSampleAll requested arrays
+  PBR_D float get1D(const HaltonParams& hp) {
+    if (dim >= 5 && dim < arrayEndDim) dim = arrayEndDim;
+    return halton_sample_dimension(index, dim++, hp);
+  }
+  PBR_D void get2D(const HaltonParams& hp, float* u0, float* u1) {
+    if (dim + 1 >= 5 && dim < arrayEndDim) dim = arrayEndDim;
+    *u0 = halton_sample_dimension(index, dim, hp);
+    *u1 = halton_sample_dimension(index, dim + 1, hp);
+    dim += 2;
+  }
+};
+
+}  // namespace pbr
