@@ -147,20 +147,27 @@ typedef struct pbrgpu_render_desc {
 } pbrgpu_render_desc;
 enum {
   PBRGPU_RENDER_ACCUMULATE = 1, /* add into the output sums instead of overwriting */
-  PBRGPU_RENDER_COUNTERS = 2    /* count nodes visited / triangles tested (slower) */
+  PBRGPU_RENDER_COUNTERS = 2,   /* count nodes visited / triangles tested (slower) */
+  PBRGPU_RENDER_TIMERS = 4      /* CUDA events around every kernel group -> pbrgpu_stats.ms_* */
 };
 
 typedef struct pbrgpu_stats {
   uint64_t camera_samples;
   uint64_t rays_closest; /* Scene::Intersect queries (path + MIS rays) */
   uint64_t rays_shadow;  /* Scene::IntersectP queries */
-  uint64_t nodes_visited;
-  uint64_t tris_tested;
+  uint64_t nodes_visited; /* only with PBRGPU_RENDER_COUNTERS */
+  uint64_t tris_tested;   /* only with PBRGPU_RENDER_COUNTERS */
   uint64_t kernel_launches;
-  double ms_total;   /* CUDA-event time of the whole render on the context's stream */
-  double ms_trace;   /* closest + shadow + MIS traversal kernels */
-  double ms_shade;
+  double ms_total; /* CUDA-event time of the whole render on the launching stream */
+  /* per-kernel CUDA-event times, only with PBRGPU_RENDER_TIMERS (sum over launches) */
   double ms_raygen;
+  double ms_trace_closest;
+  double ms_shade;
+  double ms_trace_shadow;
+  double ms_trace_mis;
+  double ms_film;
+  uint64_t n_trace_closest_launches;
+  uint64_t rays_path; /* closest-hit rays that were path segments (rays_closest - MIS rays) */
 } pbrgpu_stats;
 
 /* ---- lifecycle ---- */

@@ -7,7 +7,7 @@ CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC = 0, 1
 SAMPLER_HALTON, SAMPLER_SOBOL = 0, 1
 INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED = range(4)
 LIGHTSTRATEGY_UNIFORM, LIGHTSTRATEGY_POWER = 0, 1
-RENDER_ACCUMULATE, RENDER_COUNTERS = 1, 2
+RENDER_ACCUMULATE, RENDER_COUNTERS, RENDER_TIMERS = 1, 2, 4
 DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW = range(5)
 
 f3 = C.c_float * 3
@@ -58,8 +58,9 @@ class RenderDesc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("camera_samples", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shade", C.c_double),
-                ("ms_raygen", C.c_double)]
+                ("ms_total", C.c_double), ("ms_raygen", C.c_double), ("ms_trace_closest", C.c_double),
+                ("ms_shade", C.c_double), ("ms_trace_shadow", C.c_double), ("ms_trace_mis", C.c_double),
+                ("ms_film", C.c_double), ("n_trace_closest_launches", C.c_uint64), ("rays_path", C.c_uint64)]
 
 
 class DumpDesc(C.Structure):

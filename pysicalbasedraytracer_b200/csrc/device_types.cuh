@@ -59,7 +59,7 @@ struct SceneDev {
 struct Counters {
   uint32_t nCur, nNext, nShadow, nMis;
   uint32_t nMat[8];
-  unsigned long long raysClosest, raysShadow, nodesVisited, trisTested;
+  unsigned long long raysClosest, raysShadow, nodesVisited, trisTested, raysPath;
 };
 
 // SoA wavefront state, `capacity` slots.  slot = j*nPix + pixel (j = sample within the wave).

@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(kBlock) k_trace_closest(const __grid_constant_
     atomicAdd(&P.ws.ctr->nodesVisited, (unsigned long long)nodes);
     atomicAdd(&P.ws.ctr->trisTested, (unsigned long long)tris);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws.ctr->raysClosest, (unsigned long long)n);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&P.ws.ctr->raysClosest, (unsigned long long)n);
+    atomicAdd(&P.ws.ctr->raysPath, (unsigned long long)n);
+  }
 }
 
 // K4/K5/K7: shading for one material queue.

@@ -63,6 +63,7 @@ struct pbrgpu_ctx {
   int smCount = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> pool;  // PBRGPU_RENDER_TIMERS
 };
 
 struct pbrgpu_scene {
@@ -152,6 +153,38 @@ void env_bilinear_host(const std::vector<float>& tex, int W, int H, float s_, fl
   for (int k = 0; k < 3; ++k) out[k] = ((w0 * a[k] + w1 * b[k]) + w2 * c[k]) + w3 * d[k];
 }
 
+// CUDA-event timeline: mark(cat) closes the previous interval and opens one of category `cat`.
+enum { T_RAYGEN, T_CLOSEST, T_SHADE, T_SHADOW, T_MIS, T_FILM, T_END, T_COUNT };
+struct Timeline {
+  pbrgpu_ctx* c;
+  cudaStream_t st;
+  bool on;
+  size_t used = 0;
+  std::vector<int> cats;
+  cudaError_t mark(int cat) {
+    if (!on) return cudaSuccess;
+    if (used == c->pool.size()) {
+      cudaEvent_t e;
+      cudaError_t r = cudaEventCreate(&e);
+      if (r != cudaSuccess) return r;
+      c->pool.push_back(e);
+    }
+    cats.push_back(cat);
+    return cudaEventRecord(c->pool[used++], st);
+  }
+  cudaError_t collect(double out[T_COUNT], uint64_t counts[T_COUNT]) {
+    for (int k = 0; k < T_COUNT; ++k) { out[k] = 0; counts[k] = 0; }
+    for (size_t i = 0; i + 1 < used; ++i) {
+      float ms = 0;
+      cudaError_t r = cudaEventElapsedTime(&ms, c->pool[i], c->pool[i + 1]);
+      if (r != cudaSuccess) return r;
+      out[cats[i]] += ms;
+      counts[cats[i]]++;
+    }
+    return cudaSuccess;
+  }
+};
+
 uint32_t grid_for(const pbrgpu_ctx* c, uint64_t n, int perSm) {
   uint64_t blocks = (n + kBlock - 1) / kBlock;
   uint64_t cap = (uint64_t)c->smCount * perSm;
@@ -197,6 +230,7 @@ void pbrgpu_shutdown(pbrgpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->pool) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -491,6 +525,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   CK(cudaMemcpyAsync(s->ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(c->ev[0], st));
   uint64_t launches = 0;
+  Timeline tl{c, st, (rd->flags & PBRGPU_RENDER_TIMERS) != 0};
   for (int yb = 0; yb < H; yb += bandRows) {
     int rows = std::min(bandRows, H - yb);
     P.x0 = rd->x0; P.y0 = rd->y0 + yb; P.w = W; P.h = rows;
@@ -503,28 +538,37 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       P.ws.qCur = s->qA.p;
       P.ws.qNext = s->qB.p;
       uint32_t g = grid_for(c, nPaths, 8);
+      CK(tl.mark(T_RAYGEN));
       k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
       k_raygen<<<g, kBlock, 0, st>>>(P);
       launches += 2;
       for (int bounce = 0; bounce <= rd->max_depth; ++bounce) {
+        CK(tl.mark(T_CLOSEST));
         if (count) k_trace_closest<true><<<g, kBlock, 0, st>>>(P);
         else k_trace_closest<false><<<g, kBlock, 0, st>>>(P);
+        CK(tl.mark(T_SHADE));
         k_shade<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce);
-        if (count) { k_trace_shadow<true><<<g, kBlock, 0, st>>>(P); k_trace_mis<true><<<g, kBlock, 0, st>>>(P); }
-        else { k_trace_shadow<false><<<g, kBlock, 0, st>>>(P); k_trace_mis<false><<<g, kBlock, 0, st>>>(P); }
+        CK(tl.mark(T_SHADOW));
+        if (count) k_trace_shadow<true><<<g, kBlock, 0, st>>>(P);
+        else k_trace_shadow<false><<<g, kBlock, 0, st>>>(P);
+        CK(tl.mark(T_MIS));
+        if (count) k_trace_mis<true><<<g, kBlock, 0, st>>>(P);
+        else k_trace_mis<false><<<g, kBlock, 0, st>>>(P);
         k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
         launches += 10;
         std::swap(P.ws.qCur, P.ws.qNext);
       }
+      CK(tl.mark(T_FILM));
       k_film_accumulate<<<grid_for(c, (uint64_t)rows * W, 8), kBlock, 0, st>>>(P);
       launches += 1;
     }
   }
+  CK(tl.mark(T_END));
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev[1], st));
   if (stats) {
@@ -541,6 +585,15 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
     stats->tris_tested = hc.trisTested;
     stats->kernel_launches = launches;
     stats->ms_total = ms;
+    stats->rays_path = hc.raysPath;
+    if (tl.on) {
+      double t[T_COUNT];
+      uint64_t n[T_COUNT];
+      CK(tl.collect(t, n));
+      stats->ms_raygen = t[T_RAYGEN]; stats->ms_trace_closest = t[T_CLOSEST]; stats->ms_shade = t[T_SHADE];
+      stats->ms_trace_shadow = t[T_SHADOW]; stats->ms_trace_mis = t[T_MIS]; stats->ms_film = t[T_FILM];
+      stats->n_trace_closest_launches = n[T_CLOSEST];
+    }
   }
   return 0;
 }
