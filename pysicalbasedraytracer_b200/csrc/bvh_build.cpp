@@ -45,8 +45,12 @@ constexpr float kIsectCost = 1.2f;
 
 }  // namespace
 
-void build_bvh2(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh* out) {
-  maxLeaf = std::max(1, std::min(4, maxLeaf));
+namespace {
+struct BinaryStats { int maxLeafSize = 0; int64_t nLeaves = 0; int maxDepth = 0; };
+
+// Binned-SAH binary tree over triangle bounds; `order` = leaf-order permutation of triangle ids.
+void build_binary(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, std::vector<TmpNode>& tmp,
+                  std::vector<int32_t>& order, BinaryStats* out) {
   std::vector<Aabb> tb((size_t)nTris);
   std::vector<float> cen((size_t)nTris * 3);
   for (int64_t i = 0; i < nTris; ++i) {
@@ -61,11 +65,10 @@ void build_bvh2(const float* verts, const int32_t* indices, int64_t nTris, int m
     tb[i] = b;
     for (int k = 0; k < 3; ++k) cen[3 * i + k] = 0.5f * b.lo[k] + 0.5f * b.hi[k];
   }
-  std::vector<int32_t>& order = out->triOrder;
   order.resize((size_t)nTris);
   for (int64_t i = 0; i < nTris; ++i) order[i] = (int32_t)i;
 
-  std::vector<TmpNode> tmp;
+  tmp.clear();
   tmp.reserve((size_t)std::max<int64_t>(2 * nTris, 2));
   struct Task { int32_t node, first, count, depth; };
   std::vector<Task> stack;
@@ -159,6 +162,18 @@ void build_bvh2(const float* verts, const int32_t* indices, int64_t nTris, int m
     stack.push_back({l + 1, mid, t.first + t.count - mid, t.depth + 1});
     stack.push_back({l, t.first, mid - t.first, t.depth + 1});
   }
+}
+}  // namespace
+
+void build_bvh2(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh* out) {
+  maxLeaf = std::max(1, std::min(4, maxLeaf));
+  std::vector<TmpNode> tmp;
+  std::vector<int32_t>& order = out->triOrder;
+  BinaryStats bs;
+  build_binary(verts, indices, nTris, maxLeaf, tmp, order, &bs);
+  out->maxLeafSize = bs.maxLeafSize;
+  out->nLeaves = bs.nLeaves;
+  out->maxDepth = bs.maxDepth;
   out->bounds = tmp[0].box;
 
   // flatten: interior TmpNodes -> Bvh2Node (DFS order, children of a node adjacent when both interior)
@@ -212,6 +227,142 @@ void build_bvh2(const float* verts, const int32_t* indices, int64_t nTris, int m
     r.child[0] = L.left >= 0 ? remap[tn.left] : encode_leaf(L);
     r.child[1] = R.left >= 0 ? remap[tn.right] : encode_leaf(R);
     nodes[i] = r;
+  }
+}
+
+}  // namespace pbr
+
+// ---------------------------------------------------------------------------------------------
+// 8-wide compressed BVH: binary SAH tree (leaves <= 3 triangles) -> greedy collapse (open the
+// child with the largest surface area until 8 children) -> octant-ordered slot assignment ->
+// 8-bit quantised child boxes.  Triangles are re-ordered so that the leaf children of one node are
+// contiguous from triBase (offsets < 24).
+// ---------------------------------------------------------------------------------------------
+namespace pbr {
+
+void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh8* out) {
+  maxLeaf = std::max(1, std::min(3, maxLeaf));
+  std::vector<TmpNode> tmp;
+  std::vector<int32_t> order;
+  BinaryStats bs;
+  build_binary(verts, indices, nTris, maxLeaf, tmp, order, &bs);
+  out->bounds = tmp[0].box;
+  out->maxLeafSize = bs.maxLeafSize;
+  out->nLeaves = bs.nLeaves;
+  out->maxDepth = 0;
+  out->nodes.clear();
+  out->triOrder.clear();
+  out->triOrder.reserve((size_t)nTris);
+  out->nodes.reserve((size_t)std::max<int64_t>(nTris / 4, 1));
+
+  struct Work { int32_t bin; int32_t wide; int32_t depth; };
+  std::vector<Work> queue;
+  out->nodes.emplace_back();
+  queue.push_back({0, 0, 1});
+  size_t head = 0;
+  while (head < queue.size()) {
+    Work w = queue[head++];
+    out->maxDepth = std::max(out->maxDepth, (int)w.depth);
+    // gather up to 8 children
+    int32_t kids[8];
+    int nk = 0;
+    if (tmp[w.bin].left < 0) {
+      kids[nk++] = w.bin;  // degenerate: the whole scene is one leaf
+    } else {
+      kids[nk++] = tmp[w.bin].left;
+      kids[nk++] = tmp[w.bin].right;
+      while (nk < 8) {
+        int best = -1;
+        float bestArea = -1.f;
+        for (int i = 0; i < nk; ++i) {
+          if (tmp[kids[i]].left < 0) continue;
+          float a = half_area(tmp[kids[i]].box);
+          if (a > bestArea) { bestArea = a; best = i; }
+        }
+        if (best < 0) break;
+        int32_t b = kids[best];
+        kids[best] = tmp[b].left;
+        kids[nk++] = tmp[b].right;
+      }
+    }
+    const Aabb& box = tmp[w.bin].box;
+    // slot assignment: slot s is visited first by rays with direction sign (s&4 ? - : +, s&2 ? - : +, s&1 ? - : +);
+    // put there the child that lies most upstream along that direction (greedy min-cost matching).
+    float cost[8][8];
+    float pc[3] = {0.5f * (box.lo[0] + box.hi[0]), 0.5f * (box.lo[1] + box.hi[1]), 0.5f * (box.lo[2] + box.hi[2])};
+    for (int i = 0; i < nk; ++i) {
+      const Aabb& cb = tmp[kids[i]].box;
+      float c[3] = {0.5f * (cb.lo[0] + cb.hi[0]) - pc[0], 0.5f * (cb.lo[1] + cb.hi[1]) - pc[1], 0.5f * (cb.lo[2] + cb.hi[2]) - pc[2]};
+      for (int s = 0; s < 8; ++s) {
+        float dx = (s & 4) ? -1.f : 1.f, dy = (s & 2) ? -1.f : 1.f, dz = (s & 1) ? -1.f : 1.f;
+        cost[i][s] = c[0] * dx + c[1] * dy + c[2] * dz;
+      }
+    }
+    int slotOf[8], childAt[8];
+    for (int i = 0; i < 8; ++i) { slotOf[i] = -1; childAt[i] = -1; }
+    for (int round = 0; round < nk; ++round) {
+      int bi = -1, bsl = -1;
+      float bc = std::numeric_limits<float>::infinity();
+      for (int i = 0; i < nk; ++i) {
+        if (slotOf[i] >= 0) continue;
+        for (int s = 0; s < 8; ++s) {
+          if (childAt[s] >= 0) continue;
+          if (cost[i][s] < bc) { bc = cost[i][s]; bi = i; bsl = s; }
+        }
+      }
+      slotOf[bi] = bsl;
+      childAt[bsl] = bi;
+    }
+    // quantisation frame
+    Bvh8Node nd;
+    std::memset(&nd, 0, sizeof(nd));
+    double scale[3];
+    for (int a = 0; a < 3; ++a) {
+      nd.origin[a] = box.lo[a];
+      double ext = (double)box.hi[a] - (double)box.lo[a];
+      int e = -60;
+      if (ext > 0) {
+        e = (int)std::ceil(std::log2(ext / 255.0));
+        while (std::ldexp(255.0, e) < ext) ++e;
+      }
+      e = std::max(-100, std::min(100, e));
+      nd.e[a] = (uint8_t)(e + 127);
+      scale[a] = std::ldexp(1.0, e);
+    }
+    int nInner = 0;
+    for (int s = 0; s < 8; ++s)
+      if (childAt[s] >= 0 && tmp[kids[childAt[s]]].left >= 0) ++nInner;
+    nd.childBase = (uint32_t)out->nodes.size();
+    nd.triBase = (uint32_t)out->triOrder.size();
+    out->nodes.resize(out->nodes.size() + (size_t)nInner);
+    int innerRank = 0, triOff = 0;
+    uint8_t* qlo[3] = {nd.qlox, nd.qloy, nd.qloz};
+    uint8_t* qhi[3] = {nd.qhix, nd.qhiy, nd.qhiz};
+    for (int s = 0; s < 8; ++s) {
+      if (childAt[s] < 0) {
+        for (int a = 0; a < 3; ++a) { qlo[a][s] = 255; qhi[a][s] = 0; }
+        continue;
+      }
+      const TmpNode& ch = tmp[kids[childAt[s]]];
+      for (int a = 0; a < 3; ++a) {
+        double lo = std::floor(((double)ch.box.lo[a] - (double)nd.origin[a]) / scale[a]);
+        double hi = std::ceil(((double)ch.box.hi[a] - (double)nd.origin[a]) / scale[a]);
+        qlo[a][s] = (uint8_t)std::max(0.0, std::min(255.0, lo));
+        qhi[a][s] = (uint8_t)std::max(0.0, std::min(255.0, hi));
+      }
+      if (ch.left >= 0) {
+        nd.imask |= (uint8_t)(1u << s);
+        nd.meta[s] = (uint8_t)((1u << 5) | (24u + (unsigned)s));
+        queue.push_back({kids[childAt[s]], (int32_t)nd.childBase + innerRank, w.depth + 1});
+        ++innerRank;
+      } else {
+        unsigned unary = ch.count == 1 ? 1u : (ch.count == 2 ? 3u : 7u);
+        nd.meta[s] = (uint8_t)((unary << 5) | (unsigned)triOff);
+        for (int i = 0; i < ch.count; ++i) out->triOrder.push_back(order[ch.first + i]);
+        triOff += ch.count;
+      }
+    }
+    out->nodes[w.wide] = nd;
   }
 }
 

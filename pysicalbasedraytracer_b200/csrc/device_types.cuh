@@ -41,7 +41,7 @@ struct SceneDev {
   const float4* tv0;
   const float4* tv1;
   const float4* tv2;
-  const Bvh2Node* nodes;
+  const float4* nodes8;         // Bvh8Node[] viewed as 5 x float4 per node
   const pbrgpu_material* mats;  // roughness fields already remapped to alpha on the host (glibc logf)
   const pbrgpu_light* lights;   // AREA_TRI: .tri = LEAF-ORDER triangle index
   int nTris, nLights, nInfinite;
@@ -59,6 +59,7 @@ struct SceneDev {
 struct Counters {
   uint32_t nCur, nNext, nShadow, nMis;
   uint32_t nMat[8];
+  uint32_t cursor[4];  // persistent-kernel fetch cursors (TRACE_PATH, TRACE_MIS, TRACE_SHADOW)
   unsigned long long raysClosest, raysShadow, nodesVisited, trisTested, raysPath;
 };
 
@@ -76,7 +77,7 @@ struct WaveDev {
   float4* shD;      // d.xyz, as_float(slot)
   float4* shC;      // contribution rgb added to L[slot] when unoccluded
   // MIS-ray queue (EstimateDirect BSDF-sampling strategy; closest hit)
-  float4* miO;
+  float4* miO;      // o.xyz, tMax -> after k_trace<MIS>: as_float(hit triangle or -1)
   float4* miD;      // d.xyz, as_float(slot)
   float4* miC;      // throughput rgb, as_float(light id)
   uint32_t* qCur;
@@ -96,6 +97,7 @@ struct RenderParams {
   int nsWave;             // samples per pixel in this wave
   int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
   int countStats;
+  int triThreshold;       // lanes with candidate triangles needed to run a triangle round
   float* accum;           // [h*w] RGBA sums (A = sample count)
 };
 

@@ -30,6 +30,19 @@ inline void prime_tables(std::vector<int32_t>* primes, std::vector<int32_t>* sum
   for (int p : *primes) { sums->push_back(s); s += p; }
 }
 
+// (m, s): floor(a / p) == (uint32)(((uint64)a * m) >> 32) >> s for every a < 2^31
+inline void prime_magic(const std::vector<int32_t>& primes, std::vector<uint32_t>* out) {
+  out->clear();
+  for (int p : primes) {
+    int L = 1;
+    while ((1 << L) < p) ++L;
+    uint64_t num = 1ull << (31 + L);
+    uint64_t m = (num + (uint64_t)p - 1) / (uint64_t)p;
+    out->push_back((uint32_t)m);
+    out->push_back((uint32_t)(L - 1));
+  }
+}
+
 struct Pcg32 {
   uint64_t state = 0x853c49e6748fea9bULL, inc = 0xda3e39cb94b95bdbULL;
   uint32_t next() {

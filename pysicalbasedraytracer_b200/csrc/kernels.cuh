@@ -1,11 +1,14 @@
 // kernels.cuh - the wavefront kernels (sm_100a).  One bounce of the wavefront maps onto
 // PathIntegrator::Li's loop body (Integrator/PathIntegrator.cpp:42-108):
-//   k_trace_closest   scene.Intersect(ray)                                   :44
+//   k_trace (path)    scene.Intersect(ray)                                   :44
+//   k_classify        bins the hits into material-sorted shading queues
 //   k_shade<MAT>      emission :47-51, maxDepth :60, BSDF :63, UniformSampleOneLight :74-81,
 //                     Sample_f :88-99, Russian roulette :100-107
 //   k_shade_miss      infinite-light Le for escaped rays                     :52-56
-//   k_trace_shadow    VisibilityTester::Unoccluded (Integrator.cpp:107, Light.cpp:19-22)
-//   k_trace_mis       EstimateDirect's BSDF-sampled closest-hit ray (Integrator.cpp:157-172)
+//   k_trace (shadow)  VisibilityTester::Unoccluded (Integrator.cpp:107, Light.cpp:19-22)
+//   k_trace (MIS) + k_resolve_mis   EstimateDirect's BSDF-sampled closest-hit ray (Integrator.cpp:157-172)
+// k_trace is ONE persistent kernel: warps pull rays from a device queue and replace finished rays
+// while the rest of the warp keeps traversing (ballot / shfl aggregated fetch).
 // All paths of a wave are at the same bounce, so `bounce` is a launch argument, not path state.
 #pragma once
 #include "shade.cuh"
@@ -97,11 +100,124 @@ PBR_D uint32_t queue_push(uint32_t* counter, bool active) {
   return base + __popc(mask & ((1u << lane) - 1u));
 }
 
-// K2: closest hit for every live path; classify into material queues.
+// K2/K3/K6: the traversal kernel.  Persistent warps; each lane owns one ray at a time.  When at least
+// kFetchMinIdle lanes of a warp have finished their rays, the idle lanes fetch new ones with a single
+// warp-aggregated atomicAdd on the queue cursor (__ballot_sync / __shfl_sync), so a warp is not held
+// hostage by its longest ray.  Per iteration a lane performs one node step (80-byte node, 8 child
+// boxes) and then drains the triangle group that step produced.
+// One launch per bounce serves three queues at once: the path rays of bounce b and the shadow / MIS
+// rays emitted by the shading of bounce b-1 (independent work, so the machine stays full).
+enum { TRACE_PATH = 0, TRACE_SHADOW = 1, TRACE_MIS = 2 };
+constexpr int kTraceBlock = 128;
+constexpr int kFetchMinIdle = 8;
+
+// Triangle batching: a node step leaves a lane with 0..24 candidate triangles.  Testing them right away
+// would run the (long) watertight test with only the few lanes that happen to have candidates, so a
+// lane parks its triangle groups in a small shared-memory list and keeps descending; the warp runs a
+// triangle round (ONE triangle per lane) only when at least P.triThreshold lanes have candidates, or
+// when no lane has node work left.
+constexpr int kTriQueue = 6;
+
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_trace_closest(const __grid_constant__ RenderParams P) {
-  const uint32_t n = P.ws.ctr->nCur;
+__global__ void __launch_bounds__(kTraceBlock) k_trace(const __grid_constant__ RenderParams P) {
+  __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
+  __shared__ uint2 stri[kTraceBlock / 32][kTriQueue][32];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2* sstack = &sstk[warp][0][lane];
+  uint2* tq = &stri[warp][0][lane];
+  Counters* C = P.ws.ctr;
+  const uint32_t nPath = C->nCur, nShadow = C->nShadow, nMis = C->nMis;
+  const uint32_t n = nPath + nShadow + nMis;
+  const int triThreshold = P.triThreshold;
+  Trav T;
+  TravSpill S;
+  T.ngroup = make_uint2(0u, 0u); T.tgroup = make_uint2(0u, 0u); T.sp = 0;
+  int nt = 0;  // parked triangle groups
+  bool busy = false, exhausted = false;
+  int mode = TRACE_PATH;
+  uint32_t ray = 0;  // PATH: wavefront slot; SHADOW / MIS: index in that queue
   unsigned nodes = 0, tris = 0;
+  while (true) {
+    // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
+    const unsigned idle = __ballot_sync(full, !busy);
+    if (idle != 0u && !exhausted && (idle == full || __popc(idle) >= kFetchMinIdle)) {
+      const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&C->cursor[0], (uint32_t)nIdle);
+      base = __shfl_sync(full, base, leader);
+      exhausted = base + (uint32_t)nIdle >= n;
+      if (!busy) {
+        uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+        if (i < n) {
+          float4 ro, rd;
+          if (i < nPath) { mode = TRACE_PATH; ray = P.ws.qCur[i]; ro = P.ws.rayO[ray]; rd = P.ws.rayD[ray]; }
+          else if (i < nPath + nShadow) { mode = TRACE_SHADOW; ray = i - nPath; ro = P.ws.shO[ray]; rd = P.ws.shD[ray]; }
+          else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
+          trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w);
+          nt = 0;
+          busy = true;
+        }
+      }
+    }
+    if (exhausted && __ballot_sync(full, busy) == 0u) break;
+    // ---- node phase ----
+    bool didNode = false;
+    if (busy) {
+      if (T.ngroup.y <= 0x00FFFFFFu && T.sp > 0) T.ngroup = trav_pop(T, sstack, S);
+      if (T.ngroup.y > 0x00FFFFFFu) {
+        if (T.tgroup.y == 0u || nt < kTriQueue) {
+          if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }
+          cw_node_step(P.sc.nodes8, T, sstack, S);
+          if (COUNT) nodes++;
+          didNode = true;
+        }
+      } else if (T.tgroup.y == 0u && nt == 0) {
+        // ---- ray finished ----
+        if (mode == TRACE_PATH) {
+          P.ws.hit[ray] = make_float4(__int_as_float(T.hit.tri), T.hit.b0, T.hit.b1, T.hit.b2);
+        } else if (mode == TRACE_MIS) {
+          P.ws.miO[ray].w = __int_as_float(T.hit.tri);
+        } else if (T.hit.tri < 0) {  // unoccluded: add the light-sampling contribution
+          const uint32_t slot = __float_as_uint(P.ws.shD[ray].w);
+          const float4 c = P.ws.shC[ray];
+          float4 L = P.ws.L[slot];
+          P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
+        }
+        busy = false;
+      }
+    }
+    // ---- triangle round ----
+    const bool hasTri = busy && (T.tgroup.y != 0u || nt > 0);
+    const unsigned triMask = __ballot_sync(full, hasTri);
+    const unsigned nodeMask = __ballot_sync(full, didNode);
+    if (triMask != 0u && (__popc(triMask) >= triThreshold || nodeMask == 0u)) {
+      if (hasTri) {
+        if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
+        if (COUNT) tris++;
+        if (cw_tri_step(P.sc, T) && mode == TRACE_SHADOW) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+      }
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&C->nodesVisited, (unsigned long long)nodes);
+    atomicAdd(&C->trisTested, (unsigned long long)tris);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&C->raysShadow, (unsigned long long)nShadow);
+    atomicAdd(&C->raysClosest, (unsigned long long)(nPath + nMis));
+    atomicAdd(&C->raysPath, (unsigned long long)nPath);
+  }
+}
+
+// Bin the live paths by the material type of what they hit (material-sorted shading queues).
+__global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ RenderParams P) {
+  const uint32_t n = P.ws.ctr->nCur;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the shadow / MIS queues of the previous bounce are consumed
+    P.ws.ctr->nShadow = 0;
+    P.ws.ctr->nMis = 0;
+    P.ws.ctr->cursor[0] = 0;
+  }
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     uint32_t i = base + threadIdx.x;
     bool active = i < n;
@@ -109,13 +225,9 @@ __global__ void __launch_bounds__(kBlock) k_trace_closest(const __grid_constant_
     uint32_t slot = 0;
     if (active) {
       slot = P.ws.qCur[i];
-      float4 ro = P.ws.rayO[slot], rd = P.ws.rayD[slot];
-      HitRec h;
-      traverse<false, COUNT>(P.sc, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, &h, &nodes, &tris);
-      P.ws.hit[slot] = make_float4(__int_as_float(h.tri), h.b0, h.b1, h.b2);
-      P.ws.rayO[slot].w = h.t;
+      int tri = __float_as_int(P.ws.hit[slot].x);
       q = kQueueMiss;
-      if (h.tri >= 0) q = (int)((__float_as_uint(__ldg(&P.sc.tv1[h.tri].w)) >> kTriTypeShift) & 0xf);
+      if (tri >= 0) q = (int)((__float_as_uint(__ldg(&P.sc.tv1[tri].w)) >> kTriTypeShift) & 0xf);
     }
 #pragma unroll
     for (int k = 0; k < kNumQueues; ++k) {
@@ -123,14 +235,6 @@ __global__ void __launch_bounds__(kBlock) k_trace_closest(const __grid_constant_
       uint32_t pos = queue_push(&P.ws.ctr->nMat[k], mine);
       if (mine) P.ws.qMat[(size_t)k * P.ws.capacity + pos] = slot;
     }
-  }
-  if (COUNT) {
-    atomicAdd(&P.ws.ctr->nodesVisited, (unsigned long long)nodes);
-    atomicAdd(&P.ws.ctr->trisTested, (unsigned long long)tris);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    atomicAdd(&P.ws.ctr->raysClosest, (unsigned long long)n);
-    atomicAdd(&P.ws.ctr->raysPath, (unsigned long long)n);
   }
 }
 
@@ -290,44 +394,19 @@ __global__ void __launch_bounds__(kBlock) k_shade_miss(const __grid_constant__ R
   }
 }
 
-// K3: shadow rays (any hit).  Unoccluded => add the precomputed light-sampling contribution.
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_trace_shadow(const __grid_constant__ RenderParams P) {
-  const uint32_t n = P.ws.ctr->nShadow;
-  unsigned nodes = 0, tris = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float4 o = P.ws.shO[i], d = P.ws.shD[i];
-    HitRec h;
-    bool occluded = traverse<true, COUNT>(P.sc, V3(o.x, o.y, o.z), V3(d.x, d.y, d.z), o.w, &h, &nodes, &tris);
-    if (!occluded) {
-      uint32_t slot = __float_as_uint(d.w);
-      float4 c = P.ws.shC[i];
-      float4 L = P.ws.L[slot];
-      P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
-    }
-  }
-  if (COUNT) {
-    atomicAdd(&P.ws.ctr->nodesVisited, (unsigned long long)nodes);
-    atomicAdd(&P.ws.ctr->trisTested, (unsigned long long)tris);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws.ctr->raysShadow, (unsigned long long)n);
-}
-
-// K6: MIS rays (closest hit) + resolve (Integrator.cpp:157-172)
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_trace_mis(const __grid_constant__ RenderParams P) {
+// K6: resolve the MIS rays traced by k_trace<TRACE_MIS> (Integrator.cpp:157-172): the hit counts only
+// if it is the sampled light's own triangle; a miss asks the light for Le.
+__global__ void __launch_bounds__(kBlock) k_resolve_mis(const __grid_constant__ RenderParams P) {
   const uint32_t n = P.ws.ctr->nMis;
-  unsigned nodes = 0, tris = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 o = P.ws.miO[i], d = P.ws.miD[i], c = P.ws.miC[i];
-    HitRec h;
     V3 wi(d.x, d.y, d.z);
-    bool found = traverse<false, COUNT>(P.sc, V3(o.x, o.y, o.z), wi, o.w, &h, &nodes, &tris);
+    int tri = __float_as_int(o.w);
     int lightId = __float_as_int(c.w);
     const pbrgpu_light& light = P.sc.lights[lightId];
     Spec Li(0.f);
-    if (found) {
-      TriData t = load_tri(P.sc, h.tri);
+    if (tri >= 0) {
+      TriData t = load_tri(P.sc, tri);
       if ((int)t.w2 == lightId) Li = area_light_L(light, tri_normal_isect(t), -wi);
     } else {
       Li = light_Le(P.sc, light, wi);
@@ -338,20 +417,21 @@ __global__ void __launch_bounds__(kBlock) k_trace_mis(const __grid_constant__ Re
       P.ws.L[slot] = make_float4(L.x + c.x * Li.r, L.y + c.y * Li.g, L.z + c.z * Li.b, 0.f);
     }
   }
-  if (COUNT) {
-    atomicAdd(&P.ws.ctr->nodesVisited, (unsigned long long)nodes);
-    atomicAdd(&P.ws.ctr->trisTested, (unsigned long long)tris);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.ws.ctr->raysClosest, (unsigned long long)n);
+}
+
+// wave start: every queue empty
+__global__ void k_wave_begin(Counters* c) {
+  c->nCur = c->nNext = c->nShadow = c->nMis = 0;
+  for (int k = 0; k < 8; ++k) c->nMat[k] = 0;
+  for (int k = 0; k < 4; ++k) c->cursor[k] = 0;
 }
 
 // bounce bookkeeping (host swaps qCur/qNext pointers each bounce)
 __global__ void k_next_bounce(Counters* c) {
   c->nCur = c->nNext;
   c->nNext = 0;
-  c->nShadow = 0;
-  c->nMis = 0;
   for (int k = 0; k < 8; ++k) c->nMat[k] = 0;
+  for (int k = 0; k < 4; ++k) c->cursor[k] = 0;
 }
 
 // wave end: per pixel, add the wave's per-path radiance in sample order (deterministic).
@@ -410,7 +490,9 @@ __global__ void k_dump_sampler(HaltonParams hp, int x0, int y0, int w, int h, lo
   }
 }
 
-__global__ void k_dump_primary(const __grid_constant__ RenderParams P, int ns, float* outRays, int* outHits) {
+__global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__ RenderParams P, int ns, float* outRays, int* outHits) {
+  __shared__ uint2 sstk[kBlock / 32][kSmemStack][32];
+  uint2* sstack = &sstk[threadIdx.x >> 5][0][threadIdx.x & 31];
   long long n = (long long)P.w * P.h * ns;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int sj = (int)(i % ns);
@@ -429,7 +511,7 @@ __global__ void k_dump_primary(const __grid_constant__ RenderParams P, int ns, f
     if (outHits) {
       HitRec h;
       unsigned a = 0, b = 0;
-      traverse<false, false>(P.sc, o, d, kInfinity, &h, &a, &b);
+      traverse<false, false>(P.sc, o, d, kInfinity, &h, sstack, &a, &b);
       int* q = outHits + 4 * i;
       q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
       q[1] = __float_as_int(h.t);
@@ -439,16 +521,18 @@ __global__ void k_dump_primary(const __grid_constant__ RenderParams P, int ns, f
   }
 }
 
-__global__ void k_trace_user(const __grid_constant__ RenderParams P, const float* rays, long long n, int anyHit, int* out) {
+__global__ void __launch_bounds__(kBlock) k_trace_user(const __grid_constant__ RenderParams P, const float* rays, long long n, int anyHit, int* out) {
+  __shared__ uint2 sstk[kBlock / 32][kSmemStack][32];
+  uint2* sstack = &sstk[threadIdx.x >> 5][0][threadIdx.x & 31];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float* r = rays + 8 * i;
     HitRec h;
     unsigned a = 0, b = 0;
     V3 o(r[0], r[1], r[2]), d(r[4], r[5], r[6]);
     if (anyHit) {
-      out[i] = traverse<true, false>(P.sc, o, d, r[3], &h, &a, &b) ? 1 : 0;
+      out[i] = traverse<true, false>(P.sc, o, d, r[3], &h, sstack, &a, &b) ? 1 : 0;
     } else {
-      traverse<false, false>(P.sc, o, d, r[3], &h, &a, &b);
+      traverse<false, false>(P.sc, o, d, r[3], &h, sstack, &a, &b);
       int* q = out + 4 * i;
       q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
       q[1] = __float_as_int(h.t);

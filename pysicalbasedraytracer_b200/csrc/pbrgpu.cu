@@ -2,8 +2,8 @@
 // description into HBM-resident SoA buffers and the wavefront launch schedule.
 //
 // Launch schedule for one wave of paths (all at the same bounce; PathIntegrator.cpp:42-108):
-//   k_raygen -> for bounce in 0..maxDepth: k_trace_closest -> k_shade<MAT> x5 + k_shade_miss
-//               -> k_trace_shadow + k_trace_mis -> k_next_bounce ;  k_film_accumulate
+//   k_raygen -> for bounce b in 0..maxDepth: k_trace (path rays of b + shadow/MIS rays of b-1) -> k_resolve_mis
+//               -> k_classify -> k_shade<MAT> x5 + k_shade_miss -> k_next_bounce ;  k_film_accumulate
 // Queue sizes live in device counters; the host never reads them inside a render (no sync), grids
 // are sized for the wave capacity and the kernels loop over the live count.
 // There is NO CPU fallback: every compute entry point needs a CUDA device.
@@ -69,7 +69,7 @@ struct pbrgpu_ctx {
 struct pbrgpu_scene {
   pbrgpu_ctx* ctx = nullptr;
   SceneDev sc{};
-  BuiltBvh bvh;
+  BuiltBvh8 bvh;
   std::vector<int32_t> leafOf;  // caller's triangle index -> leaf-order position
   std::vector<pbrgpu_light> lights;  // device copy (tri remapped to leaf order)
   std::vector<float> lightPower;     // Light::Power().y() per light
@@ -77,14 +77,17 @@ struct pbrgpu_scene {
   int64_t spp = 0;
   // device buffers
   DevBuf<float4> tv0, tv1, tv2;
-  DevBuf<Bvh2Node> nodes;
+  DevBuf<Bvh8Node> nodes;
   DevBuf<pbrgpu_material> mats;
   DevBuf<pbrgpu_light> dlights;
   DevBuf<float> lightFunc, lightCdf;
   DevBuf<float> envTexels, condFunc, condCdf, condInt, margFunc, margCdf;
   DevBuf<uint16_t> perms;
   DevBuf<int32_t> primes, primeSums;
+  DevBuf<uint32_t> primeMagic;
   int lightStrategyBuilt = -1;
+  int traceBlocksPerSm = 0;
+  int triThreshold = 16;
   // wavefront state
   uint32_t capacity = 0;
   DevBuf<float4> rayO, rayD, hit, beta, L, shO, shD, shC, miO, miD, miC;
@@ -269,7 +272,9 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   s->ctx = ctx;
   cudaStream_t st = ctx->stream;
 
-  build_bvh2(d->verts, d->indices, d->n_tris, 4, &s->bvh);
+  int maxLeaf = 3;
+  if (const char* e = getenv("PBRGPU_MAX_LEAF")) maxLeaf = std::max(1, std::min(3, atoi(e)));
+  build_bvh8(d->verts, d->indices, d->n_tris, maxLeaf, &s->bvh);
   const int nT = d->n_tris;
   s->leafOf.assign((size_t)nT, -1);
   std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT);
@@ -397,7 +402,7 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   CK(s->dlights.upload(s->lights, st));
 
   s->sc.tv0 = s->tv0.p; s->sc.tv1 = s->tv1.p; s->sc.tv2 = s->tv2.p;
-  s->sc.nodes = s->nodes.p;
+  s->sc.nodes8 = reinterpret_cast<const float4*>(s->nodes.p);
   s->sc.mats = s->mats.p;
   s->sc.lights = s->dlights.p;
   s->sc.nTris = nT;
@@ -410,6 +415,10 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   CK(s->primeSums.upload(sums, st));
   s->sc.hp.primes = s->primes.p;
   s->sc.hp.primeSums = s->primeSums.p;
+  std::vector<uint32_t> magic;
+  host::prime_magic(primes, &magic);
+  CK(s->primeMagic.upload(magic, st));
+  s->sc.hp.primeMagic = reinterpret_cast<const uint2*>(s->primeMagic.p);
   CK(cudaStreamSynchronize(st));
   *out = s.release();
   return 0;
@@ -470,7 +479,7 @@ int pbrgpu_scene_info(pbrgpu_scene* s, int64_t out[8]) {
   out[0] = (int64_t)s->bvh.nodes.size();
   out[1] = s->bvh.nLeaves;
   out[2] = s->bvh.maxLeafSize;
-  out[3] = (int64_t)(s->bvh.nodes.size() * sizeof(Bvh2Node));
+  out[3] = (int64_t)(s->bvh.nodes.size() * sizeof(Bvh8Node));
   out[4] = (int64_t)s->sc.nTris * 48;
   out[5] = s->bvh.maxDepth;
   return 0;
@@ -484,7 +493,7 @@ static int check_render_args(pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
   if (rd->max_depth < 0 || rd->max_depth > 1000) return fail("pbrgpu_render: bad max_depth");
   if (rd->integrator != PBRGPU_INTEGRATOR_PATH)
     return fail("pbrgpu_render: integrator not implemented on the GPU path yet (Path only)");
-  if (s->bvh.maxDepth >= 60) return fail("pbrgpu_render: BVH deeper than the traversal stack");
+  if (s->bvh.maxDepth >= kSmemStack + kLocalStack) return fail("pbrgpu_render: BVH deeper than the traversal stack");
   return 0;
 }
 
@@ -495,6 +504,13 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   CK(cudaSetDevice(c->device));
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : c->stream;
   if (build_light_distribution(s, rd->light_strategy)) return 1;
+  if (s->traceBlocksPerSm <= 0) {
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false>, kTraceBlock, 0));
+    if (const char* e = getenv("PBRGPU_TRACE_BLOCKS_PER_SM")) nb = atoi(e);
+    s->traceBlocksPerSm = std::max(1, nb);
+    if (const char* e = getenv("PBRGPU_TRI_THRESHOLD")) s->triThreshold = std::max(1, std::min(32, atoi(e)));
+  }
   if (rd->light_strategy == PBRGPU_LIGHTSTRATEGY_POWER && s->lights.size() > 1)
     for (float p : s->lightPower)
       if (p < 0) return fail("pbrgpu_render: \"power\" light strategy with an InfiniteAreaLight is not supported (needs the MIP pyramid)");
@@ -519,6 +535,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   P.rrThreshold = rd->rr_threshold;
   P.arrayEndDim = 5;
   P.countStats = count ? 1 : 0;
+  P.triThreshold = s->triThreshold;
 
   if (!(rd->flags & PBRGPU_RENDER_ACCUMULATE)) CK(cudaMemsetAsync(d_rgba_sum, 0, sizeof(float) * 4 * (size_t)W * H, st));
   Counters zero{};
@@ -538,29 +555,31 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       P.ws.qCur = s->qA.p;
       P.ws.qNext = s->qB.p;
       uint32_t g = grid_for(c, nPaths, 8);
+      // persistent traversal grid: every SM filled to the kernel's occupancy, never more blocks than rays
+      uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths + kTraceBlock - 1) / kTraceBlock,
+                                                                      (uint64_t)c->smCount * s->traceBlocksPerSm));
       CK(tl.mark(T_RAYGEN));
-      k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
+      k_wave_begin<<<1, 1, 0, st>>>(s->ctr.p);
       k_raygen<<<g, kBlock, 0, st>>>(P);
       launches += 2;
+      // bounce b: ONE traversal launch serves the path rays of bounce b and the shadow + MIS rays that the
+      // shading of bounce b-1 emitted; then MIS resolve (b-1), classification, material-sorted shading (b).
       for (int bounce = 0; bounce <= rd->max_depth; ++bounce) {
         CK(tl.mark(T_CLOSEST));
-        if (count) k_trace_closest<true><<<g, kBlock, 0, st>>>(P);
-        else k_trace_closest<false><<<g, kBlock, 0, st>>>(P);
+        if (count) k_trace<true><<<gt, kTraceBlock, 0, st>>>(P);
+        else k_trace<false><<<gt, kTraceBlock, 0, st>>>(P);
+        CK(tl.mark(T_MIS));
+        if (bounce > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
         CK(tl.mark(T_SHADE));
+        k_classify<<<g, kBlock, 0, st>>>(P);
         k_shade<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
         k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce);
-        CK(tl.mark(T_SHADOW));
-        if (count) k_trace_shadow<true><<<g, kBlock, 0, st>>>(P);
-        else k_trace_shadow<false><<<g, kBlock, 0, st>>>(P);
-        CK(tl.mark(T_MIS));
-        if (count) k_trace_mis<true><<<g, kBlock, 0, st>>>(P);
-        else k_trace_mis<false><<<g, kBlock, 0, st>>>(P);
         k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
-        launches += 10;
+        launches += 9;
         std::swap(P.ws.qCur, P.ws.qNext);
       }
       CK(tl.mark(T_FILM));

@@ -20,22 +20,27 @@ struct HaltonParams {
   const uint16_t* perms;   // radicalInversePermutations (device)
   const int32_t* primes;   // Primes[1000]
   const int32_t* primeSums;
+  const uint2* primeMagic; // per prime: (m, s) with floor(a / p) == __umulhi(a, m) >> s for every a < 2^31
   int64_t nPerms;
 };
 
 constexpr int kPrimeTableSize = 1000;
 constexpr int kMaxResolution = 128;  // Halton.cpp:7
 
-// digits of `a` in base `base`, reversed;  returns reversedDigits, *invBaseN = invBase^nDigits (fp32 chain)
-PBR_D uint64_t reverse_digits(uint64_t a, uint32_t base, float invBase, float* invBaseN, const uint16_t* perm) {
+// digits of `a` in base `base`, reversed;  returns reversedDigits, *invBaseN = invBase^nDigits (fp32 chain).
+// The reference divides uint64 by a compile-time base (1024 template instantiations).  Here the base is
+// a run-time prime, so for a < 2^31 (every index of a <= 4096-spp 4K render) the quotient comes from a
+// precomputed multiply-shift (Granlund-Montgomery: exact for all a < 2^31) instead of a hardware-less
+// integer division; larger indices take the plain 64-bit path.  Integer results are identical.
+PBR_D uint64_t reverse_digits(uint64_t a, uint32_t base, uint2 magic, float invBase, float* invBaseN, const uint16_t* perm) {
   uint64_t rev = 0;
   float ibn = 1;
-  if ((a >> 32) == 0) {  // fast path: 32-bit divides (all indices of a <=4096-spp 4K render fit)
+  if ((a >> 31) == 0) {
     uint32_t a32 = (uint32_t)a;
     while (a32) {
-      uint32_t next = a32 / base;
+      uint32_t next = __umulhi(a32, magic.x) >> magic.y;
       uint32_t digit = a32 - next * base;
-      rev = rev * base + (perm ? (uint32_t)perm[digit] : digit);
+      rev = rev * base + (perm ? (uint32_t)__ldg(perm + digit) : digit);
       ibn *= invBase;
       a32 = next;
     }
@@ -61,7 +66,7 @@ PBR_D float radical_inverse(int baseIndex, uint64_t a, const HaltonParams& hp) {
   uint32_t base = (uint32_t)hp.primes[baseIndex];
   float invBase = (float)1 / (float)base;
   float invBaseN;
-  uint64_t rev = reverse_digits(a, base, invBase, &invBaseN, nullptr);
+  uint64_t rev = reverse_digits(a, base, __ldg(hp.primeMagic + baseIndex), invBase, &invBaseN, nullptr);
   return stdmin((float)rev * invBaseN, kOneMinusEpsilon);
 }
 
@@ -71,7 +76,7 @@ PBR_D float scrambled_radical_inverse(int baseIndex, uint64_t a, const HaltonPar
   const uint16_t* perm = hp.perms + hp.primeSums[baseIndex];
   float invBase = (float)1 / (float)base;
   float invBaseN;
-  uint64_t rev = reverse_digits(a, base, invBase, &invBaseN, perm);
+  uint64_t rev = reverse_digits(a, base, __ldg(hp.primeMagic + baseIndex), invBase, &invBaseN, perm);
   // invBaseN * (reversedDigits + invBase * perm[0] / (1 - invBase))
   float tail = (invBase * (float)(int)perm[0]) / (1 - invBase);
   return stdmin(invBaseN * ((float)rev + tail), kOneMinusEpsilon);

@@ -1,9 +1,9 @@
 // trace.cuh - ray / triangle and ray / BVH queries.
 //   Triangle::Intersect hit test   Shape/Triangle.cpp:66-145   (identical arithmetic, bit-exact t,b0,b1,b2)
 //   Triangle::IntersectP           Shape/Triangle.cpp:262-350
-//   BVHAccel::Intersect/IntersectP Accelerator/BVHAccel.cpp:285-366 (replaced: our own BVH + conservative
-//   slab test; the reference's slab test Geometry.h:1437-1468 has no gamma widening, ours does, so the
-//   set of triangles we test is a superset of what a watertight query needs).
+//   BVHAccel::Intersect/IntersectP Accelerator/BVHAccel.cpp:285-366 (replaced: our own compressed 8-wide
+//   BVH with a conservative slab test; the reference's slab test Geometry.h:1437-1468 has no gamma
+//   widening, ours is widened, so the set of triangles we test is a superset of what the reference tests).
 #pragma once
 #include "device_types.cuh"
 
@@ -95,76 +95,165 @@ PBR_D V3 ld3(const float4* p, int i) {
   return V3(v.x, v.y, v.z);
 }
 
-// Conservative slab test of both children of a node.  FMAs/fast min-max allowed here: the only
-// requirement is that no box actually pierced by the ray inside (0, tMax] is rejected.
-PBR_D void test_children(const Bvh2Node* __restrict__ nodes, int node, V3 o, V3 inv, float tMax, bool* h0, bool* h1,
-                         float* t0, float* t1, int* c0, int* c1) {
-  const float4* np = reinterpret_cast<const float4*>(nodes + node);
-  float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
-  int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
-  const float widen = 1.0000004f;  // >= 1 + 2*gamma(3)
-  float x0 = (a.x - o.x) * inv.x, x1 = (a.y - o.x) * inv.x;
-  float y0 = (a.z - o.y) * inv.y, y1 = (a.w - o.y) * inv.y;
-  float z0 = (c.x - o.z) * inv.z, z1 = (c.y - o.z) * inv.z;
-  float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
-  float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * widen;
-  *h0 = (tn <= fminf(tf, tMax));
-  *t0 = tn;
-  x0 = (b.x - o.x) * inv.x; x1 = (b.y - o.x) * inv.x;
-  y0 = (b.z - o.y) * inv.y; y1 = (b.w - o.y) * inv.y;
-  z0 = (c.z - o.z) * inv.z; z1 = (c.w - o.z) * inv.z;
-  tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
-  tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1)) * widen;
-  *h1 = (tn <= fminf(tf, tMax));
-  *t1 = tn;
-  *c0 = d.x;
-  *c1 = d.y;
+// ---------------------------------------------------------------------------------------------
+// Compressed 8-wide BVH traversal (node layout: bvh.h).  Per-lane state machine after Ylitie et al.
+// 2017: a *node group* (childBase, hit bits of inner children in [31:24] | imask in [7:0]) and a
+// *triangle group* (triBase, hit bits of up to 24 triangles).  The traversal stack holds node groups
+// (and postponed triangle groups); its first kSmemStack levels live in shared memory, one column per
+// lane ([level][lane] -> conflict-free), deeper levels spill to a small local array.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmemStack = 12;
+constexpr int kLocalStack = 36;
+
+struct Trav {
+  V3 o;
+  float idx, idy, idz;        // reciprocal direction (|d| clamped away from 0)
+  float jdx, jdy, jdz;        // 32768 * reciprocal direction
+  unsigned octinv4;           // inverse octant replicated in 4 bytes
+  RayPrep rp;
+  float tMax;
+  uint2 ngroup, tgroup;
+  int sp;
+  HitRec hit;
+};
+// deep levels of the traversal stack (beyond kSmemStack): a separate local array so that the rest of
+// the traversal state stays in registers
+struct TravSpill {
+  uint2 lstack[kLocalStack];
+};
+
+PBR_D float safe_rcp(float d) {
+  // |1/d| capped at 1e24: an axis-parallel ray gets +-huge slab distances instead of inf/NaN
+  float r = 1.f / fmaxf(fabsf(d), 1e-24f);
+  return d < 0.f ? -r : r;
 }
 
-template <bool ANY_HIT, bool COUNT>
-PBR_D bool traverse(const SceneDev& sc, V3 o, V3 d, float tMax, HitRec* hit, unsigned* nNodes, unsigned* nTris) {
-  RayPrep rp = prep_ray(o, d);
-  V3 inv(1.f / d.x, 1.f / d.y, 1.f / d.z);
-  int stack[64];
-  int sp = 0;
-  int cur = 0;
-  hit->tri = -1;
-  hit->t = tMax;
-  bool found = false;
-  while (true) {
-    if (cur >= 0) {
-      bool h0, h1;
-      float t0, t1;
-      int c0, c1;
-      test_children(sc.nodes, cur, o, inv, tMax, &h0, &h1, &t0, &t1, &c0, &c1);
-      if (COUNT) (*nNodes)++;
-      if (h0 && h1) {
-        if (t1 < t0) { int tmp = c0; c0 = c1; c1 = tmp; }
-        stack[sp++] = c1;
-        cur = c0;
-        continue;
-      } else if (h0) { cur = c0; continue; }
-      else if (h1) { cur = c1; continue; }
-    } else {
-      unsigned code = (unsigned)(~cur);
-      int first = (int)(code >> 2), cnt = (int)(code & 3u) + 1;
-      for (int i = 0; i < cnt; ++i) {
-        int ti = first + i;
-        V3 p0 = ld3(sc.tv0, ti), p1 = ld3(sc.tv1, ti), p2 = ld3(sc.tv2, ti);
-        float t, b0, b1, b2;
-        if (COUNT) (*nTris)++;
-        if (intersect_triangle(rp, tMax, p0, p1, p2, &t, &b0, &b1, &b2)) {
-          if (ANY_HIT) return true;
-          tMax = t;
-          hit->tri = ti; hit->t = t; hit->b0 = b0; hit->b1 = b1; hit->b2 = b2;
-          found = true;
-        }
-      }
+PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax) {
+  T.o = o;
+  T.idx = safe_rcp(d.x); T.idy = safe_rcp(d.y); T.idz = safe_rcp(d.z);
+  T.jdx = T.idx * 32768.f; T.jdy = T.idy * 32768.f; T.jdz = T.idz * 32768.f;
+  T.octinv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
+  T.rp = prep_ray(o, d);
+  T.tMax = tMax;
+  T.ngroup = make_uint2(0u, 0x80000000u);
+  T.tgroup = make_uint2(0u, 0u);
+  T.sp = 0;
+  T.hit.tri = -1;
+  T.hit.t = tMax;
+  T.hit.b0 = T.hit.b1 = T.hit.b2 = 0.f;
+}
+
+PBR_D void trav_push(Trav& T, uint2* sstack, TravSpill& S, uint2 v) {
+  if (T.sp < kSmemStack) sstack[T.sp * 32] = v;
+  else S.lstack[T.sp - kSmemStack] = v;
+  T.sp++;
+}
+PBR_D uint2 trav_pop(Trav& T, const uint2* sstack, const TravSpill& S) {
+  T.sp--;
+  return (T.sp < kSmemStack) ? sstack[T.sp * 32] : S.lstack[T.sp - kSmemStack];
+}
+
+// byte J of `w` -> float in [1,2): 1 + byte / 32768   (one PRMT, no int->float conversion)
+template <int J>
+PBR_D float q2f(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (J << 4))); }
+
+// One node step: pick the next inner child of the node group (front-to-back by octant), fetch its
+// 80-byte node with five 16-byte loads, slab-test the 8 quantised child boxes, emit a new node group
+// and triangle group.  The slab test is conservative: the rounding error of the fused evaluation is
+// bounded per axis and folded into the offsets (Bn = B - err, Bf = B + err).
+PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack, TravSpill& S) {
+  const unsigned hits = T.ngroup.y;
+  const int bit = 31 - __clz(hits);
+  T.ngroup.y &= ~(1u << bit);
+  if (T.ngroup.y > 0x00FFFFFFu) trav_push(T, sstack, S, T.ngroup);
+  const unsigned slot = (unsigned)(bit - 24) ^ (T.octinv4 & 0xffu);
+  const unsigned rel = __popc(hits & ~(0xFFFFFFFFu << slot));
+  const float4* np = nodes + 5 * (size_t)(T.ngroup.x + rel);
+  const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+  const unsigned ei = __float_as_uint(n0.w);
+  T.ngroup.x = __float_as_uint(n1.x);
+  T.tgroup.x = __float_as_uint(n1.y);
+  // A = 32768 * 2^e / d (exact scalings of 1/d), B = (origin - o) / d
+  const float Ax = __uint_as_float((ei & 0xffu) << 23) * T.jdx;
+  const float Ay = __uint_as_float(((ei >> 8) & 0xffu) << 23) * T.jdy;
+  const float Az = __uint_as_float(((ei >> 16) & 0xffu) << 23) * T.jdz;
+  const float Bx = (n0.x - T.o.x) * T.idx, By = (n0.y - T.o.y) * T.idy, Bz = (n0.z - T.o.z) * T.idz;
+  const float ex = 4e-7f * (fabsf(Bx) + fabsf(Ax)), ey = 4e-7f * (fabsf(By) + fabsf(Ay)), ez = 4e-7f * (fabsf(Bz) + fabsf(Az));
+  const float Bnx = (Bx - Ax) - ex, Bfx = (Bx - Ax) + ex;
+  const float Bny = (By - Ay) - ey, Bfy = (By - Ay) + ey;
+  const float Bnz = (Bz - Az) - ez, Bfz = (Bz - Az) + ez;
+  const bool px = T.idx >= 0.f, py = T.idy >= 0.f, pz = T.idz >= 0.f;
+  unsigned hitmask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const unsigned meta4 = __float_as_uint(h ? n1.w : n1.z);
+    const unsigned isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const unsigned innerMask4 = (isInner4 >> 4) * 0xffu;
+    const unsigned bitIndex4 = (meta4 ^ (T.octinv4 & innerMask4)) & 0x1f1f1f1fu;
+    const unsigned childBits4 = (meta4 >> 5) & 0x07070707u;
+    const unsigned lox = __float_as_uint(h ? n2.y : n2.x), loy = __float_as_uint(h ? n2.w : n2.z);
+    const unsigned loz = __float_as_uint(h ? n3.y : n3.x), hix = __float_as_uint(h ? n3.w : n3.z);
+    const unsigned hiy = __float_as_uint(h ? n4.y : n4.x), hiz = __float_as_uint(h ? n4.w : n4.z);
+    const unsigned nx = px ? lox : hix, fx = px ? hix : lox;
+    const unsigned ny = py ? loy : hiy, fy = py ? hiy : loy;
+    const unsigned nz = pz ? loz : hiz, fz = pz ? hiz : loz;
+#define PBR_CW_CHILD(J)                                                                               \
+    {                                                                                                 \
+      const float tn = fmaxf(fmaxf(fmaf(q2f<J>(nx), Ax, Bnx), fmaf(q2f<J>(ny), Ay, Bny)),             \
+                             fmaxf(fmaf(q2f<J>(nz), Az, Bnz), 0.f));                                  \
+      const float tf = fminf(fminf(fmaf(q2f<J>(fx), Ax, Bfx), fmaf(q2f<J>(fy), Ay, Bfy)),             \
+                             fminf(fmaf(q2f<J>(fz), Az, Bfz), T.tMax));                               \
+      if (tn <= tf) hitmask |= ((childBits4 >> (8 * J)) & 0xffu) << ((bitIndex4 >> (8 * J)) & 0xffu); \
     }
-    if (sp == 0) break;
-    cur = stack[--sp];
+    PBR_CW_CHILD(0) PBR_CW_CHILD(1) PBR_CW_CHILD(2) PBR_CW_CHILD(3)
+#undef PBR_CW_CHILD
   }
-  return found;
+  T.ngroup.y = (hitmask & 0xFF000000u) | (ei >> 24);
+  T.tgroup.y = hitmask & 0x00FFFFFFu;
+}
+
+// One triangle of the triangle group: the reference's watertight test, bit-exact (t, b0, b1, b2).
+PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T) {
+  const int bit = 31 - __clz(T.tgroup.y);
+  T.tgroup.y &= ~(1u << bit);
+  const int ti = (int)T.tgroup.x + bit;
+  V3 p0 = ld3(sc.tv0, ti), p1 = ld3(sc.tv1, ti), p2 = ld3(sc.tv2, ti);
+  float t, b0, b1, b2;
+  if (intersect_triangle(T.rp, T.tMax, p0, p1, p2, &t, &b0, &b1, &b2)) {
+    T.tMax = t;
+    T.hit.tri = ti; T.hit.t = t; T.hit.b0 = b0; T.hit.b1 = b1; T.hit.b2 = b2;
+    return true;
+  }
+  return false;
+}
+
+// Whole-ray traversal by one thread (parity hooks and small queries).  `sstack` = this lane's column
+// of the warp's shared-memory stack.
+template <bool ANY_HIT, bool COUNT>
+PBR_D bool traverse(const SceneDev& sc, V3 o, V3 d, float tMax, HitRec* hit, uint2* sstack, unsigned* nNodes, unsigned* nTris) {
+  Trav T;
+  TravSpill S;
+  trav_init(T, o, d, tMax);
+  bool done = false;
+  while (!done) {
+    if (T.ngroup.y > 0x00FFFFFFu) {
+      cw_node_step(sc.nodes8, T, sstack, S);
+      if (COUNT) (*nNodes)++;
+    } else {
+      T.tgroup = T.ngroup;
+      T.ngroup = make_uint2(0u, 0u);
+    }
+    while (T.tgroup.y != 0u) {
+      if (COUNT) (*nTris)++;
+      if (cw_tri_step(sc, T) && ANY_HIT) { T.tgroup.y = 0u; T.ngroup.y = 0u; T.sp = 0; }
+    }
+    if (T.ngroup.y <= 0x00FFFFFFu) {
+      if (T.sp > 0) T.ngroup = trav_pop(T, sstack, S);
+      else done = true;
+    }
+  }
+  *hit = T.hit;
+  return T.hit.tri >= 0;
 }
 
 }  // namespace pbr

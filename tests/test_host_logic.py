@@ -1,0 +1,122 @@
+"""CPU tests (no GPU) of the host-side logic: camera-matrix construction (bit-exact against the compiled
+reference and the golden fixtures), scene generators, sample-range sharding, and the world_size-2
+film reduce over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from pysicalbasedraytracer_b200 import _abi as A
+from pysicalbasedraytracer_b200 import scenes, shard
+from tests.util import golden
+
+KAT = golden("kat.npz")
+
+
+@pytest.mark.parametrize("name,cam_type,W,H,eye,look", [
+    ("persp512", A.CAMERA_PERSPECTIVE, 512, 512, (0.0, 0.0, 5.0), (0.0, 0.0, 0.0)),
+    ("persp320x180", A.CAMERA_PERSPECTIVE, 320, 180, (0.3, 0.2, 5.0), (0.1, -0.2, 0.0)),
+    ("ortho100x160", A.CAMERA_ORTHOGRAPHIC, 100, 160, (0.3, 0.2, 5.0), (0.1, -0.2, 0.0))])
+def test_camera_matrices_bit_exact_vs_golden(api, name, cam_type, W, H, eye, look):
+    c2w = api.Inverse(api.LookAt(eye, look, (0.0, 1.0, 0.0)))
+    cam = (api.CreatePerspectiveCamera if cam_type == A.CAMERA_PERSPECTIVE else api.CreateOrthographicCamera)(W, H, c2w)
+    d = cam.desc()
+    assert np.array_equal(np.array(d.raster_to_camera[:], dtype=np.float32).view(np.uint32), KAT[f"cam_{name}_r2c"].view(np.uint32))
+    assert np.array_equal(np.array(d.camera_to_world[:], dtype=np.float32).view(np.uint32), KAT[f"cam_{name}_c2w"].view(np.uint32))
+
+
+def test_camera_matrices_bit_exact_vs_reference(api, ref):
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        eye = rng.uniform(-6, 6, 3)
+        look = rng.uniform(-1, 1, 3)
+        W, H = int(rng.integers(16, 2000)), int(rng.integers(16, 1200))
+        for cam_type in (A.CAMERA_PERSPECTIVE, A.CAMERA_ORTHOGRAPHIC):
+            rc = ref.RefCamera(cam_type, W, H, eye, look, (0, 1, 0))
+            want = rc.desc()
+            c2w = api.Inverse(api.LookAt(eye, look, (0.0, 1.0, 0.0)))
+            cam = (api.CreatePerspectiveCamera if cam_type == A.CAMERA_PERSPECTIVE else api.CreateOrthographicCamera)(W, H, c2w)
+            got = cam.desc()
+            for f in ("raster_to_camera", "camera_to_world"):
+                g = np.array(getattr(got, f)[:], dtype=np.float32)
+                w = np.array(getattr(want, f)[:], dtype=np.float32)
+                assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), (f, W, H, cam_type)
+
+
+def test_scene_generators_are_deterministic_and_sized():
+    a, b = scenes.cornell(sphere_tess=8), scenes.cornell(sphere_tess=8)
+    assert np.array_equal(a.verts, b.verts) and np.array_equal(a.indices, b.indices)
+    assert a.n_tris == 12 + 2 * (2 * 8 * 16)
+    d = scenes.dragon_class(tess=467)
+    assert d.n_tris == 872368  # BASELINE configs[1]: ~870k triangles
+    assert len(d.lights) == 2 and d.tri_light.max() == 1
+    e = scenes.procedural_env(64, 32)
+    assert e.shape == (32, 64, 3) and e.dtype == np.float32 and np.isfinite(e).all() and e.max() > 1.0
+
+
+def test_shard_samples_partition():
+    for (s0, s1, world) in [(0, 1024, 8), (0, 16, 8), (3, 10, 4), (0, 5, 8), (0, 4096, 2), (7, 8, 1)]:
+        parts = [shard.shard_samples(s0, s1, r, world) for r in range(world)]
+        assert parts[0][0] == s0 and parts[-1][1] == s1
+        for (a, b), (c, d) in zip(parts, parts[1:]):
+            assert b == c and a <= b
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == s1 - s0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    H, W, spp = 6, 5, 11
+    lo, hi = shard.shard_samples(0, spp, rank, world)
+    # stand-in for the renderer: the "radiance" of (pixel, sample) is a closed-form function of both, so the
+    # reduced film has a known answer
+    film = torch.zeros((H, W, 4), dtype=torch.float32)
+    pix = torch.arange(H * W, dtype=torch.float32).reshape(H, W)
+    for s in range(lo, hi):
+        film[..., 0] += pix + s
+        film[..., 1] += 2 * pix - s
+        film[..., 2] += 0.5 * s
+        film[..., 3] += 1
+    shard.reduce_film(film, dst=0)
+    if rank == 0:
+        q.put(film.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_film_reduce_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    film = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    H, W, spp = 6, 5, 11
+    pix = np.arange(H * W, dtype=np.float32).reshape(H, W)
+    s = np.arange(spp, dtype=np.float32)
+    assert np.allclose(film[..., 0], spp * pix + s.sum())
+    assert np.allclose(film[..., 1], 2 * spp * pix - s.sum())
+    assert np.allclose(film[..., 2], 0.5 * s.sum())
+    assert np.all(film[..., 3] == spp)
+    import torch
+    mean = shard.resolve_mean(torch.from_numpy(film)).numpy()
+    assert np.allclose(mean[..., 0], pix + s.mean())
