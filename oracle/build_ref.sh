@@ -70,6 +70,8 @@ find . -name '*.cpp' ! -path './Main/*' ! -path './include/*' | sed 's#^\./##' >
 mkdir -p obj
 cat srcs.txt | xargs -P "$JOBS" -I{} sh -c 'o=obj/$(echo {} | tr "/" "_").o; g++ '"$CXXFLAGS"' -c {} -o $o || exit 255'
 # harness (ours) - compiled against the staged reference headers and our C-ABI header
-g++ $CXXFLAGS -I"$HERE/../include" -c "$HERE/ref_harness.cpp" -o obj/ref_harness.o
-g++ -shared -fopenmp -o "$OUT/libpbr_ref.so" obj/*.o
+PKG="$HERE/../pysicalbasedraytracer_b200"
+g++ $CXXFLAGS -I"$HERE/../include" -I"$PKG/host" -c "$HERE/ref_harness.cpp" -o obj/ref_harness.o
+# the harness also hosts the C++ drop-in test (GpuPathIntegrator), so it links the product library
+g++ -shared -fopenmp -o "$OUT/libpbr_ref.so" obj/*.o -L"$PKG" -lpbrgpu -Wl,-rpath,'$ORIGIN/../../pysicalbasedraytracer_b200'
 echo "built $OUT/libpbr_ref.so"

@@ -13,6 +13,9 @@
 // It does NOT use SamplerIntegrator::Render for parity dumps (quirk Q1: swapped loop bounds); its own
 // pixel loop iterates x in [x0,x1), y in [y0,y1) and returns linear-float sums.  ref_render_shipped()
 // calls the reference's Render() verbatim (4 threads, square images) for the as-shipped CPU baseline.
+// The C++ drop-in under test (flattener + GpuPathIntegrator); must precede every reference header.
+#include "GpuIntegrator.h"
+
 #include <atomic>
 #include <cstdio>
 #include <map>
@@ -512,5 +515,27 @@ void ref_tonemap(const float* rgb_mean, int n, unsigned char* rgba8) {
 }
 
 int ref_num_procs() { return omp_get_num_procs(); }
+
+// Drop-in test: the reference's OWN object graph (Scene / BVHAccel / GeometricPrimitive / Triangle / Material /
+// Light / PerspectiveCamera / HaltonSampler) rendered through PBR::GpuPathIntegrator::Render, i.e. through the
+// flattener of pysicalbasedraytracer_b200/host/GpuIntegrator.h and the C-ABI of libpbrgpu.so.  Needs a GPU.
+int ref_gpu_dropin_render(void* hscene, void* hc, int spp, int W, int H, int max_depth, float rr, const char* strategy,
+                          unsigned char* rgba8, float* rgb_sum, double* seconds) {
+  auto* rs = (RefScene*)hscene;
+  auto* rc = (RefCamera*)hc;
+  Scene raw(rs->bvh, rs->lights);  // the app's Scene: aggregate = BVHAccel (no counting wrapper)
+  Bounds2i b(Point2i(0, 0), Point2i(W, H));
+  std::shared_ptr<Sampler> sampler = std::make_shared<HaltonSampler>(spp, b);
+  FrameBuffer fb;
+  fb.InitBuffer(W, H, 4);
+  GpuPathIntegrator integ(max_depth, rc->cam, sampler, b, rr, strategy, &fb);
+  double t = -1;
+  integ.Render(raw, t);
+  if (seconds) *seconds = t;
+  if (t < 0) return 1;
+  if (rgba8) memcpy(rgba8, fb.getUCbuffer(), (size_t)W * H * 4);
+  if (rgb_sum) memcpy(rgb_sum, integ.rgbSum.data(), sizeof(float) * (size_t)W * H * 3);
+  return 0;
+}
 
 }  // extern "C"

@@ -63,6 +63,8 @@ def lib():
         L.ref_render_shipped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_void_p, C.POINTER(RefRenderStats)]
         L.ref_tonemap.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_gpu_dropin_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                            C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -190,3 +192,15 @@ def tonemap(rgb_mean):
     out = np.zeros((a.shape[0], 4), dtype=np.uint8)
     lib().ref_tonemap(a.ctypes.data, a.shape[0], out.ctypes.data)
     return out
+
+
+def gpu_dropin_render(scene, cam, spp, W, H, max_depth, rr, strategy="uniform"):
+    """The reference's own object graph rendered through the C++ drop-in GpuPathIntegrator (needs a GPU)."""
+    rgba = np.zeros((H, W, 4), dtype=np.uint8)
+    rgb_sum = np.zeros((H, W, 3), dtype=np.float32)
+    sec = C.c_double(0)
+    rc = lib().ref_gpu_dropin_render(scene.h, cam.h, spp, W, H, max_depth, rr, strategy.encode(), rgba.ctypes.data,
+                                     rgb_sum.ctypes.data, C.byref(sec))
+    if rc != 0:
+        raise RuntimeError("GpuPathIntegrator::Render failed (see stderr)")
+    return rgba, rgb_sum, sec.value

@@ -83,6 +83,7 @@ struct WaveDev {
   uint32_t* qCur;
   uint32_t* qNext;
   uint32_t* qMat;   // [kNumQueues][capacity]
+  uint32_t* qType;  // shading-queue id per entry of qCur (written by k_trace, read by k_classify)
   Counters* ctr;
   uint32_t capacity;
 };

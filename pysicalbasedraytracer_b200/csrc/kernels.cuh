@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace(const __grid_constant__ R
   bool busy = false, exhausted = false;
   int mode = TRACE_PATH;
   uint32_t ray = 0;  // PATH: wavefront slot; SHADOW / MIS: index in that queue
+  uint32_t qi = 0;   // PATH: position in the path queue
   unsigned nodes = 0, tris = 0;
   while (true) {
     // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace(const __grid_constant__ R
         uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
         if (i < n) {
           float4 ro, rd;
-          if (i < nPath) { mode = TRACE_PATH; ray = P.ws.qCur[i]; ro = P.ws.rayO[ray]; rd = P.ws.rayD[ray]; }
+          if (i < nPath) { mode = TRACE_PATH; qi = i; ray = P.ws.qCur[i]; ro = P.ws.rayO[ray]; rd = P.ws.rayD[ray]; }
           else if (i < nPath + nShadow) { mode = TRACE_SHADOW; ray = i - nPath; ro = P.ws.shO[ray]; rd = P.ws.shD[ray]; }
           else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
           trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w);
@@ -176,6 +177,8 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace(const __grid_constant__ R
         // ---- ray finished ----
         if (mode == TRACE_PATH) {
           P.ws.hit[ray] = make_float4(__int_as_float(T.hit.tri), T.hit.b0, T.hit.b1, T.hit.b2);
+          // shading-queue id of this path, written in QUEUE order so that k_classify reads it coalesced
+          P.ws.qType[qi] = T.hit.tri >= 0 ? ((T.hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
         } else if (mode == TRACE_MIS) {
           P.ws.miO[ray].w = __int_as_float(T.hit.tri);
         } else if (T.hit.tri < 0) {  // unoccluded: add the light-sampling contribution
@@ -225,9 +228,7 @@ __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ Ren
     uint32_t slot = 0;
     if (active) {
       slot = P.ws.qCur[i];
-      int tri = __float_as_int(P.ws.hit[slot].x);
-      q = kQueueMiss;
-      if (tri >= 0) q = (int)((__float_as_uint(__ldg(&P.sc.tv1[tri].w)) >> kTriTypeShift) & 0xf);
+      q = (int)P.ws.qType[i];
     }
 #pragma unroll
     for (int k = 0; k < kNumQueues; ++k) {

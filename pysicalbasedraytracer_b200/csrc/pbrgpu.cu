@@ -92,7 +92,7 @@ struct pbrgpu_scene {
   uint32_t capacity = 0;
   DevBuf<float4> rayO, rayD, hit, beta, L, shO, shD, shC, miO, miD, miC;
   DevBuf<uint2> hidx;
-  DevBuf<uint32_t> meta, qA, qB, qMat;
+  DevBuf<uint32_t> meta, qA, qB, qMat, qType;
   DevBuf<Counters> ctr;
   DevBuf<float> accum;
   size_t accumPix = 0;
@@ -107,6 +107,7 @@ int ensure_wave(pbrgpu_scene* s, uint32_t cap) {
   CK(s->miO.alloc(cap)); CK(s->miD.alloc(cap)); CK(s->miC.alloc(cap));
   CK(s->hidx.alloc(cap)); CK(s->meta.alloc(cap)); CK(s->qA.alloc(cap)); CK(s->qB.alloc(cap));
   CK(s->qMat.alloc((size_t)cap * kNumQueues));
+  CK(s->qType.alloc(cap));
   if (!s->ctr.p) CK(s->ctr.alloc(1));
   s->capacity = cap;
   return 0;
@@ -117,7 +118,7 @@ void fill_wave(pbrgpu_scene* s, WaveDev* w) {
   w->hidx = s->hidx.p; w->meta = s->meta.p;
   w->shO = s->shO.p; w->shD = s->shD.p; w->shC = s->shC.p;
   w->miO = s->miO.p; w->miD = s->miD.p; w->miC = s->miC.p;
-  w->qCur = s->qA.p; w->qNext = s->qB.p; w->qMat = s->qMat.p;
+  w->qCur = s->qA.p; w->qNext = s->qB.p; w->qMat = s->qMat.p; w->qType = s->qType.p;
   w->ctr = s->ctr.p;
   w->capacity = s->capacity;
 }

@@ -88,6 +88,7 @@ PBR_D bool intersect_triangle(const RayPrep& rp, float tMax, V3 p0, V3 p1, V3 p2
 struct HitRec {
   int tri;  // leaf-order triangle index, -1 = miss
   float t, b0, b1, b2;
+  uint32_t w1;  // tv1.w of the hit triangle (material id | type | flags), free with the vertex load
 };
 
 PBR_D V3 ld3(const float4* p, int i) {
@@ -141,6 +142,7 @@ PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax) {
   T.hit.tri = -1;
   T.hit.t = tMax;
   T.hit.b0 = T.hit.b1 = T.hit.b2 = 0.f;
+  T.hit.w1 = 0u;
 }
 
 PBR_D void trav_push(Trav& T, uint2* sstack, TravSpill& S, uint2 v) {
@@ -217,11 +219,13 @@ PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T) {
   const int bit = 31 - __clz(T.tgroup.y);
   T.tgroup.y &= ~(1u << bit);
   const int ti = (int)T.tgroup.x + bit;
-  V3 p0 = ld3(sc.tv0, ti), p1 = ld3(sc.tv1, ti), p2 = ld3(sc.tv2, ti);
+  const float4 v1 = __ldg(sc.tv1 + ti);
+  V3 p0 = ld3(sc.tv0, ti), p1(v1.x, v1.y, v1.z), p2 = ld3(sc.tv2, ti);
   float t, b0, b1, b2;
   if (intersect_triangle(T.rp, T.tMax, p0, p1, p2, &t, &b0, &b1, &b2)) {
     T.tMax = t;
     T.hit.tri = ti; T.hit.t = t; T.hit.b0 = b0; T.hit.b1 = b1; T.hit.b2 = b2;
+    T.hit.w1 = __float_as_uint(v1.w);
     return true;
   }
   return false;

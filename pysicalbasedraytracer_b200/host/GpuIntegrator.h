@@ -1,0 +1,358 @@
+// GpuIntegrator.h - C++ drop-in for the reference renderer (G0T-cha/PysicalBasedRaytracer).
+//
+//   PBR::GpuPathIntegrator : public PBR::Integrator
+//
+// has the SAME constructor signature as PBR::PathIntegrator (Integrator/PathIntegrator.h:14-18) and the
+// same virtual  void Render(const Scene&, double& timeConsume)  (Integrator/Integrator.h:14), so the
+// application (Main/main.cpp:399-413) switches to the GPU by changing one type name.  Render():
+//   1. flattens the reference object graph  Scene -> BVHAccel -> GeometricPrimitive -> Triangle /
+//      Material / AreaLight, scene.lights, the ProjectiveCamera and the HaltonSampler  into the POD
+//      descriptors of include/pbrgpu.h (world-space triangle soup + material / light tables),
+//   2. calls the C-ABI of libpbrgpu.so (pbrgpu_scene_create / camera_set / sampler_set / render),
+//   3. writes the 8-bit image into the caller's FrameBuffer through set_uc, exactly where
+//      SamplerIntegrator::Render would (Integrator/Integrator.cpp:339-343), and sets timeConsume.
+// The reference's own BVH is NOT used on the GPU: only the primitive list it owns is read.
+//
+// The reference exposes none of the members the flattener needs (Scene::aggregate,
+// BVHAccel::primitives, GeometricPrimitive::shape, Triangle::mesh, material textures, ...), so this
+// header includes the reference headers with `private` / `protected` redefined to `public`
+// (option 1; object layout under GCC/MSVC does not depend on access specifiers).
+// => Include this header FIRST in the translation unit that uses it, before any reference header.
+//
+// Error convention = the reference's: no exceptions, problems go to std::cerr and Render returns
+// with timeConsume = -1 (the reference has no error channel at all).
+#pragma once
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#define private public
+#define protected public
+#include "Core/PBR.h"
+#include "Core/Geometry.h"
+#include "Core/Transform.h"
+#include "Core/Spectrum.h"
+#include "Core/Interaction.h"
+#include "Core/Primitive.h"
+#include "Core/Scene.h"
+#include "Core/FrameBuffer.h"
+#include "Shape/Shape.h"
+#include "Shape/Triangle.h"
+#include "Accelerator/BVHAccel.h"
+#include "Camera/Camera.h"
+#include "Sampler/Sampler.h"
+#include "Sampler/Halton.h"
+#include "Texture/Texture.h"
+#include "Texture/ConstantTexture.h"
+#include "Texture/MIPMap.h"
+#include "Material/Material.h"
+#include "Material/MatteMaterial.h"
+#include "Material/Mirror.h"
+#include "Material/GlassMaterial.h"
+#include "Material/MetalMaterial.h"
+#include "Material/PlasticMaterial.h"
+#include "Light/Light.h"
+#include "Light/PointLight.h"
+#include "Light/DiffuseLight.h"
+#include "Light/InfiniteAreaLight.h"
+#include "Light/SkyBoxLight.h"
+#include "Integrator/Integrator.h"
+#undef private
+#undef protected
+
+#include "pbrgpu.h"
+
+namespace PBR {
+
+namespace gpu_detail {
+
+struct Flat {
+  std::vector<float> verts;
+  std::vector<int32_t> indices, triMaterial, triLight;
+  std::vector<uint8_t> triFlags;
+  std::vector<pbrgpu_material> materials;
+  std::vector<pbrgpu_light> lights;
+  std::vector<float> env;
+  int envW = 0, envH = 0;
+  std::string error;
+};
+
+inline bool constSpectrum(const std::shared_ptr<Texture<Spectrum>>& t, float out[3], std::string* err) {
+  if (!t) { out[0] = out[1] = out[2] = 0.f; return true; }
+  if (!dynamic_cast<const ConstantTexture<Spectrum>*>(t.get())) { *err = "only ConstantTexture is supported on the GPU path"; return false; }
+  SurfaceInteraction si;
+  Spectrum s = t->Evaluate(si);  // ConstantTexture::Evaluate ignores the interaction (ConstantTexture.h:14)
+  out[0] = s[0]; out[1] = s[1]; out[2] = s[2];
+  return true;
+}
+inline bool constFloat(const std::shared_ptr<Texture<float>>& t, float* out, std::string* err) {
+  if (!t) { *out = 0.f; return true; }
+  if (!dynamic_cast<const ConstantTexture<float>*>(t.get())) { *err = "only ConstantTexture is supported on the GPU path"; return false; }
+  SurfaceInteraction si;
+  *out = t->Evaluate(si);
+  return true;
+}
+
+inline bool flattenMaterial(const Material* m, pbrgpu_material* o, std::string* err) {
+  std::memset(o, 0, sizeof(*o));
+  if (auto* p = dynamic_cast<const MatteMaterial*>(m)) {
+    o->type = PBRGPU_MAT_MATTE;
+    return constSpectrum(p->Kd, o->kd, err) && constFloat(p->sigma, &o->sigma, err);
+  }
+  if (auto* p = dynamic_cast<const MirrorMaterial*>(m)) {
+    o->type = PBRGPU_MAT_MIRROR;
+    return constSpectrum(p->Kr, o->kr, err);
+  }
+  if (auto* p = dynamic_cast<const GlassMaterial*>(m)) {
+    o->type = PBRGPU_MAT_GLASS;
+    o->remap_roughness = p->remapRoughness ? 1 : 0;
+    float idx = 1.f;
+    bool ok = constSpectrum(p->Kr, o->kr, err) && constSpectrum(p->Kt, o->kt, err) && constFloat(p->uRoughness, &o->u_rough, err) &&
+              constFloat(p->vRoughness, &o->v_rough, err) && constFloat(p->index, &idx, err);
+    o->eta[0] = o->eta[1] = o->eta[2] = idx;
+    return ok;
+  }
+  if (auto* p = dynamic_cast<const MetalMaterial*>(m)) {
+    o->type = PBRGPU_MAT_METAL;
+    o->remap_roughness = p->remapRoughness ? 1 : 0;
+    float r = 0.f;
+    bool ok = constSpectrum(p->eta, o->eta, err) && constSpectrum(p->k, o->k, err) && constFloat(p->roughness, &r, err);
+    // MetalMaterial.cpp:29-32: u/vRoughness when given, else `roughness`
+    if (ok && p->uRoughness) ok = constFloat(p->uRoughness, &o->u_rough, err); else o->u_rough = r;
+    if (ok && p->vRoughness) ok = constFloat(p->vRoughness, &o->v_rough, err); else o->v_rough = r;
+    return ok;
+  }
+  if (auto* p = dynamic_cast<const PlasticMaterial*>(m)) {
+    o->type = PBRGPU_MAT_PLASTIC;
+    o->remap_roughness = p->remapRoughness ? 1 : 0;
+    bool ok = constSpectrum(p->Kd, o->kd, err) && constSpectrum(p->Ks, o->kr, err) && constFloat(p->roughness, &o->u_rough, err);
+    o->v_rough = o->u_rough;
+    return ok;
+  }
+  *err = "unsupported Material subclass (GPU path: Matte, Mirror, Glass, Metal, Plastic)";
+  return false;
+}
+
+inline void copyMatrix(const Matrix4x4& m, float out[16]) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) out[i * 4 + j] = m.m[i][j];
+}
+
+inline bool flattenScene(const Scene& scene, Flat* f) {
+  auto* bvh = dynamic_cast<const BVHAccel*>(scene.aggregate.get());
+  if (!bvh) { f->error = "Scene::aggregate is not a BVHAccel"; return false; }
+  const auto& prims = bvh->primitives;
+  const size_t n = prims.size();
+  f->verts.reserve(n * 9);
+  f->indices.reserve(n * 3);
+  f->triMaterial.resize(n);
+  f->triLight.assign(n, -1);
+  f->triFlags.assign(n, 0);
+  std::unordered_map<const Material*, int> matId;
+  std::unordered_map<const Light*, int> lightId;
+  for (size_t i = 0; i < scene.lights.size(); ++i) lightId[scene.lights[i].get()] = (int)i;
+  f->lights.resize(scene.lights.size());
+  std::vector<int> lightTri(scene.lights.size(), -1);
+  for (size_t i = 0; i < n; ++i) {
+    auto* gp = dynamic_cast<const GeometricPrimitive*>(prims[i].get());
+    if (!gp) { f->error = "primitive is not a GeometricPrimitive"; return false; }
+    auto* tri = dynamic_cast<const Triangle*>(gp->shape.get());
+    if (!tri) { f->error = "shape is not a Triangle (the reference's Sphere is a stub, SURVEY Q4)"; return false; }
+    if (tri->mesh->n || tri->mesh->uv || tri->mesh->s) { f->error = "per-vertex normals / uvs / tangents are not supported on the GPU path yet"; return false; }
+    if (!gp->material) { f->error = "primitive without material (medium boundary) is not supported"; return false; }
+    for (int k = 0; k < 3; ++k) {
+      const Point3f& p = tri->mesh->p[tri->v[k]];  // already world space (TriangleMesh ctor, Triangle.cpp:27-28)
+      f->verts.push_back(p.x); f->verts.push_back(p.y); f->verts.push_back(p.z);
+      f->indices.push_back((int32_t)(3 * i + k));
+    }
+    f->triFlags[i] = (tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0;
+    auto it = matId.find(gp->material.get());
+    if (it == matId.end()) {
+      pbrgpu_material m;
+      if (!flattenMaterial(gp->material.get(), &m, &f->error)) return false;
+      it = matId.emplace(gp->material.get(), (int)f->materials.size()).first;
+      f->materials.push_back(m);
+    }
+    f->triMaterial[i] = it->second;
+    if (gp->areaLight) {
+      auto li = lightId.find(gp->areaLight.get());
+      if (li == lightId.end()) { f->error = "area light of a primitive is not in scene.lights"; return false; }
+      f->triLight[i] = li->second;
+      lightTri[li->second] = (int)i;
+    }
+  }
+  for (size_t i = 0; i < scene.lights.size(); ++i) {
+    pbrgpu_light& o = f->lights[i];
+    std::memset(&o, 0, sizeof(o));
+    const Light* l = scene.lights[i].get();
+    o.n_samples = l->nSamples;
+    o.tri = -1;
+    if (auto* p = dynamic_cast<const PointLight*>(l)) {
+      o.type = PBRGPU_LIGHT_POINT;
+      o.pos[0] = p->pLight.x; o.pos[1] = p->pLight.y; o.pos[2] = p->pLight.z;
+      o.L[0] = p->I[0]; o.L[1] = p->I[1]; o.L[2] = p->I[2];
+    } else if (auto* p = dynamic_cast<const DiffuseAreaLight*>(l)) {
+      o.type = PBRGPU_LIGHT_AREA_TRI;
+      o.tri = lightTri[i];
+      if (o.tri < 0) { f->error = "DiffuseAreaLight whose shape is not a scene primitive"; return false; }
+      o.two_sided = p->twoSided ? 1 : 0;
+      o.L[0] = p->Lemit[0]; o.L[1] = p->Lemit[1]; o.L[2] = p->Lemit[2];
+    } else if (auto* p = dynamic_cast<const InfiniteAreaLight*>(l)) {
+      o.type = PBRGPU_LIGHT_INFINITE;
+      o.L[0] = o.L[1] = o.L[2] = 1.f;  // the MIPMap texels are already multiplied by L (InfiniteAreaLight.cpp:20-31)
+      copyMatrix(p->LightToWorld.m, o.light_to_world);
+      copyMatrix(p->WorldToLight.m, o.world_to_light);
+      const auto& lvl0 = *p->Lmap->pyramid[0];
+      f->envW = lvl0.uSize(); f->envH = lvl0.vSize();
+      f->env.resize((size_t)f->envW * f->envH * 3);
+      for (int v = 0; v < f->envH; ++v)
+        for (int u = 0; u < f->envW; ++u) {
+          const RGBSpectrum& t = lvl0(u, v);
+          float* d = &f->env[3 * ((size_t)v * f->envW + u)];
+          d[0] = t[0]; d[1] = t[1]; d[2] = t[2];
+        }
+    } else if (auto* p = dynamic_cast<const SkyBoxLight*>(l)) {
+      o.type = PBRGPU_LIGHT_SKYBOX;
+      o.world_radius = p->worldRadius;
+      if (!p->data || p->nrComponents < 3) { f->error = "SkyBoxLight without image data"; return false; }
+      f->envW = p->imageWidth; f->envH = p->imageHeight;
+      f->env.resize((size_t)f->envW * f->envH * 3);
+      for (size_t k = 0; k < (size_t)f->envW * f->envH; ++k)
+        for (int c = 0; c < 3; ++c) f->env[3 * k + c] = p->data[k * p->nrComponents + c];
+    } else {
+      f->error = "unsupported Light subclass (GPU path: Point, DiffuseArea, InfiniteArea, SkyBox)";
+      return false;
+    }
+  }
+  return true;
+}
+
+}  // namespace gpu_detail
+
+// Shared Render() of the GPU integrators: flatten -> pbrgpu_* -> FrameBuffer.
+class GpuSamplerIntegrator : public Integrator {
+ public:
+  GpuSamplerIntegrator(std::shared_ptr<const Camera> camera, std::shared_ptr<Sampler> sampler, const Bounds2i& pixelBounds,
+                       FrameBuffer* framebuffer, int device = 0)
+      : camera(camera), sampler(sampler), pixelBounds(pixelBounds), m_FrameBuffer(framebuffer), device(device) {}
+  ~GpuSamplerIntegrator() override {
+    if (gscene) pbrgpu_scene_destroy(gscene);
+    if (ctx) pbrgpu_shutdown(ctx);
+  }
+  void Render(const Scene& scene, double& timeConsume) override {
+    auto t0 = std::chrono::steady_clock::now();
+    timeConsume = -1;
+    if (!ctx && pbrgpu_init(device, &ctx)) return fail("pbrgpu_init");
+    if (!gscene || flattenedScene != &scene) {  // flatten once per Scene object
+      if (gscene) { pbrgpu_scene_destroy(gscene); gscene = nullptr; }
+      gpu_detail::Flat f;
+      if (!gpu_detail::flattenScene(scene, &f)) { std::cerr << "GpuIntegrator: " << f.error << std::endl; return; }
+      pbrgpu_scene_desc d;
+      std::memset(&d, 0, sizeof(d));
+      d.n_verts = (int32_t)(f.verts.size() / 3);
+      d.n_tris = (int32_t)(f.indices.size() / 3);
+      d.verts = f.verts.data(); d.indices = f.indices.data();
+      d.tri_material = f.triMaterial.data(); d.tri_light = f.triLight.data(); d.tri_flags = f.triFlags.data();
+      d.n_materials = (int32_t)f.materials.size(); d.materials = f.materials.data();
+      d.n_lights = (int32_t)f.lights.size(); d.lights = f.lights.data();
+      d.env_width = f.envW; d.env_height = f.envH; d.env_texels = f.env.empty() ? nullptr : f.env.data();
+      if (pbrgpu_scene_create(ctx, &d, &gscene)) return fail("pbrgpu_scene_create");
+      flattenedScene = &scene;
+    }
+    // camera (Camera/Camera.h:34-54)
+    auto* pc = dynamic_cast<const ProjectiveCamera*>(camera.get());
+    if (!pc) { std::cerr << "GpuIntegrator: camera is not a ProjectiveCamera" << std::endl; return; }
+    const int W = pixelBounds.pMax.x, H = pixelBounds.pMax.y;
+    pbrgpu_camera_desc cd;
+    std::memset(&cd, 0, sizeof(cd));
+    // an OrthographicCamera keeps its ray direction fixed at (0,0,1); tell the two apart by the projection's w row
+    cd.type = (pc->CameraToScreen.m.m[3][2] != 0.f) ? PBRGPU_CAMERA_PERSPECTIVE : PBRGPU_CAMERA_ORTHOGRAPHIC;
+    cd.width = W; cd.height = H;
+    cd.lens_radius = pc->lensRadius; cd.focal_distance = pc->focalDistance;
+    gpu_detail::copyMatrix(pc->RasterToCamera.m, cd.raster_to_camera);
+    gpu_detail::copyMatrix(pc->CameraToWorld.m, cd.camera_to_world);
+    if (pbrgpu_camera_set(gscene, &cd)) return fail("pbrgpu_camera_set");
+    // sampler (Sampler/Halton.cpp:30-58): the reference passes the same bounds to sampler and integrator
+    auto* hs = dynamic_cast<const HaltonSampler*>(sampler.get());
+    if (!hs) { std::cerr << "GpuIntegrator: sampler is not a HaltonSampler" << std::endl; return; }
+    pbrgpu_sampler_desc sd;
+    std::memset(&sd, 0, sizeof(sd));
+    sd.type = PBRGPU_SAMPLER_HALTON;
+    sd.sample_at_pixel_center = hs->sampleAtPixelCenter ? 1 : 0;
+    sd.samples_per_pixel = hs->samplesPerPixel;
+    sd.sample_bounds[0] = pixelBounds.pMin.x; sd.sample_bounds[1] = pixelBounds.pMin.y;
+    sd.sample_bounds[2] = pixelBounds.pMax.x; sd.sample_bounds[3] = pixelBounds.pMax.y;
+    int32_t p7[7];
+    pbrgpu_halton_params(sd.sample_bounds, p7);
+    if (p7[0] != hs->baseScales[0] || p7[1] != hs->baseScales[1] || p7[4] != hs->sampleStride) {
+      std::cerr << "GpuIntegrator: HaltonSampler was built for other bounds than the integrator's pixelBounds" << std::endl;
+      return;
+    }
+    sd.perms = HaltonSampler::radicalInversePermutations.data();
+    sd.n_perms = (int64_t)HaltonSampler::radicalInversePermutations.size();
+    if (pbrgpu_sampler_set(gscene, &sd)) return fail("pbrgpu_sampler_set");
+    pbrgpu_render_desc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    fillRenderDesc(&rd);
+    rd.x0 = pixelBounds.pMin.x; rd.y0 = pixelBounds.pMin.y; rd.x1 = pixelBounds.pMax.x; rd.y1 = pixelBounds.pMax.y;
+    rd.s0 = 0; rd.s1 = hs->samplesPerPixel;
+    const int rw = rd.x1 - rd.x0, rh = rd.y1 - rd.y0;
+    rgbSum.assign((size_t)rw * rh * 3, 0.f);
+    std::vector<unsigned char> rgba((size_t)rw * rh * 4);
+    if (pbrgpu_render(gscene, &rd, rgbSum.data(), rgba.data(), &stats)) return fail("pbrgpu_render");
+    if (m_FrameBuffer) {
+      // pbrgpu_render returns rows already flipped (row 0 = bottom), as set_uc(i, pMax.y - j - 1, ..) stores them
+      for (int r = 0; r < rh; ++r)
+        for (int x = 0; x < rw; ++x) {
+          const unsigned char* px = &rgba[4 * ((size_t)r * rw + x)];
+          const int fbRow = pixelBounds.pMax.y - 1 - (rd.y0 + (rh - 1 - r));
+          for (int c = 0; c < 4; ++c) m_FrameBuffer->set_uc(rd.x0 + x, fbRow, c, px[c]);
+        }
+    }
+    timeConsume = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    IntegratorRenderTime = (float)timeConsume;
+  }
+  pbrgpu_stats stats{};
+  std::vector<float> rgbSum;  // linear per-pixel SUM of Li over the samples (the reference's colObj before /= spp)
+
+ protected:
+  virtual void fillRenderDesc(pbrgpu_render_desc* rd) const = 0;
+  void fail(const char* what) { std::cerr << "GpuIntegrator: " << what << " failed: " << pbrgpu_last_error() << std::endl; }
+  std::shared_ptr<const Camera> camera;
+  std::shared_ptr<Sampler> sampler;
+  const Bounds2i pixelBounds;
+  FrameBuffer* m_FrameBuffer;
+  int device;
+  pbrgpu_ctx* ctx = nullptr;
+  pbrgpu_scene* gscene = nullptr;
+  const Scene* flattenedScene = nullptr;
+};
+
+// Same constructor as PathIntegrator (Integrator/PathIntegrator.h:14-18).
+class GpuPathIntegrator : public GpuSamplerIntegrator {
+ public:
+  GpuPathIntegrator(int maxDepth, std::shared_ptr<const Camera> camera, std::shared_ptr<Sampler> sampler, const Bounds2i& pixelBounds,
+                    float rrThreshold = 1, const std::string& lightSampleStrategy = "spatial", FrameBuffer* framebuffer = nullptr)
+      : GpuSamplerIntegrator(camera, sampler, pixelBounds, framebuffer), maxDepth(maxDepth), rrThreshold(rrThreshold),
+        lightSampleStrategy(lightSampleStrategy) {}
+
+ protected:
+  void fillRenderDesc(pbrgpu_render_desc* rd) const override {
+    rd->integrator = PBRGPU_INTEGRATOR_PATH;
+    rd->max_depth = maxDepth;
+    rd->rr_threshold = rrThreshold;
+    // LightDistrib.cpp:8-23: "power" -> PowerLightDistribution, everything else ("uniform", "spatial") -> uniform
+    rd->light_strategy = lightSampleStrategy == "power" ? PBRGPU_LIGHTSTRATEGY_POWER : PBRGPU_LIGHTSTRATEGY_UNIFORM;
+  }
+  const int maxDepth;
+  const float rrThreshold;
+  const std::string lightSampleStrategy;
+};
+
+}  // namespace PBR

@@ -107,3 +107,42 @@ def test_film_resolve_8bit(api, ref, gpu_ctx):
     diff = np.abs(rgba8.astype(int) - want.astype(int))
     assert diff.max() <= 1  # powf ulps may move a value across a rounding boundary
     assert (diff > 0).mean() < 1e-3
+
+
+def test_cpp_dropin_integrator_matches_reference_render(api, ref, gpu_ctx):
+    """The C++ drop-in (host/GpuIntegrator.h): the reference's OWN Scene / BVHAccel / Material / Light /
+    Camera / Sampler objects go through PBR::GpuPathIntegrator::Render (flattener -> C-ABI -> GPU) and the
+    FrameBuffer bytes are compared with those of the reference's own PathIntegrator::Render (CPU)."""
+    data = scenes.cornell(sphere_tess=12)
+    rsc = ref.RefScene(data)
+    rc = ref.RefCamera(A.CAMERA_PERSPECTIVE, 64, 64, (0, 0, 5), (0, 0, 0), (0, 1, 0))
+    rgba, rgb_sum, sec = ref.gpu_dropin_render(rsc, rc, 4, 64, 64, 5, 0.8, "uniform")
+    want_rgba, st, t = ref.render_shipped(rsc, rc, 4, 64, 64, 5, 0.8)
+    diff = np.abs(rgba.astype(int) - want_rgba.astype(int))
+    print("drop-in: bytes equal", (diff == 0).mean(), "max diff", diff.max(), "gpu s", sec, "cpu s", t)
+    assert (diff <= 1).mean() >= 0.995
+    assert rgba[..., 3].min() == 255
+    want_lin, _ = ref.render(rsc, rc, 4, (0, 0, 64, 64), integrator=A.INTEGRATOR_PATH, max_depth=5, rr_threshold=0.8)
+    assert (rel_err(rgb_sum / 4, want_lin / 4) <= REL_TOL).mean() >= 0.97
+
+
+@pytest.mark.parametrize("fixture,depth,frac", [("cornell64_direct.npz", 1, 0.999), ("cornell64_path5.npz", 5, 0.97)])
+def test_cornell_vs_golden_fixture(api, gpu_ctx, fixture, depth, frac):
+    """Same check without the compiled reference: committed fixtures (tests/golden/make_golden.py)."""
+    from tests.util import golden
+    g = golden(fixture)
+    p = Pair(api, None, scenes.cornell(sphere_tess=12), 64, 64, 4)
+    got, _, st = p.scene.render(integrator=A.INTEGRATOR_PATH, max_depth=depth, rr_threshold=0.8)
+    ok = (rel_err(got / 4, g["rgb_mean"]) <= REL_TOL).mean()
+    print(fixture, "pixels within 1e-3:", ok)
+    assert ok >= frac
+    assert abs(int(st.rays_closest) - int(g["rays_closest"])) <= 1e-3 * int(g["rays_closest"]) + 8
+
+
+def test_stress_direct_vs_golden_fixture(api, gpu_ctx):
+    from tests.util import golden
+    g = golden("stress96x64_direct.npz")
+    data = scenes.bsdf_stress(sphere_tess=12, env=scenes.procedural_env(128, 64))
+    p = Pair(api, None, data, 96, 64, 2, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
+    got, _, _ = p.scene.render(integrator=A.INTEGRATOR_PATH, max_depth=1)
+    assert (rel_err(got / 2, g["rgb_mean"]) <= REL_TOL).mean() >= 0.995
