@@ -16,6 +16,28 @@ enum : int {
 enum : int { LOBE_LAMBERT, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_MICRO_REFL, LOBE_MICRO_TRANS };
 enum : int { FR_NOOP, FR_DIELECTRIC, FR_CONDUCTOR };
 
+// Which lobe kinds / Fresnel kinds a material can ever create (Material/*.cpp).  The shading kernels are
+// instantiated per material, so every `case` a material cannot reach is removed at compile time; MAT = -1
+// keeps everything (generic use).
+template <int MAT>
+PBR_D constexpr bool mat_has_lobe(int kind) {
+  return MAT < 0 ? true
+       : MAT == 0 /*Matte*/   ? (kind == 0 /*LAMBERT*/ || kind == 1 /*OREN_NAYAR*/)
+       : MAT == 1 /*Mirror*/  ? (kind == 2 /*SPEC_REFL*/)
+       : MAT == 2 /*Glass*/   ? (kind >= 2)
+       : MAT == 3 /*Metal*/   ? (kind == 5 /*MICRO_REFL*/)
+       :            /*Plastic*/ (kind == 0 || kind == 5);
+}
+template <int MAT>
+PBR_D constexpr bool mat_has_fresnel(int fr) {
+  return MAT < 0 ? true
+       : MAT == 1 ? fr == 0 /*NOOP*/
+       : MAT == 2 ? fr == 1 /*DIELECTRIC*/
+       : MAT == 3 ? fr == 2 /*CONDUCTOR*/
+       : MAT == 4 ? fr == 1
+       :            fr == 0;
+}
+
 struct Lobe {
   int kind, flags, fresnel;
   Spec R;              // R (reflection lobes) or T (transmission lobes); FresnelSpecular: R
@@ -121,10 +143,12 @@ PBR_D Spec fr_conductor(float cosThetaI, Spec etai, Spec etat, Spec k) {
   Spec Rp = Rs * (t3 - t4) / (t3 + t4);
   return 0.5f * (Rp + Rs);
 }
+template <int MAT>
 PBR_D Spec fresnel_eval(const Lobe& l, float cosI) {
-  if (l.fresnel == FR_NOOP) return Spec(1.f);
-  if (l.fresnel == FR_DIELECTRIC) return Spec(fr_dielectric(cosI, l.frEtaI, l.frEtaT));
-  return fr_conductor(fabsf(cosI), Spec(1.f), l.cEta, l.T);
+  if (mat_has_fresnel<MAT>(FR_NOOP) && l.fresnel == FR_NOOP) return Spec(1.f);
+  if (mat_has_fresnel<MAT>(FR_DIELECTRIC) && l.fresnel == FR_DIELECTRIC) return Spec(fr_dielectric(cosI, l.frEtaI, l.frEtaT));
+  if (mat_has_fresnel<MAT>(FR_CONDUCTOR)) return fr_conductor(fabsf(cosI), Spec(1.f), l.cEta, l.T);
+  return Spec(1.f);
 }
 
 // ---- Trowbridge-Reitz (GGX), sampleVisibleArea = true ----
@@ -191,10 +215,14 @@ PBR_D V3 tr_sample_wh(const Lobe& l, V3 wo, float u0, float u1) {
 }
 
 // ---- BxDF::f ----
+template <int MAT>
 PBR_D Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
   switch (l.kind) {
-    case LOBE_LAMBERT: return l.R * kInvPi;
+    case LOBE_LAMBERT:
+      if (!mat_has_lobe<MAT>(LOBE_LAMBERT)) break;
+      return l.R * kInvPi;
     case LOBE_OREN_NAYAR: {
+      if (!mat_has_lobe<MAT>(LOBE_OREN_NAYAR)) break;
       float sinThetaI = sin_theta(wi), sinThetaO = sin_theta(wo);
       float maxCos = 0;
       if (sinThetaI > 1e-4 && sinThetaO > 1e-4) {
@@ -209,15 +237,17 @@ PBR_D Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
       return l.R * kInvPi * (l.A + l.B * maxCos * sinAlpha * tanBeta);
     }
     case LOBE_MICRO_REFL: {
+      if (!mat_has_lobe<MAT>(LOBE_MICRO_REFL)) break;
       float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
       V3 wh = wi + wo;
       if (cosThetaI == 0 || cosThetaO == 0) return Spec(0.f);
       if (wh.x == 0 && wh.y == 0 && wh.z == 0) return Spec(0.f);
       wh = normalize(wh);
-      Spec F = fresnel_eval(l, dot(wi, faceforward(wh, V3(0, 0, 1))));
+      Spec F = fresnel_eval<MAT>(l, dot(wi, faceforward(wh, V3(0, 0, 1))));
       return l.R * tr_D(l, wh) * tr_G(l, wo, wi) * F / (4 * cosThetaI * cosThetaO);
     }
     case LOBE_MICRO_TRANS: {
+      if (!mat_has_lobe<MAT>(LOBE_MICRO_TRANS)) break;
       if (same_hemisphere(wo, wi)) return Spec(0.f);
       float cosThetaO = cos_theta(wo), cosThetaI = cos_theta(wi);
       if (cosThetaI == 0 || cosThetaO == 0) return Spec(0.f);
@@ -232,21 +262,25 @@ PBR_D Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
              fabsf(tr_D(l, wh) * tr_G(l, wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor /
                    (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
     }
-    default: return Spec(0.f);  // specular lobes
+    default: break;  // specular lobes
   }
+  return Spec(0.f);
 }
 
 // ---- BxDF::Pdf ----
+template <int MAT>
 PBR_D float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
   switch (l.kind) {
     case LOBE_LAMBERT:
     case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0;
     case LOBE_MICRO_REFL: {
+      if (!mat_has_lobe<MAT>(LOBE_MICRO_REFL)) break;
       if (!same_hemisphere(wo, wi)) return 0;
       V3 wh = normalize(wo + wi);
       return tr_pdf(l, wo, wh) / (4 * dot(wo, wh));
     }
     case LOBE_MICRO_TRANS: {
+      if (!mat_has_lobe<MAT>(LOBE_MICRO_TRANS)) break;
       if (same_hemisphere(wo, wi)) return 0;
       float eta = cos_theta(wo) > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
       V3 wh = normalize(wo + wi * eta);
@@ -255,27 +289,32 @@ PBR_D float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
       float dwh_dwi = fabsf((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
       return tr_pdf(l, wo, wh) * dwh_dwi;
     }
-    default: return 0;
+    default: break;
   }
+  return 0;
 }
 
 // ---- BxDF::Sample_f.  *pdf is pre-set to 0 by the caller (BSDF::Sample_f, Reflection.cpp:132) and left
 // untouched on the early-out paths, as in the reference. ----
+template <int MAT>
 PBR_D Spec lobe_sample_f(const Lobe& l, V3 wo, V3* wi, float u0, float u1, float* pdf, int* sampledType) {
   switch (l.kind) {
     case LOBE_LAMBERT:
     case LOBE_OREN_NAYAR: {
+      if (!mat_has_lobe<MAT>(LOBE_LAMBERT)) break;
       *wi = cosine_sample_hemisphere(u0, u1);
       if (wo.z < 0) wi->z *= -1;
-      *pdf = lobe_pdf(l, wo, *wi);
-      return lobe_f(l, wo, *wi);
+      *pdf = lobe_pdf<MAT>(l, wo, *wi);
+      return lobe_f<MAT>(l, wo, *wi);
     }
     case LOBE_SPEC_REFL: {
+      if (!mat_has_lobe<MAT>(LOBE_SPEC_REFL)) break;
       *wi = V3(-wo.x, -wo.y, wo.z);
       *pdf = 1;
-      return fresnel_eval(l, cos_theta(*wi)) * l.R / abs_cos_theta(*wi);
+      return fresnel_eval<MAT>(l, cos_theta(*wi)) * l.R / abs_cos_theta(*wi);
     }
     case LOBE_SPEC_TRANS: {
+      if (!mat_has_lobe<MAT>(LOBE_SPEC_TRANS)) break;
       bool entering = cos_theta(wo) > 0;
       float etaI = entering ? l.etaA : l.etaB;
       float etaT = entering ? l.etaB : l.etaA;
@@ -286,6 +325,7 @@ PBR_D Spec lobe_sample_f(const Lobe& l, V3 wo, V3* wi, float u0, float u1, float
       return ft / abs_cos_theta(*wi);
     }
     case LOBE_FRESNEL_SPEC: {
+      if (!mat_has_lobe<MAT>(LOBE_FRESNEL_SPEC)) break;
       float F = fr_dielectric(cos_theta(wo), l.etaA, l.etaB);
       if (u0 < F) {
         *wi = V3(-wo.x, -wo.y, wo.z);
@@ -305,28 +345,31 @@ PBR_D Spec lobe_sample_f(const Lobe& l, V3 wo, V3* wi, float u0, float u1, float
       }
     }
     case LOBE_MICRO_REFL: {
+      if (!mat_has_lobe<MAT>(LOBE_MICRO_REFL)) break;
       if (wo.z == 0) return Spec(0.f);
       V3 wh = tr_sample_wh(l, wo, u0, u1);
       if (dot(wo, wh) < 0) return Spec(0.f);
       *wi = reflect_about(wo, wh);
       if (!same_hemisphere(wo, *wi)) return Spec(0.f);
       *pdf = tr_pdf(l, wo, wh) / (4 * dot(wo, wh));
-      return lobe_f(l, wo, *wi);
+      return lobe_f<MAT>(l, wo, *wi);
     }
     case LOBE_MICRO_TRANS: {
+      if (!mat_has_lobe<MAT>(LOBE_MICRO_TRANS)) break;
       if (wo.z == 0) return Spec(0.f);
       V3 wh = tr_sample_wh(l, wo, u0, u1);
       if (dot(wo, wh) < 0) return Spec(0.f);
       float eta = cos_theta(wo) > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
       if (!refract_dir(wo, wh, eta, wi)) return Spec(0.f);
-      *pdf = lobe_pdf(l, wo, *wi);
-      return lobe_f(l, wo, *wi);
+      *pdf = lobe_pdf<MAT>(l, wo, *wi);
+      return lobe_f<MAT>(l, wo, *wi);
     }
   }
   return Spec(0.f);
 }
 
 // ---- BSDF::f / Pdf / Sample_f (Reflection.cpp:56-164) ----
+template <int MAT>
 PBR_D Spec bsdf_f(const Bsdf& b, V3 woW, V3 wiW, int flags) {
   V3 wi = b.to_local(wiW), wo = b.to_local(woW);
   if (wo.z == 0) return Spec(0.f);
@@ -336,10 +379,11 @@ PBR_D Spec bsdf_f(const Bsdf& b, V3 woW, V3 wiW, int flags) {
     const Lobe& l = b.lobes[i];
     if ((l.flags & flags) == l.flags &&
         ((reflect && (l.flags & BSDF_REFLECTION)) || (!reflect && (l.flags & BSDF_TRANSMISSION))))
-      f = f + lobe_f(l, wo, wi);
+      f = f + lobe_f<MAT>(l, wo, wi);
   }
   return f;
 }
+template <int MAT>
 PBR_D float bsdf_pdf(const Bsdf& b, V3 woW, V3 wiW, int flags) {
   if (b.n == 0) return 0.f;
   V3 wo = b.to_local(woW), wi = b.to_local(wiW);
@@ -347,9 +391,10 @@ PBR_D float bsdf_pdf(const Bsdf& b, V3 woW, V3 wiW, int flags) {
   float pdf = 0.f;
   int matching = 0;
   for (int i = 0; i < b.n; ++i)
-    if ((b.lobes[i].flags & flags) == b.lobes[i].flags) { ++matching; pdf += lobe_pdf(b.lobes[i], wo, wi); }
+    if ((b.lobes[i].flags & flags) == b.lobes[i].flags) { ++matching; pdf += lobe_pdf<MAT>(b.lobes[i], wo, wi); }
   return matching > 0 ? pdf / matching : 0.f;
 }
+template <int MAT>
 PBR_D Spec bsdf_sample_f(const Bsdf& b, V3 woW, V3* wiW, float u0, float u1, float* pdf, int type, int* sampledType) {
   int matching = b.num_components(type);
   if (matching == 0) { *pdf = 0; *sampledType = 0; return Spec(0.f); }
@@ -365,12 +410,12 @@ PBR_D Spec bsdf_sample_f(const Bsdf& b, V3 woW, V3* wiW, float u0, float u1, flo
   if (wo.z == 0) { *pdf = 0; *sampledType = 0; return Spec(0.f); }
   *pdf = 0;
   *sampledType = l.flags;
-  Spec f = lobe_sample_f(l, wo, &wi, ur0, u1, pdf, sampledType);
+  Spec f = lobe_sample_f<MAT>(l, wo, &wi, ur0, u1, pdf, sampledType);
   if (*pdf == 0) { *sampledType = 0; return Spec(0.f); }
   *wiW = b.to_world(wi);
   if (!(l.flags & BSDF_SPECULAR) && matching > 1)
     for (int i = 0; i < b.n; ++i)
-      if (i != which && (b.lobes[i].flags & type) == b.lobes[i].flags) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+      if (i != which && (b.lobes[i].flags & type) == b.lobes[i].flags) *pdf += lobe_pdf<MAT>(b.lobes[i], wo, wi);
   if (matching > 1) *pdf /= matching;
   if (!(l.flags & BSDF_SPECULAR)) {
     bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
@@ -379,7 +424,7 @@ PBR_D Spec bsdf_sample_f(const Bsdf& b, V3 woW, V3* wiW, float u0, float u1, flo
       const Lobe& li = b.lobes[i];
       if ((li.flags & type) == li.flags &&
           ((reflect && (li.flags & BSDF_REFLECTION)) || (!reflect && (li.flags & BSDF_TRANSMISSION))))
-        f = f + lobe_f(li, wo, wi);
+        f = f + lobe_f<MAT>(li, wo, wi);
     }
   }
   return f;

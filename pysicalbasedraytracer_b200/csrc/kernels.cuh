@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ Render
             LightSample ls;
             sample_light(sc, light, is.p, uL0, uL1, &ls);
             if (ls.pdf > 0 && !ls.Li.is_black()) {
-              Spec f = bsdf_f(bsdf, is.wo, ls.wi, nonSpec) * absdot(ls.wi, is.ns);
-              float scatteringPdf = bsdf_pdf(bsdf, is.wo, ls.wi, nonSpec);
+              Spec f = bsdf_f<MAT>(bsdf, is.wo, ls.wi, nonSpec) * absdot(ls.wi, is.ns);
+              float scatteringPdf = bsdf_pdf<MAT>(bsdf, is.wo, ls.wi, nonSpec);
               if (!f.is_black()) {
                 V3 origin = offset_ray_origin(is.p, is.pError, is.n, ls.p1 - is.p);
                 V3 target = offset_ray_origin(ls.p1, ls.pErr1, ls.n1, origin - ls.p1);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ Render
               V3 wi;
               float scatteringPdf;
               int sampledType;
-              Spec f = bsdf_sample_f(bsdf, is.wo, &wi, uS0, uS1, &scatteringPdf, nonSpec, &sampledType);
+              Spec f = bsdf_sample_f<MAT>(bsdf, is.wo, &wi, uS0, uS1, &scatteringPdf, nonSpec, &sampledType);
               f = f * absdot(wi, is.ns);
               if (!f.is_black() && scatteringPdf > 0) {
                 V3 origin = offset_ray_origin(is.p, is.pError, is.n, wi);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ Render
         float pdf, u0, u1;
         int flags;
         cur.get2D(sc.hp, &u0, &u1);
-        Spec f = bsdf_sample_f(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &flags);
+        Spec f = bsdf_sample_f<MAT>(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &flags);
         if (f.is_black() || pdf == 0.f) alive = false;
         if (alive) {
           beta = beta * (f * absdot(wi, is.ns) / pdf);

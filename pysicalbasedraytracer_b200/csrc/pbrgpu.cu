@@ -87,7 +87,7 @@ struct pbrgpu_scene {
   DevBuf<uint32_t> primeMagic;
   int lightStrategyBuilt = -1;
   int traceBlocksPerSm = 0;
-  int triThreshold = 16;
+  int triThreshold = 1;
   // wavefront state
   uint32_t capacity = 0;
   DevBuf<float4> rayO, rayD, hit, beta, L, shO, shD, shC, miO, miD, miC;
