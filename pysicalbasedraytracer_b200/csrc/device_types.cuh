@@ -99,6 +99,9 @@ struct RenderParams {
   int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
   int countStats;
   int triThreshold;       // lanes with candidate triangles needed to run a triangle round
+  int atomicL;            // several shadow / MIS rays per path and bounce (Whitted / DirectLighting): atomics on L
+  // Halton offset of the pixel a global index belongs to: index = offset(pixel) + sample * stride, offset < stride
+  PBR_D int64_t pixelOffsetOf(int64_t index) const { return index % sc.hp.sampleStride; }
   float* accum;           // [h*w] RGBA sums (A = sample count)
 };
 

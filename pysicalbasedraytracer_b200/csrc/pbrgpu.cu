@@ -90,6 +90,7 @@ struct pbrgpu_scene {
   int triThreshold = 1;
   // wavefront state
   uint32_t capacity = 0;
+  size_t rayCapacity = 0;
   DevBuf<float4> rayO, rayD, hit, beta, L, shO, shD, shC, miO, miD, miC;
   DevBuf<uint2> hidx;
   DevBuf<uint32_t> meta, qA, qB, qMat, qType;
@@ -100,11 +101,16 @@ struct pbrgpu_scene {
 
 namespace {
 
-int ensure_wave(pbrgpu_scene* s, uint32_t cap) {
+int ensure_wave(pbrgpu_scene* s, uint32_t cap, uint32_t raysPerHit) {
+  // shadow / MIS queues hold up to raysPerHit rays per path and bounce (1 for the Path integrator)
+  size_t rcap = (size_t)cap * raysPerHit;
+  if (s->rayCapacity < rcap) {
+    CK(s->shO.alloc(rcap)); CK(s->shD.alloc(rcap)); CK(s->shC.alloc(rcap));
+    CK(s->miO.alloc(rcap)); CK(s->miD.alloc(rcap)); CK(s->miC.alloc(rcap));
+    s->rayCapacity = rcap;
+  }
   if (s->capacity >= cap) return 0;
   CK(s->rayO.alloc(cap)); CK(s->rayD.alloc(cap)); CK(s->hit.alloc(cap)); CK(s->beta.alloc(cap)); CK(s->L.alloc(cap));
-  CK(s->shO.alloc(cap)); CK(s->shD.alloc(cap)); CK(s->shC.alloc(cap));
-  CK(s->miO.alloc(cap)); CK(s->miD.alloc(cap)); CK(s->miC.alloc(cap));
   CK(s->hidx.alloc(cap)); CK(s->meta.alloc(cap)); CK(s->qA.alloc(cap)); CK(s->qB.alloc(cap));
   CK(s->qMat.alloc((size_t)cap * kNumQueues));
   CK(s->qType.alloc(cap));
@@ -492,8 +498,7 @@ static int check_render_args(pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
   if (rd->x1 <= rd->x0 || rd->y1 <= rd->y0) return fail("pbrgpu_render: empty pixel region");
   if (rd->s1 < rd->s0 || rd->s0 < 0) return fail("pbrgpu_render: bad sample range");
   if (rd->max_depth < 0 || rd->max_depth > 1000) return fail("pbrgpu_render: bad max_depth");
-  if (rd->integrator != PBRGPU_INTEGRATOR_PATH)
-    return fail("pbrgpu_render: integrator not implemented on the GPU path yet (Path only)");
+  if (rd->integrator < PBRGPU_INTEGRATOR_PATH || rd->integrator > PBRGPU_INTEGRATOR_WHITTED) return fail("pbrgpu_render: unknown integrator");
   if (s->bvh.maxDepth >= kSmemStack + kLocalStack) return fail("pbrgpu_render: BVH deeper than the traversal stack");
   return 0;
 }
@@ -519,14 +524,26 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
   const int64_t nS = rd->s1 - rd->s0;
   const bool count = (rd->flags & PBRGPU_RENDER_COUNTERS) != 0;
-  const uint32_t capMax = 1u << 22;
+  const bool pathInteg = rd->integrator == PBRGPU_INTEGRATOR_PATH;
+  uint32_t raysPerHit = 1;
+  if (rd->integrator == PBRGPU_INTEGRATOR_WHITTED) raysPerHit = (uint32_t)std::max<size_t>(1, s->lights.size());
+  if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) {
+    raysPerHit = 0;
+    for (const auto& l : s->lights) {
+      if (l.n_samples < 1) return fail("pbrgpu_render: light with nSamples < 1");
+      raysPerHit += (uint32_t)l.n_samples;
+    }
+    raysPerHit = std::max(1u, raysPerHit);
+  }
+  if (raysPerHit > 4096) return fail("pbrgpu_render: too many light samples per hit");
+  const uint32_t capMax = std::max(1u << 14, std::min(1u << 22, (1u << 23) / raysPerHit));
   // row bands of <= capMax pixels; inside a band, waves of nsWave samples per pixel
   int bandRows = (int)std::max<int64_t>(1, std::min<int64_t>(H, capMax / (uint32_t)W));
   if ((uint64_t)W > capMax) return fail("pbrgpu_render: region wider than the wave capacity");
   int nsWaveMax = (int)std::max<int64_t>(1, capMax / ((uint64_t)bandRows * W));
   if (rd->samples_per_wave > 0) nsWaveMax = std::min(nsWaveMax, rd->samples_per_wave);
   uint32_t cap = (uint32_t)((uint64_t)bandRows * W * std::min<int64_t>(nsWaveMax, std::max<int64_t>(nS, 1)));
-  if (ensure_wave(s, cap)) return 1;
+  if (ensure_wave(s, cap, raysPerHit)) return 1;
 
   RenderParams P{};
   P.sc = s->sc;
@@ -534,7 +551,11 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   P.integrator = rd->integrator;
   P.maxDepth = rd->max_depth;
   P.rrThreshold = rd->rr_threshold;
+  // GlobalSampler::arrayEndDim (Sampler.cpp:100-101): DirectLighting/UniformSampleAll requests two 2D arrays per
+  // light per recursion depth (DirectLightingIntegrator.cpp:8-26); nobody else requests arrays
   P.arrayEndDim = 5;
+  if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) P.arrayEndDim = 5 + 2 * (2 * (int)s->lights.size() * rd->max_depth);
+  P.atomicL = pathInteg ? 0 : 1;
   P.countStats = count ? 1 : 0;
   P.triThreshold = s->triThreshold;
 
@@ -557,7 +578,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       P.ws.qNext = s->qB.p;
       uint32_t g = grid_for(c, nPaths, 8);
       // persistent traversal grid: every SM filled to the kernel's occupancy, never more blocks than rays
-      uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths + kTraceBlock - 1) / kTraceBlock,
+      uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths * (pathInteg ? 1 : 1 + raysPerHit) + kTraceBlock - 1) / kTraceBlock,
                                                                       (uint64_t)c->smCount * s->traceBlocksPerSm));
       CK(tl.mark(T_RAYGEN));
       k_wave_begin<<<1, 1, 0, st>>>(s->ctr.p);
@@ -565,7 +586,8 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       launches += 2;
       // bounce b: ONE traversal launch serves the path rays of bounce b and the shadow + MIS rays that the
       // shading of bounce b-1 emitted; then MIS resolve (b-1), classification, material-sorted shading (b).
-      for (int bounce = 0; bounce <= rd->max_depth; ++bounce) {
+      const int lastBounce = pathInteg ? rd->max_depth : std::max(rd->max_depth - 1, 0);
+      for (int bounce = 0; bounce <= lastBounce; ++bounce) {
         CK(tl.mark(T_CLOSEST));
         if (count) k_trace<true><<<gt, kTraceBlock, 0, st>>>(P);
         else k_trace<false><<<gt, kTraceBlock, 0, st>>>(P);
@@ -573,15 +595,31 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         if (bounce > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
         CK(tl.mark(T_SHADE));
         k_classify<<<g, kBlock, 0, st>>>(P);
-        k_shade<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
-        k_shade<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
-        k_shade<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
-        k_shade<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
-        k_shade<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
+        if (pathInteg) {
+          k_shade<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
+        } else {
+          k_shade_direct<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade_direct<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade_direct<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade_direct<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
+          k_shade_direct<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
+        }
         k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce);
         k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
         launches += 9;
         std::swap(P.ws.qCur, P.ws.qNext);
+      }
+      if (!pathInteg) {  // shadow / MIS rays of the last shaded depth
+        CK(tl.mark(T_CLOSEST));
+        if (count) k_trace<true><<<gt, kTraceBlock, 0, st>>>(P);
+        else k_trace<false><<<gt, kTraceBlock, 0, st>>>(P);
+        CK(tl.mark(T_MIS));
+        k_resolve_mis<<<g, kBlock, 0, st>>>(P);
+        launches += 2;
       }
       CK(tl.mark(T_FILM));
       k_film_accumulate<<<grid_for(c, (uint64_t)rows * W, 8), kBlock, 0, st>>>(P);
