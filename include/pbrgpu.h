@@ -114,7 +114,8 @@ typedef struct pbrgpu_camera_desc {
   float camera_to_world[16];  /* Camera::CameraToWorld.m, row-major */
 } pbrgpu_camera_desc;
 
-/* ---- sampler: Sampler/Halton.cpp:30-58 ---- */
+/* ---- sampler: Sampler/Halton.cpp:30-58; Sobol: host/SobolSampler.h over the reference's tables
+ *      (Sampler/SobolMatrices.h:42-47) - the reference itself has no Sobol sampler, parity unpinned ---- */
 enum { PBRGPU_SAMPLER_HALTON = 0, PBRGPU_SAMPLER_SOBOL = 1 };
 typedef struct pbrgpu_sampler_desc {
   int32_t type;
@@ -124,6 +125,13 @@ typedef struct pbrgpu_sampler_desc {
   const uint16_t* perms;    /* optional: HaltonSampler::radicalInversePermutations; NULL -> library
                                computes them with its own PCG32 (RNG.h:93-108, LowDiscrepancy.cpp:2284-2298) */
   int64_t n_perms;
+  /* SOBOL only: the reference's own generator tables, supplied by the host (they are data of the reference,
+   * not of this library).  samples_per_pixel is rounded up to a power of two like a pbrt GlobalSampler. */
+  const uint32_t* sobol_matrices32; /* SobolMatrices32[sobol_n_dims * 52] */
+  int32_t sobol_n_dims;             /* <= 1024 */
+  int32_t pad0;
+  const uint64_t* sobol_vdc;        /* VdCSobolMatrices[log2Resolution - 1][52]    */
+  const uint64_t* sobol_vdc_inv;    /* VdCSobolMatricesInv[log2Resolution - 1][52] */
 } pbrgpu_sampler_desc;
 
 /* ---- render: Integrator ctor arguments (PathIntegrator.h:14-18, WhittedIntegrator.h:8-11,

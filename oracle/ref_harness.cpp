@@ -15,6 +15,7 @@
 // calls the reference's Render() verbatim (4 threads, square images) for the as-shipped CPU baseline.
 // The C++ drop-in under test (flattener + GpuPathIntegrator); must precede every reference header.
 #include "GpuIntegrator.h"
+#include "SobolSampler.h"  // our CPU twin of the GPU Sobol sampler (the reference has only the tables)
 
 #include <atomic>
 #include <cstdio>
@@ -145,7 +146,11 @@ Transform fromRowMajor(const float m[16], const float minv[16]) {
 }
 
 struct RefCamera { std::shared_ptr<Camera> cam; int W, H, type; };
-struct RefSampler { std::shared_ptr<HaltonSampler> s; };
+struct RefSampler { std::shared_ptr<Sampler> s; };
+std::shared_ptr<Sampler> makeSampler(int type, int spp, const Bounds2i& b) {
+  if (type == PBRGPU_SAMPLER_SOBOL) return std::make_shared<SobolSampler>(spp, b);
+  return std::make_shared<HaltonSampler>(spp, b);
+}
 
 }  // namespace
 
@@ -288,9 +293,22 @@ void* ref_sampler_create(int spp, int x0, int y0, int x1, int y1) {
   s->s = std::make_shared<HaltonSampler>(spp, Bounds2i(Point2i(x0, y0), Point2i(x1, y1)));
   return s;
 }
+void* ref_sampler_create_typed(int type, int spp, int x0, int y0, int x1, int y1) {
+  auto* s = new RefSampler;
+  s->s = makeSampler(type, spp, Bounds2i(Point2i(x0, y0), Point2i(x1, y1)));
+  return s;
+}
+// The reference's Sobol generator tables (Sampler/SobolMatrices.h:42-47), for handing to pbrgpu_sampler_set.
+void ref_sobol_tables(uint32_t* m32, int log2Resolution, uint64_t* vdc, uint64_t* vdcInv) {
+  if (m32) memcpy(m32, SobolMatrices32, sizeof(uint32_t) * NumSobolDimensions * SobolMatrixSize);
+  if (log2Resolution >= 1) {
+    if (vdc) memcpy(vdc, VdCSobolMatrices[log2Resolution - 1], sizeof(uint64_t) * SobolMatrixSize);
+    if (vdcInv) memcpy(vdcInv, VdCSobolMatricesInv[log2Resolution - 1], sizeof(uint64_t) * SobolMatrixSize);
+  }
+}
 void ref_sampler_destroy(void* h) { delete (RefSampler*)h; }
 void ref_halton_params(void* h, int32_t out7[7]) {
-  auto& s = *((RefSampler*)h)->s;
+  auto& s = *dynamic_cast<HaltonSampler*>(((RefSampler*)h)->s.get());
   out7[0] = s.baseScales[0]; out7[1] = s.baseScales[1]; out7[2] = s.baseExponents[0]; out7[3] = s.baseExponents[1];
   out7[4] = s.sampleStride; out7[5] = s.multInverse[0]; out7[6] = s.multInverse[1];
 }
@@ -328,7 +346,7 @@ int64_t ref_halton_index(void* h, int x, int y, int64_t s) {
   auto& proto = *((RefSampler*)h)->s;
   std::unique_ptr<Sampler> ps = proto.Clone(0);
   ps->StartPixel(Point2i(x, y));
-  return ((HaltonSampler*)ps.get())->GetIndexForSample(s);
+  return dynamic_cast<GlobalSampler*>(ps.get())->GetIndexForSample(s);
 }
 
 // out[pixel][sample][8] = o.xyz, tMax, d.xyz, time   (the `Ray ray(r)` slice PathIntegrator::Li starts from)
@@ -413,12 +431,18 @@ struct RefRenderStats { uint64_t samples, rays_closest, rays_shadow; double seco
 // Linear-float SUM over samples [s0,s1) of Li for each pixel of the region; own pixel loop over the
 // reference's public API (Clone / StartPixel / SetSampleNumber / GetCameraSample /
 // GenerateRayDifferential / ScaleDifferentials / Li), OpenMP over rows with `threads` threads.
+int ref_render_typed(void* hscene, void* hc, int sampler_type, int spp, const int32_t sample_bounds[4], const pbrgpu_render_desc* rd,
+                     int threads, float* out_rgb_sum, RefRenderStats* st);
 int ref_render(void* hscene, void* hc, int spp, const int32_t sample_bounds[4], const pbrgpu_render_desc* rd,
                int threads, float* out_rgb_sum, RefRenderStats* st) {
+  return ref_render_typed(hscene, hc, PBRGPU_SAMPLER_HALTON, spp, sample_bounds, rd, threads, out_rgb_sum, st);
+}
+int ref_render_typed(void* hscene, void* hc, int sampler_type, int spp, const int32_t sample_bounds[4], const pbrgpu_render_desc* rd,
+                     int threads, float* out_rgb_sum, RefRenderStats* st) {
   auto* rs = (RefScene*)hscene;
   auto* rc = (RefCamera*)hc;
   Bounds2i sb(Point2i(sample_bounds[0], sample_bounds[1]), Point2i(sample_bounds[2], sample_bounds[3]));
-  std::shared_ptr<Sampler> sampler = std::make_shared<HaltonSampler>(spp, sb);
+  std::shared_ptr<Sampler> sampler = makeSampler(sampler_type, spp, sb);
   Bounds2i pb(Point2i(rd->x0, rd->y0), Point2i(rd->x1, rd->y1));
   std::unique_ptr<SamplerIntegrator> integ;
   const char* strat = rd->light_strategy == PBRGPU_LIGHTSTRATEGY_POWER ? "power" : "uniform";

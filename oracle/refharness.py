@@ -63,6 +63,11 @@ def lib():
         L.ref_render_shipped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_void_p, C.POINTER(RefRenderStats)]
         L.ref_tonemap.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_sampler_create_typed.restype = C.c_void_p
+        L.ref_sampler_create_typed.argtypes = [C.c_int] * 6
+        L.ref_sobol_tables.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_render_typed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(A.RenderDesc),
+                                       C.c_int, C.c_void_p, C.POINTER(RefRenderStats)]
         L.ref_gpu_dropin_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                             C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
@@ -116,9 +121,9 @@ class RefCamera:
 
 
 class RefSampler:
-    def __init__(self, spp, bounds):
-        self.h = lib().ref_sampler_create(spp, *bounds)
-        self.spp, self.bounds = spp, tuple(bounds)
+    def __init__(self, spp, bounds, sampler_type=A.SAMPLER_HALTON):
+        self.h = lib().ref_sampler_create_typed(sampler_type, spp, *bounds)
+        self.spp, self.bounds, self.type = spp, tuple(bounds), sampler_type
 
     def params(self):
         out = (C.c_int32 * 7)()
@@ -161,8 +166,20 @@ def primary_hits(scene, cam, smp, region, s0, s1):
     return out
 
 
+def sobol_tables(bounds):
+    """(matrices32 uint32[1024*52], vdc uint64[52], vdc_inv uint64[52]) of the compiled reference for these sample bounds."""
+    res, lg = 1, 0
+    while res < max(bounds[2] - bounds[0], bounds[3] - bounds[1]):
+        res, lg = res * 2, lg + 1
+    m32 = np.zeros(1024 * 52, dtype=np.uint32)
+    vdc = np.zeros(52, dtype=np.uint64)
+    vdi = np.zeros(52, dtype=np.uint64)
+    lib().ref_sobol_tables(m32.ctypes.data, lg, vdc.ctypes.data, vdi.ctypes.data)
+    return m32, vdc, vdi
+
+
 def render(scene, cam, spp, sample_bounds, integrator=A.INTEGRATOR_PATH, max_depth=5, rr_threshold=1.0,
-           light_strategy=A.LIGHTSTRATEGY_UNIFORM, region=None, s0=0, s1=None, threads=0):
+           light_strategy=A.LIGHTSTRATEGY_UNIFORM, region=None, s0=0, s1=None, threads=0, sampler_type=A.SAMPLER_HALTON):
     """-> (rgb_sum float32 [H,W,3], RefRenderStats)"""
     if region is None:
         region = (0, 0, cam.W, cam.H)
@@ -174,7 +191,7 @@ def render(scene, cam, spp, sample_bounds, integrator=A.INTEGRATOR_PATH, max_dep
     out = np.zeros((y1 - y0, x1 - x0, 3), dtype=np.float32)
     st = RefRenderStats()
     sb = (C.c_int32 * 4)(*sample_bounds)
-    rc = lib().ref_render(scene.h, cam.h, spp, sb, C.byref(rd), threads, out.ctypes.data, C.byref(st))
+    rc = lib().ref_render_typed(scene.h, cam.h, sampler_type, spp, sb, C.byref(rd), threads, out.ctypes.data, C.byref(st))
     if rc != 0:
         raise RuntimeError("ref_render failed")
     return out, st

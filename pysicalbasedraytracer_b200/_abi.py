@@ -45,7 +45,9 @@ class CameraDesc(C.Structure):
 
 class SamplerDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("sample_at_pixel_center", C.c_int32), ("samples_per_pixel", C.c_int64),
-                ("sample_bounds", C.c_int32 * 4), ("perms", C.POINTER(C.c_uint16)), ("n_perms", C.c_int64)]
+                ("sample_bounds", C.c_int32 * 4), ("perms", C.POINTER(C.c_uint16)), ("n_perms", C.c_int64),
+                ("sobol_matrices32", C.POINTER(C.c_uint32)), ("sobol_n_dims", C.c_int32), ("pad0", C.c_int32),
+                ("sobol_vdc", C.POINTER(C.c_uint64)), ("sobol_vdc_inv", C.POINTER(C.c_uint64))]
 
 
 class RenderDesc(C.Structure):

@@ -159,6 +159,33 @@ class HaltonSampler:
         return d
 
 
+class SobolSampler:
+    """Sobol' (0,2)-sequence sampler (CPU twin: host/SobolSampler.h).  The reference ships the generator tables
+    (Sampler/SobolMatrices.h:42-47) but no sampler that uses them, so parity is unpinned; the tables are the
+    reference's data and must be supplied by the caller (`matrices32` uint32[n*52], `vdc`/`vdc_inv` uint64[52]
+    = VdCSobolMatrices(Inv)[log2(resolution) - 1])."""
+
+    def __init__(self, samplesPerPixel, sampleBounds, matrices32, vdc, vdc_inv):
+        spp = 1
+        while spp < int(samplesPerPixel):
+            spp *= 2
+        self.samplesPerPixel = spp  # GlobalSampler(RoundUpPow2(samplesPerPixel))
+        self.sampleBounds = tuple(int(v) for v in sampleBounds)
+        self.m32 = np.ascontiguousarray(matrices32, dtype=np.uint32)
+        self.vdc = np.ascontiguousarray(vdc, dtype=np.uint64)
+        self.vdc_inv = np.ascontiguousarray(vdc_inv, dtype=np.uint64)
+        assert self.m32.size % 52 == 0 and self.vdc.size == 52 and self.vdc_inv.size == 52
+
+    def desc(self):
+        d = A.SamplerDesc(type=A.SAMPLER_SOBOL, samples_per_pixel=self.samplesPerPixel)
+        d.sample_bounds = (C.c_int32 * 4)(*self.sampleBounds)
+        d.sobol_matrices32 = self.m32.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.sobol_n_dims = self.m32.size // 52
+        d.sobol_vdc = self.vdc.ctypes.data_as(C.POINTER(C.c_uint64))
+        d.sobol_vdc_inv = self.vdc_inv.ctypes.data_as(C.POINTER(C.c_uint64))
+        return d
+
+
 class FrameBuffer:
     """Core/FrameBuffer.h: RGBA8 `ubuffer` (row 0 = bottom, Integrator.cpp:339-341) + float `fbuffer`.
     `fbuffer` here receives the linear per-pixel mean radiance (raster order, y down)."""

@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
     int px, py; long long s; uint32_t pix;
     slot_to_pixel(P, slot, &px, &py, &s, &pix);
-    int64_t idx = halton_index_for_sample(px, py, s, P.sc.hp);
-    float u0 = halton_sample_dimension(idx, 0, P.sc.hp);
-    float u1 = halton_sample_dimension(idx, 1, P.sc.hp);
+    int64_t idx = sampler_index_for_sample(px, py, s, P.sc.hp);
+    float u0 = sampler_film_sample(idx, 0, px, P.sc.hp);
+    float u1 = sampler_film_sample(idx, 1, py, P.sc.hp);
     float lu = 0, lv = 0;
     if (P.sc.cam.lensRadius > 0) {
       lu = halton_sample_dimension(idx, 3, P.sc.hp);
@@ -668,8 +668,8 @@ __global__ void k_dump_sampler(HaltonParams hp, int x0, int y0, int w, int h, lo
     int sj = (int)(r % ns);
     long long p = r / ns;
     int px = x0 + (int)(p % w), py = y0 + (int)(p / w);
-    int64_t idx = halton_index_for_sample(px, py, s0 + sj, hp);
-    out[i] = halton_sample_dimension(idx, d, hp);
+    int64_t idx = sampler_index_for_sample(px, py, s0 + sj, hp);
+    out[i] = d < 2 ? sampler_film_sample(idx, d, d == 0 ? px : py, hp) : halton_sample_dimension(idx, d, hp);
   }
 }
 
@@ -681,8 +681,8 @@ __global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__
     int sj = (int)(i % ns);
     long long p = i / ns;
     int px = P.x0 + (int)(p % P.w), py = P.y0 + (int)(p / P.w);
-    int64_t idx = halton_index_for_sample(px, py, P.sBegin + sj, P.sc.hp);
-    float u0 = halton_sample_dimension(idx, 0, P.sc.hp), u1 = halton_sample_dimension(idx, 1, P.sc.hp);
+    int64_t idx = sampler_index_for_sample(px, py, P.sBegin + sj, P.sc.hp);
+    float u0 = sampler_film_sample(idx, 0, px, P.sc.hp), u1 = sampler_film_sample(idx, 1, py, P.sc.hp);
     float lu = 0, lv = 0;
     if (P.sc.cam.lensRadius > 0) { lu = halton_sample_dimension(idx, 3, P.sc.hp); lv = halton_sample_dimension(idx, 4, P.sc.hp); }
     V3 o, d;

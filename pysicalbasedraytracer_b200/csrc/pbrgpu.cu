@@ -84,7 +84,8 @@ struct pbrgpu_scene {
   DevBuf<float> envTexels, condFunc, condCdf, condInt, margFunc, margCdf;
   DevBuf<uint16_t> perms;
   DevBuf<int32_t> primes, primeSums;
-  DevBuf<uint32_t> primeMagic;
+  DevBuf<uint32_t> primeMagic, sobolMat;
+  DevBuf<uint64_t> sobolVdc, sobolVdcInv;
   int lightStrategyBuilt = -1;
   int traceBlocksPerSm = 0;
   int triThreshold = 1;
@@ -452,13 +453,45 @@ int pbrgpu_camera_set(pbrgpu_scene* s, const pbrgpu_camera_desc* c) {
 
 int pbrgpu_sampler_set(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
   if (!s || !d) return fail("pbrgpu_sampler_set: NULL argument");
-  if (d->type != PBRGPU_SAMPLER_HALTON)
-    return fail("pbrgpu_sampler_set: only the Halton sampler exists in the reference (SURVEY 8(c): no SobolSampler class)");
   if (d->samples_per_pixel <= 0) return fail("pbrgpu_sampler_set: samples_per_pixel <= 0");
   CK(cudaSetDevice(s->ctx->device));
+  HaltonParams& hp = s->sc.hp;
+  if (d->type == PBRGPU_SAMPLER_SOBOL) {
+    // Sobol' (parity unpinned: the reference has the tables, no sampler).  The tables are the reference's data and
+    // come through the descriptor; CPU twin = host/SobolSampler.h.
+    if (!d->sobol_matrices32 || !d->sobol_vdc || !d->sobol_vdc_inv || d->sobol_n_dims <= 0 || d->sobol_n_dims > 1024)
+      return fail("pbrgpu_sampler_set: Sobol needs the reference's SobolMatrices32 / VdCSobolMatrices(Inv) tables");
+    int dx = d->sample_bounds[2] - d->sample_bounds[0], dy = d->sample_bounds[3] - d->sample_bounds[1];
+    int res = 1, lg = 0;
+    while (res < std::max(dx, dy)) { res <<= 1; ++lg; }
+    if (lg > 26) return fail("pbrgpu_sampler_set: Sobol resolution too large");
+    std::vector<uint32_t> m32(d->sobol_matrices32, d->sobol_matrices32 + (size_t)d->sobol_n_dims * kSobolMatrixSize);
+    std::vector<uint64_t> v(d->sobol_vdc, d->sobol_vdc + kSobolMatrixSize), vi(d->sobol_vdc_inv, d->sobol_vdc_inv + kSobolMatrixSize);
+    CK(s->sobolMat.upload(m32, s->ctx->stream));
+    CK(s->sobolVdc.upload(v, s->ctx->stream));
+    CK(s->sobolVdcInv.upload(vi, s->ctx->stream));
+    CK(cudaStreamSynchronize(s->ctx->stream));
+    hp.type = PBRGPU_SAMPLER_SOBOL;
+    hp.sobolDims = d->sobol_n_dims;
+    hp.resolution = res;
+    hp.log2Resolution = lg;
+    hp.boundsMinX = d->sample_bounds[0];
+    hp.boundsMinY = d->sample_bounds[1];
+    hp.sobolMatrices32 = s->sobolMat.p;
+    hp.sobolVdc = s->sobolVdc.p;
+    hp.sobolVdcInv = s->sobolVdcInv.p;
+    hp.sampleAtPixelCenter = 0;
+    hp.sampleStride = 1;
+    int64_t spp = 1;
+    while (spp < d->samples_per_pixel) spp <<= 1;
+    s->spp = spp;
+    s->haveSampler = true;
+    return 0;
+  }
+  if (d->type != PBRGPU_SAMPLER_HALTON) return fail("pbrgpu_sampler_set: unknown sampler type");
+  hp.type = PBRGPU_SAMPLER_HALTON;
   int32_t p7[7];
   host::halton_params(d->sample_bounds, p7);
-  HaltonParams& hp = s->sc.hp;
   hp.baseScales[0] = p7[0]; hp.baseScales[1] = p7[1];
   hp.baseExponents[0] = p7[2]; hp.baseExponents[1] = p7[3];
   hp.sampleStride = p7[4];
@@ -499,6 +532,8 @@ static int check_render_args(pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
   if (rd->s1 < rd->s0 || rd->s0 < 0) return fail("pbrgpu_render: bad sample range");
   if (rd->max_depth < 0 || rd->max_depth > 1000) return fail("pbrgpu_render: bad max_depth");
   if (rd->integrator < PBRGPU_INTEGRATOR_PATH || rd->integrator > PBRGPU_INTEGRATOR_WHITTED) return fail("pbrgpu_render: unknown integrator");
+  if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL && s->sc.hp.type == PBRGPU_SAMPLER_SOBOL)
+    return fail("pbrgpu_render: UniformSampleAll sample arrays are implemented for the Halton sampler only");
   if (s->bvh.maxDepth >= kSmemStack + kLocalStack) return fail("pbrgpu_render: BVH deeper than the traversal stack");
   return 0;
 }

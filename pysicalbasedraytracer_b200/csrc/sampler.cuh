@@ -7,6 +7,7 @@
 // The reference dispatches over 1024 template instantiations; here the base is a runtime value read
 // from the prime table (same arithmetic, the digits and the fp32 product chain are identical).
 #pragma once
+#include "../../include/pbrgpu.h"
 #include "vecmath.cuh"
 
 namespace pbr {
@@ -22,7 +23,46 @@ struct HaltonParams {
   const int32_t* primeSums;
   const uint2* primeMagic; // per prime: (m, s) with floor(a / p) == __umulhi(a, m) >> s for every a < 2^31
   int64_t nPerms;
+  // ---- Sobol' (type == PBRGPU_SAMPLER_SOBOL; host/SobolSampler.h is the CPU twin) ----
+  int32_t type;                  // PBRGPU_SAMPLER_HALTON | PBRGPU_SAMPLER_SOBOL
+  int32_t sobolDims;             // rows available in sobolMatrices32
+  int32_t resolution, log2Resolution;
+  int32_t boundsMinX, boundsMinY;
+  const uint32_t* sobolMatrices32;  // [sobolDims][52]
+  const uint64_t* sobolVdc;         // VdCSobolMatrices[log2Resolution-1][52]
+  const uint64_t* sobolVdcInv;      // VdCSobolMatricesInv[log2Resolution-1][52]
 };
+constexpr int kSobolMatrixSize = 52;
+
+// SobolIntervalToIndex / SobolSampleFloat: see host/SobolSampler.h (same integer arithmetic)
+PBR_D int64_t sobol_index_for_sample(int px, int py, int64_t sampleNum, const HaltonParams& hp) {
+  const uint32_t m = (uint32_t)hp.log2Resolution;
+  if (m == 0) return 0;
+  uint64_t frame = (uint64_t)sampleNum;
+  uint64_t index = frame << (m << 1);
+  uint64_t delta = 0;
+  for (int c = 0; frame; frame >>= 1, ++c)
+    if (frame & 1) delta ^= __ldg(hp.sobolVdc + c);
+  uint64_t b = ((((uint64_t)(uint32_t)(px - hp.boundsMinX)) << m) | (uint64_t)(uint32_t)(py - hp.boundsMinY)) ^ delta;
+  for (int c = 0; b; b >>= 1, ++c)
+    if (b & 1) index ^= __ldg(hp.sobolVdcInv + c);
+  return (int64_t)index;
+}
+PBR_D float sobol_sample(int64_t index, int dim, const HaltonParams& hp) {
+  if (dim >= hp.sobolDims) return 0.f;
+  uint32_t v = 0;
+  uint64_t a = (uint64_t)index;
+  const uint32_t* row = hp.sobolMatrices32 + dim * kSobolMatrixSize;
+  for (int i = 0; a != 0; a >>= 1, ++i)
+    if (a & 1) v ^= __ldg(row + i);
+  return stdmin((float)v * 2.3283064365386963e-10f, kOneMinusEpsilon);
+}
+// dims 0 / 1 are remapped to the pixel (needs the pixel coordinate of that dimension)
+PBR_D float sobol_film_sample(int64_t index, int dim, int pixelCoord, const HaltonParams& hp) {
+  float s = sobol_sample(index, dim, hp);
+  s = s * hp.resolution + (dim == 0 ? hp.boundsMinX : hp.boundsMinY);
+  return stdmin(stdmax(s - pixelCoord, 0.f), kOneMinusEpsilon);
+}
 
 constexpr int kPrimeTableSize = 1000;
 constexpr int kMaxResolution = 128;  // Halton.cpp:7
@@ -83,6 +123,7 @@ PBR_D float scrambled_radical_inverse(int baseIndex, uint64_t a, const HaltonPar
 }
 
 PBR_D float halton_sample_dimension(int64_t index, int dim, const HaltonParams& hp) {
+  if (hp.type == PBRGPU_SAMPLER_SOBOL) return sobol_sample(index, dim, hp);  // dims >= 2 (film dims: sampler_film_sample)
   if (hp.sampleAtPixelCenter && (dim == 0 || dim == 1)) return 0.5f;
   if (dim == 0) return radical_inverse(0, (uint64_t)(index >> hp.baseExponents[0]), hp);
   if (dim == 1) return radical_inverse(1, (uint64_t)(index / hp.baseScales[1]), hp);
@@ -114,6 +155,14 @@ PBR_D int64_t halton_index_for_sample(int px, int py, int64_t sampleNum, const H
     offset %= hp.sampleStride;
   }
   return offset + sampleNum * hp.sampleStride;
+}
+
+// Sampler-agnostic entry points used by the kernels
+PBR_D int64_t sampler_index_for_sample(int px, int py, int64_t sampleNum, const HaltonParams& hp) {
+  return hp.type == PBRGPU_SAMPLER_SOBOL ? sobol_index_for_sample(px, py, sampleNum, hp) : halton_index_for_sample(px, py, sampleNum, hp);
+}
+PBR_D float sampler_film_sample(int64_t index, int dim, int pixelCoord, const HaltonParams& hp) {
+  return hp.type == PBRGPU_SAMPLER_SOBOL ? sobol_film_sample(index, dim, pixelCoord, hp) : halton_sample_dimension(index, dim, hp);
 }
 
 // Per-path sampler cursor: (index, dim) - Get1D/Get2D of GlobalSampler (Sampler.cpp:131-143) with

@@ -67,6 +67,7 @@
 #undef protected
 
 #include "pbrgpu.h"
+#include "SobolSampler.h"
 
 namespace PBR {
 
@@ -280,28 +281,40 @@ class GpuSamplerIntegrator : public Integrator {
     if (pbrgpu_camera_set(gscene, &cd)) return fail("pbrgpu_camera_set");
     // sampler (Sampler/Halton.cpp:30-58): the reference passes the same bounds to sampler and integrator
     auto* hs = dynamic_cast<const HaltonSampler*>(sampler.get());
-    if (!hs) { std::cerr << "GpuIntegrator: sampler is not a HaltonSampler" << std::endl; return; }
+    auto* ss = dynamic_cast<const SobolSampler*>(sampler.get());
+    if (!hs && !ss) { std::cerr << "GpuIntegrator: sampler is neither a HaltonSampler nor a SobolSampler" << std::endl; return; }
     pbrgpu_sampler_desc sd;
     std::memset(&sd, 0, sizeof(sd));
-    sd.type = PBRGPU_SAMPLER_HALTON;
-    sd.sample_at_pixel_center = hs->sampleAtPixelCenter ? 1 : 0;
-    sd.samples_per_pixel = hs->samplesPerPixel;
+    sd.samples_per_pixel = sampler->samplesPerPixel;
     sd.sample_bounds[0] = pixelBounds.pMin.x; sd.sample_bounds[1] = pixelBounds.pMin.y;
     sd.sample_bounds[2] = pixelBounds.pMax.x; sd.sample_bounds[3] = pixelBounds.pMax.y;
-    int32_t p7[7];
-    pbrgpu_halton_params(sd.sample_bounds, p7);
-    if (p7[0] != hs->baseScales[0] || p7[1] != hs->baseScales[1] || p7[4] != hs->sampleStride) {
-      std::cerr << "GpuIntegrator: HaltonSampler was built for other bounds than the integrator's pixelBounds" << std::endl;
-      return;
+    if (hs) {
+      sd.type = PBRGPU_SAMPLER_HALTON;
+      sd.sample_at_pixel_center = hs->sampleAtPixelCenter ? 1 : 0;
+      int32_t p7[7];
+      pbrgpu_halton_params(sd.sample_bounds, p7);
+      if (p7[0] != hs->baseScales[0] || p7[1] != hs->baseScales[1] || p7[4] != hs->sampleStride) {
+        std::cerr << "GpuIntegrator: HaltonSampler was built for other bounds than the integrator's pixelBounds" << std::endl;
+        return;
+      }
+      sd.perms = HaltonSampler::radicalInversePermutations.data();
+      sd.n_perms = (int64_t)HaltonSampler::radicalInversePermutations.size();
+    } else {
+      sd.type = PBRGPU_SAMPLER_SOBOL;
+      sd.sample_bounds[0] = ss->sampleBounds.pMin.x; sd.sample_bounds[1] = ss->sampleBounds.pMin.y;
+      sd.sample_bounds[2] = ss->sampleBounds.pMax.x; sd.sample_bounds[3] = ss->sampleBounds.pMax.y;
+      if (ss->log2Resolution < 1) { std::cerr << "GpuIntegrator: SobolSampler over a 1x1 image" << std::endl; return; }
+      sd.sobol_matrices32 = SobolMatrices32;
+      sd.sobol_n_dims = NumSobolDimensions;
+      sd.sobol_vdc = VdCSobolMatrices[ss->log2Resolution - 1];
+      sd.sobol_vdc_inv = VdCSobolMatricesInv[ss->log2Resolution - 1];
     }
-    sd.perms = HaltonSampler::radicalInversePermutations.data();
-    sd.n_perms = (int64_t)HaltonSampler::radicalInversePermutations.size();
     if (pbrgpu_sampler_set(gscene, &sd)) return fail("pbrgpu_sampler_set");
     pbrgpu_render_desc rd;
     std::memset(&rd, 0, sizeof(rd));
     fillRenderDesc(&rd);
     rd.x0 = pixelBounds.pMin.x; rd.y0 = pixelBounds.pMin.y; rd.x1 = pixelBounds.pMax.x; rd.y1 = pixelBounds.pMax.y;
-    rd.s0 = 0; rd.s1 = hs->samplesPerPixel;
+    rd.s0 = 0; rd.s1 = sampler->samplesPerPixel;
     const int rw = rd.x1 - rd.x0, rh = rd.y1 - rd.y0;
     rgbSum.assign((size_t)rw * rh * 3, 0.f);
     std::vector<unsigned char> rgba((size_t)rw * rh * 4);

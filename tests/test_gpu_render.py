@@ -17,7 +17,7 @@ REL_TOL = 1e-3
 
 def _direct_check(p, ref, max_depth, spp, frac_ok=0.999, integrator=A.INTEGRATOR_PATH, **kw):
     want, rst = ref.render(p.rscene, p.rcam, p.spp, (0, 0, p.W, p.H), integrator=integrator,
-                           max_depth=max_depth, s1=spp, **kw)
+                           max_depth=max_depth, s1=spp, sampler_type=p.sampler_type, **kw)
     got, _, st = p.scene.render(integrator=integrator, max_depth=max_depth, s1=spp, **kw)
     err = rel_err(got / spp, want / spp)
     ok = (err <= REL_TOL).mean()
@@ -167,3 +167,13 @@ def test_whitted_and_direct_lighting_integrators(api, ref, gpu_ctx, integ):
     p2 = Pair(api, ref, open_scene, 64, 64, 2)
     got, want = _direct_check(p2, ref, max_depth=3, spp=2, frac_ok=0.995, integrator=integ)
     assert abs(want[0, 0, 0] / 2 - 1.6) < 1e-5  # corner pixel escapes: 2 lights x 0.8
+
+
+def test_sobol_path_render_vs_reference_with_cpu_twin(api, ref, gpu_ctx):
+    """The reference's own PathIntegrator driven by the CPU Sobol twin vs the GPU path with the GPU Sobol sampler."""
+    # (camera off the box's symmetry planes: with Sobol the first samples of diagonal pixels have u0 == u1, and from
+    # (0,0,5) those rays run exactly along the box's corner edges - exact ties between two walls)
+    p = Pair(api, ref, scenes.cornell(sphere_tess=16), 96, 96, 4, eye=(0.3, 0.2, 5.0), look=(0.1, -0.2, 0.0),
+             sampler_type=A.SAMPLER_SOBOL)
+    _direct_check(p, ref, max_depth=1, spp=4, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=5, spp=4, frac_ok=0.97, rr_threshold=0.8)

@@ -65,3 +65,24 @@ def test_orthographic_and_nonsquare_rays(api, ref, gpu_ctx):
         want = ref.primary_rays(p.rcam, p.rsmp, region, 0, 2)
         got = p.scene.dump_primary_rays(region, 0, 2)
         assert np.array_equal(got[..., [0, 1, 2, 4, 5, 6]].view(np.uint32), want[..., [0, 1, 2, 4, 5, 6]].view(np.uint32))
+
+
+def test_sobol_sampler_bit_exact_vs_cpu_twin(api, ref, gpu_ctx):
+    """Sobol': PARITY UNPINNED by the reference (it has the matrices, no sampler).  The pin is the CPU twin
+    host/SobolSampler.h - a GlobalSampler subclass running inside the reference's own Sampler machinery over the
+    reference's own tables - against the GPU sampler: values and primary rays bit-exact."""
+    for (W, H, spp) in [(512, 512, 16), (1920, 1080, 4), (20, 9, 3)]:
+        p = Pair(api, ref, scenes.cornell(sphere_tess=0), W, H, spp, sampler_type=A.SAMPLER_SOBOL)
+        region = (W - 3, H - 2, W, H)
+        want = p.rsmp.dump(region, 0, spp, 64)
+        got = p.scene.dump_sampler(region, 0, spp, 64)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (W, H)
+        assert 0.0 <= got.min() and got.max() < 1.0
+        wr = ref.primary_rays(p.rcam, p.rsmp, region, 0, 2)
+        gr = p.scene.dump_primary_rays(region, 0, 2)
+        assert np.array_equal(gr[..., [0, 1, 2, 4, 5, 6]].view(np.uint32), wr[..., [0, 1, 2, 4, 5, 6]].view(np.uint32))
+    # (0,2)-sequence property: 16 consecutive samples of one pixel stratify the pixel into a 4x4 grid
+    p = Pair(api, ref, scenes.cornell(sphere_tess=0), 64, 64, 16, sampler_type=A.SAMPLER_SOBOL)
+    d = p.scene.dump_sampler((10, 20, 11, 21), 0, 16, 2)[0]
+    cells = set((int(u * 4), int(v * 4)) for u, v in d)
+    assert len(cells) == 16

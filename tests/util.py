@@ -8,11 +8,17 @@ EYE, LOOK, UP = (0.0, 0.0, 5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)
 
 
 class Pair:
-    def __init__(self, api, R, data, W, H, spp, eye=EYE, look=LOOK, up=UP, cam_type=A.CAMERA_PERSPECTIVE, ctx=None):
+    def __init__(self, api, R, data, W, H, spp, eye=EYE, look=LOOK, up=UP, cam_type=A.CAMERA_PERSPECTIVE, ctx=None,
+                 sampler_type=A.SAMPLER_HALTON):
         self.W, self.H, self.spp = W, H, spp
         c2w = api.Inverse(api.LookAt(eye, look, up))
         self.cam = (api.CreatePerspectiveCamera if cam_type == A.CAMERA_PERSPECTIVE else api.CreateOrthographicCamera)(W, H, c2w)
-        self.smp = api.HaltonSampler(spp, (0, 0, W, H))
+        self.sampler_type = sampler_type
+        if sampler_type == A.SAMPLER_SOBOL:
+            # the Sobol tables are the reference's data: fetched from the compiled reference
+            self.smp = api.SobolSampler(spp, (0, 0, W, H), *R.sobol_tables((0, 0, W, H)))
+        else:
+            self.smp = api.HaltonSampler(spp, (0, 0, W, H))
         self.scene = api.Scene(data, ctx)
         self.scene.set_camera(self.cam)
         self.scene.set_sampler(self.smp)
@@ -20,7 +26,7 @@ class Pair:
         if R is not None:
             self.rscene = R.RefScene(data)
             self.rcam = R.RefCamera(cam_type, W, H, eye, look, up)
-            self.rsmp = R.RefSampler(spp, (0, 0, W, H))
+            self.rsmp = R.RefSampler(spp, (0, 0, W, H), sampler_type)
 
 
 def rel_err(a, b, floor=1e-3):
