@@ -23,7 +23,7 @@ from . import _abi as A
 from . import transform as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbrgpu.so")
+LIB_PATH = os.environ.get("PBRGPU_LIB", os.path.join(_HERE, "libpbrgpu.so"))  # override: kernel-variant experiments
 _lib = None
 
 
@@ -270,8 +270,10 @@ class Scene:
     # ---- render ----
     def render(self, integrator=A.INTEGRATOR_PATH, max_depth=5, rr_threshold=1.0,
                light_strategy=A.LIGHTSTRATEGY_UNIFORM, region=None, s0=0, s1=None, flags=0, samples_per_wave=0,
-               want_rgba8=False):
-        """-> (rgb_sum float32 [H,W,3], rgba8 or None, Stats).  Host buffers in, host buffers out."""
+               want_rgba8=False, out=None):
+        """-> (rgb_sum float32 [H,W,3], rgba8 or None, Stats).  Host buffers in, host buffers out.
+        `out`: optional preallocated float32 [H,W,3] array to receive the sums (like the app's FrameBuffer, which
+        is allocated once and reused across Render calls)."""
         if region is None:
             region = (0, 0, self._camera.width, self._camera.height)
         if s1 is None:
@@ -280,7 +282,9 @@ class Scene:
         rd = A.RenderDesc(integrator=integrator, max_depth=max_depth, rr_threshold=rr_threshold,
                           light_strategy=light_strategy, x0=x0, y0=y0, x1=x1, y1=y1, s0=s0, s1=s1,
                           samples_per_wave=samples_per_wave, flags=flags)
-        out = np.zeros((y1 - y0, x1 - x0, 3), dtype=np.float32)
+        if out is None:
+            out = np.zeros((y1 - y0, x1 - x0, 3), dtype=np.float32)
+        assert out.dtype == np.float32 and out.shape == (y1 - y0, x1 - x0, 3) and out.flags["C_CONTIGUOUS"]
         rgba = np.zeros((y1 - y0, x1 - x0, 4), dtype=np.uint8) if want_rgba8 else None
         st = A.Stats()
         _check(lib().pbrgpu_render(self.h, C.byref(rd), out.ctypes.data, rgba.ctypes.data if want_rgba8 else None,

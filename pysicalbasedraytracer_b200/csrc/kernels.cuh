@@ -101,7 +101,7 @@ PBR_D uint32_t queue_push(uint32_t* counter, bool active) {
 }
 
 // K2/K3/K6: the traversal kernel.  Persistent warps; each lane owns one ray at a time.  When at least
-// kFetchMinIdle lanes of a warp have finished their rays, the idle lanes fetch new ones with a single
+// P.fetchMinIdle lanes of a warp have finished their rays, the idle lanes fetch new ones with a single
 // warp-aggregated atomicAdd on the queue cursor (__ballot_sync / __shfl_sync), so a warp is not held
 // hostage by its longest ray.  Per iteration a lane performs one node step (80-byte node, 8 child
 // boxes) and then drains the triangle group that step produced.
@@ -109,7 +109,6 @@ PBR_D uint32_t queue_push(uint32_t* counter, bool active) {
 // rays emitted by the shading of bounce b-1 (independent work, so the machine stays full).
 enum { TRACE_PATH = 0, TRACE_SHADOW = 1, TRACE_MIS = 2 };
 constexpr int kTraceBlock = 128;
-constexpr int kFetchMinIdle = 8;
 
 // Triangle batching: a node step leaves a lane with 0..24 candidate triangles.  Testing them right away
 // would run the (long) watertight test with only the few lanes that happen to have candidates, so a
@@ -118,8 +117,14 @@ constexpr int kFetchMinIdle = 8;
 // when no lane has node work left.
 constexpr int kTriQueue = 6;
 
+#ifndef PBR_TRACE_MIN_BLOCKS
+#define PBR_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef PBR_SHADE_MIN_BLOCKS
+#define PBR_SHADE_MIN_BLOCKS 1
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) k_trace(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
   __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
   __shared__ uint2 stri[kTraceBlock / 32][kTriQueue][32];
   const unsigned full = 0xffffffffu;
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace(const __grid_constant__ R
   while (true) {
     // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
     const unsigned idle = __ballot_sync(full, !busy);
-    if (idle != 0u && !exhausted && (idle == full || __popc(idle) >= kFetchMinIdle)) {
+    if (idle != 0u && !exhausted && (idle == full || __popc(idle) >= P.fetchMinIdle)) {
       const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
       uint32_t base = 0;
       if (lane == leader) base = atomicAdd(&C->cursor[0], (uint32_t)nIdle);
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ Ren
 
 // K4/K5/K7: shading for one material queue.
 template <int MAT>
-__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ RenderParams P, int bounce) {
+__global__ void __launch_bounds__(kBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderParams P, int bounce) {
   const uint32_t n = P.ws.ctr->nMat[MAT];
   const SceneDev& sc = P.sc;
   const uint32_t* queue = P.ws.qMat + (size_t)MAT * P.ws.capacity;

@@ -66,7 +66,45 @@ struct pbrgpu_ctx {
   std::vector<cudaEvent_t> pool;  // PBRGPU_RENDER_TIMERS
 };
 
+// CUDA-event timeline: mark(cat) closes the previous interval and opens one of category `cat`.
+enum { T_RAYGEN, T_CLOSEST, T_SHADE, T_SHADOW, T_MIS, T_FILM, T_END, T_COUNT };
+struct Timeline {
+  pbrgpu_ctx* c;
+  cudaStream_t st;
+  bool on;
+  size_t used = 0;
+  std::vector<int> cats;
+  cudaError_t mark(int cat) {
+    if (!on) return cudaSuccess;
+    if (used == c->pool.size()) {
+      cudaEvent_t e;
+      cudaError_t r = cudaEventCreate(&e);
+      if (r != cudaSuccess) return r;
+      c->pool.push_back(e);
+    }
+    cats.push_back(cat);
+    return cudaEventRecord(c->pool[used++], st);
+  }
+  cudaError_t collect(double out[T_COUNT], uint64_t counts[T_COUNT]) {
+    for (int k = 0; k < T_COUNT; ++k) { out[k] = 0; counts[k] = 0; }
+    for (size_t i = 0; i + 1 < used; ++i) {
+      float ms = 0;
+      cudaError_t r = cudaEventElapsedTime(&ms, c->pool[i], c->pool[i + 1]);
+      if (r != cudaSuccess) return r;
+      out[cats[i]] += ms;
+      counts[cats[i]]++;
+    }
+    return cudaSuccess;
+  }
+};
+
+struct LastRender {
+  uint64_t samples = 0, launches = 0;
+  Timeline tl{nullptr, nullptr, false};
+};
+
 struct pbrgpu_scene {
+  LastRender last;
   pbrgpu_ctx* ctx = nullptr;
   SceneDev sc{};
   BuiltBvh8 bvh;
@@ -89,6 +127,9 @@ struct pbrgpu_scene {
   int lightStrategyBuilt = -1;
   int traceBlocksPerSm = 0;
   int triThreshold = 1;
+  int fetchMinIdle = 8;
+  int waveLog2 = 25;
+  bool hasMat[PBRGPU_MAT_COUNT] = {};  // material types present in the scene (absent ones: no shade launch)
   // wavefront state
   uint32_t capacity = 0;
   size_t rayCapacity = 0;
@@ -98,6 +139,13 @@ struct pbrgpu_scene {
   DevBuf<Counters> ctr;
   DevBuf<float> accum;
   size_t accumPix = 0;
+  // host-buffer path (pbrgpu_render): persistent device RGB buffer + pinned staging so that the image leaves the
+  // GPU at PCIe speed whatever memory the caller's buffer lives in
+  DevBuf<float> drgb;
+  DevBuf<unsigned char> d8;
+  void* hstage = nullptr;
+  size_t hstageBytes = 0;
+  ~pbrgpu_scene() { if (hstage) cudaFreeHost(hstage); }
 };
 
 namespace {
@@ -163,38 +211,6 @@ void env_bilinear_host(const std::vector<float>& tex, int W, int H, float s_, fl
   float w0 = (1 - ds) * (1 - dt), w1 = (1 - ds) * dt, w2 = ds * (1 - dt), w3 = ds * dt;
   for (int k = 0; k < 3; ++k) out[k] = ((w0 * a[k] + w1 * b[k]) + w2 * c[k]) + w3 * d[k];
 }
-
-// CUDA-event timeline: mark(cat) closes the previous interval and opens one of category `cat`.
-enum { T_RAYGEN, T_CLOSEST, T_SHADE, T_SHADOW, T_MIS, T_FILM, T_END, T_COUNT };
-struct Timeline {
-  pbrgpu_ctx* c;
-  cudaStream_t st;
-  bool on;
-  size_t used = 0;
-  std::vector<int> cats;
-  cudaError_t mark(int cat) {
-    if (!on) return cudaSuccess;
-    if (used == c->pool.size()) {
-      cudaEvent_t e;
-      cudaError_t r = cudaEventCreate(&e);
-      if (r != cudaSuccess) return r;
-      c->pool.push_back(e);
-    }
-    cats.push_back(cat);
-    return cudaEventRecord(c->pool[used++], st);
-  }
-  cudaError_t collect(double out[T_COUNT], uint64_t counts[T_COUNT]) {
-    for (int k = 0; k < T_COUNT; ++k) { out[k] = 0; counts[k] = 0; }
-    for (size_t i = 0; i + 1 < used; ++i) {
-      float ms = 0;
-      cudaError_t r = cudaEventElapsedTime(&ms, c->pool[i], c->pool[i + 1]);
-      if (r != cudaSuccess) return r;
-      out[cats[i]] += ms;
-      counts[cats[i]]++;
-    }
-    return cudaSuccess;
-  }
-};
 
 uint32_t grid_for(const pbrgpu_ctx* c, uint64_t n, int perSm) {
   uint64_t blocks = (n + kBlock - 1) / kBlock;
@@ -307,6 +323,7 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   std::vector<pbrgpu_material> mats(d->materials, d->materials + d->n_materials);
   for (auto& m : mats) {
     if (m.type < 0 || m.type >= PBRGPU_MAT_COUNT) return fail("pbrgpu_scene_create: unknown material type");
+    s->hasMat[m.type] = true;
     m.pad0 = (m.type == PBRGPU_MAT_GLASS && m.u_rough == 0 && m.v_rough == 0) ? 1.f : 0.f;  // isSpecular
     if (m.remap_roughness && m.type != PBRGPU_MAT_MATTE && m.type != PBRGPU_MAT_MIRROR) {
       m.u_rough = host::roughness_to_alpha(m.u_rough);
@@ -538,6 +555,34 @@ static int check_render_args(pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
   return 0;
 }
 
+static int fetch_stats(pbrgpu_scene* s, cudaStream_t st, pbrgpu_stats* stats) {
+  pbrgpu_ctx* c = s->ctx;
+  Counters hc{};
+  CK(cudaMemcpyAsync(&hc, s->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  memset(stats, 0, sizeof(*stats));
+  stats->camera_samples = s->last.samples;
+  stats->rays_closest = hc.raysClosest;
+  stats->rays_shadow = hc.raysShadow;
+  stats->nodes_visited = hc.nodesVisited;
+  stats->tris_tested = hc.trisTested;
+  stats->kernel_launches = s->last.launches;
+  stats->ms_total = ms;
+  stats->rays_path = hc.raysPath;
+  Timeline& tl = s->last.tl;
+  if (tl.on) {
+    double t[T_COUNT];
+    uint64_t n[T_COUNT];
+    CK(tl.collect(t, n));
+    stats->ms_raygen = t[T_RAYGEN]; stats->ms_trace_closest = t[T_CLOSEST]; stats->ms_shade = t[T_SHADE];
+    stats->ms_trace_shadow = t[T_SHADOW]; stats->ms_trace_mis = t[T_MIS]; stats->ms_film = t[T_FILM];
+    stats->n_trace_closest_launches = n[T_CLOSEST];
+  }
+  return 0;
+}
+
 int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d_rgba_sum, void* stream_, pbrgpu_stats* stats) {
   if (check_render_args(s, rd)) return 1;
   if (!d_rgba_sum) return fail("pbrgpu_render_device: NULL accumulator");
@@ -551,6 +596,8 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
     if (const char* e = getenv("PBRGPU_TRACE_BLOCKS_PER_SM")) nb = atoi(e);
     s->traceBlocksPerSm = std::max(1, nb);
     if (const char* e = getenv("PBRGPU_TRI_THRESHOLD")) s->triThreshold = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("PBRGPU_FETCH_MIN_IDLE")) s->fetchMinIdle = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("PBRGPU_WAVE_LOG2")) s->waveLog2 = std::max(14, std::min(25, atoi(e)));
   }
   if (rd->light_strategy == PBRGPU_LIGHTSTRATEGY_POWER && s->lights.size() > 1)
     for (float p : s->lightPower)
@@ -571,7 +618,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
     raysPerHit = std::max(1u, raysPerHit);
   }
   if (raysPerHit > 4096) return fail("pbrgpu_render: too many light samples per hit");
-  const uint32_t capMax = std::max(1u << 14, std::min(1u << 22, (1u << 23) / raysPerHit));
+  const uint32_t capMax = std::max(1u << 14, std::min(1u << s->waveLog2, (2u << s->waveLog2) / raysPerHit));
   // row bands of <= capMax pixels; inside a band, waves of nsWave samples per pixel
   int bandRows = (int)std::max<int64_t>(1, std::min<int64_t>(H, capMax / (uint32_t)W));
   if ((uint64_t)W > capMax) return fail("pbrgpu_render: region wider than the wave capacity");
@@ -593,10 +640,10 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   P.atomicL = pathInteg ? 0 : 1;
   P.countStats = count ? 1 : 0;
   P.triThreshold = s->triThreshold;
+  P.fetchMinIdle = s->fetchMinIdle;
 
   if (!(rd->flags & PBRGPU_RENDER_ACCUMULATE)) CK(cudaMemsetAsync(d_rgba_sum, 0, sizeof(float) * 4 * (size_t)W * H, st));
-  Counters zero{};
-  CK(cudaMemcpyAsync(s->ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(s->ctr.p, 0, sizeof(Counters), st));  // (a memset, not a pageable H2D copy: never blocks the host)
   CK(cudaEventRecord(c->ev[0], st));
   uint64_t launches = 0;
   Timeline tl{c, st, (rd->flags & PBRGPU_RENDER_TIMERS) != 0};
@@ -630,22 +677,20 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         if (bounce > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
         CK(tl.mark(T_SHADE));
         k_classify<<<g, kBlock, 0, st>>>(P);
+        // one shading launch per material type PRESENT in the scene
+#define PBR_SHADE(K, M) if (s->hasMat[M]) { K<M><<<g, kBlock, 0, st>>>(P, bounce); launches++; }
         if (pathInteg) {
-          k_shade<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
+          PBR_SHADE(k_shade, PBRGPU_MAT_MATTE) PBR_SHADE(k_shade, PBRGPU_MAT_MIRROR) PBR_SHADE(k_shade, PBRGPU_MAT_GLASS)
+          PBR_SHADE(k_shade, PBRGPU_MAT_METAL) PBR_SHADE(k_shade, PBRGPU_MAT_PLASTIC)
         } else {
-          k_shade_direct<PBRGPU_MAT_MATTE><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade_direct<PBRGPU_MAT_MIRROR><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade_direct<PBRGPU_MAT_GLASS><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade_direct<PBRGPU_MAT_METAL><<<g, kBlock, 0, st>>>(P, bounce);
-          k_shade_direct<PBRGPU_MAT_PLASTIC><<<g, kBlock, 0, st>>>(P, bounce);
+          PBR_SHADE(k_shade_direct, PBRGPU_MAT_MATTE) PBR_SHADE(k_shade_direct, PBRGPU_MAT_MIRROR)
+          PBR_SHADE(k_shade_direct, PBRGPU_MAT_GLASS) PBR_SHADE(k_shade_direct, PBRGPU_MAT_METAL)
+          PBR_SHADE(k_shade_direct, PBRGPU_MAT_PLASTIC)
         }
-        k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce);
+#undef PBR_SHADE
+        if (!pathInteg || s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce); launches++; }
         k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
-        launches += 9;
+        launches += 3;
         std::swap(P.ws.qCur, P.ws.qNext);
       }
       if (!pathInteg) {  // shadow / MIS rays of the last shaded depth
@@ -664,30 +709,8 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   CK(tl.mark(T_END));
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev[1], st));
-  if (stats) {
-    Counters hc{};
-    CK(cudaMemcpyAsync(&hc, s->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
-    memset(stats, 0, sizeof(*stats));
-    stats->camera_samples = (uint64_t)W * H * (uint64_t)nS;
-    stats->rays_closest = hc.raysClosest;
-    stats->rays_shadow = hc.raysShadow;
-    stats->nodes_visited = hc.nodesVisited;
-    stats->tris_tested = hc.trisTested;
-    stats->kernel_launches = launches;
-    stats->ms_total = ms;
-    stats->rays_path = hc.raysPath;
-    if (tl.on) {
-      double t[T_COUNT];
-      uint64_t n[T_COUNT];
-      CK(tl.collect(t, n));
-      stats->ms_raygen = t[T_RAYGEN]; stats->ms_trace_closest = t[T_CLOSEST]; stats->ms_shade = t[T_SHADE];
-      stats->ms_trace_shadow = t[T_SHADOW]; stats->ms_trace_mis = t[T_MIS]; stats->ms_film = t[T_FILM];
-      stats->n_trace_closest_launches = n[T_CLOSEST];
-    }
-  }
+  s->last = LastRender{(uint64_t)W * H * (uint64_t)nS, launches, tl};
+  if (stats && fetch_stats(s, st, stats)) return 1;
   return 0;
 }
 
@@ -716,6 +739,39 @@ __global__ void k_rgba_to_rgb(const float4* in, size_t n, float* out) {
   out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
 }
 
+// D2H through the scene's pinned staging buffer in chunks: the copy of chunk k+1 overlaps the host memcpy of chunk k.
+static int staged_d2h(pbrgpu_scene* s, void* dst, const void* dsrc, size_t bytes, bool accumulateFloat) {
+  pbrgpu_ctx* c = s->ctx;
+  const size_t chunk = 4u << 20;
+  if (s->hstageBytes < 2 * chunk) {
+    if (s->hstage) cudaFreeHost(s->hstage);
+    s->hstage = nullptr;
+    CK(cudaHostAlloc(&s->hstage, 2 * chunk, cudaHostAllocDefault));
+    s->hstageBytes = 2 * chunk;
+  }
+  char* stage[2] = {(char*)s->hstage, (char*)s->hstage + chunk};
+  size_t nChunks = (bytes + chunk - 1) / chunk;
+  auto len = [&](size_t k) { return std::min(chunk, bytes - k * chunk); };
+  if (nChunks == 0) return 0;
+  CK(cudaMemcpyAsync(stage[0], dsrc, len(0), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(c->ev[2], c->stream));
+  for (size_t k = 0; k < nChunks; ++k) {
+    if (k + 1 < nChunks) {
+      CK(cudaMemcpyAsync(stage[(k + 1) & 1], (const char*)dsrc + (k + 1) * chunk, len(k + 1), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaEventRecord(c->ev[3 + ((k + 1) & 1)], c->stream));
+    }
+    CK(cudaEventSynchronize(k == 0 ? c->ev[2] : c->ev[3 + (k & 1)]));
+    if (accumulateFloat) {
+      float* d = (float*)((char*)dst + k * chunk);
+      const float* h = (const float*)stage[k & 1];
+      for (size_t i = 0, n = len(k) / sizeof(float); i < n; ++i) d[i] += h[i];
+    } else {
+      memcpy((char*)dst + k * chunk, stage[k & 1], len(k));
+    }
+  }
+  return 0;
+}
+
 int pbrgpu_render(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* out_rgb_sum, unsigned char* out_rgba8, pbrgpu_stats* stats) {
   if (check_render_args(s, rd)) return 1;
   pbrgpu_ctx* c = s->ctx;
@@ -724,29 +780,21 @@ int pbrgpu_render(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* out_rgb_
   size_t n = (size_t)W * H;
   if (s->accumPix < n) { CK(s->accum.alloc(n * 4)); s->accumPix = n; }
   pbrgpu_render_desc r2 = *rd;
-  if (rd->flags & PBRGPU_RENDER_ACCUMULATE) {
-    // host-side accumulate: caller's sums are added after the render
-    r2.flags &= ~PBRGPU_RENDER_ACCUMULATE;
-  }
-  if (pbrgpu_render_device(s, &r2, s->accum.p, c->stream, stats)) return 1;
+  r2.flags &= ~PBRGPU_RENDER_ACCUMULATE;  // PBRGPU_RENDER_ACCUMULATE on host buffers: the caller's sums are added after the render
+  if (pbrgpu_render_device(s, &r2, s->accum.p, c->stream, nullptr)) return 1;
   if (out_rgb_sum) {
-    DevBuf<float> drgb;
-    CK(drgb.alloc(n * 3));
-    k_rgba_to_rgb<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)s->accum.p, n, drgb.p);
+    if (s->drgb.n < n * 3) CK(s->drgb.alloc(n * 3));
+    k_rgba_to_rgb<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)s->accum.p, n, s->drgb.p);
     CK(cudaGetLastError());
-    if (rd->flags & PBRGPU_RENDER_ACCUMULATE) {
-      std::vector<float> tmp(n * 3);
-      CK(cudaMemcpyAsync(tmp.data(), drgb.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      for (size_t i = 0; i < n * 3; ++i) out_rgb_sum[i] += tmp[i];
-    } else {
-      CK(cudaMemcpyAsync(out_rgb_sum, drgb.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-    }
+    if (staged_d2h(s, out_rgb_sum, s->drgb.p, n * 3 * sizeof(float), (rd->flags & PBRGPU_RENDER_ACCUMULATE) != 0)) return 1;
   }
   if (out_rgba8) {
-    if (pbrgpu_resolve_film(c, s->accum.p, W, H, 0.f, nullptr, out_rgba8)) return 1;
+    if (s->d8.n < n * 4) CK(s->d8.alloc(n * 4));
+    k_resolve_film<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)s->accum.p, W, H, 0.f, 1, nullptr, s->d8.p);
+    CK(cudaGetLastError());
+    if (staged_d2h(s, out_rgba8, s->d8.p, n * 4, false)) return 1;
   }
+  if (stats && fetch_stats(s, c->stream, stats)) return 1;
   return 0;
 }
 

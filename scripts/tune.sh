@@ -1,5 +1,14 @@
 #!/bin/bash
 # development aid: sweep traversal knobs on the bench workload
-for leaf in 3 2 1; do for th in 1 8 12 16 20 24; do
-  echo "== leaf $leaf thresh $th"; PBRGPU_MAX_LEAF=$leaf PBRGPU_TRI_THRESHOLD=$th python scripts/quick_perf.py 467 4 2>&1 | grep "^ms" | tail -2
-done; done
+run() { echo "== $*"; env "$@" python scripts/quick_perf.py 467 8 2>&1 | grep "^ms" | sed -n 2p; }
+run A=1
+run PBRGPU_FETCH_MIN_IDLE=4
+run PBRGPU_FETCH_MIN_IDLE=12
+run PBRGPU_FETCH_MIN_IDLE=16
+run PBRGPU_FETCH_MIN_IDLE=24
+run PBRGPU_WAVE_LOG2=21
+run PBRGPU_WAVE_LOG2=23
+run PBRGPU_WAVE_LOG2=24
+run PBRGPU_TRACE_BLOCKS_PER_SM=4
+run PBRGPU_TRACE_BLOCKS_PER_SM=6
+run PBRGPU_TRACE_BLOCKS_PER_SM=7
