@@ -369,13 +369,28 @@ PBR_D Spec lobe_sample_f(const Lobe& l, V3 wo, V3* wi, float u0, float u1, float
 }
 
 // ---- BSDF::f / Pdf / Sample_f (Reflection.cpp:56-164) ----
+// The lobe loops run to a compile-time bound (the most lobes the material can create) with an `i < b.n`
+// guard, so that lobes[] is indexed statically and the whole Bsdf stays in registers.
+template <int MAT>
+PBR_D constexpr int mat_max_lobes() { return (MAT == 0 || MAT == 1 || MAT == 3) ? 1 : 2; }
+
+template <int MAT>
+PBR_D int bsdf_num_components(const Bsdf& b, int flags) {
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < mat_max_lobes<MAT>(); ++i)
+    if (i < b.n && (b.lobes[i].flags & flags) == b.lobes[i].flags) ++c;
+  return c;
+}
 template <int MAT>
 PBR_D Spec bsdf_f(const Bsdf& b, V3 woW, V3 wiW, int flags) {
   V3 wi = b.to_local(wiW), wo = b.to_local(woW);
   if (wo.z == 0) return Spec(0.f);
   bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
   Spec f(0.f);
-  for (int i = 0; i < b.n; ++i) {
+#pragma unroll
+  for (int i = 0; i < mat_max_lobes<MAT>(); ++i) {
+    if (i >= b.n) continue;
     const Lobe& l = b.lobes[i];
     if ((l.flags & flags) == l.flags &&
         ((reflect && (l.flags & BSDF_REFLECTION)) || (!reflect && (l.flags & BSDF_TRANSMISSION))))
@@ -390,19 +405,22 @@ PBR_D float bsdf_pdf(const Bsdf& b, V3 woW, V3 wiW, int flags) {
   if (wo.z == 0) return 0.f;
   float pdf = 0.f;
   int matching = 0;
-  for (int i = 0; i < b.n; ++i)
-    if ((b.lobes[i].flags & flags) == b.lobes[i].flags) { ++matching; pdf += lobe_pdf<MAT>(b.lobes[i], wo, wi); }
+#pragma unroll
+  for (int i = 0; i < mat_max_lobes<MAT>(); ++i)
+    if (i < b.n && (b.lobes[i].flags & flags) == b.lobes[i].flags) { ++matching; pdf += lobe_pdf<MAT>(b.lobes[i], wo, wi); }
   return matching > 0 ? pdf / matching : 0.f;
 }
 template <int MAT>
 PBR_D Spec bsdf_sample_f(const Bsdf& b, V3 woW, V3* wiW, float u0, float u1, float* pdf, int type, int* sampledType) {
-  int matching = b.num_components(type);
+  int matching = bsdf_num_components<MAT>(b, type);
   if (matching == 0) { *pdf = 0; *sampledType = 0; return Spec(0.f); }
   int comp = min((int)floorf(u0 * matching), matching - 1);
-  int which = -1, count = comp;
-  for (int i = 0; i < b.n; ++i)
-    if ((b.lobes[i].flags & type) == b.lobes[i].flags && count-- == 0) { which = i; break; }
-  const Lobe& l = b.lobes[which];
+  int which = 0, count = comp;
+  bool chosen = false;
+#pragma unroll
+  for (int i = 0; i < mat_max_lobes<MAT>(); ++i)
+    if (!chosen && i < b.n && (b.lobes[i].flags & type) == b.lobes[i].flags && count-- == 0) { which = i; chosen = true; }
+  const Lobe l = (mat_max_lobes<MAT>() == 1 || which == 0) ? b.lobes[0] : b.lobes[mat_max_lobes<MAT>() - 1];
   float ur0 = stdmin(u0 * matching - comp, kOneMinusEpsilon);
   V3 wi, wo = b.to_local(woW);
   // reference returns 0 here WITHOUT writing *pdf (Reflection.cpp:131); callers then read an
@@ -413,14 +431,18 @@ PBR_D Spec bsdf_sample_f(const Bsdf& b, V3 woW, V3* wiW, float u0, float u1, flo
   Spec f = lobe_sample_f<MAT>(l, wo, &wi, ur0, u1, pdf, sampledType);
   if (*pdf == 0) { *sampledType = 0; return Spec(0.f); }
   *wiW = b.to_world(wi);
-  if (!(l.flags & BSDF_SPECULAR) && matching > 1)
-    for (int i = 0; i < b.n; ++i)
-      if (i != which && (b.lobes[i].flags & type) == b.lobes[i].flags) *pdf += lobe_pdf<MAT>(b.lobes[i], wo, wi);
+  if (!(l.flags & BSDF_SPECULAR) && matching > 1) {
+#pragma unroll
+    for (int i = 0; i < mat_max_lobes<MAT>(); ++i)
+      if (i < b.n && i != which && (b.lobes[i].flags & type) == b.lobes[i].flags) *pdf += lobe_pdf<MAT>(b.lobes[i], wo, wi);
+  }
   if (matching > 1) *pdf /= matching;
   if (!(l.flags & BSDF_SPECULAR)) {
     bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
     f = Spec(0.f);
-    for (int i = 0; i < b.n; ++i) {
+#pragma unroll
+    for (int i = 0; i < mat_max_lobes<MAT>(); ++i) {
+      if (i >= b.n) continue;
       const Lobe& li = b.lobes[i];
       if ((li.flags & type) == li.flags &&
           ((reflect && (li.flags & BSDF_REFLECTION)) || (!reflect && (li.flags & BSDF_TRANSMISSION))))

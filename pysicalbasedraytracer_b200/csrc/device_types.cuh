@@ -41,6 +41,12 @@ struct SceneDev {
   const float4* tv0;
   const float4* tv1;
   const float4* tv2;
+  // per-triangle shading frame, host-precomputed with the reference's own operation order (bit-identical to
+  // what Triangle::Intersect / the BSDF ctor would compute per hit): removes two fp64 cross products, two
+  // normalisations and ~30 conversions per shaded hit (the shading kernels were XU-pipe bound on them)
+  const float4* tvN;   // geometric normal of Triangle::Intersect (Triangle.cpp:182-184), orientation flip applied
+  const float4* tvS;   // ss = Normalize(dpdu)            (Reflection.h:105-110)
+  const float4* tvT;   // ts = Cross(ns, ss)
   const float4* nodes8;         // Bvh8Node[] viewed as 5 x float4 per node
   const pbrgpu_material* mats;  // roughness fields already remapped to alpha on the host (glibc logf)
   const pbrgpu_light* lights;   // AREA_TRI: .tri = LEAF-ORDER triangle index

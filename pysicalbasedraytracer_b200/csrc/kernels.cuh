@@ -16,6 +16,7 @@
 namespace pbr {
 
 constexpr int kBlock = 256;
+constexpr int kShadeBlock = 128;  // shading kernels: ~100 registers/thread, 128-thread blocks pack the register file better
 
 PBR_D V3 xform_point(const float* m, V3 p) {  // Transform::operator()(Point3) Core/Transform.h:138-150
   float x = p.x, y = p.y, z = p.z;
@@ -121,7 +122,7 @@ constexpr int kTriQueue = 6;
 #define PBR_TRACE_MIN_BLOCKS 8
 #endif
 #ifndef PBR_SHADE_MIN_BLOCKS
-#define PBR_SHADE_MIN_BLOCKS 1
+#define PBR_SHADE_MIN_BLOCKS 5
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ Ren
 
 // K4/K5/K7: shading for one material queue.
 template <int MAT>
-__global__ void __launch_bounds__(kBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderParams P, int bounce) {
+__global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderParams P, int bounce) {
   const uint32_t n = P.ws.ctr->nMat[MAT];
   const SceneDev& sc = P.sc;
   const uint32_t* queue = P.ws.qMat + (size_t)MAT * P.ws.capacity;
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __
       cur.arrayEndDim = P.arrayEndDim;
       TriData tri = load_tri(sc, __float_as_int(h4.x));
       Isect is;
-      make_isect(sc, tri, h4.y, h4.z, h4.w, rayD, &is);
+      make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is);
       Spec Ladd(0.f);
       // emitted light for camera rays / after specular bounces
       if ((bounce == 0 || specularBounce) && is.lightId >= 0)
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __
         Bsdf bsdf;
         make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf);
         const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
-        if (bsdf.num_components(nonSpec) > 0 && sc.nLights > 0) {
+        if (bsdf_num_components<MAT>(bsdf, nonSpec) > 0 && sc.nLights > 0) {
           // UniformSampleOneLight (Integrator.cpp:46-69)
           float pickPdf;
           int lightNum = sample_discrete(sc.lightFunc, sc.lightCdf, sc.lightFuncInt, sc.nLights, cur.get1D(sc.hp), &pickPdf);
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
       cur.arrayEndDim = P.arrayEndDim;
       TriData tri = load_tri(sc, __float_as_int(h4.x));
       Isect is;
-      make_isect(sc, tri, h4.y, h4.z, h4.w, rayD, &is);
+      make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is);
       // L += isect.Le(wo) at every depth (WhittedIntegrator.cpp:33, DirectLightingIntegrator.cpp:41)
       if (is.lightId >= 0) {
         Spec Le = beta * area_light_L(sc.lights[is.lightId], is.n, is.wo);
@@ -590,8 +591,10 @@ __global__ void __launch_bounds__(kBlock) k_resolve_mis(const __grid_constant__ 
     const pbrgpu_light& light = P.sc.lights[lightId];
     Spec Li(0.f);
     if (tri >= 0) {
-      TriData t = load_tri(P.sc, tri);
-      if ((int)t.w2 == lightId) Li = area_light_L(light, tri_normal_isect(t), -wi);
+      if (__float_as_int(__ldg(&P.sc.tv2[tri].w)) == lightId) {
+        const float4 n4 = __ldg(P.sc.tvN + tri);
+        Li = area_light_L(light, V3(n4.x, n4.y, n4.z), -wi);
+      }
     } else {
       Li = light_Le(P.sc, light, wi);
     }

@@ -114,7 +114,7 @@ struct pbrgpu_scene {
   bool haveCamera = false, haveSampler = false;
   int64_t spp = 0;
   // device buffers
-  DevBuf<float4> tv0, tv1, tv2;
+  DevBuf<float4> tv0, tv1, tv2, tvN, tvS, tvT;
   DevBuf<Bvh8Node> nodes;
   DevBuf<pbrgpu_material> mats;
   DevBuf<pbrgpu_light> dlights;
@@ -123,6 +123,7 @@ struct pbrgpu_scene {
   DevBuf<uint16_t> perms;
   DevBuf<int32_t> primes, primeSums;
   DevBuf<uint32_t> primeMagic, sobolMat;
+  DevBuf<float> dimConst;
   DevBuf<uint64_t> sobolVdc, sobolVdcInv;
   int lightStrategyBuilt = -1;
   int traceBlocksPerSm = 0;
@@ -301,7 +302,7 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   build_bvh8(d->verts, d->indices, d->n_tris, maxLeaf, &s->bvh);
   const int nT = d->n_tris;
   s->leafOf.assign((size_t)nT, -1);
-  std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT);
+  std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT), vN((size_t)nT), vS((size_t)nT), vT((size_t)nT);
   for (int k = 0; k < nT; ++k) {
     int ti = s->bvh.triOrder[k];
     s->leafOf[ti] = k;
@@ -315,7 +316,13 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
     v0[k] = make_float4(a[0], a[1], a[2], u2f((uint32_t)ti));
     v1[k] = make_float4(b[0], b[1], b[2], u2f(w1));
     v2[k] = make_float4(c[0], c[1], c[2], u2f((uint32_t)lid));
+    V3 n, ss, ts;
+    triangle_frame(V3(a[0], a[1], a[2]), V3(b[0], b[1], b[2]), V3(c[0], c[1], c[2]), flags != 0, &n, &ss, &ts);
+    vN[k] = make_float4(n.x, n.y, n.z, 0.f);
+    vS[k] = make_float4(ss.x, ss.y, ss.z, 0.f);
+    vT[k] = make_float4(ts.x, ts.y, ts.z, 0.f);
   }
+  CK(s->tvN.upload(vN, st)); CK(s->tvS.upload(vS, st)); CK(s->tvT.upload(vT, st));
   CK(s->tv0.upload(v0, st)); CK(s->tv1.upload(v1, st)); CK(s->tv2.upload(v2, st));
   CK(s->nodes.upload(s->bvh.nodes, st));
 
@@ -364,6 +371,15 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
         float area = 0.5f * length(cross(p1 - p0, p2 - p0));
         Spec p = ((l.two_sided ? 2.f : 1.f) * Spec(l.L[0], l.L[1], l.L[2])) * area * kPi;
         s->lightPower[i] = p.y();
+        // device-side constants of this light (the light_to_world slots are unused by area lights):
+        //   [0..2] Triangle::Sample's normal (Triangle.cpp:371), [3] Area(), [4..6] Triangle::Intersect's normal
+        const bool flip = d->tri_flags && (d->tri_flags[l.tri] & 1);
+        V3 nS = normalize(cross(p1 - p0, p2 - p0));
+        if (flip) nS = nS * -1.f;
+        V3 nI, ss, ts;
+        triangle_frame(p0, p1, p2, flip, &nI, &ss, &ts);
+        l.light_to_world[0] = nS.x; l.light_to_world[1] = nS.y; l.light_to_world[2] = nS.z; l.light_to_world[3] = area;
+        l.light_to_world[4] = nI.x; l.light_to_world[5] = nI.y; l.light_to_world[6] = nI.z;
         l.tri = s->leafOf[l.tri];
         break;
       }
@@ -427,6 +443,7 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   CK(s->dlights.upload(s->lights, st));
 
   s->sc.tv0 = s->tv0.p; s->sc.tv1 = s->tv1.p; s->sc.tv2 = s->tv2.p;
+  s->sc.tvN = s->tvN.p; s->sc.tvS = s->tvS.p; s->sc.tvT = s->tvT.p;
   s->sc.nodes8 = reinterpret_cast<const float4*>(s->nodes.p);
   s->sc.mats = s->mats.p;
   s->sc.lights = s->dlights.p;
@@ -522,6 +539,20 @@ int pbrgpu_sampler_set(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
     perms = host::radical_inverse_permutations(primes);
   }
   CK(s->perms.upload(perms, s->ctx->stream));
+  {  // per-dimension float constants of (Scrambled)RadicalInverseSpecialized (LowDiscrepancy.cpp:214,2303,2314)
+    std::vector<int32_t> primes, sums;
+    host::prime_tables(&primes, &sums);
+    std::vector<float> dc(2 * primes.size());
+    for (size_t i = 0; i < primes.size(); ++i) {
+      const float invBase = (float)1 / (float)primes[i];
+      float tail = 0.f;
+      if ((size_t)sums[i] < perms.size()) tail = invBase * (float)(int)perms[(size_t)sums[i]] / (1 - invBase);
+      dc[2 * i] = invBase;
+      dc[2 * i + 1] = tail;
+    }
+    CK(s->dimConst.upload(dc, s->ctx->stream));
+    hp.dimConst = reinterpret_cast<const float2*>(s->dimConst.p);
+  }
   CK(cudaStreamSynchronize(s->ctx->stream));
   hp.perms = s->perms.p;
   hp.nPerms = (int64_t)perms.size();
@@ -659,6 +690,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       P.ws.qCur = s->qA.p;
       P.ws.qNext = s->qB.p;
       uint32_t g = grid_for(c, nPaths, 8);
+      uint32_t gs = g * (kBlock / kShadeBlock);
       // persistent traversal grid: every SM filled to the kernel's occupancy, never more blocks than rays
       uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths * (pathInteg ? 1 : 1 + raysPerHit) + kTraceBlock - 1) / kTraceBlock,
                                                                       (uint64_t)c->smCount * s->traceBlocksPerSm));
@@ -678,15 +710,16 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         CK(tl.mark(T_SHADE));
         k_classify<<<g, kBlock, 0, st>>>(P);
         // one shading launch per material type PRESENT in the scene
-#define PBR_SHADE(K, M) if (s->hasMat[M]) { K<M><<<g, kBlock, 0, st>>>(P, bounce); launches++; }
+#define PBR_SHADE(M) if (s->hasMat[M]) { k_shade<M><<<gs, kShadeBlock, 0, st>>>(P, bounce); launches++; }
+#define PBR_SHADE_D(M) if (s->hasMat[M]) { k_shade_direct<M><<<g, kBlock, 0, st>>>(P, bounce); launches++; }
         if (pathInteg) {
-          PBR_SHADE(k_shade, PBRGPU_MAT_MATTE) PBR_SHADE(k_shade, PBRGPU_MAT_MIRROR) PBR_SHADE(k_shade, PBRGPU_MAT_GLASS)
-          PBR_SHADE(k_shade, PBRGPU_MAT_METAL) PBR_SHADE(k_shade, PBRGPU_MAT_PLASTIC)
+          PBR_SHADE(PBRGPU_MAT_MATTE) PBR_SHADE(PBRGPU_MAT_MIRROR) PBR_SHADE(PBRGPU_MAT_GLASS)
+          PBR_SHADE(PBRGPU_MAT_METAL) PBR_SHADE(PBRGPU_MAT_PLASTIC)
         } else {
-          PBR_SHADE(k_shade_direct, PBRGPU_MAT_MATTE) PBR_SHADE(k_shade_direct, PBRGPU_MAT_MIRROR)
-          PBR_SHADE(k_shade_direct, PBRGPU_MAT_GLASS) PBR_SHADE(k_shade_direct, PBRGPU_MAT_METAL)
-          PBR_SHADE(k_shade_direct, PBRGPU_MAT_PLASTIC)
+          PBR_SHADE_D(PBRGPU_MAT_MATTE) PBR_SHADE_D(PBRGPU_MAT_MIRROR) PBR_SHADE_D(PBRGPU_MAT_GLASS)
+          PBR_SHADE_D(PBRGPU_MAT_METAL) PBR_SHADE_D(PBRGPU_MAT_PLASTIC)
         }
+#undef PBR_SHADE_D
 #undef PBR_SHADE
         if (!pathInteg || s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce); launches++; }
         k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);

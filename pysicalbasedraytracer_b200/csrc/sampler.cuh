@@ -22,6 +22,8 @@ struct HaltonParams {
   const int32_t* primes;   // Primes[1000]
   const int32_t* primeSums;
   const uint2* primeMagic; // per prime: (m, s) with floor(a / p) == __umulhi(a, m) >> s for every a < 2^31
+  const float2* dimConst;  // per dimension: (invBase = 1/(float)p, tail = invBase * perm[0] / (1 - invBase)), host-computed
+                           // with the same IEEE float operations the reference performs per call
   int64_t nPerms;
   // ---- Sobol' (type == PBRGPU_SAMPLER_SOBOL; host/SobolSampler.h is the CPU twin) ----
   int32_t type;                  // PBRGPU_SAMPLER_HALTON | PBRGPU_SAMPLER_SOBOL
@@ -76,13 +78,21 @@ PBR_D uint64_t reverse_digits(uint64_t a, uint32_t base, uint2 magic, float invB
   uint64_t rev = 0;
   float ibn = 1;
   if ((a >> 31) == 0) {
+    // all digits but the last accumulate in 32 bits (rev < base^(n-1) <= a < 2^31); only the final
+    // rev * base + digit can exceed 32 bits
     uint32_t a32 = (uint32_t)a;
-    while (a32) {
-      uint32_t next = __umulhi(a32, magic.x) >> magic.y;
+    uint32_t rev32 = 0;
+    uint32_t next = __umulhi(a32, magic.x) >> magic.y;
+    while (next) {
       uint32_t digit = a32 - next * base;
-      rev = rev * base + (perm ? (uint32_t)__ldg(perm + digit) : digit);
+      rev32 = rev32 * base + (perm ? (uint32_t)__ldg(perm + digit) : digit);
       ibn *= invBase;
       a32 = next;
+      next = __umulhi(a32, magic.x) >> magic.y;
+    }
+    if (a32) {  // most significant digit (a32 < base)
+      rev = (uint64_t)rev32 * base + (perm ? (uint32_t)__ldg(perm + a32) : a32);
+      ibn *= invBase;
     }
   } else {
     while (a) {
@@ -104,7 +114,7 @@ PBR_D float radical_inverse(int baseIndex, uint64_t a, const HaltonParams& hp) {
   }
   if (baseIndex >= 1024) return 0.f;  // LowDiscrepancy.cpp:2279-2280 (table itself has 1000 primes)
   uint32_t base = (uint32_t)hp.primes[baseIndex];
-  float invBase = (float)1 / (float)base;
+  float invBase = __ldg(hp.dimConst + baseIndex).x;
   float invBaseN;
   uint64_t rev = reverse_digits(a, base, __ldg(hp.primeMagic + baseIndex), invBase, &invBaseN, nullptr);
   return stdmin((float)rev * invBaseN, kOneMinusEpsilon);
@@ -114,12 +124,10 @@ PBR_D float scrambled_radical_inverse(int baseIndex, uint64_t a, const HaltonPar
   if (baseIndex >= 1024) return 0.f;
   uint32_t base = (uint32_t)hp.primes[baseIndex];
   const uint16_t* perm = hp.perms + hp.primeSums[baseIndex];
-  float invBase = (float)1 / (float)base;
+  const float2 dc = __ldg(hp.dimConst + baseIndex);  // invBase, invBase * perm[0] / (1 - invBase)
   float invBaseN;
-  uint64_t rev = reverse_digits(a, base, __ldg(hp.primeMagic + baseIndex), invBase, &invBaseN, perm);
-  // invBaseN * (reversedDigits + invBase * perm[0] / (1 - invBase))
-  float tail = (invBase * (float)(int)perm[0]) / (1 - invBase);
-  return stdmin(invBaseN * ((float)rev + tail), kOneMinusEpsilon);
+  uint64_t rev = reverse_digits(a, base, __ldg(hp.primeMagic + baseIndex), dc.x, &invBaseN, perm);
+  return stdmin(invBaseN * ((float)rev + dc.y), kOneMinusEpsilon);
 }
 
 PBR_D float halton_sample_dimension(int64_t index, int dim, const HaltonParams& hp) {

@@ -17,7 +17,7 @@ namespace pbr {
 struct Isect {
   V3 p, pError, n, ns;  // n = geometric normal (after orientation flip), ns = shading normal
   V3 wo;                // Normalize(-ray.d)  (Interaction ctor normalises)
-  V3 dpdu;
+  V3 ss, ts;            // BSDF shading frame (host-precomputed per triangle)
   int matId, matType, lightId;
 };
 
@@ -41,10 +41,30 @@ PBR_D V3 tri_normal_isect(const TriData& t) {
   return n;
 }
 
-PBR_D void make_isect(const SceneDev& sc, const TriData& t, float b0, float b1, float b2, V3 rayD, Isect* is) {
+PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, float b1, float b2, V3 rayD, Isect* is) {
   const V3 p0 = t.p0, p1 = t.p1, p2 = t.p2;
+  float xAbsSum = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x) + fabsf(b2 * p2.x));
+  float yAbsSum = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y) + fabsf(b2 * p2.y));
+  float zAbsSum = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z) + fabsf(b2 * p2.z));
+  is->pError = gamma_f(7) * V3(xAbsSum, yAbsSum, zAbsSum);
+  is->p = b0 * p0 + b1 * p1 + b2 * p2;
+  const float4 n4 = __ldg(sc.tvN + tri), s4 = __ldg(sc.tvS + tri), t4 = __ldg(sc.tvT + tri);
+  is->n = V3(n4.x, n4.y, n4.z);
+  is->ns = is->n;
+  is->ss = V3(s4.x, s4.y, s4.z);
+  is->ts = V3(t4.x, t4.y, t4.z);
+  is->wo = normalize(-rayD);
+  is->matId = (int)(t.w1 & kTriMatMask);
+  is->matType = (int)((t.w1 >> kTriTypeShift) & 0xf);
+  is->lightId = (int)t.w2;
+}
+
+// Host + device: the per-triangle frame exactly as the reference computes it per hit
+//   n  = Normalize(Cross(p0 - p2, p1 - p2)), flipped by reverseOrientation ^ transformSwapsHandedness  (Triangle.cpp:152,182-184)
+//   dpdu from the default UVs (0,0),(1,0),(1,1)                                                        (Triangle.cpp:147-160, Triangle.h:50-54)
+//   ss = Normalize(dpdu), ts = Cross(ns, ss)                                                          (Reflection.h:105-110)
+PBR_HD void triangle_frame(V3 p0, V3 p1, V3 p2, bool flip, V3* n, V3* ss, V3* ts) {
   V3 dp02 = p0 - p2, dp12 = p1 - p2;
-  // default UVs (0,0),(1,0),(1,1) (Triangle.h:50-54): duv02 = (-1,-1), duv12 = (0,-1), determinant = 1
   const float duv02x = 0.f - 1.f, duv02y = 0.f - 1.f, duv12x = 1.f - 1.f, duv12y = 0.f - 1.f;
   float determinant = duv02x * duv12y - duv02y * duv12x;
   V3 dpdu;
@@ -52,20 +72,11 @@ PBR_D void make_isect(const SceneDev& sc, const TriData& t, float b0, float b1, 
     float invdet = 1 / determinant;
     dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
   }
-  float xAbsSum = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x) + fabsf(b2 * p2.x));
-  float yAbsSum = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y) + fabsf(b2 * p2.y));
-  float zAbsSum = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z) + fabsf(b2 * p2.z));
-  is->pError = gamma_f(7) * V3(xAbsSum, yAbsSum, zAbsSum);
-  is->p = b0 * p0 + b1 * p1 + b2 * p2;
-  V3 n = normalize(cross(dp02, dp12));
-  if ((t.w1 >> kTriFlagShift) & kTriFlagFlipNormal) n = -n;
-  is->n = n;
-  is->ns = n;
-  is->dpdu = dpdu;
-  is->wo = normalize(-rayD);
-  is->matId = (int)(t.w1 & kTriMatMask);
-  is->matType = (int)((t.w1 >> kTriTypeShift) & 0xf);
-  is->lightId = (int)t.w2;
+  V3 nn = normalize(cross(dp02, dp12));
+  if (flip) nn = -nn;
+  *n = nn;
+  *ss = normalize(dpdu);
+  *ts = cross(nn, *ss);
 }
 
 // DiffuseAreaLight::L (DiffuseLight.h:17-19)
@@ -88,8 +99,8 @@ PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobe
   b->eta = 1.f;
   b->ns = is.ns;
   b->ng = is.n;
-  b->ss = normalize(is.dpdu);
-  b->ts = cross(b->ns, b->ss);
+  b->ss = is.ss;
+  b->ts = is.ts;
   b->n = 0;
   switch (MAT) {  // == m.type: the shading queues are sorted by material type
     case PBRGPU_MAT_MATTE: {
@@ -265,11 +276,12 @@ PBR_D void sample_area_light(const SceneDev& sc, const pbrgpu_light& l, V3 refP,
   float b0 = 1 - su0, b1 = u1 * su0;
   float b2 = 1 - b0 - b1;
   V3 p = b0 * t.p0 + b1 * t.p1 + b2 * t.p2;
-  V3 n = normalize(cross(t.p1 - t.p0, t.p2 - t.p0));
-  if ((t.w1 >> kTriFlagShift) & kTriFlagFlipNormal) n = n * -1.f;
+  // n = Normalize(Cross(p1 - p0, p2 - p0)) (orientation flip applied) and Area() of Triangle::Sample
+  // (Triangle.cpp:352-387) are per-light constants, precomputed on the host into the light record
+  V3 n(l.light_to_world[0], l.light_to_world[1], l.light_to_world[2]);
   V3 pAbsSum = vabs(b0 * t.p0) + vabs(b1 * t.p1) + vabs(b2 * t.p2);
   ls->pErr1 = gamma_f(6) * pAbsSum;
-  float area = 0.5f * length(cross(t.p1 - t.p0, t.p2 - t.p0));
+  float area = l.light_to_world[3];
   float pdf = 1 / area;
   V3 wi = p - refP;
   if (length_sq(wi) == 0) pdf = 0;
@@ -292,8 +304,8 @@ PBR_D float area_light_pdf(const SceneDev& sc, const pbrgpu_light& l, V3 rayO, V
   float th, b0, b1, b2;
   if (!intersect_triangle(rp, kInfinity, t.p0, t.p1, t.p2, &th, &b0, &b1, &b2)) return 0;
   V3 pl = b0 * t.p0 + b1 * t.p1 + b2 * t.p2;
-  V3 nl = tri_normal_isect(t);
-  float area = 0.5f * length(cross(t.p1 - t.p0, t.p2 - t.p0));
+  V3 nl(l.light_to_world[4], l.light_to_world[5], l.light_to_world[6]);  // Triangle::Intersect's normal of the light
+  float area = l.light_to_world[3];
   float pdf = dist_sq(refP, pl) / (absdot(nl, -wi) * area);
   if (isinf(pdf)) pdf = 0.f;
   return pdf;
