@@ -122,7 +122,7 @@ constexpr int kTriQueue = 6;
 #define PBR_TRACE_MIN_BLOCKS 8
 #endif
 #ifndef PBR_SHADE_MIN_BLOCKS
-#define PBR_SHADE_MIN_BLOCKS 5
+#define PBR_SHADE_MIN_BLOCKS 6
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   unsigned nodes = 0, tris = 0;
   while (true) {
     // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
+    // (a per-warp reserve of 128 rays per atomicAdd was measured: no faster - the cursor is not a bottleneck)
     const unsigned idle = __ballot_sync(full, !busy);
     if (idle != 0u && !exhausted && (idle == full || __popc(idle) >= P.fetchMinIdle)) {
       const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
@@ -223,35 +224,67 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   }
 }
 
-// Bin the live paths by the material type of what they hit (material-sorted shading queues).
+// Bin the live paths by the material type of what they hit (material-sorted shading queues).  Each block
+// bins a tile of kClassifyTile entries: per-queue counts in shared memory, ONE global atomicAdd per
+// (block, queue), then scattered writes - three orders of magnitude fewer same-address atomics than one
+// per warp.  (The order of entries inside a queue does not influence any result: per-path state only.)
+constexpr int kClassifyItems = 8;
+constexpr int kClassifyTile = kBlock * kClassifyItems;
+
 __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ RenderParams P) {
+  __shared__ uint32_t cnt[kNumQueues], basePos[kNumQueues];
   const uint32_t n = P.ws.ctr->nCur;
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // the shadow / MIS queues of the previous bounce are consumed
     P.ws.ctr->nShadow = 0;
     P.ws.ctr->nMis = 0;
     P.ws.ctr->cursor[0] = 0;
   }
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    bool active = i < n;
-    int q = -1;
-    uint32_t slot = 0;
-    if (active) {
-      slot = P.ws.qCur[i];
-      q = (int)P.ws.qType[i];
-    }
+  for (uint32_t tile = blockIdx.x * kClassifyTile; tile < n; tile += gridDim.x * kClassifyTile) {
+    if (threadIdx.x < kNumQueues) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t slot[kClassifyItems], rank[kClassifyItems];
+    int q[kClassifyItems];
 #pragma unroll
-    for (int k = 0; k < kNumQueues; ++k) {
-      bool mine = active && q == k;
-      uint32_t pos = queue_push(&P.ws.ctr->nMat[k], mine);
-      if (mine) P.ws.qMat[(size_t)k * P.ws.capacity + pos] = slot;
+    for (int k = 0; k < kClassifyItems; ++k) {
+      const uint32_t i = tile + k * kBlock + threadIdx.x;
+      q[k] = -1;
+      if (i < n) {
+        slot[k] = P.ws.qCur[i];
+        q[k] = (int)P.ws.qType[i];
+        rank[k] = atomicAdd(&cnt[q[k]], 1u);  // shared-memory atomic: rank inside this block's tile
+      }
     }
+    __syncthreads();
+    if (threadIdx.x < kNumQueues) basePos[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&P.ws.ctr->nMat[threadIdx.x], cnt[threadIdx.x]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kClassifyItems; ++k)
+      if (q[k] >= 0) P.ws.qMat[(size_t)q[k] * P.ws.capacity + basePos[q[k]] + rank[k]] = slot[k];
+    __syncthreads();
   }
+}
+
+// Block-aggregated queue append for the shading kernels: every thread of the block calls it (uniform
+// control flow); one global atomicAdd per block per call.
+template <int BLOCK>
+PBR_D uint32_t block_queue_push(uint32_t* counter, bool active, uint32_t* sCount, uint32_t* sBase) {
+  if (threadIdx.x == 0) *sCount = 0;
+  __syncthreads();
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  const int lane = threadIdx.x & 31;
+  uint32_t warpBase = 0;
+  if (lane == 0 && mask) warpBase = atomicAdd(sCount, (uint32_t)__popc(mask));
+  warpBase = __shfl_sync(0xffffffffu, warpBase, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) *sBase = *sCount ? atomicAdd(counter, *sCount) : 0u;
+  __syncthreads();
+  return *sBase + warpBase + __popc(mask & ((1u << lane) - 1u));
 }
 
 // K4/K5/K7: shading for one material queue.
 template <int MAT>
 __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderParams P, int bounce) {
+  __shared__ uint32_t sCount, sBase;
   const uint32_t n = P.ws.ctr->nMat[MAT];
   const SceneDev& sc = P.sc;
   const uint32_t* queue = P.ws.qMat + (size_t)MAT * P.ws.capacity;
@@ -377,11 +410,11 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
         P.ws.L[slot] = make_float4(L.x + Ladd.r, L.y + Ladd.g, L.z + Ladd.b, 0.f);
       }
     }
-    uint32_t pos = queue_push(&P.ws.ctr->nShadow, pushShadow);
+    uint32_t pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nShadow, pushShadow, &sCount, &sBase);
     if (pushShadow) { P.ws.shO[pos] = shO; P.ws.shD[pos] = shD; P.ws.shC[pos] = shC; }
-    pos = queue_push(&P.ws.ctr->nMis, pushMis);
+    pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nMis, pushMis, &sCount, &sBase);
     if (pushMis) { P.ws.miO[pos] = miO; P.ws.miD[pos] = miD; P.ws.miC[pos] = miC; }
-    pos = queue_push(&P.ws.ctr->nNext, pushNext);
+    pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nNext, pushNext, &sCount, &sBase);
     if (pushNext) P.ws.qNext[pos] = slot;
   }
 }

@@ -433,9 +433,47 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
       s->sc.env.condFunc = s->condFunc.p; s->sc.env.condCdf = s->condCdf.p; s->sc.env.condInt = s->condInt.p;
       s->sc.env.margFunc = s->margFunc.p; s->sc.env.margCdf = s->margCdf.p;
       s->sc.env.margInt = marg.funcInt;
-      // Power (InfiniteAreaLight.cpp:63-67) needs Lookup(st, .5f) on the MIP pyramid; only the "power"
-      // light strategy with >1 light reads it.  Approximated by the mean texel * pi * r^2 * 4pi... see render().
-      s->lightPower[envUser] = -1.f;  // marks "needs pyramid"
+      // Power() (InfiniteAreaLight.cpp:63-67) = 4pi * pi * r^2 * Lmap->Lookup((.5,.5), .5f): a trilinear lookup, so
+      // the MIP pyramid (MIPMap.h:146-168: 2x2 box filter per level) is rebuilt here, host-side, once.
+      {
+        std::vector<std::vector<float>> pyr;
+        std::vector<int> pw, ph;
+        pyr.push_back(tex); pw.push_back(W); ph.push_back(H);
+        int nLevels = 1;
+        for (int m = std::max(W, H); m > 1; m >>= 1) ++nLevels;
+        for (int i = 1; i < nLevels; ++i) {
+          int sRes = std::max(1, pw[i - 1] / 2), tRes = std::max(1, ph[i - 1] / 2);
+          std::vector<float> lv((size_t)sRes * tRes * 3);
+          const std::vector<float>& pr = pyr[i - 1];
+          const int w0 = pw[i - 1], h0 = ph[i - 1];
+          auto texel = [&](int a, int b, int c) { return pr[3 * ((size_t)mod_i(b, h0) * w0 + mod_i(a, w0)) + c]; };
+          for (int t = 0; t < tRes; ++t)
+            for (int u = 0; u < sRes; ++u)
+              for (int c = 0; c < 3; ++c)
+                lv[3 * ((size_t)t * sRes + u) + c] =
+                    .25f * (((texel(2 * u, 2 * t, c) + texel(2 * u + 1, 2 * t, c)) + texel(2 * u, 2 * t + 1, c)) + texel(2 * u + 1, 2 * t + 1, c));
+          pyr.push_back(std::move(lv)); pw.push_back(sRes); ph.push_back(tRes);
+        }
+        auto tri = [&](int level, float out[3]) {  // MIPMap::triangle(level, (.5,.5))
+          level = std::max(0, std::min(nLevels - 1, level));
+          env_bilinear_host(pyr[level], pw[level], ph[level], .5f, .5f, out);
+        };
+        const float invLog2 = 1.442695040888963387004650940071f;
+        float level = nLevels - 1 + std::log(std::max(.5f, (float)1e-8)) * invLog2;  // MIPMap::Lookup(st, width = .5f)
+        float rgb[3];
+        if (level < 0) tri(0, rgb);
+        else if (level >= nLevels - 1) { for (int c = 0; c < 3; ++c) rgb[c] = pyr[nLevels - 1][c]; }
+        else {
+          int iLevel = (int)std::floor(level);
+          float delta = level - iLevel, a[3], b[3];
+          tri(iLevel, a); tri(iLevel + 1, b);
+          for (int c = 0; c < 3; ++c) rgb[c] = (1 - delta) * a[c] + delta * b[c];
+        }
+        const float r = s->sc.worldRadius;
+        const float k = (4 * kPi) * kPi * r * r;
+        Spec pwr = k * Spec(rgb[0], rgb[1], rgb[2]);
+        s->lightPower[envUser] = pwr.y();
+      }
     }
     CK(s->envTexels.upload(tex, st));
     s->sc.env.texels = s->envTexels.p;
@@ -630,9 +668,6 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
     if (const char* e = getenv("PBRGPU_FETCH_MIN_IDLE")) s->fetchMinIdle = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("PBRGPU_WAVE_LOG2")) s->waveLog2 = std::max(14, std::min(25, atoi(e)));
   }
-  if (rd->light_strategy == PBRGPU_LIGHTSTRATEGY_POWER && s->lights.size() > 1)
-    for (float p : s->lightPower)
-      if (p < 0) return fail("pbrgpu_render: \"power\" light strategy with an InfiniteAreaLight is not supported (needs the MIP pyramid)");
 
   const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
   const int64_t nS = rd->s1 - rd->s0;
@@ -691,6 +726,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       P.ws.qNext = s->qB.p;
       uint32_t g = grid_for(c, nPaths, 8);
       uint32_t gs = g * (kBlock / kShadeBlock);
+      uint32_t gc = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths + kClassifyTile - 1) / kClassifyTile, (uint64_t)c->smCount * 8));
       // persistent traversal grid: every SM filled to the kernel's occupancy, never more blocks than rays
       uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths * (pathInteg ? 1 : 1 + raysPerHit) + kTraceBlock - 1) / kTraceBlock,
                                                                       (uint64_t)c->smCount * s->traceBlocksPerSm));
@@ -708,7 +744,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         CK(tl.mark(T_MIS));
         if (bounce > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
         CK(tl.mark(T_SHADE));
-        k_classify<<<g, kBlock, 0, st>>>(P);
+        k_classify<<<gc, kBlock, 0, st>>>(P);
         // one shading launch per material type PRESENT in the scene
 #define PBR_SHADE(M) if (s->hasMat[M]) { k_shade<M><<<gs, kShadeBlock, 0, st>>>(P, bounce); launches++; }
 #define PBR_SHADE_D(M) if (s->hasMat[M]) { k_shade_direct<M><<<g, kBlock, 0, st>>>(P, bounce); launches++; }

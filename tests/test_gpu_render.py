@@ -177,3 +177,13 @@ def test_sobol_path_render_vs_reference_with_cpu_twin(api, ref, gpu_ctx):
              sampler_type=A.SAMPLER_SOBOL)
     _direct_check(p, ref, max_depth=1, spp=4, rr_threshold=0.8)
     _direct_check(p, ref, max_depth=5, spp=4, frac_ok=0.97, rr_threshold=0.8)
+
+
+def test_power_strategy_with_infinite_light(api, ref, gpu_ctx):
+    """PowerLightDistribution with an InfiniteAreaLight among several lights: Power() needs the trilinear MIP lookup
+    (InfiniteAreaLight.cpp:63-67), rebuilt on the host; SkyBoxLight::Power() is 0 and is never picked."""
+    env = scenes.procedural_env(64, 32, sun=30.0)
+    data = scenes.bsdf_stress(sphere_tess=8, env=env)
+    data.add_point_light([0.0, 4.0, 0.0], [40.0, 40.0, 40.0])
+    p = Pair(api, ref, data, 64, 48, 2, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
+    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.99, light_strategy=A.LIGHTSTRATEGY_POWER)
