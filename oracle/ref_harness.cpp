@@ -275,6 +275,23 @@ void* ref_camera_create(int type, int W, int H, const float eye[3], const float 
   else rc->cam.reset(CreateOrthographicCamera(W, H, c2w, nullptr));
   return rc;
 }
+// thin-lens variant: the factories fix lensRadius = 0 (Perspective.cpp:84-104), the class itself supports a lens
+void* ref_camera_create_lens(int type, int W, int H, const float eye[3], const float look[3], const float up[3], float lensRadius,
+                             float focalDistance) {
+  Transform c2w = Inverse(LookAt(Point3f(eye[0], eye[1], eye[2]), Point3f(look[0], look[1], look[2]), Vector3f(up[0], up[1], up[2])));
+  float frame = (float)W / (float)H;
+  Bounds2f screen;
+  if (frame > 1.f) { screen.pMin.x = -frame; screen.pMax.x = frame; screen.pMin.y = -1.f; screen.pMax.y = 1.f; }
+  else { screen.pMin.x = -1.f; screen.pMax.x = 1.f; screen.pMin.y = -1.f / frame; screen.pMax.y = 1.f / frame; }
+  auto* rc = new RefCamera;
+  rc->W = W; rc->H = H; rc->type = type;
+  if (type == PBRGPU_CAMERA_PERSPECTIVE) rc->cam.reset(new PerspectiveCamera(W, H, c2w, screen, lensRadius, focalDistance, 90.0f, nullptr));
+  else {
+    screen.pMin.x *= 2.f; screen.pMax.x *= 2.f; screen.pMin.y *= 2.f; screen.pMax.y *= 2.f;
+    rc->cam.reset(new OrthographicCamera(W, H, c2w, screen, lensRadius, focalDistance, nullptr));
+  }
+  return rc;
+}
 void ref_camera_destroy(void* h) { delete (RefCamera*)h; }
 void ref_camera_desc(void* h, pbrgpu_camera_desc* out) {
   auto* rc = (RefCamera*)h;

@@ -38,6 +38,9 @@ def lib():
         L.ref_camera_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                         C.POINTER(C.c_float)]
         L.ref_camera_destroy.argtypes = [C.c_void_p]
+        L.ref_camera_create_lens.restype = C.c_void_p
+        L.ref_camera_create_lens.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                             C.POINTER(C.c_float), C.c_float, C.c_float]
         L.ref_camera_desc.argtypes = [C.c_void_p, C.POINTER(A.CameraDesc)]
         L.ref_sampler_create.restype = C.c_void_p
         L.ref_sampler_create.argtypes = [C.c_int] * 5
@@ -105,8 +108,11 @@ class RefScene:
 
 
 class RefCamera:
-    def __init__(self, cam_type, W, H, eye, look, up):
-        self.h = lib().ref_camera_create(cam_type, W, H, _f3(eye), _f3(look), _f3(up))
+    def __init__(self, cam_type, W, H, eye, look, up, lens_radius=0.0, focal_distance=0.0):
+        if lens_radius > 0:
+            self.h = lib().ref_camera_create_lens(cam_type, W, H, _f3(eye), _f3(look), _f3(up), lens_radius, focal_distance)
+        else:
+            self.h = lib().ref_camera_create(cam_type, W, H, _f3(eye), _f3(look), _f3(up))
         self.W, self.H = W, H
 
     def desc(self):

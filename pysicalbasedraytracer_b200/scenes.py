@@ -52,6 +52,7 @@ class SceneData:
         self.materials = []
         self.lights = []
         self.env = None  # (H, W, 3) float32
+        self.tri_flags = None  # optional uint8[n_tris]: bit0 = reverseOrientation ^ transformSwapsHandedness
         self._nverts = 0
         self._ntris = 0
         self._frozen = None
@@ -145,6 +146,11 @@ class SceneData:
         d.materials = mats
         d.lights = lights
         keep = [fz, mats, lights]
+        if self.tri_flags is not None:
+            fl = np.ascontiguousarray(self.tri_flags, dtype=np.uint8)
+            assert fl.shape[0] == d.n_tris
+            d.tri_flags = fl.ctypes.data_as(C.POINTER(C.c_uint8))
+            keep.append(fl)
         if self.env is not None:
             d.env_height, d.env_width = self.env.shape[0], self.env.shape[1]
             d.env_texels = self.env.ctypes.data_as(C.POINTER(C.c_float))

@@ -187,3 +187,37 @@ def test_power_strategy_with_infinite_light(api, ref, gpu_ctx):
     data.add_point_light([0.0, 4.0, 0.0], [40.0, 40.0, 40.0])
     p = Pair(api, ref, data, 64, 48, 2, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
     _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.99, light_strategy=A.LIGHTSTRATEGY_POWER)
+
+
+def test_oren_nayar_two_sided_light_and_reversed_orientation(api, ref, gpu_ctx):
+    """Less-travelled branches of the path: OrenNayar (Matte sigma > 0, MatteMaterial.cpp:22-26), a two-sided
+    DiffuseAreaLight, and triangles created with reverseOrientation (normal flip, Triangle.cpp:184,374-375)."""
+    s = scenes.SceneData()
+    rough = s.add_material(scenes.matte([0.7, 0.6, 0.5], sigma=25.0))
+    white = s.add_material(scenes.matte([0.8, 0.8, 0.8]))
+    scenes.cornell_walls(s, rough, rough, white)
+    # a two-sided emitter floating in the box, facing sideways
+    P = np.array([[0.0, -0.5, -0.8], [0.0, -0.5, 0.8], [0.0, 1.0, 0.8], [0.0, 1.0, -0.8]], dtype=np.float32)
+    s.add_mesh(P, np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32), white, emit=[4.0, 3.5, 3.0], two_sided=True)
+    v, t = scenes.uv_sphere([-1.3, -1.5, 0.2], 0.8, 12, 24)
+    s.add_mesh(v, t, rough)
+    flags = np.zeros(s.n_tris, dtype=np.uint8)
+    flags[-t.shape[0]:] = 1          # sphere triangles: reverseOrientation
+    flags[0:2] = 1                   # floor too
+    s.tri_flags = flags
+    p = Pair(api, ref, s, 96, 96, 2, eye=(0.4, 0.3, 5.0), look=(0.0, -0.3, 0.0))
+    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.998)
+    _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.97, rr_threshold=0.8)
+
+
+def test_thin_lens_and_orthographic_cameras(api, ref, gpu_ctx):
+    """lensRadius > 0 (ConcentricSampleDisk on camera dims 3,4: Perspective.cpp:51-58) and the orthographic camera."""
+    data = scenes.cornell(sphere_tess=12)
+    p = Pair(api, ref, data, 80, 80, 4, eye=(0.2, 0.1, 5.0), look=(0.0, -0.2, 0.0), lens_radius=0.08, focal_distance=5.5)
+    want = ref.primary_rays(p.rcam, p.rsmp, (10, 10, 20, 12), 0, 4)
+    got = p.scene.dump_primary_rays((10, 10, 20, 12), 0, 4)
+    # cosf/sinf of the lens disk differ from glibc by ulps: rays agree to 1e-6, not bit for bit
+    np.testing.assert_allclose(got[..., [0, 1, 2, 4, 5, 6]], want[..., [0, 1, 2, 4, 5, 6]], rtol=0, atol=2e-6)
+    _direct_check(p, ref, max_depth=1, spp=4, frac_ok=0.99)
+    po = Pair(api, ref, data, 64, 64, 2, eye=(0.0, 0.0, 4.0), cam_type=A.CAMERA_ORTHOGRAPHIC)
+    _direct_check(po, ref, max_depth=2, spp=2, frac_ok=0.995)

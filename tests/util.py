@@ -9,10 +9,11 @@ EYE, LOOK, UP = (0.0, 0.0, 5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)
 
 class Pair:
     def __init__(self, api, R, data, W, H, spp, eye=EYE, look=LOOK, up=UP, cam_type=A.CAMERA_PERSPECTIVE, ctx=None,
-                 sampler_type=A.SAMPLER_HALTON):
+                 sampler_type=A.SAMPLER_HALTON, lens_radius=0.0, focal_distance=0.0):
         self.W, self.H, self.spp = W, H, spp
         c2w = api.Inverse(api.LookAt(eye, look, up))
         self.cam = (api.CreatePerspectiveCamera if cam_type == A.CAMERA_PERSPECTIVE else api.CreateOrthographicCamera)(W, H, c2w)
+        self.cam.lens_radius, self.cam.focal_distance = lens_radius, focal_distance
         self.sampler_type = sampler_type
         if sampler_type == A.SAMPLER_SOBOL:
             # the Sobol tables are the reference's data: fetched from the compiled reference
@@ -25,7 +26,7 @@ class Pair:
         self.R = R
         if R is not None:
             self.rscene = R.RefScene(data)
-            self.rcam = R.RefCamera(cam_type, W, H, eye, look, up)
+            self.rcam = R.RefCamera(cam_type, W, H, eye, look, up, lens_radius, focal_distance)
             self.rsmp = R.RefSampler(spp, (0, 0, W, H), sampler_type)
 
 
