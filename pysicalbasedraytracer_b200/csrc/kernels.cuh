@@ -177,6 +177,14 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         if (T.tgroup.y == 0u || nt < kTriQueue) {
           if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }
           cw_node_step(P.sc.nodes8, T, sstack, S);
+#if PBR_TRACE_PREFETCH
+          if (T.tgroup.y != 0u) {  // first candidate triangle of the group this step produced
+            const int ti = (int)T.tgroup.x + (31 - __clz(T.tgroup.y));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv0 + ti));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv1 + ti));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv2 + ti));
+          }
+#endif
           if (COUNT) nodes++;
           didNode = true;
         }

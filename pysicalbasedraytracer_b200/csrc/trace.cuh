@@ -13,18 +13,24 @@ namespace pbr {
 // recomputes these per triangle from the same inputs (Triangle.cpp:74-86) - same values.
 struct RayPrep {
   V3 o;
-  int kx, ky, kz;
+  int kz;  // (kx, ky, kz) is the cyclic rotation of (0, 1, 2) that ends in kz
   float Sx, Sy, Sz;
 };
+
+// Permute(v, kx, ky, kz) (Geometry.h) for the cyclic (kx, ky, kz): two selects per component instead of a
+// run-time indexed component fetch (which cost ~10 % of the traversal kernel's instructions)
+PBR_D V3 permute_cyclic(V3 v, int kz) {
+  return kz == 2 ? v : (kz == 0 ? V3(v.y, v.z, v.x) : V3(v.z, v.x, v.y));
+}
 
 PBR_D RayPrep prep_ray(V3 o, V3 d) {
   RayPrep rp;
   rp.o = o;
   int kz = max_dimension(vabs(d));
-  int kx = kz + 1; if (kx == 3) kx = 0;
-  int ky = kx + 1; if (ky == 3) ky = 0;
-  float dx = d[kx], dy = d[ky], dz = d[kz];
-  rp.kx = kx; rp.ky = ky; rp.kz = kz;
+  // kx = kz + 1 (mod 3), ky = kx + 1 (mod 3)   (Triangle.cpp:74-78)
+  V3 dp = permute_cyclic(d, kz);
+  float dx = dp.x, dy = dp.y, dz = dp.z;
+  rp.kz = kz;
   rp.Sx = -dx / dz;
   rp.Sy = -dy / dz;
   rp.Sz = 1.f / dz;
@@ -35,9 +41,9 @@ PBR_D RayPrep prep_ray(V3 o, V3 d) {
 PBR_D bool intersect_triangle(const RayPrep& rp, float tMax, V3 p0, V3 p1, V3 p2, float* tOut, float* b0Out,
                               float* b1Out, float* b2Out) {
   V3 q0 = p0 - rp.o, q1 = p1 - rp.o, q2 = p2 - rp.o;
-  V3 p0t(q0[rp.kx], q0[rp.ky], q0[rp.kz]);
-  V3 p1t(q1[rp.kx], q1[rp.ky], q1[rp.kz]);
-  V3 p2t(q2[rp.kx], q2[rp.ky], q2[rp.kz]);
+  V3 p0t = permute_cyclic(q0, rp.kz);
+  V3 p1t = permute_cyclic(q1, rp.kz);
+  V3 p2t = permute_cyclic(q2, rp.kz);
   p0t.x += rp.Sx * p0t.z;
   p0t.y += rp.Sy * p0t.z;
   p1t.x += rp.Sx * p1t.z;
@@ -103,6 +109,9 @@ PBR_D V3 ld3(const float4* p, int i) {
 // (and postponed triangle groups); its first kSmemStack levels live in shared memory, one column per
 // lane ([level][lane] -> conflict-free), deeper levels spill to a small local array.
 // ---------------------------------------------------------------------------------------------
+#ifndef PBR_TRACE_PREFETCH
+#define PBR_TRACE_PREFETCH 0
+#endif
 constexpr int kSmemStack = 12;
 constexpr int kLocalStack = 36;
 
@@ -212,6 +221,17 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
   }
   T.ngroup.y = (hitmask & 0xFF000000u) | (ei >> 24);
   T.tgroup.y = hitmask & 0x00FFFFFFu;
+#if PBR_TRACE_PREFETCH
+  // The next node and the first candidate triangle are known now; their loads are issued one loop
+  // iteration later (after the triangle round).  Prefetch them into L1 so that those loads hit.
+  if (T.ngroup.y > 0x00FFFFFFu) {
+    const int nb = 31 - __clz(T.ngroup.y);
+    const unsigned ns = (unsigned)(nb - 24) ^ (T.octinv4 & 0xffu);
+    const float4* nn = nodes + 5 * (size_t)(T.ngroup.x + __popc(T.ngroup.y & ~(0xFFFFFFFFu << ns)));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(nn));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(nn + 4));
+  }
+#endif
 }
 
 // One triangle of the triangle group: the reference's watertight test, bit-exact (t, b0, b1, b2).

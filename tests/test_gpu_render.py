@@ -221,3 +221,20 @@ def test_thin_lens_and_orthographic_cameras(api, ref, gpu_ctx):
     _direct_check(p, ref, max_depth=1, spp=4, frac_ok=0.99)
     po = Pair(api, ref, data, 64, 64, 2, eye=(0.0, 0.0, 4.0), cam_type=A.CAMERA_ORTHOGRAPHIC)
     _direct_check(po, ref, max_depth=2, spp=2, frac_ok=0.995)
+
+
+def test_progressive_film_checkpoint_resume(api, gpu_ctx, tmp_path):
+    """accumulator + next sample index is the whole state; resume == one-shot, bit for bit."""
+    from pysicalbasedraytracer_b200.film import ProgressiveFilm
+    p = Pair(api, None, scenes.cornell(sphere_tess=8), 64, 64, 8)
+    kw = dict(integrator=A.INTEGRATOR_PATH, max_depth=4, rr_threshold=0.8)
+    whole, _, _ = p.scene.render(s0=0, s1=8, **kw)
+    f1 = ProgressiveFilm(p.scene, 64, 64, **kw).render(3)
+    f1.save(tmp_path / "ckpt.npz")
+    f2 = ProgressiveFilm(p.scene, 64, 64, **kw).load(tmp_path / "ckpt.npz")
+    assert f2.next_sample == 3
+    f2.render(2).render(3)
+    sd = f2.state_dict()
+    assert np.array_equal(sd["accum"][..., :3], whole)
+    assert np.all(sd["accum"][..., 3] == 8)
+    np.testing.assert_allclose(f2.mean(), whole / 8, rtol=1e-6)
