@@ -208,13 +208,16 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
     const unsigned nx = px ? lox : hix, fx = px ? hix : lox;
     const unsigned ny = py ? loy : hiy, fy = py ? hiy : loy;
     const unsigned nz = pz ? loz : hiz, fz = pz ? hiz : loz;
+    // branch-free mask update: (hit ? childBits : 0) << bitIndex, bytes extracted with one PRMT each
 #define PBR_CW_CHILD(J)                                                                               \
     {                                                                                                 \
       const float tn = fmaxf(fmaxf(fmaf(q2f<J>(nx), Ax, Bnx), fmaf(q2f<J>(ny), Ay, Bny)),             \
                              fmaxf(fmaf(q2f<J>(nz), Az, Bnz), 0.f));                                  \
       const float tf = fminf(fminf(fmaf(q2f<J>(fx), Ax, Bfx), fmaf(q2f<J>(fy), Ay, Bfy)),             \
                              fminf(fmaf(q2f<J>(fz), Az, Bfz), T.tMax));                               \
-      if (tn <= tf) hitmask |= ((childBits4 >> (8 * J)) & 0xffu) << ((bitIndex4 >> (8 * J)) & 0xffu); \
+      const unsigned cb = __byte_perm(childBits4, 0u, 0x4440u | J);                                   \
+      const unsigned bi = __byte_perm(bitIndex4, 0u, 0x4440u | J);                                    \
+      hitmask |= (tn <= tf ? cb : 0u) << bi;                                                          \
     }
     PBR_CW_CHILD(0) PBR_CW_CHILD(1) PBR_CW_CHILD(2) PBR_CW_CHILD(3)
 #undef PBR_CW_CHILD
