@@ -51,6 +51,7 @@ struct SceneDev {
   const pbrgpu_material* mats;  // roughness fields already remapped to alpha on the host (glibc logf)
   const pbrgpu_light* lights;   // AREA_TRI: .tri = LEAF-ORDER triangle index
   int nTris, nLights, nInfinite;
+  unsigned f32one;              // 0x3F800000 (opaque to ptxas: keeps the PRMT selector an immediate, trace.cuh q2f)
   int infinite[4];              // indices of infinite lights (Scene::infiniteLights)
   const float* lightFunc;       // Distribution1D of the active light-sampling strategy
   const float* lightCdf;

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
           if (i < nPath) { mode = TRACE_PATH; qi = i; ray = P.ws.qCur[i]; ro = P.ws.rayO[ray]; rd = P.ws.rayD[ray]; }
           else if (i < nPath + nShadow) { mode = TRACE_SHADOW; ray = i - nPath; ro = P.ws.shO[ray]; rd = P.ws.shD[ray]; }
           else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
-          trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w);
+          trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, P.sc.f32one);
           nt = 0;
           busy = true;
         }

@@ -486,6 +486,7 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   s->sc.mats = s->mats.p;
   s->sc.lights = s->dlights.p;
   s->sc.nTris = nT;
+  s->sc.f32one = 0x3F800000u;
   s->sc.nLights = d->n_lights;
 
   // sampler tables

@@ -120,6 +120,7 @@ struct Trav {
   float idx, idy, idz;        // reciprocal direction (|d| clamped away from 0)
   float jdx, jdy, jdz;        // 32768 * reciprocal direction
   unsigned octinv4;           // inverse octant replicated in 4 bytes
+  unsigned f32one;            // 0x3F800000, from RenderParams::f32one (see q2f)
   RayPrep rp;
   float tMax;
   uint2 ngroup, tgroup;
@@ -138,8 +139,9 @@ PBR_D float safe_rcp(float d) {
   return d < 0.f ? -r : r;
 }
 
-PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax) {
+PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax, unsigned f32one) {
   T.o = o;
+  T.f32one = f32one;
   T.idx = safe_rcp(d.x); T.idy = safe_rcp(d.y); T.idz = safe_rcp(d.z);
   T.jdx = T.idx * 32768.f; T.jdy = T.idy * 32768.f; T.jdz = T.idz * 32768.f;
   T.octinv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
@@ -164,9 +166,11 @@ PBR_D uint2 trav_pop(Trav& T, const uint2* sstack, const TravSpill& S) {
   return (T.sp < kSmemStack) ? sstack[T.sp * 32] : S.lstack[T.sp - kSmemStack];
 }
 
-// byte J of `w` -> float in [1,2): 1 + byte / 32768   (one PRMT, no int->float conversion)
+// byte J of `w` -> float in [1,2): 1 + byte / 32768   (one PRMT, no int->float conversion).  `one` holds
+// 0x3F800000 in a REGISTER (made opaque by the caller): PRMT takes one immediate, and with the constant as
+// the immediate ptxas re-materialised the selector in a register before almost every PRMT.
 template <int J>
-PBR_D float q2f(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (J << 4))); }
+PBR_D float q2f(unsigned w, unsigned one) { return __uint_as_float(__byte_perm(w, one, 0x7604u | (J << 4))); }
 
 // One node step: pick the next inner child of the node group (front-to-back by octant), fetch its
 // 80-byte node with five 16-byte loads, slab-test the 8 quantised child boxes, emit a new node group
@@ -195,6 +199,7 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
   const float Bnz = (Bz - Az) - ez, Bfz = (Bz - Az) + ez;
   const bool px = T.idx >= 0.f, py = T.idy >= 0.f, pz = T.idz >= 0.f;
   unsigned hitmask = 0;
+  const unsigned one = T.f32one;  // 0x3F800000 read from a kernel parameter, so ptxas cannot fold it (see q2f)
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const unsigned meta4 = __float_as_uint(h ? n1.w : n1.z);
@@ -211,10 +216,10 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
     // branch-free mask update: (hit ? childBits : 0) << bitIndex, bytes extracted with one PRMT each
 #define PBR_CW_CHILD(J)                                                                               \
     {                                                                                                 \
-      const float tn = fmaxf(fmaxf(fmaf(q2f<J>(nx), Ax, Bnx), fmaf(q2f<J>(ny), Ay, Bny)),             \
-                             fmaxf(fmaf(q2f<J>(nz), Az, Bnz), 0.f));                                  \
-      const float tf = fminf(fminf(fmaf(q2f<J>(fx), Ax, Bfx), fmaf(q2f<J>(fy), Ay, Bfy)),             \
-                             fminf(fmaf(q2f<J>(fz), Az, Bfz), T.tMax));                               \
+      const float tn = fmaxf(fmaxf(fmaf(q2f<J>(nx, one), Ax, Bnx), fmaf(q2f<J>(ny, one), Ay, Bny)),             \
+                             fmaxf(fmaf(q2f<J>(nz, one), Az, Bnz), 0.f));                                  \
+      const float tf = fminf(fminf(fmaf(q2f<J>(fx, one), Ax, Bfx), fmaf(q2f<J>(fy, one), Ay, Bfy)),             \
+                             fminf(fmaf(q2f<J>(fz, one), Az, Bfz), T.tMax));                               \
       const unsigned cb = __byte_perm(childBits4, 0u, 0x4440u | J);                                   \
       const unsigned bi = __byte_perm(bitIndex4, 0u, 0x4440u | J);                                    \
       hitmask |= (tn <= tf ? cb : 0u) << bi;                                                          \
@@ -260,7 +265,7 @@ template <bool ANY_HIT, bool COUNT>
 PBR_D bool traverse(const SceneDev& sc, V3 o, V3 d, float tMax, HitRec* hit, uint2* sstack, unsigned* nNodes, unsigned* nTris) {
   Trav T;
   TravSpill S;
-  trav_init(T, o, d, tMax);
+  trav_init(T, o, d, tMax, sc.f32one);
   bool done = false;
   while (!done) {
     if (T.ngroup.y > 0x00FFFFFFu) {
