@@ -111,11 +111,10 @@ PBR_D uint32_t queue_push(uint32_t* counter, bool active) {
 enum { TRACE_PATH = 0, TRACE_SHADOW = 1, TRACE_MIS = 2 };
 constexpr int kTraceBlock = 128;
 
-// Triangle batching: a node step leaves a lane with 0..24 candidate triangles.  Testing them right away
-// would run the (long) watertight test with only the few lanes that happen to have candidates, so a
-// lane parks its triangle groups in a small shared-memory list and keeps descending; the warp runs a
-// triangle round (ONE triangle per lane) only when at least P.triThreshold lanes have candidates, or
-// when no lane has node work left.
+// Triangle batching: a node step leaves a lane with 0..24 candidate triangles.  Draining them right away
+// (a while loop) would run the long watertight test with only the few lanes that happen to have several
+// candidates, so a lane parks unfinished triangle groups in a small shared-memory list and keeps
+// descending; every loop iteration tests at most ONE triangle per lane.
 constexpr int kTriQueue = 6;
 
 #ifndef PBR_TRACE_MIN_BLOCKS
@@ -135,7 +134,6 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   Counters* C = P.ws.ctr;
   const uint32_t nPath = C->nCur, nShadow = C->nShadow, nMis = C->nMis;
   const uint32_t n = nPath + nShadow + nMis;
-  const int triThreshold = P.triThreshold;
   Trav T;
   TravSpill S;
   T.ngroup = make_uint2(0u, 0u); T.tgroup = make_uint2(0u, 0u); T.sp = 0;
@@ -169,27 +167,31 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
       }
     }
     if (exhausted && __ballot_sync(full, busy) == 0u) break;
-    // ---- node phase ----
-    bool didNode = false;
+    // ---- node phase: pop if the node group is exhausted, then one node step ----
     if (busy) {
       if (T.ngroup.y <= 0x00FFFFFFu && T.sp > 0) T.ngroup = trav_pop(T, sstack, S);
-      if (T.ngroup.y > 0x00FFFFFFu) {
-        if (T.tgroup.y == 0u || nt < kTriQueue) {
-          if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }
-          cw_node_step(P.sc.nodes8, T, sstack, S);
+      if (T.ngroup.y > 0x00FFFFFFu && (T.tgroup.y == 0u || nt < kTriQueue)) {
+        if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }  // park the unfinished triangle group
+        cw_node_step(P.sc.nodes8, T, sstack, S);
 #if PBR_TRACE_PREFETCH
-          if (T.tgroup.y != 0u) {  // first candidate triangle of the group this step produced
-            const int ti = (int)T.tgroup.x + (31 - __clz(T.tgroup.y));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv0 + ti));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv1 + ti));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv2 + ti));
-          }
-#endif
-          if (COUNT) nodes++;
-          didNode = true;
+        if (T.tgroup.y != 0u) {  // first candidate triangle of the group this step produced
+          const int ti = (int)T.tgroup.x + (31 - __clz(T.tgroup.y));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv0 + ti));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv1 + ti));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv2 + ti));
         }
-      } else if (T.tgroup.y == 0u && nt == 0) {
-        // ---- ray finished ----
+#endif
+        if (COUNT) nodes++;
+      }
+      // ---- triangle round: ONE candidate triangle per lane (a threshold on the number of lanes with candidates
+      // was measured: lanes always have a backlog, so the round runs every iteration anyway) ----
+      if (T.tgroup.y != 0u || nt > 0) {
+        if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
+        if (COUNT) tris++;
+        if (cw_tri_step(P.sc, T) && mode == TRACE_SHADOW) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+      }
+      // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
+      if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {
         if (mode == TRACE_PATH) {
           P.ws.hit[ray] = make_float4(__int_as_float(T.hit.tri), T.hit.b0, T.hit.b1, T.hit.b2);
           // shading-queue id of this path, written in QUEUE order so that k_classify reads it coalesced
@@ -207,17 +209,6 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
           }
         }
         busy = false;
-      }
-    }
-    // ---- triangle round ----
-    const bool hasTri = busy && (T.tgroup.y != 0u || nt > 0);
-    const unsigned triMask = __ballot_sync(full, hasTri);
-    const unsigned nodeMask = __ballot_sync(full, didNode);
-    if (triMask != 0u && (__popc(triMask) >= triThreshold || nodeMask == 0u)) {
-      if (hasTri) {
-        if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
-        if (COUNT) tris++;
-        if (cw_tri_step(P.sc, T) && mode == TRACE_SHADOW) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
       }
     }
   }

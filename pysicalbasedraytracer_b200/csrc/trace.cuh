@@ -20,7 +20,8 @@ struct RayPrep {
 // Permute(v, kx, ky, kz) (Geometry.h) for the cyclic (kx, ky, kz): two selects per component instead of a
 // run-time indexed component fetch (which cost ~10 % of the traversal kernel's instructions)
 PBR_D V3 permute_cyclic(V3 v, int kz) {
-  return kz == 2 ? v : (kz == 0 ? V3(v.y, v.z, v.x) : V3(v.z, v.x, v.y));
+  const bool r0 = kz == 0, r1 = kz == 1;  // kz == 0: (y,z,x)   kz == 1: (z,x,y)   kz == 2: (x,y,z)
+  return V3(r0 ? v.y : (r1 ? v.z : v.x), r0 ? v.z : (r1 ? v.x : v.y), r0 ? v.x : (r1 ? v.y : v.z));
 }
 
 PBR_D RayPrep prep_ray(V3 o, V3 d) {
