@@ -105,7 +105,6 @@ struct RenderParams {
   int nsWave;             // samples per pixel in this wave
   int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
   int countStats;
-  int triThreshold;       // lanes with candidate triangles needed to run a triangle round
   int fetchMinIdle;       // idle lanes of a warp that trigger a ray fetch
   int atomicL;            // several shadow / MIS rays per path and bounce (Whitted / DirectLighting): atomics on L
   // Halton offset of the pixel a global index belongs to: index = offset(pixel) + sample * stride, offset < stride

@@ -115,7 +115,10 @@ constexpr int kTraceBlock = 128;
 // (a while loop) would run the long watertight test with only the few lanes that happen to have several
 // candidates, so a lane parks unfinished triangle groups in a small shared-memory list and keeps
 // descending; every loop iteration tests at most ONE triangle per lane.
-constexpr int kTriQueue = 6;
+#ifndef PBR_TRI_QUEUE
+#define PBR_TRI_QUEUE 6
+#endif
+constexpr int kTriQueue = PBR_TRI_QUEUE;
 
 #ifndef PBR_TRACE_MIN_BLOCKS
 #define PBR_TRACE_MIN_BLOCKS 8

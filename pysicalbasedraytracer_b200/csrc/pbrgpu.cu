@@ -127,7 +127,6 @@ struct pbrgpu_scene {
   DevBuf<uint64_t> sobolVdc, sobolVdcInv;
   int lightStrategyBuilt = -1;
   int traceBlocksPerSm = 0;
-  int triThreshold = 1;
   int fetchMinIdle = 8;
   int waveLog2 = 25;
   bool hasMat[PBRGPU_MAT_COUNT] = {};  // material types present in the scene (absent ones: no shade launch)
@@ -665,7 +664,6 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false>, kTraceBlock, 0));
     if (const char* e = getenv("PBRGPU_TRACE_BLOCKS_PER_SM")) nb = atoi(e);
     s->traceBlocksPerSm = std::max(1, nb);
-    if (const char* e = getenv("PBRGPU_TRI_THRESHOLD")) s->triThreshold = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("PBRGPU_FETCH_MIN_IDLE")) s->fetchMinIdle = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("PBRGPU_WAVE_LOG2")) s->waveLog2 = std::max(14, std::min(25, atoi(e)));
   }
@@ -706,7 +704,6 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) P.arrayEndDim = 5 + 2 * (2 * (int)s->lights.size() * rd->max_depth);
   P.atomicL = pathInteg ? 0 : 1;
   P.countStats = count ? 1 : 0;
-  P.triThreshold = s->triThreshold;
   P.fetchMinIdle = s->fetchMinIdle;
 
   if (!(rd->flags & PBRGPU_RENDER_ACCUMULATE)) CK(cudaMemsetAsync(d_rgba_sum, 0, sizeof(float) * 4 * (size_t)W * H, st));

@@ -113,7 +113,10 @@ PBR_D V3 ld3(const float4* p, int i) {
 #ifndef PBR_TRACE_PREFETCH
 #define PBR_TRACE_PREFETCH 0
 #endif
-constexpr int kSmemStack = 12;
+#ifndef PBR_SMEM_STACK
+#define PBR_SMEM_STACK 12
+#endif
+constexpr int kSmemStack = PBR_SMEM_STACK;
 constexpr int kLocalStack = 36;
 
 struct Trav {

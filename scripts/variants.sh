@@ -1,4 +1,5 @@
 #!/bin/bash
-for v in s3 s4 s6; do
+echo "== base"; python scripts/quick_perf.py 467 16 2>&1 | grep "^ms" | sed -n 2p
+for v in "$@"; do
   echo "== $v"; PBRGPU_LIB=$PWD/build_variants/$v.so python scripts/quick_perf.py 467 16 2>&1 | grep "^ms" | sed -n 2p
 done
