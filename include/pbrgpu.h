@@ -233,6 +233,13 @@ int pbrgpu_halton_params(const int32_t sample_bounds[4], int32_t out7[7]);
 /* Radical-inverse permutations for the first n_bases primes (n_bases<=1000); returns count written. */
 int64_t pbrgpu_compute_perms(uint16_t* out, int64_t capacity);
 
+/* Scene ingestion helper (host only): the reference's private ".3d" mesh text format, Shape/plyRead.h:17-47
+ * ("vertex N face M", N vertices scaled by `scale` - the reference uses 20 -, M faces "<count> i0 i1 i2").
+ * Returns malloc'd arrays (release with pbrgpu_free); non-zero on error. */
+int pbrgpu_load_3d(const char* path, float scale, float** out_verts, int32_t* out_n_verts, int32_t** out_indices,
+                   int32_t* out_n_tris);
+void pbrgpu_free(void* p);
+
 /* BVH statistics: out[0]=n_nodes, out[1]=n_leaves, out[2]=max_leaf_size, out[3]=bytes_nodes, out[4]=bytes_tris */
 int pbrgpu_scene_info(pbrgpu_scene* scene, int64_t out[8]);
 

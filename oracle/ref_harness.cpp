@@ -35,6 +35,7 @@
 #include "Core/FrameBuffer.h"
 #include "Shape/Shape.h"
 #include "Shape/Triangle.h"
+#include "Shape/plyRead.h"
 #include "Accelerator/BVHAccel.h"
 #include "Camera/Camera.h"
 #include "Camera/Perspective.h"
@@ -556,6 +557,17 @@ void ref_tonemap(const float* rgb_mean, int n, unsigned char* rgba8) {
 }
 
 int ref_num_procs() { return omp_get_num_procs(); }
+
+// The reference's own .3d loader (Shape/plyRead.h): copies what plyInfo parsed into caller buffers.
+int ref_ply_read(const char* path, float* verts, int cap_verts, int32_t* indices, int cap_tris, int32_t* n_verts, int32_t* n_tris) {
+  plyInfo info(path);
+  *n_verts = info.nVertices; *n_tris = info.nTriangles;
+  if (info.nVertices > cap_verts || info.nTriangles > cap_tris) return 1;
+  for (int i = 0; i < info.nVertices; ++i)
+    for (int k = 0; k < 3; ++k) verts[3 * i + k] = info.vertexArray[i][k];
+  memcpy(indices, info.vertexIndices, sizeof(int32_t) * 3 * (size_t)info.nTriangles);
+  return 0;
+}
 
 // Drop-in test: the reference's OWN object graph (Scene / BVHAccel / GeometricPrimitive / Triangle / Material /
 // Light / PerspectiveCamera / HaltonSampler) rendered through PBR::GpuPathIntegrator::Render, i.e. through the

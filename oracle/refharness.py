@@ -66,6 +66,7 @@ def lib():
         L.ref_render_shipped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_void_p, C.POINTER(RefRenderStats)]
         L.ref_tonemap.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_ply_read.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.ref_sampler_create_typed.restype = C.c_void_p
         L.ref_sampler_create_typed.argtypes = [C.c_int] * 6
         L.ref_sobol_tables.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -227,3 +228,14 @@ def gpu_dropin_render(scene, cam, spp, W, H, max_depth, rr, strategy="uniform"):
     if rc != 0:
         raise RuntimeError("GpuPathIntegrator::Render failed (see stderr)")
     return rgba, rgb_sum, sec.value
+
+
+def ply_read(path, cap_verts=1 << 20, cap_tris=1 << 21):
+    """The reference's own plyInfo loader (Shape/plyRead.h) -> (verts [N,3] float32, tris [M,3] int32)."""
+    v = np.zeros((cap_verts, 3), dtype=np.float32)
+    t = np.zeros((cap_tris, 3), dtype=np.int32)
+    nv, nt = C.c_int32(0), C.c_int32(0)
+    rc = lib().ref_ply_read(str(path).encode(), v.ctypes.data, cap_verts, t.ctypes.data, cap_tris, C.byref(nv), C.byref(nt))
+    if rc != 0:
+        raise RuntimeError("ref_ply_read: buffers too small")
+    return v[:nv.value].copy(), t[:nt.value].copy()

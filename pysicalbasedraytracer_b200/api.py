@@ -55,6 +55,9 @@ def lib():
         L.pbrgpu_compute_perms.restype = C.c_int64
         L.pbrgpu_compute_perms.argtypes = [vp, C.c_int64]
         L.pbrgpu_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.pbrgpu_load_3d.argtypes = [C.c_char_p, C.c_float, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
+                                     C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
+        L.pbrgpu_free.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -79,6 +82,23 @@ def compute_perms():
     out = np.zeros(n, dtype=np.uint16)
     lib().pbrgpu_compute_perms(out.ctypes.data, n)
     return out
+
+
+def load_3d(path, scale=20.0):
+    """The reference's ".3d" mesh text format (Shape/plyRead.h:17-47; vertices scaled by 20 like plyInfo).
+    -> (verts float32 [N,3], tris int32 [M,3])"""
+    v, i = C.POINTER(C.c_float)(), C.POINTER(C.c_int32)()
+    nv, nt = C.c_int32(0), C.c_int32(0)
+    rc = lib().pbrgpu_load_3d(str(path).encode(), scale, C.byref(v), C.byref(nv), C.byref(i), C.byref(nt))
+    if rc != 0:
+        raise PbrGpuError(f"pbrgpu_load_3d({path}) failed with code {rc}")
+    try:
+        verts = np.ctypeslib.as_array(v, shape=(nv.value, 3)).copy()
+        tris = np.ctypeslib.as_array(i, shape=(nt.value, 3)).copy()
+    finally:
+        lib().pbrgpu_free(v)
+        lib().pbrgpu_free(i)
+    return verts, tris
 
 
 class Context:

@@ -120,3 +120,30 @@ def test_film_reduce_world2_gloo():
     import torch
     mean = shard.resolve_mean(torch.from_numpy(film)).numpy()
     assert np.allclose(mean[..., 0], pix + s.mean())
+
+
+def test_3d_mesh_loader_matches_reference_plyinfo(api, ref, tmp_path):
+    """Scene ingestion: the reference's private .3d text format (Shape/plyRead.h:17-47)."""
+    rng = np.random.default_rng(9)
+    nv, nt = 257, 400
+    verts = rng.normal(size=(nv, 3)) * 0.07
+    tris = rng.integers(0, nv, size=(nt, 3))
+    path = tmp_path / "mesh.3d"
+    with open(path, "w") as f:
+        f.write(f"vertex {nv}\nface {nt}\n")
+        for v in verts:
+            f.write(f"{v[0]:.9g} {v[1]:.7f} {v[2]:.6e}\n")
+        for t in tris:
+            f.write(f"3 {t[0]} {t[1]} {t[2]}\n")
+    gv, gt = api.load_3d(path)
+    wv, wt = ref.ply_read(path)
+    assert gv.shape == (nv, 3) and gt.shape == (nt, 3)
+    assert np.array_equal(gv.view(np.uint32), wv.view(np.uint32))  # same parse, same x20 float multiply
+    assert np.array_equal(gt, wt)
+    with pytest.raises(api.PbrGpuError):
+        api.load_3d(tmp_path / "missing.3d")
+    # the loaded soup feeds straight into the scene description
+    s = scenes.SceneData()
+    m = s.add_material(scenes.matte([0.5, 0.5, 0.5]))
+    s.add_mesh(gv, gt, m)
+    assert s.n_tris == nt
