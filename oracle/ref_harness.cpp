@@ -517,20 +517,32 @@ int ref_render_typed(void* hscene, void* hc, int sampler_type, int spp, const in
 
 // The reference's OWN SamplerIntegrator::Render, verbatim (4 threads hard-coded, square images only,
 // Integrator.cpp:280-356).  Returns wall seconds reported by the reference; rgba8 = FrameBuffer bytes.
+double ref_render_shipped_integrator(void* hscene, void* hc, int integrator, int spp, int W, int H, int max_depth, float rr,
+                                     unsigned char* rgba8, RefRenderStats* st);
 double ref_render_shipped(void* hscene, void* hc, int spp, int W, int H, int max_depth, float rr, unsigned char* rgba8,
                           RefRenderStats* st) {
+  return ref_render_shipped_integrator(hscene, hc, PBRGPU_INTEGRATOR_PATH, spp, W, H, max_depth, rr, rgba8, st);
+}
+double ref_render_shipped_integrator(void* hscene, void* hc, int integrator, int spp, int W, int H, int max_depth, float rr,
+                                     unsigned char* rgba8, RefRenderStats* st) {
   auto* rs = (RefScene*)hscene;
   auto* rc = (RefCamera*)hc;
   Bounds2i b(Point2i(0, 0), Point2i(W, H));
   std::shared_ptr<Sampler> sampler = std::make_shared<HaltonSampler>(spp, b);
   FrameBuffer fb;
   fb.InitBuffer(W, H, 4);
-  PathIntegrator integ(max_depth, rc->cam, sampler, b, rr, "uniform", &fb);
+  std::unique_ptr<SamplerIntegrator> integ;
+  switch (integrator) {
+    case PBRGPU_INTEGRATOR_WHITTED: integ.reset(new WhittedIntegrator(max_depth, rc->cam, sampler, b, &fb)); break;
+    case PBRGPU_INTEGRATOR_DIRECT_ONE: integ.reset(new DirectLightingIntegrator(LightStrategy::UniformSampleOne, max_depth, rc->cam, sampler, b, &fb)); break;
+    case PBRGPU_INTEGRATOR_DIRECT_ALL: integ.reset(new DirectLightingIntegrator(LightStrategy::UniformSampleAll, max_depth, rc->cam, sampler, b, &fb)); break;
+    default: integ.reset(new PathIntegrator(max_depth, rc->cam, sampler, b, rr, "uniform", &fb)); break;
+  }
   rs->agg->reset();
   double t = 0;
   // silence the progress bar
   std::streambuf* old = std::cout.rdbuf(nullptr);
-  integ.Render(*rs->scene, t);
+  integ->Render(*rs->scene, t);
   std::cout.rdbuf(old);
   if (rgba8) memcpy(rgba8, fb.getUCbuffer(), (size_t)W * H * 4);
   if (st) {
@@ -572,7 +584,7 @@ int ref_ply_read(const char* path, float* verts, int cap_verts, int32_t* indices
 // Drop-in test: the reference's OWN object graph (Scene / BVHAccel / GeometricPrimitive / Triangle / Material /
 // Light / PerspectiveCamera / HaltonSampler) rendered through PBR::GpuPathIntegrator::Render, i.e. through the
 // flattener of pysicalbasedraytracer_b200/host/GpuIntegrator.h and the C-ABI of libpbrgpu.so.  Needs a GPU.
-int ref_gpu_dropin_render(void* hscene, void* hc, int spp, int W, int H, int max_depth, float rr, const char* strategy,
+int ref_gpu_dropin_render(void* hscene, void* hc, int integrator, int spp, int W, int H, int max_depth, float rr, const char* strategy,
                           unsigned char* rgba8, float* rgb_sum, double* seconds) {
   auto* rs = (RefScene*)hscene;
   auto* rc = (RefCamera*)hc;
@@ -581,13 +593,22 @@ int ref_gpu_dropin_render(void* hscene, void* hc, int spp, int W, int H, int max
   std::shared_ptr<Sampler> sampler = std::make_shared<HaltonSampler>(spp, b);
   FrameBuffer fb;
   fb.InitBuffer(W, H, 4);
-  GpuPathIntegrator integ(max_depth, rc->cam, sampler, b, rr, strategy, &fb);
+  std::unique_ptr<GpuSamplerIntegrator> integ;
+  switch (integrator) {
+    case PBRGPU_INTEGRATOR_PATH: integ.reset(new GpuPathIntegrator(max_depth, rc->cam, sampler, b, rr, strategy, &fb)); break;
+    case PBRGPU_INTEGRATOR_WHITTED: integ.reset(new GpuWhittedIntegrator(max_depth, rc->cam, sampler, b, &fb)); break;
+    case PBRGPU_INTEGRATOR_DIRECT_ONE:
+      integ.reset(new GpuDirectLightingIntegrator(LightStrategy::UniformSampleOne, max_depth, rc->cam, sampler, b, &fb)); break;
+    case PBRGPU_INTEGRATOR_DIRECT_ALL:
+      integ.reset(new GpuDirectLightingIntegrator(LightStrategy::UniformSampleAll, max_depth, rc->cam, sampler, b, &fb)); break;
+    default: return 2;
+  }
   double t = -1;
-  integ.Render(raw, t);
+  integ->Render(raw, t);
   if (seconds) *seconds = t;
   if (t < 0) return 1;
   if (rgba8) memcpy(rgba8, fb.getUCbuffer(), (size_t)W * H * 4);
-  if (rgb_sum) memcpy(rgb_sum, integ.rgbSum.data(), sizeof(float) * (size_t)W * H * 3);
+  if (rgb_sum) memcpy(rgb_sum, integ->rgbSum.data(), sizeof(float) * (size_t)W * H * 3);
   return 0;
 }
 

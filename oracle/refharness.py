@@ -72,8 +72,11 @@ def lib():
         L.ref_sobol_tables.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_render_typed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(A.RenderDesc),
                                        C.c_int, C.c_void_p, C.POINTER(RefRenderStats)]
-        L.ref_gpu_dropin_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+        L.ref_gpu_dropin_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                             C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_render_shipped_integrator.restype = C.c_double
+        L.ref_render_shipped_integrator.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                                    C.c_void_p, C.POINTER(RefRenderStats)]
         _lib = L
     return _lib
 
@@ -204,10 +207,11 @@ def render(scene, cam, spp, sample_bounds, integrator=A.INTEGRATOR_PATH, max_dep
     return out, st
 
 
-def render_shipped(scene, cam, spp, W, H, max_depth, rr):
+def render_shipped(scene, cam, spp, W, H, max_depth, rr, integrator=A.INTEGRATOR_PATH):
+    """The reference's OWN SamplerIntegrator::Render (4 OpenMP threads, square images) -> FrameBuffer bytes."""
     out = np.zeros((H, W, 4), dtype=np.uint8)
     st = RefRenderStats()
-    t = lib().ref_render_shipped(scene.h, cam.h, spp, W, H, max_depth, rr, out.ctypes.data, C.byref(st))
+    t = lib().ref_render_shipped_integrator(scene.h, cam.h, integrator, spp, W, H, max_depth, rr, out.ctypes.data, C.byref(st))
     return out, st, t
 
 
@@ -218,12 +222,12 @@ def tonemap(rgb_mean):
     return out
 
 
-def gpu_dropin_render(scene, cam, spp, W, H, max_depth, rr, strategy="uniform"):
+def gpu_dropin_render(scene, cam, spp, W, H, max_depth, rr, strategy="uniform", integrator=A.INTEGRATOR_PATH):
     """The reference's own object graph rendered through the C++ drop-in GpuPathIntegrator (needs a GPU)."""
     rgba = np.zeros((H, W, 4), dtype=np.uint8)
     rgb_sum = np.zeros((H, W, 3), dtype=np.float32)
     sec = C.c_double(0)
-    rc = lib().ref_gpu_dropin_render(scene.h, cam.h, spp, W, H, max_depth, rr, strategy.encode(), rgba.ctypes.data,
+    rc = lib().ref_gpu_dropin_render(scene.h, cam.h, integrator, spp, W, H, max_depth, rr, strategy.encode(), rgba.ctypes.data,
                                      rgb_sum.ctypes.data, C.byref(sec))
     if rc != 0:
         raise RuntimeError("GpuPathIntegrator::Render failed (see stderr)")

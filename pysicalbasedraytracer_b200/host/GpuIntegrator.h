@@ -368,4 +368,37 @@ class GpuPathIntegrator : public GpuSamplerIntegrator {
   const std::string lightSampleStrategy;
 };
 
+// Same constructor as WhittedIntegrator (Integrator/WhittedIntegrator.h:8-11).
+class GpuWhittedIntegrator : public GpuSamplerIntegrator {
+ public:
+  GpuWhittedIntegrator(int maxDepth, std::shared_ptr<const Camera> camera, std::shared_ptr<Sampler> sampler, const Bounds2i& pixelBounds,
+                       FrameBuffer* framebuffer = nullptr)
+      : GpuSamplerIntegrator(camera, sampler, pixelBounds, framebuffer), maxDepth(maxDepth) {}
+
+ protected:
+  void fillRenderDesc(pbrgpu_render_desc* rd) const override {
+    rd->integrator = PBRGPU_INTEGRATOR_WHITTED;
+    rd->max_depth = maxDepth;
+  }
+  const int maxDepth;
+};
+
+// Same constructor as DirectLightingIntegrator (Integrator/DirectLightingIntegrator.h:10-17); `strategy` is the
+// reference's own LightStrategy enum when that header is included, else an int (0 = UniformSampleAll, 1 = UniformSampleOne).
+class GpuDirectLightingIntegrator : public GpuSamplerIntegrator {
+ public:
+  template <typename Strategy>
+  GpuDirectLightingIntegrator(Strategy strategy, int maxDepth, std::shared_ptr<const Camera> camera, std::shared_ptr<Sampler> sampler,
+                              const Bounds2i& pixelBounds, FrameBuffer* framebuffer = nullptr)
+      : GpuSamplerIntegrator(camera, sampler, pixelBounds, framebuffer), sampleAll((int)strategy == 0), maxDepth(maxDepth) {}
+
+ protected:
+  void fillRenderDesc(pbrgpu_render_desc* rd) const override {
+    rd->integrator = sampleAll ? PBRGPU_INTEGRATOR_DIRECT_ALL : PBRGPU_INTEGRATOR_DIRECT_ONE;
+    rd->max_depth = maxDepth;
+  }
+  const bool sampleAll;
+  const int maxDepth;
+};
+
 }  // namespace PBR

@@ -238,3 +238,17 @@ def test_progressive_film_checkpoint_resume(api, gpu_ctx, tmp_path):
     assert np.array_equal(sd["accum"][..., :3], whole)
     assert np.all(sd["accum"][..., 3] == 8)
     np.testing.assert_allclose(f2.mean(), whole / 8, rtol=1e-6)
+
+
+@pytest.mark.parametrize("integ", [A.INTEGRATOR_WHITTED, A.INTEGRATOR_DIRECT_ONE, A.INTEGRATOR_DIRECT_ALL])
+def test_cpp_dropin_whitted_and_direct_twins(api, ref, gpu_ctx, integ):
+    """GpuWhittedIntegrator / GpuDirectLightingIntegrator (host/GpuIntegrator.h) against the reference's own Render."""
+    data = scenes.cornell(sphere_tess=12, floor_mirror=True)
+    data.add_point_light([0.5, 1.5, 0.5], [20.0, 18.0, 15.0])
+    rsc = ref.RefScene(data)
+    rc = ref.RefCamera(A.CAMERA_PERSPECTIVE, 64, 64, (0, 0, 5), (0, 0, 0), (0, 1, 0))
+    rgba, _, sec = ref.gpu_dropin_render(rsc, rc, 2, 64, 64, 4, 1.0, "uniform", integrator=integ)
+    want, _, _ = ref.render_shipped(rsc, rc, 2, 64, 64, 4, 1.0, integrator=integ)
+    diff = np.abs(rgba.astype(int) - want.astype(int))
+    print("drop-in twin", integ, "bytes equal", (diff == 0).mean(), "max diff", diff.max())
+    assert (diff <= 1).mean() >= 0.995
