@@ -92,7 +92,9 @@ typedef struct pbrgpu_scene_desc {
   const float* uvs;            /* optional n_verts*2 (mesh->uv) or NULL -> default (0,0),(1,0),(1,1) Triangle.h:50-54 */
   const int32_t* tri_material; /* n_tris: index into materials */
   const int32_t* tri_light;    /* n_tris: index into lights for emissive triangles, else -1 */
-  const uint8_t* tri_flags;    /* optional n_tris: bit0 = reverseOrientation^transformSwapsHandedness */
+  const uint8_t* tri_flags;    /* optional n_tris: bit0 = reverseOrientation ^ transformSwapsHandedness, bit1 = reverseOrientation,
+                                  bit2 / bit3 = the triangle's mesh has per-vertex normals / uvs (when NULL: no flips, and
+                                  every triangle uses whichever of `normals` / `uvs` is given) */
   int32_t n_materials;
   int32_t n_lights;
   const pbrgpu_material* materials;

@@ -18,6 +18,9 @@ constexpr uint32_t kTriMatMask = 0x00ffffffu;
 constexpr int kTriTypeShift = 24;
 constexpr int kTriFlagShift = 28;
 constexpr uint32_t kTriFlagFlipNormal = 1u;  // reverseOrientation ^ transformSwapsHandedness
+constexpr uint32_t kTriFlagReverse = 2u;     // reverseOrientation alone (Triangle.cpp:248: `if (reverseOrientation) ts = -ts`)
+constexpr uint32_t kTriFlagNormals = 4u;     // the triangle's mesh has per-vertex shading normals (TriangleMesh::n)
+constexpr uint32_t kTriFlagUVs = 8u;         // the triangle's mesh has per-vertex uv (TriangleMesh::uv)
 
 struct CameraDev {
   int type, width, height;
@@ -47,6 +50,12 @@ struct SceneDev {
   const float4* tvN;   // geometric normal of Triangle::Intersect (Triangle.cpp:182-184), orientation flip applied
   const float4* tvS;   // ss = Normalize(dpdu)            (Reflection.h:105-110)
   const float4* tvT;   // ts = Cross(ns, ss)
+  // optional per-vertex shading data (NULL when no mesh has it): smooth normals are interpolated per hit
+  const float4* tn0;   // normal of vertex 0 | -          (triangles of meshes with TriangleMesh::n)
+  const float4* tn1;
+  const float4* tn2;
+  const float4* tuv0;  // uv0.xy, uv1.xy
+  const float4* tuv1;  // uv2.xy, -, -
   const float4* nodes8;         // Bvh8Node[] viewed as 5 x float4 per node
   const pbrgpu_material* mats;  // roughness fields already remapped to alpha on the host (glibc logf)
   const pbrgpu_light* lights;   // AREA_TRI: .tri = LEAF-ORDER triangle index

@@ -114,7 +114,7 @@ struct pbrgpu_scene {
   bool haveCamera = false, haveSampler = false;
   int64_t spp = 0;
   // device buffers
-  DevBuf<float4> tv0, tv1, tv2, tvN, tvS, tvT;
+  DevBuf<float4> tv0, tv1, tv2, tvN, tvS, tvT, tn0, tn1, tn2, tuv0, tuv1;
   DevBuf<Bvh8Node> nodes;
   DevBuf<pbrgpu_material> mats;
   DevBuf<pbrgpu_light> dlights;
@@ -282,8 +282,6 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
     return fail("pbrgpu_scene_create: empty scene");
   if (d->n_tris >= (1 << 29)) return fail("pbrgpu_scene_create: too many triangles");
   if (d->n_materials <= 0 || d->n_materials > (int)kTriMatMask) return fail("pbrgpu_scene_create: bad material count");
-  if (d->normals || d->uvs)
-    return fail("pbrgpu_scene_create: per-vertex normals / uvs are not supported yet (flat-shaded triangles only)");
   for (int64_t i = 0; i < (int64_t)d->n_tris * 3; ++i)
     if (d->indices[i] < 0 || d->indices[i] >= d->n_verts) return fail("pbrgpu_scene_create: vertex index out of range");
   for (int i = 0; i < d->n_tris; ++i) {
@@ -302,6 +300,8 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   const int nT = d->n_tris;
   s->leafOf.assign((size_t)nT, -1);
   std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT), vN((size_t)nT), vS((size_t)nT), vT((size_t)nT);
+  std::vector<float4> vn0, vn1, vn2, vuv0, vuv1;  // only when some mesh has shading normals / uvs
+  bool anyNormals = false;
   for (int k = 0; k < nT; ++k) {
     int ti = s->bvh.triOrder[k];
     s->leafOf[ti] = k;
@@ -309,19 +309,47 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
     const float* b = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti + 1];
     const float* c = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti + 2];
     int m = d->tri_material[ti];
-    uint32_t flags = (d->tri_flags && (d->tri_flags[ti] & 1)) ? kTriFlagFlipNormal : 0u;
+    // tri_flags: bit0 reverseOrientation ^ transformSwapsHandedness, bit1 reverseOrientation, bit2 / bit3 "this triangle's
+    // mesh has per-vertex normals / uvs" (default when tri_flags is NULL: every triangle uses the arrays that are given)
+    const uint8_t tf = d->tri_flags ? d->tri_flags[ti] : (uint8_t)((d->normals ? 4 : 0) | (d->uvs ? 8 : 0));
+    uint32_t flags = (tf & 1 ? kTriFlagFlipNormal : 0u) | (tf & 2 ? kTriFlagReverse : 0u) |
+                     ((tf & 4) && d->normals ? kTriFlagNormals : 0u) | ((tf & 8) && d->uvs ? kTriFlagUVs : 0u);
     uint32_t w1 = (uint32_t)m | ((uint32_t)d->materials[m].type << kTriTypeShift) | (flags << kTriFlagShift);
     int32_t lid = d->tri_light ? d->tri_light[ti] : -1;
     v0[k] = make_float4(a[0], a[1], a[2], u2f((uint32_t)ti));
     v1[k] = make_float4(b[0], b[1], b[2], u2f(w1));
     v2[k] = make_float4(c[0], c[1], c[2], u2f((uint32_t)lid));
     V3 n, ss, ts;
-    triangle_frame(V3(a[0], a[1], a[2]), V3(b[0], b[1], b[2]), V3(c[0], c[1], c[2]), flags != 0, &n, &ss, &ts);
+    float uv[6] = {0.f, 0.f, 1.f, 0.f, 1.f, 1.f};  // Triangle::GetUVs default (Triangle.h:50-54)
+    if (flags & kTriFlagUVs)
+      for (int q = 0; q < 3; ++q) {
+        uv[2 * q] = d->uvs[2 * (size_t)d->indices[3 * (size_t)ti + q]];
+        uv[2 * q + 1] = d->uvs[2 * (size_t)d->indices[3 * (size_t)ti + q] + 1];
+      }
+    triangle_frame(V3(a[0], a[1], a[2]), V3(b[0], b[1], b[2]), V3(c[0], c[1], c[2]), uv, (flags & kTriFlagFlipNormal) != 0, &n, &ss, &ts);
+    if (flags & kTriFlagNormals) {
+      anyNormals = true;
+      if (lid >= 0) return fail("pbrgpu_scene_create: an area light on a mesh with per-vertex shading normals is not supported");
+      const float* n0 = d->normals + 3 * (size_t)d->indices[3 * (size_t)ti];
+      const float* n1 = d->normals + 3 * (size_t)d->indices[3 * (size_t)ti + 1];
+      const float* n2 = d->normals + 3 * (size_t)d->indices[3 * (size_t)ti + 2];
+      if (vn0.empty()) { vn0.assign((size_t)nT, make_float4(0, 0, 0, 0)); vn1 = vn0; vn2 = vn0; }
+      vn0[k] = make_float4(n0[0], n0[1], n0[2], 0.f);
+      vn1[k] = make_float4(n1[0], n1[1], n1[2], 0.f);
+      vn2[k] = make_float4(n2[0], n2[1], n2[2], 0.f);
+    }
+    if (flags & kTriFlagUVs) {
+      if (vuv0.empty()) { vuv0.assign((size_t)nT, make_float4(0, 0, 0, 0)); vuv1 = vuv0; }
+      vuv0[k] = make_float4(uv[0], uv[1], uv[2], uv[3]);
+      vuv1[k] = make_float4(uv[4], uv[5], 0.f, 0.f);
+    }
     vN[k] = make_float4(n.x, n.y, n.z, 0.f);
     vS[k] = make_float4(ss.x, ss.y, ss.z, 0.f);
     vT[k] = make_float4(ts.x, ts.y, ts.z, 0.f);
   }
   CK(s->tvN.upload(vN, st)); CK(s->tvS.upload(vS, st)); CK(s->tvT.upload(vT, st));
+  if (anyNormals) { CK(s->tn0.upload(vn0, st)); CK(s->tn1.upload(vn1, st)); CK(s->tn2.upload(vn2, st)); }
+  if (!vuv0.empty()) { CK(s->tuv0.upload(vuv0, st)); CK(s->tuv1.upload(vuv1, st)); }
   CK(s->tv0.upload(v0, st)); CK(s->tv1.upload(v1, st)); CK(s->tv2.upload(v2, st));
   CK(s->nodes.upload(s->bvh.nodes, st));
 
@@ -376,7 +404,8 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
         V3 nS = normalize(cross(p1 - p0, p2 - p0));
         if (flip) nS = nS * -1.f;
         V3 nI, ss, ts;
-        triangle_frame(p0, p1, p2, flip, &nI, &ss, &ts);
+        const float uvDefault[6] = {0.f, 0.f, 1.f, 0.f, 1.f, 1.f};
+        triangle_frame(p0, p1, p2, uvDefault, flip, &nI, &ss, &ts);
         l.light_to_world[0] = nS.x; l.light_to_world[1] = nS.y; l.light_to_world[2] = nS.z; l.light_to_world[3] = area;
         l.light_to_world[4] = nI.x; l.light_to_world[5] = nI.y; l.light_to_world[6] = nI.z;
         l.tri = s->leafOf[l.tri];
@@ -481,6 +510,7 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
 
   s->sc.tv0 = s->tv0.p; s->sc.tv1 = s->tv1.p; s->sc.tv2 = s->tv2.p;
   s->sc.tvN = s->tvN.p; s->sc.tvS = s->tvS.p; s->sc.tvT = s->tvT.p;
+  s->sc.tn0 = s->tn0.p; s->sc.tn1 = s->tn1.p; s->sc.tn2 = s->tn2.p; s->sc.tuv0 = s->tuv0.p; s->sc.tuv1 = s->tuv1.p;
   s->sc.nodes8 = reinterpret_cast<const float4*>(s->nodes.p);
   s->sc.mats = s->mats.p;
   s->sc.lights = s->dlights.p;

@@ -33,12 +33,32 @@ PBR_D TriData load_tri(const SceneDev& sc, int ti) {
   return t;
 }
 
-// Geometric normal exactly as Triangle::Intersect does (Triangle.cpp:152,182-184)
-PBR_D V3 tri_normal_isect(const TriData& t) {
-  V3 dp02 = t.p0 - t.p2, dp12 = t.p1 - t.p2;
-  V3 n = normalize(cross(dp02, dp12));
-  if ((t.w1 >> kTriFlagShift) & kTriFlagFlipNormal) n = -n;
-  return n;
+// dpdu of Triangle::Intersect (Triangle.cpp:147-160) for the given vertex uvs; zero when the uvs are degenerate
+// (the reference leaves dpdu = dpdv = 0 there)
+PBR_HD V3 triangle_dpdu(V3 p0, V3 p1, V3 p2, float u0x, float u0y, float u1x, float u1y, float u2x, float u2y) {
+  V3 dp02 = p0 - p2, dp12 = p1 - p2;
+  const float duv02x = u0x - u2x, duv02y = u0y - u2y, duv12x = u1x - u2x, duv12y = u1y - u2y;
+  float determinant = duv02x * duv12y - duv02y * duv12x;
+  V3 dpdu;
+  if (!(fabsf(determinant) < 1e-8)) {
+    float invdet = 1 / determinant;
+    dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+  }
+  return dpdu;
+}
+
+// Host + device: the per-triangle frame of a FLAT-shaded triangle exactly as the reference computes it per hit
+//   n  = Normalize(Cross(p0 - p2, p1 - p2)), flipped by reverseOrientation ^ transformSwapsHandedness  (Triangle.cpp:152,182-184)
+//   dpdu from the vertex uvs (default (0,0),(1,0),(1,1), Triangle.h:50-54)                             (Triangle.cpp:147-160)
+//   ss = Normalize(dpdu), ts = Cross(ns, ss)                                                          (Reflection.h:105-110)
+PBR_HD void triangle_frame(V3 p0, V3 p1, V3 p2, const float uv[6], bool flip, V3* n, V3* ss, V3* ts) {
+  V3 dp02 = p0 - p2, dp12 = p1 - p2;
+  V3 dpdu = triangle_dpdu(p0, p1, p2, uv[0], uv[1], uv[2], uv[3], uv[4], uv[5]);
+  V3 nn = normalize(cross(dp02, dp12));
+  if (flip) nn = -nn;
+  *n = nn;
+  *ss = normalize(dpdu);
+  *ts = cross(nn, *ss);
 }
 
 PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, float b1, float b2, V3 rayD, Isect* is) {
@@ -48,35 +68,50 @@ PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, f
   float zAbsSum = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z) + fabsf(b2 * p2.z));
   is->pError = gamma_f(7) * V3(xAbsSum, yAbsSum, zAbsSum);
   is->p = b0 * p0 + b1 * p1 + b2 * p2;
-  const float4 n4 = __ldg(sc.tvN + tri), s4 = __ldg(sc.tvS + tri), t4 = __ldg(sc.tvT + tri);
-  is->n = V3(n4.x, n4.y, n4.z);
-  is->ns = is->n;
-  is->ss = V3(s4.x, s4.y, s4.z);
-  is->ts = V3(t4.x, t4.y, t4.z);
+  const float4 n4 = __ldg(sc.tvN + tri);
+  const uint32_t fl = t.w1 >> kTriFlagShift;
+  if (!(fl & kTriFlagNormals)) {
+    // flat-shaded triangle: the whole frame is a per-triangle constant (host-precomputed, uvs included)
+    const float4 s4 = __ldg(sc.tvS + tri), t4 = __ldg(sc.tvT + tri);
+    is->n = V3(n4.x, n4.y, n4.z);
+    is->ns = is->n;
+    is->ss = V3(s4.x, s4.y, s4.z);
+    is->ts = V3(t4.x, t4.y, t4.z);
+  } else {
+    // per-vertex shading normals: Triangle.cpp:186-250 + SurfaceInteraction::SetShadingGeometry (Interaction.cpp:98-113)
+    float uv[6] = {0.f, 0.f, 1.f, 0.f, 1.f, 1.f};
+    if (fl & kTriFlagUVs) {
+      const float4 a = __ldg(sc.tuv0 + tri), b = __ldg(sc.tuv1 + tri);
+      uv[0] = a.x; uv[1] = a.y; uv[2] = a.z; uv[3] = a.w; uv[4] = b.x; uv[5] = b.y;
+    }
+    V3 n(n4.x, n4.y, n4.z);
+    const V3 dpdu = triangle_dpdu(p0, p1, p2, uv[0], uv[1], uv[2], uv[3], uv[4], uv[5]);
+    const float4 a0 = __ldg(sc.tn0 + tri), a1 = __ldg(sc.tn1 + tri), a2 = __ldg(sc.tn2 + tri);
+    V3 ns = b0 * V3(a0.x, a0.y, a0.z) + b1 * V3(a1.x, a1.y, a1.z) + b2 * V3(a2.x, a2.y, a2.z);
+    if (length_sq(ns) > 0) ns = normalize(ns);
+    else ns = n;
+    V3 ss = normalize(dpdu);
+    V3 ts = cross(ss, ns);
+    if (length_sq(ts) > 0.f) {
+      ts = normalize(ts);
+      ss = cross(ts, ns);
+    } else {
+      coordinate_system(ns, &ss, &ts);
+    }
+    if (fl & kTriFlagReverse) ts = -ts;
+    // SetShadingGeometry(ss, ts, .., orientationIsAuthoritative = true)
+    V3 sn = normalize(cross(ss, ts));
+    n = faceforward(n, sn);
+    is->n = n;
+    is->ns = sn;
+    // BSDF ctor (Reflection.h:105-110): ss = Normalize(shading.dpdu), ts = Cross(ns, ss)
+    is->ss = normalize(ss);
+    is->ts = cross(sn, is->ss);
+  }
   is->wo = normalize(-rayD);
   is->matId = (int)(t.w1 & kTriMatMask);
   is->matType = (int)((t.w1 >> kTriTypeShift) & 0xf);
   is->lightId = (int)t.w2;
-}
-
-// Host + device: the per-triangle frame exactly as the reference computes it per hit
-//   n  = Normalize(Cross(p0 - p2, p1 - p2)), flipped by reverseOrientation ^ transformSwapsHandedness  (Triangle.cpp:152,182-184)
-//   dpdu from the default UVs (0,0),(1,0),(1,1)                                                        (Triangle.cpp:147-160, Triangle.h:50-54)
-//   ss = Normalize(dpdu), ts = Cross(ns, ss)                                                          (Reflection.h:105-110)
-PBR_HD void triangle_frame(V3 p0, V3 p1, V3 p2, bool flip, V3* n, V3* ss, V3* ts) {
-  V3 dp02 = p0 - p2, dp12 = p1 - p2;
-  const float duv02x = 0.f - 1.f, duv02y = 0.f - 1.f, duv12x = 1.f - 1.f, duv12y = 0.f - 1.f;
-  float determinant = duv02x * duv12y - duv02y * duv12x;
-  V3 dpdu;
-  if (!(fabsf(determinant) < 1e-8)) {
-    float invdet = 1 / determinant;
-    dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
-  }
-  V3 nn = normalize(cross(dp02, dp12));
-  if (flip) nn = -nn;
-  *n = nn;
-  *ss = normalize(dpdu);
-  *ts = cross(nn, *ss);
 }
 
 // DiffuseAreaLight::L (DiffuseLight.h:17-19)

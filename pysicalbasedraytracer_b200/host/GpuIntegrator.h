@@ -74,7 +74,8 @@ namespace PBR {
 namespace gpu_detail {
 
 struct Flat {
-  std::vector<float> verts;
+  std::vector<float> verts, normals, uvs;  // normals / uvs: per emitted vertex, filled only if some mesh has them
+  bool anyNormals = false, anyUVs = false;
   std::vector<int32_t> indices, triMaterial, triLight;
   std::vector<uint8_t> triFlags;
   std::vector<pbrgpu_material> materials;
@@ -165,14 +166,29 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
     if (!gp) { f->error = "primitive is not a GeometricPrimitive"; return false; }
     auto* tri = dynamic_cast<const Triangle*>(gp->shape.get());
     if (!tri) { f->error = "shape is not a Triangle (the reference's Sphere is a stub, SURVEY Q4)"; return false; }
-    if (tri->mesh->n || tri->mesh->uv || tri->mesh->s) { f->error = "per-vertex normals / uvs / tangents are not supported on the GPU path yet"; return false; }
+    if (tri->mesh->s) { f->error = "per-vertex tangents (TriangleMesh::s) are not supported on the GPU path"; return false; }
     if (!gp->material) { f->error = "primitive without material (medium boundary) is not supported"; return false; }
+    if ((tri->mesh->n && !f->anyNormals) || (tri->mesh->uv && !f->anyUVs)) {
+      // first mesh with shading normals / uvs: materialise the optional arrays (zero for everything before it)
+      if (tri->mesh->n && !f->anyNormals) { f->anyNormals = true; f->normals.assign(n * 9, 0.f); }
+      if (tri->mesh->uv && !f->anyUVs) { f->anyUVs = true; f->uvs.assign(n * 6, 0.f); }
+    }
     for (int k = 0; k < 3; ++k) {
       const Point3f& p = tri->mesh->p[tri->v[k]];  // already world space (TriangleMesh ctor, Triangle.cpp:27-28)
       f->verts.push_back(p.x); f->verts.push_back(p.y); f->verts.push_back(p.z);
       f->indices.push_back((int32_t)(3 * i + k));
+      if (tri->mesh->n) {
+        const Normal3f& nn = tri->mesh->n[tri->v[k]];
+        float* d = &f->normals[9 * i + 3 * k];
+        d[0] = nn.x; d[1] = nn.y; d[2] = nn.z;
+      }
+      if (tri->mesh->uv) {
+        const Point2f& t = tri->mesh->uv[tri->v[k]];
+        f->uvs[6 * i + 2 * k] = t.x; f->uvs[6 * i + 2 * k + 1] = t.y;
+      }
     }
-    f->triFlags[i] = (tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0;
+    f->triFlags[i] = (uint8_t)(((tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0) | (tri->reverseOrientation ? 2 : 0) |
+                               (tri->mesh->n ? 4 : 0) | (tri->mesh->uv ? 8 : 0));
     auto it = matId.find(gp->material.get());
     if (it == matId.end()) {
       pbrgpu_material m;
@@ -260,6 +276,8 @@ class GpuSamplerIntegrator : public Integrator {
       d.n_tris = (int32_t)(f.indices.size() / 3);
       d.verts = f.verts.data(); d.indices = f.indices.data();
       d.tri_material = f.triMaterial.data(); d.tri_light = f.triLight.data(); d.tri_flags = f.triFlags.data();
+      d.normals = f.anyNormals ? f.normals.data() : nullptr;
+      d.uvs = f.anyUVs ? f.uvs.data() : nullptr;
       d.n_materials = (int32_t)f.materials.size(); d.materials = f.materials.data();
       d.n_lights = (int32_t)f.lights.size(); d.lights = f.lights.data();
       d.env_width = f.envW; d.env_height = f.envH; d.env_texels = f.env.empty() ? nullptr : f.env.data();

@@ -46,6 +46,9 @@ class SceneData:
 
     def __init__(self):
         self._verts = []
+        self._normals = []
+        self._uvs = []
+        self._mesh_flags = []
         self._tris = []
         self._tri_mat = []
         self._tri_light = []
@@ -62,11 +65,17 @@ class SceneData:
         self.materials.append(m)
         return len(self.materials) - 1
 
-    def add_mesh(self, verts, tris, material, emit=None, two_sided=False, n_samples=1):
-        """material: int id or per-triangle int array.  emit: RGB Lemit -> one DiffuseAreaLight per triangle."""
+    def add_mesh(self, verts, tris, material, emit=None, two_sided=False, n_samples=1, normals=None, uvs=None,
+                 reverse_orientation=False):
+        """material: int id or per-triangle int array.  emit: RGB Lemit -> one DiffuseAreaLight per triangle.
+        normals / uvs: optional per-vertex shading normals (world space) and uv (TriangleMesh::n / ::uv)."""
         verts = np.ascontiguousarray(verts, dtype=F).reshape(-1, 3)
         tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
         n = tris.shape[0]
+        self._normals.append(np.zeros_like(verts) if normals is None else np.ascontiguousarray(normals, dtype=F).reshape(-1, 3))
+        self._uvs.append(np.zeros((verts.shape[0], 2), dtype=F) if uvs is None else np.ascontiguousarray(uvs, dtype=F).reshape(-1, 2))
+        self._mesh_flags.append(np.full(n, (3 if reverse_orientation else 0) | (4 if normals is not None else 0) |
+                                        (8 if uvs is not None else 0), dtype=np.uint8))
         mats = np.full(n, material, dtype=np.int32) if np.isscalar(material) else np.asarray(material, dtype=np.int32)
         lights = np.full(n, -1, dtype=np.int32)
         if emit is not None:
@@ -146,11 +155,22 @@ class SceneData:
         d.materials = mats
         d.lights = lights
         keep = [fz, mats, lights]
-        if self.tri_flags is not None:
-            fl = np.ascontiguousarray(self.tri_flags, dtype=np.uint8)
-            assert fl.shape[0] == d.n_tris
+        fl = np.ascontiguousarray(np.concatenate(self._mesh_flags), dtype=np.uint8)
+        if self.tri_flags is not None:  # caller-supplied bit0: reverseOrientation (identity transforms: bit1 = bit0)
+            user = np.ascontiguousarray(self.tri_flags, dtype=np.uint8)
+            assert user.shape[0] == d.n_tris
+            fl = (fl | np.where(user & 1, 3, 0)).astype(np.uint8)
+        if fl.any():
             d.tri_flags = fl.ctypes.data_as(C.POINTER(C.c_uint8))
             keep.append(fl)
+        if (fl & 4).any():
+            nrm = np.ascontiguousarray(np.concatenate(self._normals), dtype=F)
+            d.normals = nrm.ctypes.data_as(C.POINTER(C.c_float))
+            keep.append(nrm)
+        if (fl & 8).any():
+            uv = np.ascontiguousarray(np.concatenate(self._uvs), dtype=F)
+            d.uvs = uv.ctypes.data_as(C.POINTER(C.c_float))
+            keep.append(uv)
         if self.env is not None:
             d.env_height, d.env_width = self.env.shape[0], self.env.shape[1]
             d.env_texels = self.env.ctypes.data_as(C.POINTER(C.c_float))

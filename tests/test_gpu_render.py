@@ -252,3 +252,30 @@ def test_cpp_dropin_whitted_and_direct_twins(api, ref, gpu_ctx, integ):
     diff = np.abs(rgba.astype(int) - want.astype(int))
     print("drop-in twin", integ, "bytes equal", (diff == 0).mean(), "max diff", diff.max())
     assert (diff <= 1).mean() >= 0.995
+
+
+def test_smooth_shading_normals_and_uvs(api, ref, gpu_ctx):
+    """TriangleMesh::n / ::uv (Triangle.cpp:147-250, SetShadingGeometry Interaction.cpp:98-113): interpolated shading
+    normals, uv-derived dpdu, the shading frame of the BSDF.  Every mesh of the scene carries normals and uvs because the
+    reference harness builds one TriangleMesh for the whole soup."""
+    s = scenes.SceneData()
+    white = s.add_material(scenes.matte([0.8, 0.8, 0.8]))
+    shiny = s.add_material(scenes.plastic([0.3, 0.5, 0.2], [0.5, 0.5, 0.5], 0.15, True))
+    chrome = s.add_material(scenes.metal([0.2, 0.9, 1.1], [3.9, 2.4, 2.2], 0.1, 0.1, False))
+    # ground quad with exact normals and a stretched uv chart
+    g = 4.0
+    P = np.array([[-g, -1, -g], [g, -1, -g], [g, -1, g], [-g, -1, g]], dtype=np.float32)
+    s.add_mesh(P, np.array([[0, 2, 1], [0, 3, 2]], dtype=np.int32), white, normals=np.tile([0, 1, 0], (4, 1)),
+               uvs=np.array([[0, 0], [3, 0], [3, 2], [0, 2]], dtype=np.float32))
+    for cx, mat in ((-1.1, shiny), (1.1, chrome)):
+        v, t = scenes.uv_sphere([cx, 0.0, 0.0], 1.0, 10, 20)
+        nrm = (v - np.array([cx, 0.0, 0.0], dtype=np.float32))
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        th = np.arccos(np.clip(nrm[:, 1], -1, 1)) / np.pi
+        ph = (np.arctan2(nrm[:, 2], nrm[:, 0]) / (2 * np.pi)) % 1.0
+        s.add_mesh(v, t, mat, normals=nrm, uvs=np.stack([ph, th], -1))
+    s.add_point_light([0.0, 4.0, 3.0], [60.0, 55.0, 50.0])
+    s.add_point_light([-3.0, 2.0, -1.0], [15.0, 20.0, 30.0])
+    p = Pair(api, ref, s, 96, 72, 2, eye=(0.0, 1.5, 5.0), look=(0.0, -0.2, 0.0))
+    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.995)
+    _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.97)
