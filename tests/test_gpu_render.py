@@ -279,3 +279,42 @@ def test_smooth_shading_normals_and_uvs(api, ref, gpu_ctx):
     p = Pair(api, ref, s, 96, 72, 2, eye=(0.0, 1.5, 5.0), look=(0.0, -0.2, 0.0))
     _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.995)
     _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.97)
+
+
+def test_full_size_dragon_class_properties(api, ref, gpu_ctx):
+    """BASELINE configs[1] at FULL size (872 368 triangles, 1920x1080): the oracle cannot render this in seconds, so the
+    check is through size-independent properties plus a sampled comparison of ray queries with the reference:
+    run-to-run determinism, sample-range additivity (the multi-GPU sharding contract), independence of the wave size,
+    and primary hits / random rays against the reference's BVHAccel on the full mesh."""
+    W, H = 1920, 1080
+    data = scenes.dragon_class(tess=467)
+    assert data.n_tris == 872368
+    p = Pair(api, ref, data, W, H, 1024)
+    kw = dict(integrator=A.INTEGRATOR_PATH, max_depth=8, rr_threshold=1.0)
+    a, _, st = p.scene.render(s0=100, s1=102, **kw)
+    b, _, _ = p.scene.render(s0=100, s1=102, **kw)
+    assert np.array_equal(a, b)                                   # deterministic, bit for bit
+    assert np.isfinite(a).all() and 0.2 < a.mean() / 2 < 2.0
+    c0, _, _ = p.scene.render(s0=100, s1=101, **kw)
+    c1, _, _ = p.scene.render(s0=101, s1=102, **kw)
+    np.testing.assert_allclose(c0 + c1, a, rtol=2e-6, atol=1e-6)  # shards add up
+    d, _, _ = p.scene.render(s0=100, s1=102, samples_per_wave=1, **kw)
+    assert np.array_equal(d, a)                                   # wave size is not observable
+    assert 3.5 < (st.rays_closest + st.rays_shadow) / st.camera_samples < 5.0
+    # ray queries against the reference on the full mesh (a strip of primary rays + random rays)
+    region = (900, 500, 1028, 516)
+    want = ref.primary_hits(p.rscene, p.rcam, p.rsmp, region, 0, 1)
+    got = p.scene.dump_primary_hits(region, 0, 1)
+    assert (got[..., 0] != want[..., 0]).mean() < 1e-4
+    same = got[..., 0] == want[..., 0]
+    assert np.array_equal(got[..., 1][same], want[..., 1][same])
+    rng = np.random.default_rng(4)
+    rays = np.zeros((50_000, 8), dtype=np.float32)
+    rays[:, 0:3] = rng.uniform(-2.4, 2.4, (50_000, 3))
+    dd = rng.normal(size=(50_000, 3))
+    rays[:, 4:7] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    rays[:, 3] = np.inf
+    wr, gr = p.rscene.trace(rays), p.scene.trace(rays)
+    assert (wr[:, 0] != gr[:, 0]).mean() < 1e-4
+    rays[:, 3] = rng.uniform(0.05, 3.0, 50_000)
+    assert (p.rscene.trace(rays, any_hit=True) != p.scene.trace(rays, any_hit=True)).mean() < 1e-4
