@@ -280,7 +280,7 @@ def run_gpu(args):
 
     if rank == 0:
         info = scene.info()
-        # roofline of the dominant kernel (k_trace_closest over path segments): algorithmic bytes per ray
+        # roofline of the dominant kernel (k_trace: path + shadow + MIS rays of a bounce): algorithmic bytes per ray
         #   B_ray = 32 (ray record) + 16 (hit record) + nodes/ray * S_node + tris/ray * S_tri   
         S_NODE, S_TRI = 80, 48
         b_ray = 32 + 16 + nodes_per_ray * S_NODE + tris_per_ray * S_TRI

@@ -12,24 +12,6 @@ struct Aabb {
   float lo[3], hi[3];
 };
 
-// Binary node holding BOTH children's boxes (one 64-byte record = four 16-byte loads).
-//   a = c0.lo.x c0.hi.x c0.lo.y c0.hi.y     b = c1.lo.x c1.hi.x c1.lo.y c1.hi.y
-//   c = c0.lo.z c0.hi.z c1.lo.z c1.hi.z     d = child0, child1, 0, 0
-// child >= 0: index of an interior node; child < 0: leaf, ~child = (firstTri << 2) | (count-1), count in 1..4.
-struct alignas(16) Bvh2Node {
-  float a[4], b[4], c[4];
-  int32_t child[4];
-};
-
-struct BuiltBvh {
-  std::vector<Bvh2Node> nodes;      // nodes[0] is the root
-  std::vector<int32_t> triOrder;    // leaf-order position -> caller's triangle index
-  Aabb bounds;
-  int maxLeafSize = 0;
-  int64_t nLeaves = 0;
-  int maxDepth = 0;
-};
-
 // 8-wide compressed node (80 bytes = five 16-byte loads), after Ylitie, Karras & Laine,
 // "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017):
 //   n0 = origin.xyz | ex ey ez imask          n1 = childBase, triBase, meta[0..3], meta[4..7]
@@ -60,6 +42,5 @@ struct BuiltBvh8 {
 
 // verts: float[nVerts*3], indices: int[nTris*3].  Deterministic binned-SAH build.
 void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh8* out);
-void build_bvh2(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh* out);
 
 }  // namespace pbr

@@ -1,8 +1,8 @@
-// bvh_build.cpp - deterministic binned-SAH builder (host) producing the paired-box binary BVH the
-// GPU traversal kernel reads with 16-byte loads.  See bvh.h.  (The reference's own build,
-// Accelerator/BVHAccel.cpp:97-258, is a recursive 12-bucket SAH over shared_ptr<Primitive>; this one
-// works on index arrays, builds leaves of up to `maxLeaf` triangles and is free to differ: only the
-// answers of ray queries must match.)
+// bvh_build.cpp - deterministic host builder of the compressed 8-wide BVH the GPU traversal kernel reads with
+// 16-byte loads (see bvh.h): binned-SAH binary tree -> greedy collapse to 8 children -> quantisation.
+// (The reference's own build, Accelerator/BVHAccel.cpp:97-258, is a recursive 12-bucket SAH over
+// shared_ptr<Primitive>; this one works on index arrays and is free to differ: only the answers of ray
+// queries must match.)
 #include "bvh.h"
 
 #include <algorithm>
@@ -164,71 +164,6 @@ void build_binary(const float* verts, const int32_t* indices, int64_t nTris, int
   }
 }
 }  // namespace
-
-void build_bvh2(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh* out) {
-  maxLeaf = std::max(1, std::min(4, maxLeaf));
-  std::vector<TmpNode> tmp;
-  std::vector<int32_t>& order = out->triOrder;
-  BinaryStats bs;
-  build_binary(verts, indices, nTris, maxLeaf, tmp, order, &bs);
-  out->maxLeafSize = bs.maxLeafSize;
-  out->nLeaves = bs.nLeaves;
-  out->maxDepth = bs.maxDepth;
-  out->bounds = tmp[0].box;
-
-  // flatten: interior TmpNodes -> Bvh2Node (DFS order, children of a node adjacent when both interior)
-  auto encode_leaf = [](const TmpNode& n) { return ~(int32_t)((n.first << 2) | (n.count - 1)); };
-  std::vector<int32_t> remap(tmp.size(), -1);
-  std::vector<Bvh2Node>& nodes = out->nodes;
-  nodes.clear();
-  auto put_child = [&](Bvh2Node& dst, int which, const Aabb& b) {
-    if (which == 0) {
-      dst.a[0] = b.lo[0]; dst.a[1] = b.hi[0]; dst.a[2] = b.lo[1]; dst.a[3] = b.hi[1];
-      dst.c[0] = b.lo[2]; dst.c[1] = b.hi[2];
-    } else {
-      dst.b[0] = b.lo[0]; dst.b[1] = b.hi[0]; dst.b[2] = b.lo[1]; dst.b[3] = b.hi[1];
-      dst.c[2] = b.lo[2]; dst.c[3] = b.hi[2];
-    }
-  };
-  if (tmp[0].left < 0) {
-    // single-leaf scene: synthesize a root whose second child is an empty box
-    Bvh2Node r;
-    std::memset(&r, 0, sizeof(r));
-    put_child(r, 0, tmp[0].box);
-    put_child(r, 1, empty_box());
-    r.child[0] = tmp[0].count > 0 ? encode_leaf(tmp[0]) : ~0;
-    r.child[1] = r.child[0];
-    if (tmp[0].count == 0) { put_child(r, 0, empty_box()); }
-    nodes.push_back(r);
-    return;
-  }
-  std::vector<int32_t> dfs;
-  dfs.push_back(0);
-  // first pass: assign indices in DFS order
-  std::vector<int32_t> orderIdx;
-  while (!dfs.empty()) {
-    int32_t n = dfs.back();
-    dfs.pop_back();
-    remap[n] = (int32_t)orderIdx.size();
-    orderIdx.push_back(n);
-    const TmpNode& tn = tmp[n];
-    if (tmp[tn.right].left >= 0) dfs.push_back(tn.right);
-    if (tmp[tn.left].left >= 0) dfs.push_back(tn.left);
-  }
-  nodes.resize(orderIdx.size());
-  for (size_t i = 0; i < orderIdx.size(); ++i) {
-    const TmpNode& tn = tmp[orderIdx[i]];
-    Bvh2Node r;
-    std::memset(&r, 0, sizeof(r));
-    const TmpNode& L = tmp[tn.left];
-    const TmpNode& R = tmp[tn.right];
-    put_child(r, 0, L.box);
-    put_child(r, 1, R.box);
-    r.child[0] = L.left >= 0 ? remap[tn.left] : encode_leaf(L);
-    r.child[1] = R.left >= 0 ? remap[tn.right] : encode_leaf(R);
-    nodes[i] = r;
-  }
-}
 
 }  // namespace pbr
 
