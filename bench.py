@@ -313,7 +313,7 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_ray": b_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_ms,
-                         "note": "k_trace serves path + shadow + MIS rays of one bounce in one launch; the scene (12 MB compressed 8-wide nodes + 42 MB triangles) is L2-resident, so the algorithmic node/triangle bytes are served by L1/L2 (measured DRAM traffic is ~94 B/ray, profiles/r01_k_trace_traffic.json); ncu shows the kernel issue-slot bound (0.77 issue/cycle/SMSP, 14.6 of 32 lanes per instruction), not bandwidth bound"},
+                         "note": "k_trace serves path + shadow + MIS rays of one bounce in one launch; the scene (12 MB compressed 8-wide nodes + 42 MB triangles) is L2-resident, so the algorithmic node/triangle bytes are served by L1/L2 (measured DRAM traffic is ~95 B/ray, profiles/r01_k_trace_traffic.json); ncu shows the kernel issue-slot bound (0.73 issue/cycle/SMSP, 17 of 32 lanes per instruction), not bandwidth bound"},
             "kernel_ms_per_step": {k: tsum[k] / args.steps for k in ("raygen", "closest", "shade", "mis", "film", "total")},
             "bvh": info,
         }
