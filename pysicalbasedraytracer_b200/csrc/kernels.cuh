@@ -119,6 +119,10 @@ constexpr int kTraceBlock = 128;
 #define PBR_TRI_QUEUE 6
 #endif
 constexpr int kTriQueue = PBR_TRI_QUEUE;
+#ifndef PBR_NODE_STEPS
+#define PBR_NODE_STEPS 1
+#endif
+constexpr int kNodeStepsPerIter = PBR_NODE_STEPS;
 
 #ifndef PBR_TRACE_MIN_BLOCKS
 #define PBR_TRACE_MIN_BLOCKS 8
@@ -170,21 +174,18 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
       }
     }
     if (exhausted && __ballot_sync(full, busy) == 0u) break;
-    // ---- node phase: pop if the node group is exhausted, then one node step ----
+    // ---- node phase: kNodeStepsPerIter x (pop if the node group is exhausted, then one node step).  More than one
+    // node step per triangle round was measured (2: +4 % time, 3: +19 %): the extra speculative node visits cost more
+    // than the fuller triangle rounds save, so kNodeStepsPerIter = 1 ----
     if (busy) {
-      if (T.ngroup.y <= 0x00FFFFFFu && T.sp > 0) T.ngroup = trav_pop(T, sstack, S);
-      if (T.ngroup.y > 0x00FFFFFFu && (T.tgroup.y == 0u || nt < kTriQueue)) {
-        if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }  // park the unfinished triangle group
-        cw_node_step(P.sc.nodes8, T, sstack, S);
-#if PBR_TRACE_PREFETCH
-        if (T.tgroup.y != 0u) {  // first candidate triangle of the group this step produced
-          const int ti = (int)T.tgroup.x + (31 - __clz(T.tgroup.y));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv0 + ti));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv1 + ti));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sc.tv2 + ti));
+#pragma unroll 1
+      for (int rep = 0; rep < kNodeStepsPerIter; ++rep) {
+        if (T.ngroup.y <= 0x00FFFFFFu && T.sp > 0) T.ngroup = trav_pop(T, sstack, S);
+        if (T.ngroup.y > 0x00FFFFFFu && (T.tgroup.y == 0u || nt < kTriQueue)) {
+          if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }  // park the unfinished triangle group
+          cw_node_step(P.sc.nodes8, T, sstack, S);
+          if (COUNT) nodes++;
         }
-#endif
-        if (COUNT) nodes++;
       }
       // ---- triangle round: ONE candidate triangle per lane (a threshold on the number of lanes with candidates
       // was measured: lanes always have a backlog, so the round runs every iteration anyway) ----

@@ -110,9 +110,6 @@ PBR_D V3 ld3(const float4* p, int i) {
 // (and postponed triangle groups); its first kSmemStack levels live in shared memory, one column per
 // lane ([level][lane] -> conflict-free), deeper levels spill to a small local array.
 // ---------------------------------------------------------------------------------------------
-#ifndef PBR_TRACE_PREFETCH
-#define PBR_TRACE_PREFETCH 0
-#endif
 #ifndef PBR_SMEM_STACK
 #define PBR_SMEM_STACK 12
 #endif
@@ -233,17 +230,6 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
   }
   T.ngroup.y = (hitmask & 0xFF000000u) | (ei >> 24);
   T.tgroup.y = hitmask & 0x00FFFFFFu;
-#if PBR_TRACE_PREFETCH
-  // The next node and the first candidate triangle are known now; their loads are issued one loop
-  // iteration later (after the triangle round).  Prefetch them into L1 so that those loads hit.
-  if (T.ngroup.y > 0x00FFFFFFu) {
-    const int nb = 31 - __clz(T.ngroup.y);
-    const unsigned ns = (unsigned)(nb - 24) ^ (T.octinv4 & 0xffu);
-    const float4* nn = nodes + 5 * (size_t)(T.ngroup.x + __popc(T.ngroup.y & ~(0xFFFFFFFFu << ns)));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(nn));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(nn + 4));
-  }
-#endif
 }
 
 // One triangle of the triangle group: the reference's watertight test, bit-exact (t, b0, b1, b2).
