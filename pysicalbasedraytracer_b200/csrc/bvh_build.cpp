@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -90,6 +91,8 @@ void build_binary(const float* verts, const int32_t* indices, int64_t nTris, int
       }
     }
     tmp[t.node].box = box;
+    tmp[t.node].first = t.first;   // every node records its (contiguous) triangle range
+    tmp[t.node].count = t.count;
     out->maxDepth = std::max(out->maxDepth, (int)t.depth);
     auto make_leaf = [&]() {
       tmp[t.node].first = t.first;
@@ -175,15 +178,83 @@ void build_binary(const float* verts, const int32_t* indices, int64_t nTris, int
 // ---------------------------------------------------------------------------------------------
 namespace pbr {
 
+// SAH-optimal widening of the binary tree (Ylitie et al. 2017, section 4.1): for every binary node n,
+//   C(n,1) = min( C_leaf(n), C_distribute(n,8) + A_n c_node ),   C_leaf(n) = A_n P_n c_prim  if P_n <= maxLeaf
+//   C(n,i) = min( C_distribute(n,i), C(n,i-1) )                  C_distribute(n,j) = min_k C(left,k) + C(right,j-k)
+// i.e. the cheapest way to represent the subtree as a forest of at most i roots; the wide node of n takes the forest
+// that C_distribute(n,8) found as its children, and a subtree of <= maxLeaf triangles may become one leaf child.
+namespace {
+constexpr float kNodeCost = 1.0f;
+float kPrimCost = 0.7f;  // paper: 0.3; 0.45-1.0 measured equal here (fewer triangle tests per ray). Override: PBRGPU_PRIM_COST
+struct Widening {
+  std::vector<float> C;        // [node][7]: C(n, i+1)
+  std::vector<uint8_t> split;  // [node][8]: k of C_distribute(n, j) for j = 2..8 at [j-1]; 0 = "use C(n, j-1)"
+  std::vector<uint8_t> leaf;   // C(n,1) was realised as a leaf
+};
+
+void compute_widening(const std::vector<TmpNode>& tmp, int maxLeaf, Widening* w) {
+  const size_t n = tmp.size();
+  w->C.assign(n * 7, 0.f);
+  w->split.assign(n * 8, 0);
+  w->leaf.assign(n, 0);
+  const float inf = std::numeric_limits<float>::infinity();
+  for (size_t idx = n; idx-- > 0;) {  // children always have larger indices than their parent
+    const TmpNode& t = tmp[idx];
+    const float A = half_area(t.box);
+    float* C = &w->C[idx * 7];
+    uint8_t* sp = &w->split[idx * 8];
+    const float cLeaf = t.count <= maxLeaf ? A * t.count * kPrimCost : inf;
+    if (t.left < 0) {
+      for (int i = 0; i < 7; ++i) C[i] = cLeaf;
+      w->leaf[idx] = 1;
+      continue;
+    }
+    const float* L = &w->C[(size_t)t.left * 7];
+    const float* R = &w->C[(size_t)t.right * 7];
+    float dist[9];
+    for (int j = 2; j <= 8; ++j) {
+      float best = inf;
+      int bk = 1;
+      for (int k = 1; k < j; ++k) {
+        if (k > 7 || j - k > 7) continue;
+        float c = L[k - 1] + R[j - k - 1];
+        if (c < best) { best = c; bk = k; }
+      }
+      dist[j] = best;
+      sp[j - 1] = (uint8_t)bk;
+    }
+    const float cInternal = dist[8] + A * kNodeCost;
+    if (cLeaf <= cInternal) { C[0] = cLeaf; w->leaf[idx] = 1; }
+    else C[0] = cInternal;
+    for (int i = 2; i <= 7; ++i) {
+      if (dist[i] < C[i - 2]) C[i - 1] = dist[i];
+      else { C[i - 1] = C[i - 2]; sp[i - 1] = 0; }
+    }
+  }
+}
+
+// roots of the cheapest forest of at most `i` trees that represents subtree m
+void collect_forest(const std::vector<TmpNode>& tmp, const Widening& w, int32_t m, int i, int32_t* kids, int* nk) {
+  while (i > 1 && (tmp[m].left < 0 || w.split[(size_t)m * 8 + i - 1] == 0)) --i;  // the extra roots were not worth it
+  if (i == 1) { kids[(*nk)++] = m; return; }
+  const int k = w.split[(size_t)m * 8 + i - 1];
+  collect_forest(tmp, w, tmp[m].left, k, kids, nk);
+  collect_forest(tmp, w, tmp[m].right, i - k, kids, nk);
+}
+}  // namespace
+
 void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh8* out) {
   maxLeaf = std::max(1, std::min(3, maxLeaf));
   std::vector<TmpNode> tmp;
   std::vector<int32_t> order;
   BinaryStats bs;
-  build_binary(verts, indices, nTris, maxLeaf, tmp, order, &bs);
+  build_binary(verts, indices, nTris, 1, tmp, order, &bs);  // one triangle per binary leaf: the widening forms the leaves
+  Widening wd;
+  if (const char* e = std::getenv("PBRGPU_PRIM_COST")) kPrimCost = (float)std::atof(e);
+  compute_widening(tmp, maxLeaf, &wd);
   out->bounds = tmp[0].box;
-  out->maxLeafSize = bs.maxLeafSize;
-  out->nLeaves = bs.nLeaves;
+  out->maxLeafSize = 0;
+  out->nLeaves = 0;
   out->maxDepth = 0;
   out->nodes.clear();
   out->triOrder.clear();
@@ -198,28 +269,17 @@ void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int m
   while (head < queue.size()) {
     Work w = queue[head++];
     out->maxDepth = std::max(out->maxDepth, (int)w.depth);
-    // gather up to 8 children
+    // children of this wide node = the cheapest forest of <= 8 roots of the binary subtree
     int32_t kids[8];
     int nk = 0;
-    if (tmp[w.bin].left < 0) {
+    if (tmp[w.bin].left < 0 || (w.bin == 0 && wd.leaf[0])) {
       kids[nk++] = w.bin;  // degenerate: the whole scene is one leaf
     } else {
-      kids[nk++] = tmp[w.bin].left;
-      kids[nk++] = tmp[w.bin].right;
-      while (nk < 8) {
-        int best = -1;
-        float bestArea = -1.f;
-        for (int i = 0; i < nk; ++i) {
-          if (tmp[kids[i]].left < 0) continue;
-          float a = half_area(tmp[kids[i]].box);
-          if (a > bestArea) { bestArea = a; best = i; }
-        }
-        if (best < 0) break;
-        int32_t b = kids[best];
-        kids[best] = tmp[b].left;
-        kids[nk++] = tmp[b].right;
-      }
+      const int k = wd.split[(size_t)w.bin * 8 + 7];
+      collect_forest(tmp, wd, tmp[w.bin].left, k, kids, &nk);
+      collect_forest(tmp, wd, tmp[w.bin].right, 8 - k, kids, &nk);
     }
+    auto is_leaf_kid = [&](int32_t m) { return tmp[m].left < 0 || wd.leaf[m] != 0; };
     const Aabb& box = tmp[w.bin].box;
     // slot assignment: slot s is visited first by rays with direction sign (s&4 ? - : +, s&2 ? - : +, s&1 ? - : +);
     // put there the child that lies most upstream along that direction (greedy min-cost matching).
@@ -266,7 +326,7 @@ void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int m
     }
     int nInner = 0;
     for (int s = 0; s < 8; ++s)
-      if (childAt[s] >= 0 && tmp[kids[childAt[s]]].left >= 0) ++nInner;
+      if (childAt[s] >= 0 && !is_leaf_kid(kids[childAt[s]])) ++nInner;
     nd.childBase = (uint32_t)out->nodes.size();
     nd.triBase = (uint32_t)out->triOrder.size();
     out->nodes.resize(out->nodes.size() + (size_t)nInner);
@@ -285,7 +345,7 @@ void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int m
         qlo[a][s] = (uint8_t)std::max(0.0, std::min(255.0, lo));
         qhi[a][s] = (uint8_t)std::max(0.0, std::min(255.0, hi));
       }
-      if (ch.left >= 0) {
+      if (!is_leaf_kid(kids[childAt[s]])) {
         nd.imask |= (uint8_t)(1u << s);
         nd.meta[s] = (uint8_t)((1u << 5) | (24u + (unsigned)s));
         queue.push_back({kids[childAt[s]], (int32_t)nd.childBase + innerRank, w.depth + 1});
@@ -295,6 +355,8 @@ void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int m
         nd.meta[s] = (uint8_t)((unary << 5) | (unsigned)triOff);
         for (int i = 0; i < ch.count; ++i) out->triOrder.push_back(order[ch.first + i]);
         triOff += ch.count;
+        out->nLeaves++;
+        out->maxLeafSize = std::max(out->maxLeafSize, (int)ch.count);
       }
     }
     out->nodes[w.wide] = nd;
