@@ -40,7 +40,7 @@ inline float half_area(const Aabb& b) {
   return dx * dy + dy * dz + dz * dx;
 }
 
-constexpr int kBins = 16;
+constexpr int kBins = 32;
 constexpr float kTravCost = 1.0f;
 constexpr float kIsectCost = 1.2f;
 
