@@ -9,6 +9,8 @@
  *     PerspectiveCamera::GenerateRay...   Camera/Perspective.cpp:21-80, Camera/Orthographic.cpp:7-63
  *     BVHAccel::Intersect / IntersectP    Accelerator/BVHAccel.cpp:285-366, Shape/Triangle.cpp:62-350
  *     PathIntegrator::Li                  Integrator/PathIntegrator.cpp:32-110
+ *     VolPathIntegrator::Li               Integrator/VolPathIntegrator.cpp:21-107  (+ Media/HomogeneousMedium.cpp:10-45,
+ *                                         Media/Medium.cpp:7-28, VisibilityTester::Tr Light/Light.cpp:31-47)
  *     UniformSampleOneLight/EstimateDirect Integrator/Integrator.cpp:46-177
  *     Material::ComputeScatteringFunctions + BSDF::{f,Pdf,Sample_f}   Material/*.cpp
  *     Light::{Sample_Li,Pdf_Li,Le,L}      Light/*.cpp
@@ -62,6 +64,15 @@ typedef struct pbrgpu_material {
   float pad3;
 } pbrgpu_material; /* 96 bytes */
 
+/* ---- participating media: Media/HomogeneousMedium.{h,cpp}, phase function Media/Medium.{h,cpp} ---- */
+enum { PBRGPU_MEDIUM_HOMOGENEOUS = 0 };
+typedef struct pbrgpu_medium {
+  int32_t type;
+  float g;          /* Henyey-Greenstein asymmetry */
+  float sigma_a[3]; /* absorption */
+  float sigma_s[3]; /* scattering; sigma_t = sigma_s + sigma_a (HomogeneousMedium.h:13-16) */
+} pbrgpu_medium; /* 32 bytes */
+
 /* ---- lights: Light/{PointLight,DiffuseLight,InfiniteAreaLight,SkyBoxLight}.cpp ---- */
 enum {
   PBRGPU_LIGHT_POINT = 0,    /* pos, L = intensity I */
@@ -90,7 +101,9 @@ typedef struct pbrgpu_scene_desc {
   const int32_t* indices;      /* n_tris*3 */
   const float* normals;        /* optional n_verts*3 world-space shading normals (mesh->n) or NULL */
   const float* uvs;            /* optional n_verts*2 (mesh->uv) or NULL -> default (0,0),(1,0),(1,1) Triangle.h:50-54 */
-  const int32_t* tri_material; /* n_tris: index into materials */
+  const int32_t* tri_material; /* n_tris: index into materials; -1 = no material (GeometricPrimitive with a NULL
+                                  Material: a pure medium boundary, Core/Primitive.cpp:39-46) - such scenes render
+                                  with PBRGPU_INTEGRATOR_VOLPATH only */
   const int32_t* tri_light;    /* n_tris: index into lights for emissive triangles, else -1 */
   const uint8_t* tri_flags;    /* optional n_tris: bit0 = reverseOrientation ^ transformSwapsHandedness, bit1 = reverseOrientation,
                                   bit2 / bit3 = the triangle's mesh has per-vertex normals / uvs (when NULL: no flips, and
@@ -102,6 +115,12 @@ typedef struct pbrgpu_scene_desc {
   int32_t env_width;  /* env map for INFINITE / SKYBOX lights (power-of-two sizes) */
   int32_t env_height;
   const float* env_texels; /* env_width*env_height*3 RGB, row-major, raw (unscaled) */
+  /* participating media (GeometricPrimitive::mediumInterface, Core/Primitive.h:43): all optional */
+  int32_t n_media;
+  int32_t pad0;
+  const pbrgpu_medium* media;
+  const int32_t* tri_medium_inside;  /* n_tris: index into media or -1 (MediumInterface::inside);  NULL = none */
+  const int32_t* tri_medium_outside; /* n_tris: index into media or -1 (MediumInterface::outside); NULL = none */
 } pbrgpu_scene_desc;
 
 /* ---- camera: Camera/Camera.h:34-54, Perspective.cpp, Orthographic.cpp ---- */
@@ -114,6 +133,10 @@ typedef struct pbrgpu_camera_desc {
   float focal_distance;
   float raster_to_camera[16]; /* ProjectiveCamera::RasterToCamera.m, row-major */
   float camera_to_world[16];  /* Camera::CameraToWorld.m, row-major */
+  int32_t medium_plus1;       /* Camera::medium as (index into media) + 1; 0 = vacuum.  Read by VOLPATH only.  NOTE: the
+                                 reference itself never delivers Camera::medium to the integrator (Perspective.cpp:44-80 does
+                                 not set ray->medium; Orthographic.cpp:59-60 sets it before CameraToWorld(*ray), which rebuilds
+                                 the ray without it, Transform.h:169), so the host mirrors pass 0 to stay identical */
 } pbrgpu_camera_desc;
 
 /* ---- sampler: Sampler/Halton.cpp:30-58; Sobol: host/SobolSampler.h over the reference's tables
@@ -142,7 +165,8 @@ enum {
   PBRGPU_INTEGRATOR_PATH = 0,
   PBRGPU_INTEGRATOR_DIRECT_ONE = 1, /* LightStrategy::UniformSampleOne */
   PBRGPU_INTEGRATOR_DIRECT_ALL = 2, /* LightStrategy::UniformSampleAll */
-  PBRGPU_INTEGRATOR_WHITTED = 3
+  PBRGPU_INTEGRATOR_WHITTED = 3,
+  PBRGPU_INTEGRATOR_VOLPATH = 4     /* VolPathIntegrator (Integrator/VolPathIntegrator.cpp): media + null-material boundaries */
 };
 enum { PBRGPU_LIGHTSTRATEGY_UNIFORM = 0, PBRGPU_LIGHTSTRATEGY_POWER = 1 };
 typedef struct pbrgpu_render_desc {

@@ -9,7 +9,7 @@
 //   sampler streams   HaltonSampler::{StartPixel,SetSampleNumber,Get1D}   Sampler/Sampler.cpp:97-143
 //   primary rays      Camera::GenerateRayDifferential                    Camera/Perspective.cpp:44-80
 //   primary hits      Scene::Intersect                                   Core/Scene.cpp:20-23
-//   radiance          {Path,DirectLighting,Whitted}Integrator::Li        Integrator/*.cpp
+//   radiance          {Path,VolPath,DirectLighting,Whitted}Integrator::Li  Integrator/*.cpp
 // It does NOT use SamplerIntegrator::Render for parity dumps (quirk Q1: swapped loop bounds); its own
 // pixel loop iterates x in [x0,x1), y in [y0,y1) and returns linear-float sums.  ref_render_shipped()
 // calls the reference's Render() verbatim (4 threads, square images) for the as-shipped CPU baseline.
@@ -64,6 +64,9 @@
 #include "Integrator/PathIntegrator.h"
 #include "Integrator/WhittedIntegrator.h"
 #include "Integrator/DirectLightingIntegrator.h"
+#include "Integrator/VolPathIntegrator.h"
+#include "Media/Medium.h"
+#include "Media/HomogeneousMedium.h"
 #undef private
 #undef protected
 
@@ -101,6 +104,7 @@ struct RefScene {
   std::vector<std::shared_ptr<TriangleMesh>> meshes;
   std::vector<std::shared_ptr<Shape>> tris;
   std::vector<std::shared_ptr<Material>> materials;
+  std::vector<std::unique_ptr<HomogeneousMedium>> media;
   std::vector<std::shared_ptr<Light>> lights;
   std::vector<std::shared_ptr<Primitive>> prims;  // caller's order
   std::unordered_map<const Primitive*, int> primIndex;
@@ -146,7 +150,7 @@ Transform fromRowMajor(const float m[16], const float minv[16]) {
   return Transform(a, b);
 }
 
-struct RefCamera { std::shared_ptr<Camera> cam; int W, H, type; };
+struct RefCamera { std::shared_ptr<Camera> cam; int W, H, type; bool honourMedium = false; };
 struct RefSampler { std::shared_ptr<Sampler> s; };
 std::shared_ptr<Sampler> makeSampler(int type, int spp, const Bounds2i& b) {
   if (type == PBRGPU_SAMPLER_SOBOL) return std::make_shared<SobolSampler>(spp, b);
@@ -177,6 +181,8 @@ void* ref_scene_create(const pbrgpu_scene_desc* d) {
                                              d->normals ? N.data() : nullptr, d->uvs ? UV.data() : nullptr, nullptr);
   rs->meshes.push_back(mesh);
   for (int i = 0; i < d->n_materials; ++i) rs->materials.push_back(makeMaterial(d->materials[i]));
+  for (int i = 0; i < d->n_media; ++i)
+    rs->media.emplace_back(new HomogeneousMedium(rgb(d->media[i].sigma_a), rgb(d->media[i].sigma_s), d->media[i].g));
   rs->tris.reserve(d->n_tris);
   for (int i = 0; i < d->n_tris; ++i) {
     bool rev = d->tri_flags ? (d->tri_flags[i] & 1) != 0 : false;
@@ -248,7 +254,10 @@ void* ref_scene_create(const pbrgpu_scene_desc* d) {
   rs->prims.reserve(d->n_tris);
   for (int i = 0; i < d->n_tris; ++i) {
     std::shared_ptr<AreaLight> al = d->tri_light[i] >= 0 ? areaOfLight[d->tri_light[i]] : nullptr;
-    auto gp = std::make_shared<GeometricPrimitive>(rs->tris[i], rs->materials[d->tri_material[i]], al, MediumInterface());
+    const Medium* mIn = d->tri_medium_inside && d->tri_medium_inside[i] >= 0 ? rs->media[d->tri_medium_inside[i]].get() : nullptr;
+    const Medium* mOut = d->tri_medium_outside && d->tri_medium_outside[i] >= 0 ? rs->media[d->tri_medium_outside[i]].get() : nullptr;
+    std::shared_ptr<Material> mat = d->tri_material[i] >= 0 ? rs->materials[d->tri_material[i]] : nullptr;
+    auto gp = std::make_shared<GeometricPrimitive>(rs->tris[i], mat, al, MediumInterface(mIn, mOut));
     rs->primIndex[gp.get()] = i;
     rs->prims.push_back(gp);
   }
@@ -294,11 +303,23 @@ void* ref_camera_create_lens(int type, int W, int H, const float eye[3], const f
   return rc;
 }
 void ref_camera_destroy(void* h) { delete (RefCamera*)h; }
+// Camera::medium (Camera.h:29): the medium the camera sits in (index into the scene's media, -1 = vacuum).
+// The reference never delivers it: PerspectiveCamera does not set ray->medium at all, OrthographicCamera sets it
+// BEFORE `*ray = CameraToWorld(*ray)` and Transform::operator()(const Ray&) rebuilds the ray without it
+// (Core/Transform.h:169).  honour != 0 makes the harness loop re-attach it after GenerateRayDifferential, so that the
+// GPU library's camera-medium support can still be checked against the reference's own VolPathIntegrator::Li.
+void ref_camera_set_medium(void* h, void* hscene, int medium, int honour) {
+  auto* rc = (RefCamera*)h;
+  auto* rs = (RefScene*)hscene;
+  rc->cam->medium = medium >= 0 ? rs->media[medium].get() : nullptr;
+  rc->honourMedium = honour != 0;
+}
 void ref_camera_desc(void* h, pbrgpu_camera_desc* out) {
   auto* rc = (RefCamera*)h;
   auto* pc = dynamic_cast<const ProjectiveCamera*>(rc->cam.get());
   out->type = rc->type; out->width = rc->W; out->height = rc->H;
   out->lens_radius = pc->lensRadius; out->focal_distance = pc->focalDistance;
+  out->medium_plus1 = 0;  // the caller knows the scene's medium indices, the camera holds only a pointer
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) {
       out->raster_to_camera[i * 4 + j] = pc->RasterToCamera.m.m[i][j];
@@ -477,6 +498,9 @@ int ref_render_typed(void* hscene, void* hc, int sampler_type, int spp, const in
     case PBRGPU_INTEGRATOR_WHITTED:
       integ.reset(new WhittedIntegrator(rd->max_depth, rc->cam, sampler, pb, nullptr));
       break;
+    case PBRGPU_INTEGRATOR_VOLPATH:
+      integ.reset(new VolPathIntegrator(rd->max_depth, rc->cam, sampler, pb, rd->rr_threshold, strat, nullptr));
+      break;
     default: return 1;
   }
   if (threads <= 0) threads = omp_get_num_procs();
@@ -497,6 +521,7 @@ int ref_render_typed(void* hscene, void* hc, int sampler_type, int spp, const in
         CameraSample cs = ps->GetCameraSample(pixel);
         RayDifferential r;
         rc->cam->GenerateRayDifferential(cs, &r);
+        if (rc->honourMedium) r.medium = rc->cam->medium;
         r.ScaleDifferentials(1 / std::sqrt((float)ps->samplesPerPixel));
         col += integ->Li(r, *rs->scene, *ps, 0);
       }

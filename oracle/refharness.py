@@ -42,6 +42,7 @@ def lib():
         L.ref_camera_create_lens.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.c_float, C.c_float]
         L.ref_camera_desc.argtypes = [C.c_void_p, C.POINTER(A.CameraDesc)]
+        L.ref_camera_set_medium.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ref_sampler_create.restype = C.c_void_p
         L.ref_sampler_create.argtypes = [C.c_int] * 5
         L.ref_sampler_destroy.argtypes = [C.c_void_p]
@@ -123,6 +124,11 @@ class RefCamera:
         d = A.CameraDesc()
         lib().ref_camera_desc(self.h, C.byref(d))
         return d
+
+    def set_medium(self, rscene, medium, honour=False):
+        """Camera::medium = medium id of `rscene` (or None).  The reference loses it on the way to the world-space ray
+        (Transform.h:169); honour=True re-attaches it in the harness loop (see ref_harness.cpp)."""
+        lib().ref_camera_set_medium(self.h, rscene.h, -1 if medium is None else int(medium), int(honour))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -5,7 +5,8 @@ MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_METAL, MAT_PLASTIC = range(5)
 LIGHT_POINT, LIGHT_AREA_TRI, LIGHT_INFINITE, LIGHT_SKYBOX = range(4)
 CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC = 0, 1
 SAMPLER_HALTON, SAMPLER_SOBOL = 0, 1
-INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED = range(4)
+INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED, INTEGRATOR_VOLPATH = range(5)
+MEDIUM_HOMOGENEOUS = 0
 LIGHTSTRATEGY_UNIFORM, LIGHTSTRATEGY_POWER = 0, 1
 RENDER_ACCUMULATE, RENDER_COUNTERS, RENDER_TIMERS = 1, 2, 4
 DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW = range(5)
@@ -26,6 +27,10 @@ class Light(C.Structure):
                 ("light_to_world", f16), ("world_to_light", f16)]
 
 
+class Medium(C.Structure):
+    _fields_ = [("type", C.c_int32), ("g", C.c_float), ("sigma_a", f3), ("sigma_s", f3)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("n_verts", C.c_int32), ("n_tris", C.c_int32),
                 ("verts", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_int32)),
@@ -34,13 +39,15 @@ class SceneDesc(C.Structure):
                 ("tri_flags", C.POINTER(C.c_uint8)),
                 ("n_materials", C.c_int32), ("n_lights", C.c_int32),
                 ("materials", C.POINTER(Material)), ("lights", C.POINTER(Light)),
-                ("env_width", C.c_int32), ("env_height", C.c_int32), ("env_texels", C.POINTER(C.c_float))]
+                ("env_width", C.c_int32), ("env_height", C.c_int32), ("env_texels", C.POINTER(C.c_float)),
+                ("n_media", C.c_int32), ("pad0", C.c_int32), ("media", C.POINTER(Medium)),
+                ("tri_medium_inside", C.POINTER(C.c_int32)), ("tri_medium_outside", C.POINTER(C.c_int32))]
 
 
 class CameraDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("lens_radius", C.c_float), ("focal_distance", C.c_float),
-                ("raster_to_camera", f16), ("camera_to_world", f16)]
+                ("raster_to_camera", f16), ("camera_to_world", f16), ("medium_plus1", C.c_int32)]
 
 
 class SamplerDesc(C.Structure):
@@ -70,4 +77,4 @@ class DumpDesc(C.Structure):
                 ("s0", C.c_int64), ("s1", C.c_int64), ("n_dims", C.c_int32), ("pad", C.c_int32)]
 
 
-assert C.sizeof(Material) == 96 and C.sizeof(Light) == 176
+assert C.sizeof(Material) == 96 and C.sizeof(Light) == 176 and C.sizeof(Medium) == 32

@@ -128,8 +128,14 @@ def default_context(device=0):
 # Camera / Sampler / FrameBuffer: POD mirrors of the reference objects the integrator ctor takes
 # ---------------------------------------------------------------------------------------------
 class Camera:
-    def __init__(self, cam_type, width, height, camera_to_world, lens_radius=0.0, focal_distance=0.0):
+    def __init__(self, cam_type, width, height, camera_to_world, lens_radius=0.0, focal_distance=0.0, medium=None):
         self.type, self.width, self.height = cam_type, width, height
+        # Camera::medium (Camera.h:29).  The reference never delivers it to the integrator: PerspectiveCamera does not
+        # set ray->medium (Perspective.cpp:44-80) and OrthographicCamera sets it before `*ray = CameraToWorld(*ray)`,
+        # which rebuilds the ray without it (Transform.h:169).  The mirror therefore records the argument and keeps
+        # `medium = None`; assign `camera.medium = id` explicitly to make the GPU start its rays inside that medium.
+        self.ctor_medium = medium
+        self.medium = None
         self.camera_to_world = camera_to_world
         ortho = cam_type == A.CAMERA_ORTHOGRAPHIC
         window = T.screen_window(width, height, ortho)
@@ -142,17 +148,19 @@ class Camera:
                          focal_distance=self.focal_distance)
         d.raster_to_camera = (C.c_float * 16)(*[float(x) for x in self.raster_to_camera.m.reshape(-1)])
         d.camera_to_world = (C.c_float * 16)(*[float(x) for x in self.camera_to_world.m.reshape(-1)])
+        d.medium_plus1 = 0 if self.medium is None else int(self.medium) + 1
         return d
 
 
-def CreatePerspectiveCamera(width, height, cam2world):
-    """Camera/Perspective.cpp:84-104 (fov 90, lens radius 0)."""
-    return Camera(A.CAMERA_PERSPECTIVE, width, height, cam2world)
+def CreatePerspectiveCamera(width, height, cam2world, media=None):
+    """Camera/Perspective.cpp:84-104 (fov 90, lens radius 0).  `media` is accepted and - as in the reference - has no effect."""
+    return Camera(A.CAMERA_PERSPECTIVE, width, height, cam2world, medium=media)
 
 
-def CreateOrthographicCamera(width, height, cam2world):
-    """Camera/Orthographic.cpp:65-98 (screen window scaled by 2)."""
-    return Camera(A.CAMERA_ORTHOGRAPHIC, width, height, cam2world)
+def CreateOrthographicCamera(width, height, cam2world, media=None):
+    """Camera/Orthographic.cpp:65-98 (screen window scaled by 2).  `media` is accepted and - as in the reference - has no
+    effect (see Camera.__init__)."""
+    return Camera(A.CAMERA_ORTHOGRAPHIC, width, height, cam2world, medium=media)
 
 
 def LookAt(eye, look, up):
@@ -384,6 +392,12 @@ class PathIntegrator(_GpuSamplerIntegrator):
     def _render_args(self):
         return dict(max_depth=self.maxDepth, rr_threshold=self.rrThreshold,
                     light_strategy=_STRATEGY.get(self.lightSampleStrategy, A.LIGHTSTRATEGY_UNIFORM))
+
+
+class VolPathIntegrator(PathIntegrator):
+    """Integrator/VolPathIntegrator.h:11-19 - same constructor arguments as PathIntegrator; handles participating
+    media (SceneData.add_medium / medium_interface) and surfaces without a material."""
+    kind = A.INTEGRATOR_VOLPATH
 
 
 class WhittedIntegrator(_GpuSamplerIntegrator):

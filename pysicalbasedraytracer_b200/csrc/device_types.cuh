@@ -7,9 +7,17 @@
 
 namespace pbr {
 
-// ---- shading queues: 5 material types + "ray escaped" ----
-constexpr int kQueueMiss = PBRGPU_MAT_COUNT;  // 5
-constexpr int kNumQueues = PBRGPU_MAT_COUNT + 1;
+// ---- shading queues: 5 material types + "ray escaped"; VolPath adds "surface without a material" (medium
+// boundary) and "scattered inside a medium" ----
+constexpr int kQueueMiss = PBRGPU_MAT_COUNT;        // 5
+constexpr int kQueueNull = PBRGPU_MAT_COUNT + 1;    // 6: GeometricPrimitive with a NULL material (also the triangle's type code)
+constexpr int kQueueMedium = PBRGPU_MAT_COUNT + 2;  // 7: MediumInteraction sampled on this segment
+constexpr int kNumQueues = PBRGPU_MAT_COUNT + 3;
+constexpr uint32_t kQueueDead = 15u;                // path ended before shading (beta went black in Medium::Sample)
+// per-path word `meta`: sampler dimension (bits 0-15) | specularBounce (bit 16) | VolPath: bounces (bits 17-23)
+constexpr int kMetaSpecBit = 16;
+constexpr int kMetaBounceShift = 17;
+constexpr uint32_t kMetaBounceMask = 0x7fu;
 
 // ---- triangle record (leaf order): three float4 = three 16-byte loads ----
 //   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-23), material type (24-27), flags (28-31)
@@ -27,6 +35,7 @@ struct CameraDev {
   float lensRadius, focalDistance;
   float r2c[16];
   float c2w[16];
+  int medium;  // Camera::medium (index into SceneDev::media) or -1
 };
 
 struct EnvDev {
@@ -59,6 +68,9 @@ struct SceneDev {
   const float4* nodes8;         // Bvh8Node[] viewed as 5 x float4 per node
   const pbrgpu_material* mats;  // roughness fields already remapped to alpha on the host (glibc logf)
   const pbrgpu_light* lights;   // AREA_TRI: .tri = LEAF-ORDER triangle index
+  const pbrgpu_medium* media;   // HomogeneousMedium table (VolPath)
+  const uint32_t* triMedium;    // per leaf-order triangle: (inside + 1) | (outside + 1) << 16, 0 = none; NULL = no interfaces
+  int nMedia;
   int nTris, nLights, nInfinite;
   unsigned f32one;              // 0x3F800000 (opaque to ptxas: keeps the PRMT selector an immediate, trace.cuh q2f)
   int infinite[4];              // indices of infinite lights (Scene::infiniteLights)
@@ -81,17 +93,22 @@ struct Counters {
 
 // SoA wavefront state, `capacity` slots.  slot = j*nPix + pixel (j = sample within the wave).
 struct WaveDev {
-  float4* rayO;     // o.xyz, tMax
-  float4* rayD;     // d.xyz, time
+  float4* rayO;     // o.xyz, tMax (VolPath: k_trace stores the hit distance here for Medium::Sample)
+  float4* rayD;     // d.xyz, time (VolPath: as_float(Ray::medium id or -1))
   float4* hit;      // as_float(leaf tri index or -1), b0, b1, b2
   float4* beta;     // beta.rgb, etaScale
   float4* L;        // L.rgb (per-path radiance, summed in launch order => deterministic)
   uint2* hidx;      // Halton index (lo, hi)
-  uint32_t* meta;   // dim (bits 0-15) | specularBounce (bit 16)
+  uint32_t* meta;   // dim (bits 0-15) | specularBounce (bit 16) | VolPath: bounces (bits 17-23)
   // shadow-ray queue (EstimateDirect light-sampling strategy)
   float4* shO;      // o.xyz, tMax
   float4* shD;      // d.xyz, as_float(slot)
   float4* shC;      // contribution rgb added to L[slot] when unoccluded
+  // VolPath only: far endpoint of the shadow segment (VisibilityTester::p1) so that the ray can be re-spawned at
+  // every medium boundary it crosses (VisibilityTester::Tr, Light.cpp:31-47), and the medium of the current segment
+  float4* shP1;     // p1.xyz, as_float(medium id of the segment or -1)
+  float4* shE1;     // p1.pError
+  float4* shN1;     // p1.n
   // MIS-ray queue (EstimateDirect BSDF-sampling strategy; closest hit)
   float4* miO;      // o.xyz, tMax -> after k_trace<MIS>: as_float(hit triangle or -1)
   float4* miD;      // d.xyz, as_float(slot)

@@ -10,8 +10,15 @@
 // k_trace is ONE persistent kernel: warps pull rays from a device queue and replace finished rays
 // while the rest of the warp keeps traversing (ballot / shfl aggregated fetch).
 // All paths of a wave are at the same bounce, so `bounce` is a launch argument, not path state.
+//
+// VolPathIntegrator::Li (Integrator/VolPathIntegrator.cpp:21-107) runs on the same wavefront with VOL = true
+// instantiations: rays carry a medium id, k_trace stores the hit distance, k_medium_sample draws
+// Medium::Sample per segment, two more queues (surface without material, scattering inside a medium) are shaded
+// by k_shade_null / k_shade_medium, shadow rays march through medium boundaries inside k_trace
+// (VisibilityTester::Tr), and the bounce count is path state (a boundary crossing does not count as a bounce).
 #pragma once
 #include "shade.cuh"
+#include "media.cuh"
 
 namespace pbr {
 
@@ -79,7 +86,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
     V3 o, d;
     generate_ray(P.sc.cam, (float)px + u0, (float)py + u1, lu, lv, &o, &d);
     P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
-    P.ws.rayD[slot] = make_float4(d.x, d.y, d.z, 0.f);
+    P.ws.rayD[slot] = make_float4(d.x, d.y, d.z, P.integrator == PBRGPU_INTEGRATOR_VOLPATH ? __int_as_float(P.sc.cam.medium) : 0.f);
     P.ws.beta[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
     P.ws.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     P.ws.hidx[slot] = make_uint2((uint32_t)((uint64_t)idx & 0xffffffffu), (uint32_t)((uint64_t)idx >> 32));
@@ -130,7 +137,47 @@ constexpr int kNodeStepsPerIter = PBR_NODE_STEPS;
 #ifndef PBR_SHADE_MIN_BLOCKS
 #define PBR_SHADE_MIN_BLOCKS 6
 #endif
-template <bool COUNT>
+// VisibilityTester::Tr (Light/Light.cpp:31-47) for one finished segment of a VolPath shadow ray: returns true when the
+// ray continues behind a medium boundary (state re-initialised in T), false when it is done (blocked, or arrived and
+// its contribution x transmittance added to L).
+constexpr int kMaxShadowCrossings = 256;
+PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T, int* hops) {
+  const SceneDev& sc = P.sc;
+  if (T.hit.tri >= 0 && ((T.hit.w1 >> kTriTypeShift) & 0xfu) != (uint32_t)kQueueNull) return false;  // opaque surface: Tr = 0
+  float4 c = P.ws.shC[ray];
+  const float4 p1m = P.ws.shP1[ray], dd = P.ws.shD[ray];
+  const int med = __float_as_int(p1m.w);
+  const V3 d(dd.x, dd.y, dd.z);
+  if (med >= 0) {  // ray.medium->Tr(ray): ray.tMax is the hit distance after Intersect, else 1 - ShadowEpsilon
+    const Spec tr = medium_Tr(sc.media[med], T.hit.t, length(d));
+    c.x *= tr.r; c.y *= tr.g; c.z *= tr.b;
+  }
+  if (T.hit.tri < 0) {
+    const uint32_t slot = __float_as_uint(dd.w);
+    atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
+    return false;
+  }
+  if (++*hops > kMaxShadowCrossings) return false;
+  // ray = isect.SpawnRayTo(p1)   (Interaction.h:38-43; isect.mediumInterface from GeometricPrimitive::Intersect)
+  const TriData tri = load_tri(sc, T.hit.tri);
+  Isect is;
+  make_isect(sc, tri, T.hit.tri, T.hit.b0, T.hit.b1, T.hit.b2, d, &is);
+  const float4 e1 = P.ws.shE1[ray], n1 = P.ws.shN1[ray];
+  const V3 p1(p1m.x, p1m.y, p1m.z);
+  const V3 origin = offset_ray_origin(is.p, is.pError, is.n, p1 - is.p);
+  const V3 target = offset_ray_origin(p1, V3(e1.x, e1.y, e1.z), V3(n1.x, n1.y, n1.z), origin - p1);
+  const V3 nd = target - origin;
+  int mIn, mOut;
+  isect_media(sc, T.hit.tri, med, &mIn, &mOut);
+  const int nmed = dot(nd, is.n) > 0 ? mOut : mIn;
+  P.ws.shC[ray] = c;
+  P.ws.shP1[ray].w = __int_as_float(nmed);
+  P.ws.shD[ray] = make_float4(nd.x, nd.y, nd.z, dd.w);
+  trav_init(T, origin, nd, 1 - kShadowEpsilon, sc.f32one);
+  return true;
+}
+
+template <bool COUNT, bool VOL = false>
 __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
   __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
   __shared__ uint2 stri[kTraceBlock / 32][kTriQueue][32];
@@ -149,6 +196,8 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   int mode = TRACE_PATH;
   uint32_t ray = 0;  // PATH: wavefront slot; SHADOW / MIS: index in that queue
   uint32_t qi = 0;   // PATH: position in the path queue
+  int hops = 0;      // VOL: medium boundaries this shadow ray has crossed
+  unsigned segs = 0; // VOL: shadow-ray segments traced by this lane (each is one Scene::Intersect of VisibilityTester::Tr)
   unsigned nodes = 0, tris = 0;
   while (true) {
     // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
@@ -169,6 +218,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
           else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
           trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, P.sc.f32one);
           nt = 0;
+          hops = 0;
           busy = true;
         }
       }
@@ -192,16 +242,22 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
       if (T.tgroup.y != 0u || nt > 0) {
         if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
         if (COUNT) tris++;
-        if (cw_tri_step(P.sc, T) && mode == TRACE_SHADOW) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+        // any-hit exit for shadow rays; VolPath shadow rays need the CLOSEST surface (it may be a medium boundary)
+        if (cw_tri_step(P.sc, T) && !VOL && mode == TRACE_SHADOW) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
       }
       // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
       if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {
+        bool again = false;
         if (mode == TRACE_PATH) {
           P.ws.hit[ray] = make_float4(__int_as_float(T.hit.tri), T.hit.b0, T.hit.b1, T.hit.b2);
           // shading-queue id of this path, written in QUEUE order so that k_classify reads it coalesced
           P.ws.qType[qi] = T.hit.tri >= 0 ? ((T.hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
+          if (VOL) P.ws.rayO[ray].w = T.hit.t;  // ray.tMax after Scene::Intersect, read by Medium::Sample
         } else if (mode == TRACE_MIS) {
           P.ws.miO[ray].w = __int_as_float(T.hit.tri);
+        } else if (VOL) {
+          segs++;
+          again = vol_shadow_next_segment(P, ray, T, &hops);  // true: next segment, same lane
         } else if (T.hit.tri < 0) {  // unoccluded: add the light-sampling contribution
           const uint32_t slot = __float_as_uint(P.ws.shD[ray].w);
           const float4 c = P.ws.shC[ray];
@@ -212,7 +268,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
             P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
           }
         }
-        busy = false;
+        busy = again;
       }
     }
   }
@@ -220,8 +276,12 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
     atomicAdd(&C->nodesVisited, (unsigned long long)nodes);
     atomicAdd(&C->trisTested, (unsigned long long)tris);
   }
+  if (VOL) {  // VolPath has no IntersectP queries: every shadow segment is a closest-hit query
+    segs = __reduce_add_sync(full, segs);
+    if (lane == 0 && segs) atomicAdd(&C->raysClosest, (unsigned long long)segs);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    atomicAdd(&C->raysShadow, (unsigned long long)nShadow);
+    if (!VOL) atomicAdd(&C->raysShadow, (unsigned long long)nShadow);
     atomicAdd(&C->raysClosest, (unsigned long long)(nPath + nMis));
     atomicAdd(&C->raysPath, (unsigned long long)nPath);
   }
@@ -254,7 +314,8 @@ __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ Ren
       if (i < n) {
         slot[k] = P.ws.qCur[i];
         q[k] = (int)P.ws.qType[i];
-        rank[k] = atomicAdd(&cnt[q[k]], 1u);  // shared-memory atomic: rank inside this block's tile
+        if (q[k] >= kNumQueues) q[k] = -1;  // kQueueDead: the path ended in k_medium_sample
+        else rank[k] = atomicAdd(&cnt[q[k]], 1u);  // shared-memory atomic: rank inside this block's tile
       }
     }
     __syncthreads();
@@ -285,7 +346,10 @@ PBR_D uint32_t block_queue_push(uint32_t* counter, bool active, uint32_t* sCount
 }
 
 // K4/K5/K7: shading for one material queue.
-template <int MAT>
+// VOL = true is VolPathIntegrator::Li's surface branch (VolPathIntegrator.cpp:56-93): the bounce count comes from
+// the path (`bounce` is ignored), UniformSampleOneLight runs for every BSDF (no NumComponents guard), the shadow
+// ray carries what VisibilityTester::Tr needs, and the spawned ray takes the medium on its side of the surface.
+template <int MAT, bool VOL = false>
 __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderParams P, int bounce) {
   __shared__ uint32_t sCount, sBase;
   const uint32_t n = P.ws.ctr->nMat[MAT];
@@ -296,12 +360,15 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
     bool active = i < n;
     bool pushShadow = false, pushMis = false, pushNext = false;
     uint32_t slot = 0;
-    float4 shO, shD, shC, miO, miD, miC;
+    float4 shO, shD, shC, miO, miD, miC, shP1, shE1, shN1;
     if (active) {
       slot = queue[i];
-      float4 ro4 = P.ws.rayO[slot], rd4 = P.ws.rayD[slot], h4 = P.ws.hit[slot], be4 = P.ws.beta[slot];
+      float4 rd4 = P.ws.rayD[slot], h4 = P.ws.hit[slot], be4 = P.ws.beta[slot];
       uint2 hi = P.ws.hidx[slot];
       uint32_t meta = P.ws.meta[slot];
+      if (VOL) bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
+      int medIn = -1, medOut = -1;
+      if (VOL) isect_media(sc, __float_as_int(h4.x), __float_as_int(rd4.w), &medIn, &medOut);
       V3 rayD(rd4.x, rd4.y, rd4.z);
       Spec beta(be4.x, be4.y, be4.z);
       float etaScale = be4.w;
@@ -322,7 +389,7 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
         Bsdf bsdf;
         make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf);
         const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
-        if (bsdf_num_components<MAT>(bsdf, nonSpec) > 0 && sc.nLights > 0) {
+        if ((VOL || bsdf_num_components<MAT>(bsdf, nonSpec) > 0) && sc.nLights > 0) {
           // UniformSampleOneLight (Integrator.cpp:46-69)
           float pickPdf;
           int lightNum = sample_discrete(sc.lightFunc, sc.lightCdf, sc.lightFuncInt, sc.nLights, cur.get1D(sc.hp), &pickPdf);
@@ -348,6 +415,11 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
                 shO = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
                 shD = make_float4(dd.x, dd.y, dd.z, __uint_as_float(slot));
                 shC = make_float4(c.r, c.g, c.b, 0.f);
+                if (VOL) {  // p0.SpawnRayTo(p1): Ray::medium = GetMedium(d)  (Interaction.h:38-50)
+                  shP1 = make_float4(ls.p1.x, ls.p1.y, ls.p1.z, __int_as_float(dot(dd, is.n) > 0 ? medOut : medIn));
+                  shE1 = make_float4(ls.pErr1.x, ls.pErr1.y, ls.pErr1.z, 0.f);
+                  shN1 = make_float4(ls.n1.x, ls.n1.y, ls.n1.z, 0.f);
+                }
                 pushShadow = true;
               }
             }
@@ -401,9 +473,10 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
           }
           if (alive) {
             P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
-            P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, 0.f);
+            P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, VOL ? __int_as_float(dot(wi, is.n) > 0 ? medOut : medIn) : 0.f);
             P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, etaScale);
-            P.ws.meta[slot] = (uint32_t)cur.dim | (specularBounce ? (1u << 16) : 0u);
+            P.ws.meta[slot] = (uint32_t)cur.dim | (specularBounce ? (1u << kMetaSpecBit) : 0u) |
+                              (VOL ? ((uint32_t)(bounce + 1) << kMetaBounceShift) : 0u);
             pushNext = true;
           }
         }
@@ -414,7 +487,10 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
       }
     }
     uint32_t pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nShadow, pushShadow, &sCount, &sBase);
-    if (pushShadow) { P.ws.shO[pos] = shO; P.ws.shD[pos] = shD; P.ws.shC[pos] = shC; }
+    if (pushShadow) {
+      P.ws.shO[pos] = shO; P.ws.shD[pos] = shD; P.ws.shC[pos] = shC;
+      if (VOL) { P.ws.shP1[pos] = shP1; P.ws.shE1[pos] = shE1; P.ws.shN1[pos] = shN1; }
+    }
     pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nMis, pushMis, &sCount, &sBase);
     if (pushMis) { P.ws.miO[pos] = miO; P.ws.miD[pos] = miD; P.ws.miC[pos] = miC; }
     pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nNext, pushNext, &sCount, &sBase);
@@ -588,15 +664,212 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// VolPathIntegrator (Integrator/VolPathIntegrator.cpp:21-107), the parts that have no PathIntegrator twin.
+// ---------------------------------------------------------------------------------------------
+PBR_D SamplerCursor load_cursor(const RenderParams& P, uint32_t slot, uint32_t meta) {
+  const uint2 hi = P.ws.hidx[slot];
+  SamplerCursor cur;
+  cur.index = (int64_t)(((uint64_t)hi.y << 32) | hi.x);
+  cur.dim = (int)(meta & 0xffffu);
+  cur.arrayEndDim = P.arrayEndDim;
+  return cur;
+}
+
+// `if (ray.medium) beta *= ray.medium->Sample(ray, sampler, &mi); if (beta.IsBlack()) break;`  (:35-36) for every
+// live path whose segment lies in a medium; a sampled MediumInteraction re-routes the path to the medium queue.
+__global__ void __launch_bounds__(kBlock) k_medium_sample(const __grid_constant__ RenderParams P) {
+  const uint32_t n = P.ws.ctr->nCur;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = P.ws.qCur[i];
+    const float4 rd4 = P.ws.rayD[slot];
+    const int med = __float_as_int(rd4.w);
+    if (med < 0) continue;
+    const uint32_t meta = P.ws.meta[slot];
+    SamplerCursor cur = load_cursor(P, slot, meta);
+    const float u0 = cur.get1D(P.sc.hp);
+    const float u1 = cur.get1D(P.sc.hp);
+    float t;
+    bool sampled;
+    const Spec w = medium_sample(P.sc.media[med], u0, u1, P.ws.rayO[slot].w, length(V3(rd4.x, rd4.y, rd4.z)), &t, &sampled);
+    const float4 be4 = P.ws.beta[slot];
+    const Spec beta = Spec(be4.x, be4.y, be4.z) * w;
+    if (beta.is_black()) { P.ws.qType[i] = kQueueDead; continue; }
+    P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, be4.w);
+    P.ws.meta[slot] = (meta & ~0xffffu) | (uint32_t)cur.dim;
+    if (sampled) {
+      P.ws.qType[i] = (uint32_t)kQueueMedium;
+      P.ws.rayO[slot].w = t;  // mi.p = ray(t)
+    }
+  }
+}
+
+// Surface without a material = medium boundary (:65-70): emission rule, maxDepth test, then
+// `ray = isect.SpawnRay(ray.d); bounces--; continue;` - same direction, same bounce count, no Russian roulette.
+__global__ void __launch_bounds__(kBlock) k_shade_null(const __grid_constant__ RenderParams P) {
+  const uint32_t n = P.ws.ctr->nMat[kQueueNull];
+  const SceneDev& sc = P.sc;
+  const uint32_t* queue = P.ws.qMat + (size_t)kQueueNull * P.ws.capacity;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    bool pushNext = false;
+    uint32_t slot = 0;
+    if (i < n) {
+      slot = queue[i];
+      const float4 rd4 = P.ws.rayD[slot], h4 = P.ws.hit[slot];
+      const uint32_t meta = P.ws.meta[slot];
+      const int bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
+      const bool specularBounce = (meta >> kMetaSpecBit) & 1u;
+      const V3 rayD(rd4.x, rd4.y, rd4.z);
+      const int tri = __float_as_int(h4.x);
+      const TriData td = load_tri(sc, tri);
+      Isect is;
+      make_isect(sc, td, tri, h4.y, h4.z, h4.w, rayD, &is);
+      if ((bounce == 0 || specularBounce) && is.lightId >= 0) {
+        const float4 be4 = P.ws.beta[slot];
+        const Spec Ladd = Spec(be4.x, be4.y, be4.z) * area_light_L(sc.lights[is.lightId], is.n, -rayD);
+        if (!Ladd.is_black()) {
+          const float4 L = P.ws.L[slot];
+          P.ws.L[slot] = make_float4(L.x + Ladd.r, L.y + Ladd.g, L.z + Ladd.b, 0.f);
+        }
+      }
+      if (bounce < P.maxDepth) {
+        int mIn, mOut;
+        isect_media(sc, tri, __float_as_int(rd4.w), &mIn, &mOut);
+        const V3 o = offset_ray_origin(is.p, is.pError, is.n, rayD);
+        P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
+        P.ws.rayD[slot] = make_float4(rayD.x, rayD.y, rayD.z, __int_as_float(dot(rayD, is.n) > 0 ? mOut : mIn));
+        pushNext = true;
+      }
+    }
+    const uint32_t pos = queue_push(&P.ws.ctr->nNext, pushNext);
+    if (pushNext) P.ws.qNext[pos] = slot;
+  }
+}
+
+// Scattering inside a medium (:39-54): direct lighting with the phase function in place of the BSDF
+// (EstimateDirect's MediumInteraction branches, Integrator.cpp:95-100,137-142), then Sample_p for the next direction.
+__global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_constant__ RenderParams P) {
+  __shared__ uint32_t sCount, sBase;
+  const uint32_t n = P.ws.ctr->nMat[kQueueMedium];
+  const SceneDev& sc = P.sc;
+  const uint32_t* queue = P.ws.qMat + (size_t)kQueueMedium * P.ws.capacity;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    bool pushShadow = false, pushMis = false, pushNext = false;
+    uint32_t slot = 0;
+    float4 shO, shD, shC, miO, miD, miC, shP1, shE1, shN1;
+    if (i < n) {
+      slot = queue[i];
+      const float4 ro4 = P.ws.rayO[slot], rd4 = P.ws.rayD[slot], be4 = P.ws.beta[slot];
+      const uint32_t meta = P.ws.meta[slot];
+      const int bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
+      if (bounce < P.maxDepth) {
+        const int med = __float_as_int(rd4.w);
+        const float g = sc.media[med].g;
+        const V3 rayD(rd4.x, rd4.y, rd4.z);
+        const V3 p = V3(ro4.x, ro4.y, ro4.z) + rayD * ro4.w;  // mi.p = ray(t)
+        const V3 wo = -rayD;                                  // mi.wo (not normalised: Interaction.h:21-22)
+        const V3 zero(0, 0, 0);
+        Spec beta(be4.x, be4.y, be4.z);
+        const float etaScale = be4.w;
+        SamplerCursor cur = load_cursor(P, slot, meta);
+        if (sc.nLights > 0) {
+          float pickPdf;
+          const int lightNum = sample_discrete(sc.lightFunc, sc.lightCdf, sc.lightFuncInt, sc.nLights, cur.get1D(sc.hp), &pickPdf);
+          if (pickPdf != 0) {
+            float uL0, uL1, uS0, uS1;
+            cur.get2D(sc.hp, &uL0, &uL1);
+            cur.get2D(sc.hp, &uS0, &uS1);
+            const pbrgpu_light& light = sc.lights[lightNum];
+            LightSample ls;
+            sample_light(sc, light, p, uL0, uL1, &ls);
+            if (ls.pdf > 0 && !ls.Li.is_black()) {
+              const Spec f(hg_p(wo, ls.wi, g));
+              // the reference leaves scatteringPdf = 0 in this branch (Integrator.cpp:95-100), so the light-sampling
+              // strategy gets PowerHeuristic(1, lightPdf, 1, 0): reproduced as is
+              const float scatteringPdf = 0;
+              if (!f.is_black()) {
+                const V3 origin = offset_ray_origin(p, zero, zero, ls.p1 - p);
+                const V3 target = offset_ray_origin(ls.p1, ls.pErr1, ls.n1, origin - ls.p1);
+                const V3 dd = target - origin;
+                Spec Ld;
+                if (is_delta_light(light)) Ld = f * ls.Li / ls.pdf;
+                else Ld = f * ls.Li * power_heuristic(1, ls.pdf, 1, scatteringPdf) / ls.pdf;
+                const Spec c = beta * (Ld / pickPdf);
+                shO = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
+                shD = make_float4(dd.x, dd.y, dd.z, __uint_as_float(slot));
+                shC = make_float4(c.r, c.g, c.b, 0.f);
+                shP1 = make_float4(ls.p1.x, ls.p1.y, ls.p1.z, __int_as_float(med));
+                shE1 = make_float4(ls.pErr1.x, ls.pErr1.y, ls.pErr1.z, 0.f);
+                shN1 = make_float4(ls.n1.x, ls.n1.y, ls.n1.z, 0.f);
+                pushShadow = true;
+              }
+            }
+            if (!is_delta_light(light)) {
+              V3 wi;
+              const float ph = hg_sample_p(wo, &wi, uS0, uS1, g);
+              const Spec f(ph);
+              const float scatteringPdf = ph;
+              if (!f.is_black() && scatteringPdf > 0) {
+                const float lightPdf = light_pdf_li(sc, light, p, p, wi);
+                if (lightPdf != 0) {
+                  const float weight = power_heuristic(1, scatteringPdf, 1, lightPdf);
+                  const Spec c = beta * ((f * weight / scatteringPdf) / pickPdf);
+                  miO = make_float4(p.x, p.y, p.z, kInfinity);
+                  miD = make_float4(wi.x, wi.y, wi.z, __uint_as_float(slot));
+                  miC = make_float4(c.r, c.g, c.b, __int_as_float(lightNum));
+                  pushMis = true;
+                }
+              }
+            }
+          }
+        }
+        // mi.phase->Sample_p(wo, &wi, sampler.Get2D()); ray = mi.SpawnRay(wi); specularBounce = false
+        float u0, u1;
+        cur.get2D(sc.hp, &u0, &u1);
+        V3 wi;
+        hg_sample_p(wo, &wi, u0, u1, g);
+        bool alive = true;
+        const Spec rrBeta = beta * etaScale;
+        if (rrBeta.max_value() < P.rrThreshold && bounce > 3) {
+          const float q = stdmax(.05f, 1 - rrBeta.max_value());
+          if (cur.get1D(sc.hp) < q) alive = false;
+          else beta = beta / (1 - q);
+        }
+        if (alive) {
+          P.ws.rayO[slot] = make_float4(p.x, p.y, p.z, kInfinity);
+          P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, __int_as_float(med));
+          P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, etaScale);
+          P.ws.meta[slot] = (uint32_t)cur.dim | ((uint32_t)(bounce + 1) << kMetaBounceShift);
+          pushNext = true;
+        }
+      }
+    }
+    uint32_t pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nShadow, pushShadow, &sCount, &sBase);
+    if (pushShadow) {
+      P.ws.shO[pos] = shO; P.ws.shD[pos] = shD; P.ws.shC[pos] = shC;
+      P.ws.shP1[pos] = shP1; P.ws.shE1[pos] = shE1; P.ws.shN1[pos] = shN1;
+    }
+    pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nMis, pushMis, &sCount, &sBase);
+    if (pushMis) { P.ws.miO[pos] = miO; P.ws.miD[pos] = miD; P.ws.miC[pos] = miC; }
+    pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nNext, pushNext, &sCount, &sBase);
+    if (pushNext) P.ws.qNext[pos] = slot;
+  }
+}
+
 // Rays that left the scene: Le of the infinite lights (PathIntegrator.cpp:52-56), path ends (:60).
 __global__ void __launch_bounds__(kBlock) k_shade_miss(const __grid_constant__ RenderParams P, int bounce) {
   const uint32_t n = P.ws.ctr->nMat[kQueueMiss];
   const uint32_t* queue = P.ws.qMat + (size_t)kQueueMiss * P.ws.capacity;
-  const bool pathInteg = P.integrator == PBRGPU_INTEGRATOR_PATH;
+  const bool volInteg = P.integrator == PBRGPU_INTEGRATOR_VOLPATH;
+  const bool pathInteg = P.integrator == PBRGPU_INTEGRATOR_PATH || volInteg;
   if (pathInteg && P.sc.nInfinite == 0) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t slot = queue[i];
-    bool specularBounce = (P.ws.meta[slot] >> 16) & 1u;
+    const uint32_t meta = P.ws.meta[slot];
+    bool specularBounce = (meta >> kMetaSpecBit) & 1u;
+    if (volInteg) bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
     if (pathInteg && !(bounce == 0 || specularBounce)) continue;
     float4 rd = P.ws.rayD[slot], be = P.ws.beta[slot];
     Spec beta(be.x, be.y, be.z);

@@ -130,6 +130,12 @@ struct pbrgpu_scene {
   int fetchMinIdle = 8;
   int waveLog2 = 25;
   bool hasMat[PBRGPU_MAT_COUNT] = {};  // material types present in the scene (absent ones: no shade launch)
+  bool hasNullMat = false;             // some triangle has no material (medium boundary): VolPath only
+  DevBuf<pbrgpu_medium> media;
+  DevBuf<uint32_t> triMedium;
+  DevBuf<float4> shP1, shE1, shN1;     // VolPath shadow-ray endpoints (allocated on first VolPath render)
+  size_t volRayCapacity = 0;
+  uint32_t* hNCur = nullptr;           // pinned: live-path count read back by the VolPath loop
   // wavefront state
   uint32_t capacity = 0;
   size_t rayCapacity = 0;
@@ -145,14 +151,19 @@ struct pbrgpu_scene {
   DevBuf<unsigned char> d8;
   void* hstage = nullptr;
   size_t hstageBytes = 0;
-  ~pbrgpu_scene() { if (hstage) cudaFreeHost(hstage); }
+  ~pbrgpu_scene() { if (hstage) cudaFreeHost(hstage); if (hNCur) cudaFreeHost(hNCur); }
 };
 
 namespace {
 
-int ensure_wave(pbrgpu_scene* s, uint32_t cap, uint32_t raysPerHit) {
+int ensure_wave(pbrgpu_scene* s, uint32_t cap, uint32_t raysPerHit, bool vol) {
   // shadow / MIS queues hold up to raysPerHit rays per path and bounce (1 for the Path integrator)
   size_t rcap = (size_t)cap * raysPerHit;
+  if (vol && s->volRayCapacity < rcap) {
+    CK(s->shP1.alloc(rcap)); CK(s->shE1.alloc(rcap)); CK(s->shN1.alloc(rcap));
+    s->volRayCapacity = rcap;
+  }
+  if (vol && !s->hNCur) CK(cudaHostAlloc((void**)&s->hNCur, 4 * sizeof(uint32_t), cudaHostAllocDefault));
   if (s->rayCapacity < rcap) {
     CK(s->shO.alloc(rcap)); CK(s->shD.alloc(rcap)); CK(s->shC.alloc(rcap));
     CK(s->miO.alloc(rcap)); CK(s->miD.alloc(rcap)); CK(s->miC.alloc(rcap));
@@ -172,6 +183,7 @@ void fill_wave(pbrgpu_scene* s, WaveDev* w) {
   w->rayO = s->rayO.p; w->rayD = s->rayD.p; w->hit = s->hit.p; w->beta = s->beta.p; w->L = s->L.p;
   w->hidx = s->hidx.p; w->meta = s->meta.p;
   w->shO = s->shO.p; w->shD = s->shD.p; w->shC = s->shC.p;
+  w->shP1 = s->shP1.p; w->shE1 = s->shE1.p; w->shN1 = s->shN1.p;
   w->miO = s->miO.p; w->miD = s->miD.p; w->miC = s->miC.p;
   w->qCur = s->qA.p; w->qNext = s->qB.p; w->qMat = s->qMat.p; w->qType = s->qType.p;
   w->ctr = s->ctr.p;
@@ -282,11 +294,16 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
     return fail("pbrgpu_scene_create: empty scene");
   if (d->n_tris >= (1 << 29)) return fail("pbrgpu_scene_create: too many triangles");
   if (d->n_materials <= 0 || d->n_materials > (int)kTriMatMask) return fail("pbrgpu_scene_create: bad material count");
+  if (d->n_media < 0 || d->n_media > 0xfffe || (d->n_media > 0 && !d->media)) return fail("pbrgpu_scene_create: bad media table");
+  for (int i = 0; i < d->n_media; ++i)
+    if (d->media[i].type != PBRGPU_MEDIUM_HOMOGENEOUS) return fail("pbrgpu_scene_create: unknown medium type (HomogeneousMedium only)");
   for (int64_t i = 0; i < (int64_t)d->n_tris * 3; ++i)
     if (d->indices[i] < 0 || d->indices[i] >= d->n_verts) return fail("pbrgpu_scene_create: vertex index out of range");
   for (int i = 0; i < d->n_tris; ++i) {
-    if (d->tri_material[i] < 0 || d->tri_material[i] >= d->n_materials)
-      return fail("pbrgpu_scene_create: triangle without a material (null-BSDF pass-through is not supported)");
+    if (d->tri_material[i] < -1 || d->tri_material[i] >= d->n_materials)
+      return fail("pbrgpu_scene_create: tri_material out of range");
+    for (const int32_t* tm : {d->tri_medium_inside, d->tri_medium_outside})
+      if (tm && (tm[i] < -1 || tm[i] >= d->n_media)) return fail("pbrgpu_scene_create: triangle medium index out of range");
     if (d->tri_light && d->tri_light[i] >= d->n_lights) return fail("pbrgpu_scene_create: tri_light out of range");
   }
   CK(cudaSetDevice(ctx->device));
@@ -314,7 +331,10 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
     const uint8_t tf = d->tri_flags ? d->tri_flags[ti] : (uint8_t)((d->normals ? 4 : 0) | (d->uvs ? 8 : 0));
     uint32_t flags = (tf & 1 ? kTriFlagFlipNormal : 0u) | (tf & 2 ? kTriFlagReverse : 0u) |
                      ((tf & 4) && d->normals ? kTriFlagNormals : 0u) | ((tf & 8) && d->uvs ? kTriFlagUVs : 0u);
-    uint32_t w1 = (uint32_t)m | ((uint32_t)d->materials[m].type << kTriTypeShift) | (flags << kTriFlagShift);
+    // a triangle without a material carries the queue id of "medium boundary" as its type code
+    if (m < 0) s->hasNullMat = true;
+    uint32_t w1 = m < 0 ? ((uint32_t)kQueueNull << kTriTypeShift) | (flags << kTriFlagShift)
+                        : (uint32_t)m | ((uint32_t)d->materials[m].type << kTriTypeShift) | (flags << kTriFlagShift);
     int32_t lid = d->tri_light ? d->tri_light[ti] : -1;
     v0[k] = make_float4(a[0], a[1], a[2], u2f((uint32_t)ti));
     v1[k] = make_float4(b[0], b[1], b[2], u2f(w1));
@@ -352,6 +372,24 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   if (!vuv0.empty()) { CK(s->tuv0.upload(vuv0, st)); CK(s->tuv1.upload(vuv1, st)); }
   CK(s->tv0.upload(v0, st)); CK(s->tv1.upload(v1, st)); CK(s->tv2.upload(v2, st));
   CK(s->nodes.upload(s->bvh.nodes, st));
+  // participating media + per-triangle MediumInterface (leaf order)
+  if (d->n_media > 0) {
+    std::vector<pbrgpu_medium> media(d->media, d->media + d->n_media);
+    CK(s->media.upload(media, st));
+    s->sc.media = s->media.p;
+    s->sc.nMedia = d->n_media;
+    if (d->tri_medium_inside || d->tri_medium_outside) {
+      std::vector<uint32_t> tm((size_t)nT);
+      for (int k = 0; k < nT; ++k) {
+        const int ti = s->bvh.triOrder[k];
+        const int in = d->tri_medium_inside ? d->tri_medium_inside[ti] : -1;
+        const int out = d->tri_medium_outside ? d->tri_medium_outside[ti] : -1;
+        tm[k] = (uint32_t)(in + 1) | ((uint32_t)(out + 1) << 16);
+      }
+      CK(s->triMedium.upload(tm, st));
+      s->sc.triMedium = s->triMedium.p;
+    }
+  }
 
   // materials: RoughnessToAlpha applied on the host (glibc logf, as the reference would)
   std::vector<pbrgpu_material> mats(d->materials, d->materials + d->n_materials);
@@ -549,6 +587,8 @@ int pbrgpu_camera_set(pbrgpu_scene* s, const pbrgpu_camera_desc* c) {
   cd.lensRadius = c->lens_radius; cd.focalDistance = c->focal_distance;
   memcpy(cd.r2c, c->raster_to_camera, sizeof(cd.r2c));
   memcpy(cd.c2w, c->camera_to_world, sizeof(cd.c2w));
+  if (c->medium_plus1 < 0 || c->medium_plus1 > s->sc.nMedia) return fail("pbrgpu_camera_set: camera medium out of range");
+  cd.medium = c->medium_plus1 - 1;
   s->haveCamera = true;
   return 0;
 }
@@ -647,7 +687,11 @@ static int check_render_args(pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
   if (rd->x1 <= rd->x0 || rd->y1 <= rd->y0) return fail("pbrgpu_render: empty pixel region");
   if (rd->s1 < rd->s0 || rd->s0 < 0) return fail("pbrgpu_render: bad sample range");
   if (rd->max_depth < 0 || rd->max_depth > 1000) return fail("pbrgpu_render: bad max_depth");
-  if (rd->integrator < PBRGPU_INTEGRATOR_PATH || rd->integrator > PBRGPU_INTEGRATOR_WHITTED) return fail("pbrgpu_render: unknown integrator");
+  if (rd->integrator < PBRGPU_INTEGRATOR_PATH || rd->integrator > PBRGPU_INTEGRATOR_VOLPATH) return fail("pbrgpu_render: unknown integrator");
+  if (rd->integrator != PBRGPU_INTEGRATOR_VOLPATH && s->hasNullMat)
+    return fail("pbrgpu_render: the scene has triangles without a material (medium boundaries); only the VolPath integrator renders them");
+  if (rd->integrator == PBRGPU_INTEGRATOR_VOLPATH && rd->max_depth > (int)kMetaBounceMask - 1)
+    return fail("pbrgpu_render: VolPath max_depth > 126");
   if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL && s->sc.hp.type == PBRGPU_SAMPLER_SOBOL)
     return fail("pbrgpu_render: UniformSampleAll sample arrays are implemented for the Halton sampler only");
   if (s->bvh.maxDepth >= kSmemStack + kLocalStack) return fail("pbrgpu_render: BVH deeper than the traversal stack");
@@ -702,6 +746,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   const int64_t nS = rd->s1 - rd->s0;
   const bool count = (rd->flags & PBRGPU_RENDER_COUNTERS) != 0;
   const bool pathInteg = rd->integrator == PBRGPU_INTEGRATOR_PATH;
+  const bool volInteg = rd->integrator == PBRGPU_INTEGRATOR_VOLPATH;
   uint32_t raysPerHit = 1;
   if (rd->integrator == PBRGPU_INTEGRATOR_WHITTED) raysPerHit = (uint32_t)std::max<size_t>(1, s->lights.size());
   if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) {
@@ -720,7 +765,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   int nsWaveMax = (int)std::max<int64_t>(1, capMax / ((uint64_t)bandRows * W));
   if (rd->samples_per_wave > 0) nsWaveMax = std::min(nsWaveMax, rd->samples_per_wave);
   uint32_t cap = (uint32_t)((uint64_t)bandRows * W * std::min<int64_t>(nsWaveMax, std::max<int64_t>(nS, 1)));
-  if (ensure_wave(s, cap, raysPerHit)) return 1;
+  if (ensure_wave(s, cap, raysPerHit, volInteg)) return 1;
 
   RenderParams P{};
   P.sc = s->sc;
@@ -732,7 +777,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   // light per recursion depth (DirectLightingIntegrator.cpp:8-26); nobody else requests arrays
   P.arrayEndDim = 5;
   if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) P.arrayEndDim = 5 + 2 * (2 * (int)s->lights.size() * rd->max_depth);
-  P.atomicL = pathInteg ? 0 : 1;
+  P.atomicL = (pathInteg || volInteg) ? 0 : 1;
   P.countStats = count ? 1 : 0;
   P.fetchMinIdle = s->fetchMinIdle;
 
@@ -764,7 +809,38 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       launches += 2;
       // bounce b: ONE traversal launch serves the path rays of bounce b and the shadow + MIS rays that the
       // shading of bounce b-1 emitted; then MIS resolve (b-1), classification, material-sorted shading (b).
-      const int lastBounce = pathInteg ? rd->max_depth : std::max(rd->max_depth - 1, 0);
+      if (volInteg) {
+        // VolPathIntegrator::Li: the bounce count is path state (crossing a medium boundary repeats the bounce), so the
+        // number of iterations is not known up front: max_depth + 1 iterations are launched blind, then the live-path
+        // and pending-ray counters are read back after every iteration until the wave has drained.
+        const int kMaxExtraIters = 4096;
+        for (int iter = 0;; ++iter) {
+          CK(tl.mark(T_CLOSEST));
+          if (count) k_trace<true, true><<<gt, kTraceBlock, 0, st>>>(P);
+          else k_trace<false, true><<<gt, kTraceBlock, 0, st>>>(P);
+          CK(tl.mark(T_MIS));
+          if (iter > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
+          CK(tl.mark(T_SHADE));
+          if (s->sc.nMedia > 0) { k_medium_sample<<<g, kBlock, 0, st>>>(P); launches++; }
+          k_classify<<<gc, kBlock, 0, st>>>(P);
+#define PBR_SHADE_V(M) if (s->hasMat[M]) { k_shade<M, true><<<gs, kShadeBlock, 0, st>>>(P, 0); launches++; }
+          PBR_SHADE_V(PBRGPU_MAT_MATTE) PBR_SHADE_V(PBRGPU_MAT_MIRROR) PBR_SHADE_V(PBRGPU_MAT_GLASS)
+          PBR_SHADE_V(PBRGPU_MAT_METAL) PBR_SHADE_V(PBRGPU_MAT_PLASTIC)
+#undef PBR_SHADE_V
+          if (s->hasNullMat) { k_shade_null<<<g, kBlock, 0, st>>>(P); launches++; }
+          if (s->sc.nMedia > 0) { k_shade_medium<<<gs, kShadeBlock, 0, st>>>(P); launches++; }
+          if (s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, 0); launches++; }
+          k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
+          launches += 3;
+          std::swap(P.ws.qCur, P.ws.qNext);
+          if (iter >= rd->max_depth) {
+            CK(cudaMemcpyAsync(s->hNCur, s->ctr.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));  // nCur, nNext, nShadow, nMis
+            CK(cudaStreamSynchronize(st));
+            if (s->hNCur[0] + s->hNCur[2] + s->hNCur[3] == 0 || iter >= rd->max_depth + kMaxExtraIters) break;
+          }
+        }
+      }
+      const int lastBounce = volInteg ? -1 : (pathInteg ? rd->max_depth : std::max(rd->max_depth - 1, 0));
       for (int bounce = 0; bounce <= lastBounce; ++bounce) {
         CK(tl.mark(T_CLOSEST));
         if (count) k_trace<true><<<gt, kTraceBlock, 0, st>>>(P);
@@ -790,7 +866,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         launches += 3;
         std::swap(P.ws.qCur, P.ws.qNext);
       }
-      if (!pathInteg) {  // shadow / MIS rays of the last shaded depth
+      if (!pathInteg && !volInteg) {  // shadow / MIS rays of the last shaded depth
         CK(tl.mark(T_CLOSEST));
         if (count) k_trace<true><<<gt, kTraceBlock, 0, st>>>(P);
         else k_trace<false><<<gt, kTraceBlock, 0, st>>>(P);

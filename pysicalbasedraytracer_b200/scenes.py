@@ -52,6 +52,9 @@ class SceneData:
         self._tris = []
         self._tri_mat = []
         self._tri_light = []
+        self._tri_med_in = []
+        self._tri_med_out = []
+        self.media = []
         self.materials = []
         self.lights = []
         self.env = None  # (H, W, 3) float32
@@ -65,10 +68,19 @@ class SceneData:
         self.materials.append(m)
         return len(self.materials) - 1
 
+    def add_medium(self, sigma_a, sigma_s, g):
+        """HomogeneousMedium(sigma_a, sigma_s, g)  (Media/HomogeneousMedium.h:12-16) -> medium id."""
+        self.media.append(A.Medium(type=A.MEDIUM_HOMOGENEOUS, g=float(g), sigma_a=_f3(sigma_a), sigma_s=_f3(sigma_s)))
+        return len(self.media) - 1
+
     def add_mesh(self, verts, tris, material, emit=None, two_sided=False, n_samples=1, normals=None, uvs=None,
-                 reverse_orientation=False):
-        """material: int id or per-triangle int array.  emit: RGB Lemit -> one DiffuseAreaLight per triangle.
-        normals / uvs: optional per-vertex shading normals (world space) and uv (TriangleMesh::n / ::uv)."""
+                 reverse_orientation=False, medium_interface=None):
+        """material: int id or per-triangle int array; None / -1 = no material (a pure medium boundary, VolPath only).
+        emit: RGB Lemit -> one DiffuseAreaLight per triangle.
+        normals / uvs: optional per-vertex shading normals (world space) and uv (TriangleMesh::n / ::uv).
+        medium_interface: (inside, outside) medium ids or None each  (MediumInterface, Media/Medium.h:51-59)."""
+        if material is None:
+            material = -1
         verts = np.ascontiguousarray(verts, dtype=F).reshape(-1, 3)
         tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
         n = tris.shape[0]
@@ -87,6 +99,9 @@ class SceneData:
         self._tris.append(tris + self._nverts)
         self._tri_mat.append(mats)
         self._tri_light.append(lights)
+        mi = medium_interface if medium_interface is not None else (None, None)
+        self._tri_med_in.append(np.full(n, -1 if mi[0] is None else mi[0], dtype=np.int32))
+        self._tri_med_out.append(np.full(n, -1 if mi[1] is None else mi[1], dtype=np.int32))
         self._nverts += verts.shape[0]
         self._ntris += n
         self._frozen = None
@@ -175,6 +190,15 @@ class SceneData:
             d.env_height, d.env_width = self.env.shape[0], self.env.shape[1]
             d.env_texels = self.env.ctypes.data_as(C.POINTER(C.c_float))
             keep.append(self.env)
+        if self.media:
+            media = (A.Medium * len(self.media))(*self.media)
+            mi = np.ascontiguousarray(np.concatenate(self._tri_med_in), dtype=np.int32)
+            mo = np.ascontiguousarray(np.concatenate(self._tri_med_out), dtype=np.int32)
+            d.n_media = len(self.media)
+            d.media = media
+            d.tri_medium_inside = mi.ctypes.data_as(C.POINTER(C.c_int32))
+            d.tri_medium_outside = mo.ctypes.data_as(C.POINTER(C.c_int32))
+            keep += [media, mi, mo]
         return d, keep
 
 
@@ -244,6 +268,34 @@ def cornell(sphere_tess=48, floor_mirror=False):
         v, t = uv_sphere([1.0, -1.6, 0.7], 0.9, sphere_tess, 2 * sphere_tess)
         s.add_mesh(v, t, mir)
     return s
+
+
+def cornell_media(kind="smoke", sphere_tess=24, sigma_a=(0.5, 0.5, 0.5), sigma_s=(4.4, 4.4, 4.4), g=-0.5):
+    """Cornell box with a participating medium, the set-ups Main/main.cpp:242-243,346-348 sketches
+    (HomogeneousMedium(0.5, 4.4, -0.5), MediumInterface(&medium, nullptr) on a closed mesh):
+      "smoke"  the medium fills a sphere whose surface has NO material (pure medium boundary)
+      "glass"  the medium fills a glass sphere (main.cpp:348)
+      "fog"    no boundary at all: every primitive has an empty MediumInterface, so a ray keeps the medium it was
+               born in - render it with an orthographic camera created with `media=0` (global fog)
+    Returns (SceneData, medium id)."""
+    s = SceneData()
+    white = s.add_material(matte([1, 1, 1]))
+    red = s.add_material(matte([0.9, 0.1, 0.17]))
+    blue = s.add_material(matte([0.14, 0.21, 0.87]))
+    mir = s.add_material(mirror([1, 1, 1]))
+    gls = s.add_material(glass([0.98] * 3, [0.98] * 3, 1.5))
+    cornell_walls(s, white, red, blue)
+    cornell_area_light(s, white)
+    med = s.add_medium(sigma_a, sigma_s, g)
+    if kind == "fog":
+        v, t = uv_sphere([0.9, -1.6, 0.4], 0.9, sphere_tess, 2 * sphere_tess)
+        s.add_mesh(v, t, mir)
+        return s, med
+    v, t = uv_sphere([-0.9, -1.2, 0.2], 1.1, sphere_tess, 2 * sphere_tess)
+    s.add_mesh(v, t, None if kind == "smoke" else gls, medium_interface=(med, None))
+    v, t = uv_sphere([1.2, -1.7, 0.9], 0.8, sphere_tess, 2 * sphere_tess)
+    s.add_mesh(v, t, mir)
+    return s, med
 
 
 def dragon_class(tess=467, with_point_light=False, block=8192):

@@ -318,3 +318,79 @@ def test_full_size_dragon_class_properties(api, ref, gpu_ctx):
     assert (wr[:, 0] != gr[:, 0]).mean() < 1e-4
     rays[:, 3] = rng.uniform(0.05, 3.0, 50_000)
     assert (p.rscene.trace(rays, any_hit=True) != p.scene.trace(rays, any_hit=True)).mean() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# VolPathIntegrator (Integrator/VolPathIntegrator.cpp) + HomogeneousMedium: the integrator Main/main.cpp:399 runs
+# ---------------------------------------------------------------------------------------------
+def _vol_check(p, ref, max_depth, spp, frac_ok, **kw):
+    V = A.INTEGRATOR_VOLPATH
+    want, rst = ref.render(p.rscene, p.rcam, p.spp, (0, 0, p.W, p.H), integrator=V, max_depth=max_depth, s1=spp, **kw)
+    got, _, st = p.scene.render(integrator=V, max_depth=max_depth, s1=spp, **kw)
+    err = rel_err(got / spp, want / spp)
+    ok = (err <= REL_TOL).mean()
+    print(f"volpath depth {max_depth}: pixels within {REL_TOL}: {ok:.5f}, median err {np.median(err):.2e}, "
+          f"mean gpu {got.mean() / spp:.5f} ref {want.mean() / spp:.5f}, rays gpu {st.rays_closest}+{st.rays_shadow} "
+          f"ref {rst.rays_closest}+{rst.rays_shadow}")
+    assert ok >= frac_ok
+    assert abs(got.mean() - want.mean()) <= 0.01 * want.mean()
+    # VolPath has no IntersectP: path segments, MIS rays and every VisibilityTester::Tr segment are Intersect queries
+    assert int(st.rays_shadow) == 0 and int(rst.rays_shadow) == 0
+    assert abs(int(st.rays_closest) - int(rst.rays_closest)) <= 5e-3 * rst.rays_closest + 8
+    return got, want
+
+
+def test_volpath_without_media_matches_reference(api, ref, gpu_ctx):
+    """No medium anywhere: VolPath differs from Path only in the shadow test (closest-hit Tr marching) and in calling
+    UniformSampleOneLight for specular BSDFs too (it consumes sampler dimensions)."""
+    data = scenes.cornell(sphere_tess=16)
+    data.add_point_light([0.5, 1.5, 0.5], [20.0, 18.0, 15.0])
+    p = Pair(api, ref, data, 96, 96, 2)
+    _vol_check(p, ref, max_depth=1, spp=2, frac_ok=0.999, rr_threshold=0.8)
+    _vol_check(p, ref, max_depth=5, spp=2, frac_ok=0.97, rr_threshold=0.8)
+
+
+@pytest.mark.parametrize("kind", ["smoke", "glass"])
+def test_volpath_medium_in_a_sphere(api, ref, gpu_ctx, kind):
+    data, _ = scenes.cornell_media(kind, sphere_tess=16)
+    data.add_point_light([0.5, 1.5, 0.5], [20.0, 18.0, 15.0])
+    p = Pair(api, ref, data, 96, 96, 2)
+    _vol_check(p, ref, max_depth=1, spp=2, frac_ok=0.995, rr_threshold=0.8)
+    got, want = _vol_check(p, ref, max_depth=6, spp=2, frac_ok=0.93, rr_threshold=0.8)
+    # the medium matters: same scene without it renders differently
+    plain, _, _ = p.scene.render(integrator=A.INTEGRATOR_VOLPATH, max_depth=0, s1=1)
+    assert np.isfinite(got).all() and np.isfinite(plain).all()
+
+
+def test_volpath_camera_medium(api, ref, gpu_ctx):
+    """Camera::medium never reaches the integrator in the reference (Perspective.cpp:44-80 does not set it,
+    Orthographic.cpp:59-60 loses it in CameraToWorld(*ray), Transform.h:169): the mirrors ignore it too.  The library
+    itself can start rays inside a medium (pbrgpu_camera_desc::medium_plus1); that is checked against the reference's
+    Li with the harness re-attaching the medium to the camera ray.  Without medium boundaries every spawned ray
+    inherits the medium (Primitive.cpp:32-35), i.e. the whole scene is fog."""
+    data, med = scenes.cornell_media("fog", sphere_tess=12, sigma_a=(0.05, 0.04, 0.03), sigma_s=(0.25, 0.3, 0.35), g=0.3)
+    views = dict(eye=(0.1, 0.2, 2.3), look=(0.0, 0.1, 0.0))
+    for cam_type in (A.CAMERA_ORTHOGRAPHIC, A.CAMERA_PERSPECTIVE):
+        p = Pair(api, ref, data, 64, 64, 2, cam_type=cam_type, camera_medium=med, **views)
+        clear, _ = _vol_check(p, ref, max_depth=1, spp=2, frac_ok=0.999)  # as shipped: no fog on either side
+        q = Pair(api, ref, data, 64, 64, 2, cam_type=cam_type, camera_medium=med, honour_camera_medium=True, **views)
+        _vol_check(q, ref, max_depth=1, spp=2, frac_ok=0.99)
+        fog, _ = _vol_check(q, ref, max_depth=4, spp=2, frac_ok=0.90, rr_threshold=0.8)
+        assert abs(fog.mean() - clear.mean()) > 0.02 * clear.mean()
+
+
+def test_volpath_rmse_vs_reference_high_spp(api, ref, gpu_ctx):
+    """Noise level: RMSE(gpu@N, ref@high) <= 1.05 * RMSE(ref@N, ref@high) with the smoke sphere in view."""
+    W = H = 40
+    n, hi = 8, 384
+    data, _ = scenes.cornell_media("smoke", sphere_tess=12)
+    p = Pair(api, ref, data, W, H, hi)
+    V = A.INTEGRATOR_VOLPATH
+    kw = dict(max_depth=6, rr_threshold=0.8)
+    truth, _ = ref.render(p.rscene, p.rcam, hi, (0, 0, W, H), integrator=V, s0=n, s1=hi, **kw)
+    truth = truth / (hi - n)
+    cpu, _ = ref.render(p.rscene, p.rcam, hi, (0, 0, W, H), integrator=V, s0=0, s1=n, **kw)
+    gpu, _, _ = p.scene.render(integrator=V, s0=0, s1=n, **kw)
+    r_cpu, r_gpu = rmse(cpu / n, truth), rmse(gpu / n, truth)
+    print(f"volpath RMSE cpu {r_cpu:.5f} gpu {r_gpu:.5f} ratio {r_gpu / r_cpu:.4f}")
+    assert r_gpu <= 1.05 * r_cpu

@@ -9,11 +9,14 @@ EYE, LOOK, UP = (0.0, 0.0, 5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)
 
 class Pair:
     def __init__(self, api, R, data, W, H, spp, eye=EYE, look=LOOK, up=UP, cam_type=A.CAMERA_PERSPECTIVE, ctx=None,
-                 sampler_type=A.SAMPLER_HALTON, lens_radius=0.0, focal_distance=0.0):
+                 sampler_type=A.SAMPLER_HALTON, lens_radius=0.0, focal_distance=0.0, camera_medium=None,
+                 honour_camera_medium=False):
         self.W, self.H, self.spp = W, H, spp
         c2w = api.Inverse(api.LookAt(eye, look, up))
-        self.cam = (api.CreatePerspectiveCamera if cam_type == A.CAMERA_PERSPECTIVE else api.CreateOrthographicCamera)(W, H, c2w)
+        self.cam = (api.CreatePerspectiveCamera if cam_type == A.CAMERA_PERSPECTIVE else api.CreateOrthographicCamera)(W, H, c2w, camera_medium)
         self.cam.lens_radius, self.cam.focal_distance = lens_radius, focal_distance
+        if honour_camera_medium:  # library extension, checked against the harness loop that re-attaches the medium
+            self.cam.medium = camera_medium
         self.sampler_type = sampler_type
         if sampler_type == A.SAMPLER_SOBOL:
             # the Sobol tables are the reference's data: fetched from the compiled reference
@@ -27,6 +30,8 @@ class Pair:
         if R is not None:
             self.rscene = R.RefScene(data)
             self.rcam = R.RefCamera(cam_type, W, H, eye, look, up, lens_radius, focal_distance)
+            if camera_medium is not None:
+                self.rcam.set_medium(self.rscene, camera_medium, honour=honour_camera_medium)
             self.rsmp = R.RefSampler(spp, (0, 0, W, H), sampler_type)
 
 
