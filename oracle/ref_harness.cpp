@@ -561,6 +561,7 @@ double ref_render_shipped_integrator(void* hscene, void* hc, int integrator, int
     case PBRGPU_INTEGRATOR_WHITTED: integ.reset(new WhittedIntegrator(max_depth, rc->cam, sampler, b, &fb)); break;
     case PBRGPU_INTEGRATOR_DIRECT_ONE: integ.reset(new DirectLightingIntegrator(LightStrategy::UniformSampleOne, max_depth, rc->cam, sampler, b, &fb)); break;
     case PBRGPU_INTEGRATOR_DIRECT_ALL: integ.reset(new DirectLightingIntegrator(LightStrategy::UniformSampleAll, max_depth, rc->cam, sampler, b, &fb)); break;
+    case PBRGPU_INTEGRATOR_VOLPATH: integ.reset(new VolPathIntegrator(max_depth, rc->cam, sampler, b, rr, "uniform", &fb)); break;
     default: integ.reset(new PathIntegrator(max_depth, rc->cam, sampler, b, rr, "uniform", &fb)); break;
   }
   rs->agg->reset();
@@ -621,6 +622,7 @@ int ref_gpu_dropin_render(void* hscene, void* hc, int integrator, int spp, int W
   std::unique_ptr<GpuSamplerIntegrator> integ;
   switch (integrator) {
     case PBRGPU_INTEGRATOR_PATH: integ.reset(new GpuPathIntegrator(max_depth, rc->cam, sampler, b, rr, strategy, &fb)); break;
+    case PBRGPU_INTEGRATOR_VOLPATH: integ.reset(new GpuVolPathIntegrator(max_depth, rc->cam, sampler, b, rr, strategy, &fb)); break;
     case PBRGPU_INTEGRATOR_WHITTED: integ.reset(new GpuWhittedIntegrator(max_depth, rc->cam, sampler, b, &fb)); break;
     case PBRGPU_INTEGRATOR_DIRECT_ONE:
       integ.reset(new GpuDirectLightingIntegrator(LightStrategy::UniformSampleOne, max_depth, rc->cam, sampler, b, &fb)); break;

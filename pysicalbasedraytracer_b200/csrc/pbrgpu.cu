@@ -293,7 +293,8 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   if (d->n_tris <= 0 || d->n_verts <= 0 || !d->verts || !d->indices || !d->tri_material)
     return fail("pbrgpu_scene_create: empty scene");
   if (d->n_tris >= (1 << 29)) return fail("pbrgpu_scene_create: too many triangles");
-  if (d->n_materials <= 0 || d->n_materials > (int)kTriMatMask) return fail("pbrgpu_scene_create: bad material count");
+  if (d->n_materials < 0 || d->n_materials > (int)kTriMatMask || (d->n_materials > 0 && !d->materials))
+    return fail("pbrgpu_scene_create: bad material count");
   if (d->n_media < 0 || d->n_media > 0xfffe || (d->n_media > 0 && !d->media)) return fail("pbrgpu_scene_create: bad media table");
   for (int i = 0; i < d->n_media; ++i)
     if (d->media[i].type != PBRGPU_MEDIUM_HOMOGENEOUS) return fail("pbrgpu_scene_create: unknown medium type (HomogeneousMedium only)");
@@ -392,7 +393,9 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   }
 
   // materials: RoughnessToAlpha applied on the host (glibc logf, as the reference would)
-  std::vector<pbrgpu_material> mats(d->materials, d->materials + d->n_materials);
+  std::vector<pbrgpu_material> mats;
+  if (d->n_materials > 0) mats.assign(d->materials, d->materials + d->n_materials);
+  else mats.push_back(pbrgpu_material{});  // a scene of medium boundaries only: keep the table non-empty
   for (auto& m : mats) {
     if (m.type < 0 || m.type >= PBRGPU_MAT_COUNT) return fail("pbrgpu_scene_create: unknown material type");
     s->hasMat[m.type] = true;

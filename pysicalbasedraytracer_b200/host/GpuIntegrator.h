@@ -1,6 +1,7 @@
 // GpuIntegrator.h - C++ drop-in for the reference renderer (G0T-cha/PysicalBasedRaytracer).
 //
-//   PBR::GpuPathIntegrator : public PBR::Integrator
+//   PBR::GpuPathIntegrator : public PBR::Integrator        (+ GpuVolPathIntegrator, GpuWhittedIntegrator,
+//                                                            GpuDirectLightingIntegrator)
 //
 // has the SAME constructor signature as PBR::PathIntegrator (Integrator/PathIntegrator.h:14-18) and the
 // same virtual  void Render(const Scene&, double& timeConsume)  (Integrator/Integrator.h:14), so the
@@ -62,6 +63,8 @@
 #include "Light/DiffuseLight.h"
 #include "Light/InfiniteAreaLight.h"
 #include "Light/SkyBoxLight.h"
+#include "Media/Medium.h"
+#include "Media/HomogeneousMedium.h"
 #include "Integrator/Integrator.h"
 #undef private
 #undef protected
@@ -80,6 +83,8 @@ struct Flat {
   std::vector<uint8_t> triFlags;
   std::vector<pbrgpu_material> materials;
   std::vector<pbrgpu_light> lights;
+  std::vector<pbrgpu_medium> media;              // distinct HomogeneousMedium objects met on the primitives
+  std::vector<int32_t> triMediumIn, triMediumOut;  // MediumInterface::inside / ::outside per triangle (-1 = none)
   std::vector<float> env;
   int envW = 0, envH = 0;
   std::string error;
@@ -141,6 +146,26 @@ inline bool flattenMaterial(const Material* m, pbrgpu_material* o, std::string* 
   return false;
 }
 
+// Medium* -> index into Flat::media (-1 for nullptr); only HomogeneousMedium has a GPU twin
+inline bool flattenMedium(const Medium* m, std::unordered_map<const Medium*, int>* ids, Flat* f, int* out) {
+  *out = -1;
+  if (!m) return true;
+  auto it = ids->find(m);
+  if (it == ids->end()) {
+    auto* h = dynamic_cast<const HomogeneousMedium*>(m);
+    if (!h) { f->error = "unsupported Medium subclass (GPU path: HomogeneousMedium)"; return false; }
+    pbrgpu_medium o;
+    std::memset(&o, 0, sizeof(o));
+    o.type = PBRGPU_MEDIUM_HOMOGENEOUS;
+    o.g = h->g;
+    for (int c = 0; c < 3; ++c) { o.sigma_a[c] = h->sigma_a[c]; o.sigma_s[c] = h->sigma_s[c]; }
+    it = ids->emplace(m, (int)f->media.size()).first;
+    f->media.push_back(o);
+  }
+  *out = it->second;
+  return true;
+}
+
 inline void copyMatrix(const Matrix4x4& m, float out[16]) {
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) out[i * 4 + j] = m.m[i][j];
@@ -156,6 +181,9 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
   f->triMaterial.resize(n);
   f->triLight.assign(n, -1);
   f->triFlags.assign(n, 0);
+  f->triMediumIn.assign(n, -1);
+  f->triMediumOut.assign(n, -1);
+  std::unordered_map<const Medium*, int> mediumId;
   std::unordered_map<const Material*, int> matId;
   std::unordered_map<const Light*, int> lightId;
   for (size_t i = 0; i < scene.lights.size(); ++i) lightId[scene.lights[i].get()] = (int)i;
@@ -167,7 +195,9 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
     auto* tri = dynamic_cast<const Triangle*>(gp->shape.get());
     if (!tri) { f->error = "shape is not a Triangle (the reference's Sphere is a stub, SURVEY Q4)"; return false; }
     if (tri->mesh->s) { f->error = "per-vertex tangents (TriangleMesh::s) are not supported on the GPU path"; return false; }
-    if (!gp->material) { f->error = "primitive without material (medium boundary) is not supported"; return false; }
+    if (!flattenMedium(gp->mediumInterface.inside, &mediumId, f, &f->triMediumIn[i]) ||
+        !flattenMedium(gp->mediumInterface.outside, &mediumId, f, &f->triMediumOut[i]))
+      return false;
     if ((tri->mesh->n && !f->anyNormals) || (tri->mesh->uv && !f->anyUVs)) {
       // first mesh with shading normals / uvs: materialise the optional arrays (zero for everything before it)
       if (tri->mesh->n && !f->anyNormals) { f->anyNormals = true; f->normals.assign(n * 9, 0.f); }
@@ -189,14 +219,18 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
     }
     f->triFlags[i] = (uint8_t)(((tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0) | (tri->reverseOrientation ? 2 : 0) |
                                (tri->mesh->n ? 4 : 0) | (tri->mesh->uv ? 8 : 0));
-    auto it = matId.find(gp->material.get());
-    if (it == matId.end()) {
-      pbrgpu_material m;
-      if (!flattenMaterial(gp->material.get(), &m, &f->error)) return false;
-      it = matId.emplace(gp->material.get(), (int)f->materials.size()).first;
-      f->materials.push_back(m);
+    if (!gp->material) {
+      f->triMaterial[i] = -1;  // medium boundary: rendered by GpuVolPathIntegrator only
+    } else {
+      auto it = matId.find(gp->material.get());
+      if (it == matId.end()) {
+        pbrgpu_material m;
+        if (!flattenMaterial(gp->material.get(), &m, &f->error)) return false;
+        it = matId.emplace(gp->material.get(), (int)f->materials.size()).first;
+        f->materials.push_back(m);
+      }
+      f->triMaterial[i] = it->second;
     }
-    f->triMaterial[i] = it->second;
     if (gp->areaLight) {
       auto li = lightId.find(gp->areaLight.get());
       if (li == lightId.end()) { f->error = "area light of a primitive is not in scene.lights"; return false; }
@@ -281,6 +315,10 @@ class GpuSamplerIntegrator : public Integrator {
       d.n_materials = (int32_t)f.materials.size(); d.materials = f.materials.data();
       d.n_lights = (int32_t)f.lights.size(); d.lights = f.lights.data();
       d.env_width = f.envW; d.env_height = f.envH; d.env_texels = f.env.empty() ? nullptr : f.env.data();
+      if (!f.media.empty()) {
+        d.n_media = (int32_t)f.media.size(); d.media = f.media.data();
+        d.tri_medium_inside = f.triMediumIn.data(); d.tri_medium_outside = f.triMediumOut.data();
+      }
       if (pbrgpu_scene_create(ctx, &d, &gscene)) return fail("pbrgpu_scene_create");
       flattenedScene = &scene;
     }
@@ -296,6 +334,8 @@ class GpuSamplerIntegrator : public Integrator {
     cd.lens_radius = pc->lensRadius; cd.focal_distance = pc->focalDistance;
     gpu_detail::copyMatrix(pc->RasterToCamera.m, cd.raster_to_camera);
     gpu_detail::copyMatrix(pc->CameraToWorld.m, cd.camera_to_world);
+    // Camera::medium is deliberately NOT forwarded: the reference loses it before the integrator sees the ray
+    // (Perspective.cpp:44-80 never sets it; Orthographic.cpp:59-60 + Transform.h:169), so cd.medium_plus1 stays 0.
     if (pbrgpu_camera_set(gscene, &cd)) return fail("pbrgpu_camera_set");
     // sampler (Sampler/Halton.cpp:30-58): the reference passes the same bounds to sampler and integrator
     auto* hs = dynamic_cast<const HaltonSampler*>(sampler.get());
@@ -384,6 +424,18 @@ class GpuPathIntegrator : public GpuSamplerIntegrator {
   const int maxDepth;
   const float rrThreshold;
   const std::string lightSampleStrategy;
+};
+
+// Same constructor as VolPathIntegrator (Integrator/VolPathIntegrator.h:11-19) - the integrator Main/main.cpp:399 builds.
+class GpuVolPathIntegrator : public GpuPathIntegrator {
+ public:
+  using GpuPathIntegrator::GpuPathIntegrator;
+
+ protected:
+  void fillRenderDesc(pbrgpu_render_desc* rd) const override {
+    GpuPathIntegrator::fillRenderDesc(rd);
+    rd->integrator = PBRGPU_INTEGRATOR_VOLPATH;
+  }
 };
 
 // Same constructor as WhittedIntegrator (Integrator/WhittedIntegrator.h:8-11).

@@ -394,3 +394,40 @@ def test_volpath_rmse_vs_reference_high_spp(api, ref, gpu_ctx):
     r_cpu, r_gpu = rmse(cpu / n, truth), rmse(gpu / n, truth)
     print(f"volpath RMSE cpu {r_cpu:.5f} gpu {r_gpu:.5f} ratio {r_gpu / r_cpu:.4f}")
     assert r_gpu <= 1.05 * r_cpu
+
+
+def test_cpp_dropin_volpath_twin_with_media(api, ref, gpu_ctx):
+    """GpuVolPathIntegrator (host/GpuIntegrator.h): the reference's object graph - HomogeneousMedium, MediumInterface on
+    the primitives, a primitive with a NULL material - flattened and rendered, against the reference's own
+    VolPathIntegrator::Render (the integrator Main/main.cpp:399 builds)."""
+    data, _ = scenes.cornell_media("smoke", sphere_tess=12)
+    rsc = ref.RefScene(data)
+    rc = ref.RefCamera(A.CAMERA_PERSPECTIVE, 64, 64, (0, 0, 5), (0, 0, 0), (0, 1, 0))
+    V = A.INTEGRATOR_VOLPATH
+    rgba, _, sec = ref.gpu_dropin_render(rsc, rc, 2, 64, 64, 5, 0.8, "uniform", integrator=V)
+    want, _, _ = ref.render_shipped(rsc, rc, 2, 64, 64, 5, 0.8, integrator=V)
+    diff = np.abs(rgba.astype(int) - want.astype(int))
+    print("drop-in volpath bytes equal", (diff == 0).mean(), "max diff", diff.max())
+    assert (diff <= 1).mean() >= 0.99
+
+
+def test_volpath_error_behaviour(api, gpu_ctx):
+    """Scenes with medium boundaries (no material) render with VolPath only; bad medium indices are rejected."""
+    data, med = scenes.cornell_media("smoke", sphere_tess=8)
+    sc = api.Scene(data)
+    cam = api.CreatePerspectiveCamera(32, 32, api.Inverse(api.LookAt((0, 0, 5), (0, 0, 0), (0, 1, 0))))
+    sc.set_camera(cam)
+    sc.set_sampler(api.HaltonSampler(1, (0, 0, 32, 32)))
+    with pytest.raises(api.PbrGpuError, match="VolPath"):
+        sc.render(integrator=A.INTEGRATOR_PATH, max_depth=2)
+    with pytest.raises(api.PbrGpuError, match="max_depth"):
+        sc.render(integrator=A.INTEGRATOR_VOLPATH, max_depth=127)
+    out, _, _ = sc.render(integrator=A.INTEGRATOR_VOLPATH, max_depth=2)
+    assert np.isfinite(out).all() and out.max() > 0
+    cam.medium = med + 5
+    with pytest.raises(api.PbrGpuError, match="camera medium"):
+        sc.set_camera(cam)
+    bad, _ = scenes.cornell_media("smoke", sphere_tess=8)
+    bad._tri_med_in[-1][:] = 7
+    with pytest.raises(api.PbrGpuError, match="medium index"):
+        api.Scene(bad)
