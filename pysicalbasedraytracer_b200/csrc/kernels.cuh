@@ -157,7 +157,8 @@ PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T,
     atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
     return false;
   }
-  if (++*hops > kMaxShadowCrossings) return false;
+  if (++*hops > kMaxShadowCrossings) { atomicAdd(&P.ws.ctr->volCapHits, 1u); return false; }
+  if (P.countStats) atomicMax(&P.ws.ctr->volMaxHops, (uint32_t)*hops);
   // ray = isect.SpawnRayTo(p1)   (Interaction.h:38-43; isect.mediumInterface from GeometricPrimitive::Intersect)
   const TriData tri = load_tri(sc, T.hit.tri);
   Isect is;

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -717,6 +718,7 @@ static int fetch_stats(pbrgpu_scene* s, cudaStream_t st, pbrgpu_stats* stats) {
   stats->kernel_launches = s->last.launches;
   stats->ms_total = ms;
   stats->rays_path = hc.raysPath;
+  if (getenv("PBRGPU_VOL_LOG")) fprintf(stderr, "vol shadow rays: max hops %u, stopped at the cap %u\n", hc.volMaxHops, hc.volCapHits);
   Timeline& tl = s->last.tl;
   if (tl.on) {
     double t[T_COUNT];
@@ -817,10 +819,22 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         // number of iterations is not known up front: max_depth + 1 iterations are launched blind, then the live-path
         // and pending-ray counters are read back after every iteration until the wave has drained.
         const int kMaxExtraIters = 4096;
+        const bool volLog = getenv("PBRGPU_VOL_LOG") != nullptr;  // development aid: per-iteration queue sizes + wall time
         for (int iter = 0;; ++iter) {
+          std::chrono::steady_clock::time_point t0;
+          if (volLog) {
+            CK(cudaMemcpyAsync(s->hNCur, s->ctr.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            t0 = std::chrono::steady_clock::now();
+          }
           CK(tl.mark(T_CLOSEST));
           if (count) k_trace<true, true><<<gt, kTraceBlock, 0, st>>>(P);
           else k_trace<false, true><<<gt, kTraceBlock, 0, st>>>(P);
+          if (volLog) {
+            CK(cudaStreamSynchronize(st));
+            fprintf(stderr, "vol iter %d: paths %u shadow %u mis %u  k_trace %.3f ms\n", iter, s->hNCur[0], s->hNCur[2], s->hNCur[3],
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+          }
           CK(tl.mark(T_MIS));
           if (iter > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
           CK(tl.mark(T_SHADE));

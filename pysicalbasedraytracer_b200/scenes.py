@@ -298,9 +298,11 @@ def cornell_media(kind="smoke", sphere_tess=24, sigma_a=(0.5, 0.5, 0.5), sigma_s
     return s, med
 
 
-def dragon_class(tess=467, with_point_light=False, block=8192):
+def dragon_class(tess=467, with_point_light=False, block=8192, volume=None):
     """BASELINE config 2 (and 4): ~872k-triangle bumpy sphere, half Matte(0,1,0) / half Mirror in
-    triangle-index blocks, inside the Cornell walls under the Cornell area light."""
+    triangle-index blocks, inside the Cornell walls under the Cornell area light.
+    volume = "smoke" | "glass": the mesh becomes the boundary of HomogeneousMedium(0.5, 4.4, -0.5) (Main/main.cpp:242-243,
+    346-348) - without material, or as glass - for the VolPath integrator."""
     s = SceneData()
     white = s.add_material(matte([1, 1, 1]))
     red = s.add_material(matte([0.9, 0.1, 0.17]))
@@ -315,7 +317,12 @@ def dragon_class(tess=467, with_point_light=False, block=8192):
 
     v, t = uv_sphere([0.0, -0.6, 0.0], radius, tess, 2 * tess)
     mats = np.where((np.arange(t.shape[0]) // block) % 2 == 0, green, mir).astype(np.int32)
-    s.add_mesh(v, t, mats)
+    if volume is None:
+        s.add_mesh(v, t, mats)
+    else:
+        med = s.add_medium([0.5] * 3, [4.4] * 3, -0.5)
+        gls = s.add_material(glass([0.98] * 3, [0.98] * 3, 1.5))
+        s.add_mesh(v, t, None if volume == "smoke" else gls, medium_interface=(med, None))
     if with_point_light:
         s.add_point_light([0.0, 2.0, 0.0], [50.0, 50.0, 50.0])
     return s

@@ -44,3 +44,9 @@ if __name__ == "__main__":
     d5 = scenes.dragon_class(tess=467)
     d5.add_skybox_light(env, world_radius=20.0, n_samples=1)
     run("5 dragon + SkyBox 3840x2160 (4 of 4096 spp) path d8", d5, 3840, 2160, 4096, 4)
+    # VolPathIntegrator (the integrator Main/main.cpp:399 builds): same dragon-class mesh without media, as the boundary of a
+    # HomogeneousMedium without material ("smoke"), and as a glass container of the medium (main.cpp:346-348)
+    V = A.INTEGRATOR_VOLPATH
+    run("6a dragon-class VolPath (no media) 1080p (16 of 1024 spp) d8", scenes.dragon_class(tess=467), 1920, 1080, 1024, 16, integrator=V)
+    run("6b dragon-class smoke volume VolPath 1080p (16 of 1024 spp) d8", scenes.dragon_class(tess=467, volume="smoke"), 1920, 1080, 1024, 16, integrator=V)
+    run("6c dragon-class glass + medium VolPath 1080p (16 of 1024 spp) d8", scenes.dragon_class(tess=467, volume="glass"), 1920, 1080, 1024, 16, integrator=V)

@@ -96,6 +96,13 @@ def main():
     img, st = R.render(rsc, rc2, 2, (0, 0, 96, 64), integrator=A.INTEGRATOR_PATH, max_depth=1)
     np.savez_compressed(os.path.join(HERE, "stress96x64_direct.npz"), rgb_mean=(img / np.float32(2)).astype(np.float32),
                         rays_closest=np.int64(st.rays_closest), rays_shadow=np.int64(st.rays_shadow))
+    # VolPathIntegrator: smoke sphere (medium behind a material-less boundary) + glass sphere filled with the medium
+    for kind in ("smoke", "glass"):
+        data, _ = scenes.cornell_media(kind, sphere_tess=12)
+        rsc = R.RefScene(data)
+        img, st = R.render(rsc, rc, 4, (0, 0, 64, 64), integrator=A.INTEGRATOR_VOLPATH, max_depth=5, rr_threshold=0.8)
+        np.savez_compressed(os.path.join(HERE, f"volpath64_{kind}.npz"), rgb_mean=(img / np.float32(4)).astype(np.float32),
+                            rays_closest=np.int64(st.rays_closest), rays_shadow=np.int64(st.rays_shadow))
     # ---- film tone map ----
     rgb = rng.uniform(0, 1.5, (512, 3)).astype(np.float32)
     rgb[:8] = [[0, 0, 0], [1, 1, 1], [0.0031308, 0.0031308, 0.0031308], [2, 0.5, 0.1], [1e-4, 1e-3, 1e-2], [0.5, 0.5, 0.5],

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(api):
 
 
 def test_struct_layouts_match_header():
-    structs = {"pbrgpu_material": A.Material, "pbrgpu_light": A.Light, "pbrgpu_scene_desc": A.SceneDesc,
+    structs = {"pbrgpu_material": A.Material, "pbrgpu_light": A.Light, "pbrgpu_medium": A.Medium, "pbrgpu_scene_desc": A.SceneDesc,
                "pbrgpu_camera_desc": A.CameraDesc, "pbrgpu_sampler_desc": A.SamplerDesc,
                "pbrgpu_render_desc": A.RenderDesc, "pbrgpu_stats": A.Stats, "pbrgpu_dump_desc": A.DumpDesc}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "pbrgpu.h"\nint main(){\n'

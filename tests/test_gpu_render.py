@@ -396,6 +396,20 @@ def test_volpath_rmse_vs_reference_high_spp(api, ref, gpu_ctx):
     assert r_gpu <= 1.05 * r_cpu
 
 
+@pytest.mark.parametrize("kind", ["smoke", "glass"])
+def test_volpath_vs_golden_fixture(api, gpu_ctx, kind):
+    """Committed fixture from the compiled reference's VolPathIntegrator::Li (tests/golden/make_golden.py)."""
+    from tests.util import golden
+    g = golden(f"volpath64_{kind}.npz")
+    data, _ = scenes.cornell_media(kind, sphere_tess=12)
+    p = Pair(api, None, data, 64, 64, 4)
+    got, _, st = p.scene.render(integrator=A.INTEGRATOR_VOLPATH, max_depth=5, rr_threshold=0.8)
+    ok = (rel_err(got / 4, g["rgb_mean"]) <= REL_TOL).mean()
+    print("volpath fixture", kind, "pixels within 1e-3:", ok)
+    assert ok >= 0.95
+    assert abs(int(st.rays_closest) - int(g["rays_closest"])) <= 5e-3 * int(g["rays_closest"]) + 8
+
+
 def test_cpp_dropin_volpath_twin_with_media(api, ref, gpu_ctx):
     """GpuVolPathIntegrator (host/GpuIntegrator.h): the reference's object graph - HomogeneousMedium, MediumInterface on
     the primitives, a primitive with a NULL material - flattened and rendered, against the reference's own

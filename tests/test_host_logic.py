@@ -147,3 +147,34 @@ def test_3d_mesh_loader_matches_reference_plyinfo(api, ref, tmp_path):
     m = s.add_material(scenes.matte([0.5, 0.5, 0.5]))
     s.add_mesh(gv, gt, m)
     assert s.n_tris == nt
+
+
+def test_media_scene_description_and_golden_fixture_match_reference(ref):
+    """SceneData.add_medium / medium_interface / material-less meshes flatten into the descriptor the C-ABI documents, and the
+    committed VolPath fixtures are what the compiled reference's VolPathIntegrator::Li renders today."""
+    from tests.util import golden
+    data, med = scenes.cornell_media("smoke", sphere_tess=12)
+    d, keep = data.desc()
+    assert d.n_media == 1 and med == 0
+    assert abs(d.media[0].sigma_s[1] - 4.4) < 1e-6 and abs(d.media[0].g + 0.5) < 1e-6
+    tri_mat = np.ctypeslib.as_array(d.tri_material, (d.n_tris,))
+    m_in = np.ctypeslib.as_array(d.tri_medium_inside, (d.n_tris,))
+    m_out = np.ctypeslib.as_array(d.tri_medium_outside, (d.n_tris,))
+    boundary = tri_mat == -1
+    assert 0 < boundary.sum() < d.n_tris
+    assert (m_in[boundary] == 0).all() and (m_in[~boundary] == -1).all() and (m_out == -1).all()
+    cam = api_camera_desc_default()
+    assert cam.medium_plus1 == 0
+    # fixture == reference (CPU, 64x64x4 spp)
+    g = golden("volpath64_smoke.npz")
+    rsc = ref.RefScene(data)
+    rc = ref.RefCamera(A.CAMERA_PERSPECTIVE, 64, 64, (0.0, 0.0, 5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0))
+    img, st = ref.render(rsc, rc, 4, (0, 0, 64, 64), integrator=A.INTEGRATOR_VOLPATH, max_depth=5, rr_threshold=0.8)
+    assert np.array_equal((img / np.float32(4)).astype(np.float32), g["rgb_mean"])
+    assert int(st.rays_closest) == int(g["rays_closest"]) and int(st.rays_shadow) == 0
+
+
+def api_camera_desc_default():
+    from pysicalbasedraytracer_b200 import api
+    cam = api.CreateOrthographicCamera(16, 16, api.Inverse(api.LookAt((0, 0, 5), (0, 0, 0), (0, 1, 0))), media=0)
+    return cam.desc()  # Camera::medium is recorded but, as in the reference, not delivered to the rays
