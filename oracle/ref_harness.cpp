@@ -607,6 +607,53 @@ int ref_ply_read(const char* path, float* verts, int cap_verts, int32_t* indices
   return 0;
 }
 
+// ---- known-answer hooks for the participating-media functions (pin oracle/restate.c and the GPU twins) ----
+namespace {
+// a Sampler that replays a fixed list of values (HomogeneousMedium::Sample draws two Get1D)
+struct ReplaySampler : public Sampler {
+  std::vector<float> v;
+  size_t k = 0;
+  ReplaySampler(std::initializer_list<float> l) : Sampler(1), v(l) {}
+  float Get1D() override { return v[k++ % v.size()]; }
+  Point2f Get2D() override { float a = Get1D(); float b = Get1D(); return Point2f(a, b); }
+  std::unique_ptr<Sampler> Clone(int) override { return nullptr; }
+};
+}  // namespace
+
+// in[n][8] = d.xyz, tMax, u0, u1, -, -  ->  out[n][8] = weight rgb, mi.p along d's dominant axis (or tMax), sampled flag, Tr rgb
+// HomogeneousMedium::Sample / ::Tr (Media/HomogeneousMedium.cpp:10-45) on the ray (0, d, tMax)
+void ref_medium_kat(const pbrgpu_medium* m, const float* in, int n, float* out) {
+  HomogeneousMedium med(rgb(m->sigma_a), rgb(m->sigma_s), m->g);
+  for (int i = 0; i < n; ++i) {
+    const float* r = in + 8 * i;
+    Ray ray(Point3f(0, 0, 0), Vector3f(r[0], r[1], r[2]), r[3], 0.f, &med);
+    ReplaySampler smp{r[4], r[5]};
+    MediumInteraction mi;
+    Spectrum w = med.Sample(ray, smp, &mi);
+    float* o = out + 8 * i;
+    o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+    // t itself is not stored by the reference: report mi.p = ray(t) = d * t along the dominant axis of d
+    int ax = std::abs(r[0]) > std::abs(r[1]) ? (std::abs(r[0]) > std::abs(r[2]) ? 0 : 2) : (std::abs(r[1]) > std::abs(r[2]) ? 1 : 2);
+    o[3] = mi.IsValid() ? mi.p[ax] : r[3];
+    o[4] = mi.IsValid() ? 1.f : 0.f;
+    Spectrum tr = med.Tr(ray, smp);
+    o[5] = tr[0]; o[6] = tr[1]; o[7] = tr[2];
+  }
+}
+// in[n][8] = wo.xyz, u0, u1, wi2.xyz  ->  out[n][8] = Sample_p: wi.xyz, p ; p(wo, wi2), -, -, -    (Media/Medium.cpp:7-28)
+void ref_hg_kat(float g, const float* in, int n, float* out) {
+  HenyeyGreenstein hg(g);
+  for (int i = 0; i < n; ++i) {
+    const float* r = in + 8 * i;
+    Vector3f wo(r[0], r[1], r[2]), wi;
+    float p = hg.Sample_p(wo, &wi, Point2f(r[3], r[4]));
+    float* o = out + 8 * i;
+    o[0] = wi.x; o[1] = wi.y; o[2] = wi.z; o[3] = p;
+    o[4] = hg.p(wo, Vector3f(r[5], r[6], r[7]));
+    o[5] = o[6] = o[7] = 0.f;
+  }
+}
+
 // Drop-in test: the reference's OWN object graph (Scene / BVHAccel / GeometricPrimitive / Triangle / Material /
 // Light / PerspectiveCamera / HaltonSampler) rendered through PBR::GpuPathIntegrator::Render, i.e. through the
 // flattener of pysicalbasedraytracer_b200/host/GpuIntegrator.h and the C-ABI of libpbrgpu.so.  Needs a GPU.

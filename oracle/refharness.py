@@ -42,6 +42,8 @@ def lib():
         L.ref_camera_create_lens.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.c_float, C.c_float]
         L.ref_camera_desc.argtypes = [C.c_void_p, C.POINTER(A.CameraDesc)]
+        L.ref_medium_kat.argtypes = [C.POINTER(A.Medium), C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_hg_kat.argtypes = [C.c_float, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_camera_set_medium.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ref_sampler_create.restype = C.c_void_p
         L.ref_sampler_create.argtypes = [C.c_int] * 5
@@ -249,3 +251,20 @@ def ply_read(path, cap_verts=1 << 20, cap_tris=1 << 21):
     if rc != 0:
         raise RuntimeError("ref_ply_read: buffers too small")
     return v[:nv.value].copy(), t[:nt.value].copy()
+
+
+def medium_kat(sigma_a, sigma_s, g, rows):
+    """The reference's HomogeneousMedium::Sample / ::Tr on rays (0, d, tMax) with sampler values (u0, u1); see ref_harness.cpp."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 8)
+    out = np.zeros_like(rows)
+    m = A.Medium(type=0, g=g, sigma_a=_f3(sigma_a), sigma_s=_f3(sigma_s))
+    lib().ref_medium_kat(C.byref(m), rows.ctypes.data, rows.shape[0], out.ctypes.data)
+    return out
+
+
+def hg_kat(g, rows):
+    """The reference's HenyeyGreenstein::Sample_p / ::p; see ref_harness.cpp."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 8)
+    out = np.zeros_like(rows)
+    lib().ref_hg_kat(g, rows.ctypes.data, rows.shape[0], out.ctypes.data)
+    return out

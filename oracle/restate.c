@@ -360,3 +360,81 @@ void rs_tonemap(const float* rgbMean, int n, unsigned char* rgba8) {
     rgba8[4 * i + 3] = 255;
   }
 }
+
+/* ---- participating media: HomogeneousMedium::{Sample,Tr} (Media/HomogeneousMedium.cpp:10-45),
+ *      PhaseHG / HenyeyGreenstein::{p,Sample_p} (Media/Medium.h:21-24, Media/Medium.cpp:7-28),
+ *      CoordinateSystem (Core/Geometry.h), SphericalDirection (Core/Geometry.h:1510-1515).
+ *      Same argument layout as ref_medium_kat / ref_hg_kat in ref_harness.cpp. ---- */
+static float vlen3(const float v[3]) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+#define RS_MAXFLOAT 3.402823466e+38f
+void rs_medium_kat(const float sigma_a[3], const float sigma_s[3], float g, const float* in, int n, float* out) {
+  (void)g;
+  float sigma_t[3];
+  for (int c = 0; c < 3; ++c) sigma_t[c] = sigma_s[c] + sigma_a[c];
+  for (int i = 0; i < n; ++i) {
+    const float* r = in + 8 * i;
+    float* o = out + 8 * i;
+    const float dLen = vlen3(r), tMax = r[3], u0 = r[4], u1 = r[5];
+    int channel = (int)(u0 * 3);
+    if (channel > 2) channel = 2;
+    float dist = -logf(1 - u1) / sigma_t[channel];
+    float t = dist / dLen;
+    if (tMax < t) t = tMax;
+    int sampled = t < tMax;
+    float Tr[3], density[3], pdf = 0;
+    float tc = RS_MAXFLOAT < t ? RS_MAXFLOAT : t;  /* std::min(t, MaxFloat): a NaN t stays NaN */
+    for (int c = 0; c < 3; ++c) {
+      Tr[c] = expf(-sigma_t[c] * tc * dLen);
+      density[c] = sampled ? sigma_t[c] * Tr[c] : Tr[c];
+    }
+    for (int c = 0; c < 3; ++c) pdf += density[c];
+    pdf *= 1 / (float)3;
+    if (pdf == 0) pdf = 1;
+    for (int c = 0; c < 3; ++c) o[c] = sampled ? Tr[c] * sigma_s[c] / pdf : Tr[c] / pdf;
+    int ax = fabsf(r[0]) > fabsf(r[1]) ? (fabsf(r[0]) > fabsf(r[2]) ? 0 : 2) : (fabsf(r[1]) > fabsf(r[2]) ? 1 : 2);
+    o[3] = sampled ? 0.f + r[ax] * t : tMax;
+    o[4] = sampled ? 1.f : 0.f;
+    float tl = tMax * dLen;
+    if (RS_MAXFLOAT < tl) tl = RS_MAXFLOAT;
+    for (int c = 0; c < 3; ++c) o[5 + c] = expf(-sigma_t[c] * tl);
+  }
+}
+static float phase_hg(float cosTheta, float g) {
+  float denom = 1 + g * g + 2 * g * cosTheta;
+  return 0.07957747154594766788f * (1 - g * g) / (denom * sqrtf(denom));
+}
+void rs_hg_kat(float g, const float* in, int n, float* out) {
+  for (int i = 0; i < n; ++i) {
+    const float* r = in + 8 * i;
+    float* o = out + 8 * i;
+    const float wo[3] = {r[0], r[1], r[2]}, u0 = r[3], u1 = r[4];
+    float cosTheta;
+    if (fabsf(g) < 1e-3)
+      cosTheta = 1 - 2 * u0;
+    else {
+      float sqrTerm = (1 - g * g) / (1 + g - 2 * g * u0);
+      cosTheta = -(1 + g * g - sqrTerm * sqrTerm) / (2 * g);
+    }
+    float s2 = 1 - cosTheta * cosTheta;
+    float sinTheta = sqrtf(s2 > 0 ? s2 : 0.f);
+    float phi = 2 * 3.14159265358979323846f * u1;
+    float v1[3], v2[3];
+    if (fabsf(wo[0]) > fabsf(wo[1])) {  /* CoordinateSystem; Vector3::operator/ multiplies by the reciprocal */
+      float inv = (float)1 / sqrtf(wo[0] * wo[0] + wo[2] * wo[2]);
+      v1[0] = -wo[2] * inv; v1[1] = 0 * inv; v1[2] = wo[0] * inv;
+    } else {
+      float inv = (float)1 / sqrtf(wo[1] * wo[1] + wo[2] * wo[2]);
+      v1[0] = 0 * inv; v1[1] = wo[2] * inv; v1[2] = -wo[1] * inv;
+    }
+    /* Cross(v1, v2 = wo x v1) in double like Core/Geometry.h */
+    {
+      double ax = wo[0], ay = wo[1], az = wo[2], bx = v1[0], by = v1[1], bz = v1[2];
+      v2[0] = (float)((ay * bz) - (az * by)); v2[1] = (float)((az * bx) - (ax * bz)); v2[2] = (float)((ax * by) - (ay * bx));
+    }
+    float a = sinTheta * cosf(phi), b = sinTheta * sinf(phi);
+    for (int c = 0; c < 3; ++c) o[c] = (a * v1[c] + b * v2[c]) + cosTheta * wo[c];
+    o[3] = phase_hg(cosTheta, g);
+    o[4] = phase_hg(wo[0] * r[5] + wo[1] * r[6] + wo[2] * r[7], g);
+    o[5] = o[6] = o[7] = 0.f;
+  }
+}

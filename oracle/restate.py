@@ -39,6 +39,8 @@ def lib():
         L.rs_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                C.POINTER(C.c_int64)]
         L.rs_tonemap.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.rs_medium_kat.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+        L.rs_hg_kat.argtypes = [C.c_float, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -100,4 +102,21 @@ def tonemap(rgb_mean):
     a = np.ascontiguousarray(rgb_mean, dtype=np.float32).reshape(-1, 3)
     out = np.zeros((a.shape[0], 4), dtype=np.uint8)
     lib().rs_tonemap(a.ctypes.data, a.shape[0], out.ctypes.data)
+    return out
+
+
+def medium_kat(sigma_a, sigma_s, g, rows):
+    """rows [n,8] = d.xyz, tMax, u0, u1, -, - -> [n,8] = weight rgb, mi.p on d's dominant axis (or tMax), sampled, Tr rgb"""
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 8)
+    out = np.zeros_like(rows)
+    f3 = C.c_float * 3
+    lib().rs_medium_kat(f3(*sigma_a), f3(*sigma_s), g, rows.ctypes.data, rows.shape[0], out.ctypes.data)
+    return out
+
+
+def hg_kat(g, rows):
+    """rows [n,8] = wo.xyz, u0, u1, wi2.xyz -> [n,8] = Sample_p wi.xyz, p; p(wo, wi2)"""
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 8)
+    out = np.zeros_like(rows)
+    lib().rs_hg_kat(g, rows.ctypes.data, rows.shape[0], out.ctypes.data)
     return out

@@ -133,6 +133,7 @@ struct RenderParams {
   int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
   int countStats;
   int fetchMinIdle;       // idle lanes of a warp that trigger a ray fetch
+  int volShadowAnyHit;    // VolPath, scene without material-less surfaces: a shadow ray ends at ANY surface it finds
   int atomicL;            // several shadow / MIS rays per path and bounce (Whitted / DirectLighting): atomics on L
   // Halton offset of the pixel a global index belongs to: index = offset(pixel) + sample * stride, offset < stride
   PBR_D int64_t pixelOffsetOf(int64_t index) const { return index % sc.hp.sampleStride; }

@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
         if (COUNT) tris++;
         // any-hit exit for shadow rays; VolPath shadow rays need the CLOSEST surface (it may be a medium boundary)
-        if (cw_tri_step(P.sc, T) && !VOL && mode == TRACE_SHADOW) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+        // (unless the scene has no such boundary at all: then the first surface found ends the ray either way)
+        if (cw_tri_step(P.sc, T) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
       }
       // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
       if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {
@@ -678,8 +679,11 @@ PBR_D SamplerCursor load_cursor(const RenderParams& P, uint32_t slot, uint32_t m
 }
 
 // `if (ray.medium) beta *= ray.medium->Sample(ray, sampler, &mi); if (beta.IsBlack()) break;`  (:35-36) for every
-// live path whose segment lies in a medium; a sampled MediumInteraction re-routes the path to the medium queue.
-__global__ void __launch_bounds__(kBlock) k_medium_sample(const __grid_constant__ RenderParams P) {
+// live path whose segment lies in a medium, in two halves around k_trace (media.cuh: medium_sample_distance):
+//   k_medium_presample  draws the two sampler values and makes the sampled free-flight distance the ray's tMax
+//   k_medium_sample     after the trace: hit below that distance -> surface, weight Tr/pdf; no hit -> MediumInteraction
+//                       at that distance, weight Tr*sigma_s/pdf, path re-routed to the medium queue
+__global__ void __launch_bounds__(kBlock) k_medium_presample(const __grid_constant__ RenderParams P) {
   const uint32_t n = P.ws.ctr->nCur;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = P.ws.qCur[i];
@@ -690,18 +694,27 @@ __global__ void __launch_bounds__(kBlock) k_medium_sample(const __grid_constant_
     SamplerCursor cur = load_cursor(P, slot, meta);
     const float u0 = cur.get1D(P.sc.hp);
     const float u1 = cur.get1D(P.sc.hp);
-    float t;
-    bool sampled;
-    const Spec w = medium_sample(P.sc.media[med], u0, u1, P.ws.rayO[slot].w, length(V3(rd4.x, rd4.y, rd4.z)), &t, &sampled);
+    P.ws.rayO[slot].w = medium_sample_distance(P.sc.media[med], u0, u1, length(V3(rd4.x, rd4.y, rd4.z)));
+    P.ws.meta[slot] = (meta & ~0xffffu) | (uint32_t)cur.dim;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_medium_sample(const __grid_constant__ RenderParams P) {
+  const uint32_t n = P.ws.ctr->nCur;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = P.ws.qCur[i];
+    const float4 rd4 = P.ws.rayD[slot];
+    const int med = __float_as_int(rd4.w);
+    if (med < 0) continue;
+    const bool hit = __float_as_int(P.ws.hit[slot].x) >= 0;
+    const float t = P.ws.rayO[slot].w;           // k_trace: hit distance, or the sampled distance when nothing was hit
+    const bool sampled = !hit && t < kInfinity;  // t < ray.tMax
+    const Spec w = medium_sample_weight(P.sc.media[med], t, sampled, length(V3(rd4.x, rd4.y, rd4.z)));
     const float4 be4 = P.ws.beta[slot];
     const Spec beta = Spec(be4.x, be4.y, be4.z) * w;
     if (beta.is_black()) { P.ws.qType[i] = kQueueDead; continue; }
     P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, be4.w);
-    P.ws.meta[slot] = (meta & ~0xffffu) | (uint32_t)cur.dim;
-    if (sampled) {
-      P.ws.qType[i] = (uint32_t)kQueueMedium;
-      P.ws.rayO[slot].w = t;  // mi.p = ray(t)
-    }
+    if (sampled) P.ws.qType[i] = (uint32_t)kQueueMedium;  // mi.p = ray(t), t stays in rayO.w
   }
 }
 

@@ -23,24 +23,32 @@ PBR_D Spec medium_Tr(const pbrgpu_medium& m, float tMax, float dLen) {
   return spec_exp(spec_neg(medium_sigma_t(m)) * stdmin(tMax * dLen, kMaxFloat));
 }
 
-// HomogeneousMedium::Sample.  u0 picks the channel, u1 the distance.  Returns the path weight; *tOut < tMax and
-// *sampled = true when a scattering event was sampled before the surface.
-PBR_D Spec medium_sample(const pbrgpu_medium& m, float u0, float u1, float tMax, float dLen, float* tOut, bool* sampled) {
+// HomogeneousMedium::Sample, split in two so that the distance can be drawn BEFORE the ray is traced:
+//   reference:  found = Intersect(ray)            -> ray.tMax = tHit (or inf)
+//               t = min(dist / |d|, ray.tMax); sampledMedium = t < ray.tMax
+//   here:       tS = dist / |d| is drawn first and used as the ray's tMax.  A hit found below tS is the reference's hit
+//               (the watertight test does not depend on tMax except for the range rejection) and means "no scattering";
+//               no hit below tS means the reference's tHit is >= tS, i.e. it scatters at tS.  Same decisions, same
+//               values (a hit at exactly t == tS is the only tie), but rays inside a dense medium are traced over
+//               their short free path instead of to the far wall.
+// The two sampler values are consumed in the reference's order: Intersect draws none.
+PBR_D float medium_sample_distance(const pbrgpu_medium& m, float u0, float u1, float dLen) {
   const Spec sigma_t = medium_sigma_t(m);
-  const Spec sigma_s(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
   int channel = min((int)(u0 * 3), 2);
   const float st = channel == 0 ? sigma_t.r : (channel == 1 ? sigma_t.g : sigma_t.b);
   float dist = -logf(1 - u1) / st;
-  float t = stdmin(dist / dLen, tMax);
-  bool sampledMedium = t < tMax;
+  return dist / dLen;
+}
+// t = min(dist / |d|, ray.tMax) and sampledMedium as established by the trace; returns the path weight.
+PBR_D Spec medium_sample_weight(const pbrgpu_medium& m, float t, bool sampledMedium, float dLen) {
+  const Spec sigma_t = medium_sigma_t(m);
+  const Spec sigma_s(m.sigma_s[0], m.sigma_s[1], m.sigma_s[2]);
   Spec Tr = spec_exp(spec_neg(sigma_t) * stdmin(t, kMaxFloat) * dLen);
   Spec density = sampledMedium ? (sigma_t * Tr) : Tr;
   float pdf = 0;
   pdf += density.r; pdf += density.g; pdf += density.b;
   pdf *= 1 / (float)3;
   if (pdf == 0) pdf = 1;
-  *tOut = t;
-  *sampled = sampledMedium;
   return sampledMedium ? (Tr * sigma_s / pdf) : (Tr / pdf);
 }
 

@@ -783,6 +783,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   P.arrayEndDim = 5;
   if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) P.arrayEndDim = 5 + 2 * (2 * (int)s->lights.size() * rd->max_depth);
   P.atomicL = (pathInteg || volInteg) ? 0 : 1;
+  P.volShadowAnyHit = s->hasNullMat ? 0 : 1;
   P.countStats = count ? 1 : 0;
   P.fetchMinIdle = s->fetchMinIdle;
 
@@ -827,6 +828,8 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
             CK(cudaStreamSynchronize(st));
             t0 = std::chrono::steady_clock::now();
           }
+          CK(tl.mark(T_SHADE));
+          if (s->sc.nMedia > 0) { k_medium_presample<<<g, kBlock, 0, st>>>(P); launches++; }
           CK(tl.mark(T_CLOSEST));
           if (count) k_trace<true, true><<<gt, kTraceBlock, 0, st>>>(P);
           else k_trace<false, true><<<gt, kTraceBlock, 0, st>>>(P);
@@ -932,6 +935,16 @@ __global__ void k_rgba_to_rgb(const float4* in, size_t n, float* out) {
 // D2H through the scene's pinned staging buffer in chunks: the copy of chunk k+1 overlaps the host memcpy of chunk k.
 static int staged_d2h(pbrgpu_scene* s, void* dst, const void* dsrc, size_t bytes, bool accumulateFloat) {
   pbrgpu_ctx* c = s->ctx;
+  if (!accumulateFloat) {
+    // the caller's buffer is itself page-locked (cudaHostAlloc / cudaHostRegister): one DMA, no staging, no host copy
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+      CK(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      return 0;
+    }
+    cudaGetLastError();
+  }
   const size_t chunk = 4u << 20;
   if (s->hstageBytes < 2 * chunk) {
     if (s->hstage) cudaFreeHost(s->hstage);

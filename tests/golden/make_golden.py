@@ -103,6 +103,27 @@ def main():
         img, st = R.render(rsc, rc, 4, (0, 0, 64, 64), integrator=A.INTEGRATOR_VOLPATH, max_depth=5, rr_threshold=0.8)
         np.savez_compressed(os.path.join(HERE, f"volpath64_{kind}.npz"), rgb_mean=(img / np.float32(4)).astype(np.float32),
                             rays_closest=np.int64(st.rays_closest), rays_shadow=np.int64(st.rays_shadow))
+    # ---- participating media known answers: HomogeneousMedium::Sample / Tr, HenyeyGreenstein::Sample_p / p ----
+    rows = np.zeros((512, 8), dtype=np.float32)
+    d = rng.normal(size=(512, 3))
+    rows[:, 0:3] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.2, 3.0, (512, 1))
+    rows[:, 3] = np.where(rng.uniform(size=512) < 0.2, np.inf, rng.uniform(0.01, 4.0, 512))
+    rows[:, 4:6] = rng.uniform(0, 1, (512, 2))
+    rows[:4, 4:6] = [[0.0, 0.0], [0.99999994, 0.99999994], [0.33333334, 0.5], [0.6666667, 1e-7]]
+    out["medium_kat_in"] = rows
+    for tag, (sa, ss, g) in {"a": ((0.5, 0.5, 0.5), (4.4, 4.4, 4.4), -0.5), "b": ((0.05, 0.04, 0.03), (0.25, 0.3, 0.35), 0.3),
+                             "c": ((0.0, 1.0, 0.2), (0.0, 0.0, 2.0), 0.0)}.items():
+        out[f"medium_kat_{tag}_params"] = np.array(list(sa) + list(ss) + [g], dtype=np.float32)
+        out[f"medium_kat_{tag}_out"] = R.medium_kat(sa, ss, g, rows)
+    rows = np.zeros((512, 8), dtype=np.float32)
+    wo = rng.normal(size=(512, 3)); wi = rng.normal(size=(512, 3))
+    rows[:, 0:3] = wo / np.linalg.norm(wo, axis=1, keepdims=True)
+    rows[:, 3:5] = rng.uniform(0, 1, (512, 2))
+    rows[:, 5:8] = wi / np.linalg.norm(wi, axis=1, keepdims=True)
+    rows[:3, 0:3] = [[0, 0, 1], [1, 0, 0], [0, -1, 0]]
+    out["hg_kat_in"] = rows
+    for g in (-0.5, 0.0, 0.3, 0.0005, 0.95):
+        out[f"hg_kat_out_{g}"] = R.hg_kat(g, rows)
     # ---- film tone map ----
     rgb = rng.uniform(0, 1.5, (512, 3)).astype(np.float32)
     rgb[:8] = [[0, 0, 0], [1, 1, 1], [0.0031308, 0.0031308, 0.0031308], [2, 0.5, 0.1], [1e-4, 1e-3, 1e-2], [0.5, 0.5, 0.5],
