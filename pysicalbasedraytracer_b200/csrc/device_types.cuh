@@ -89,6 +89,7 @@ struct Counters {
   uint32_t nMat[8];
   uint32_t cursor[4];  // persistent-kernel fetch cursors (TRACE_PATH, TRACE_MIS, TRACE_SHADOW)
   unsigned long long raysClosest, raysShadow, nodesVisited, trisTested, raysPath;
+  uint32_t maxRayWork;              // COUNT: most node steps + triangle tests spent on one ray (segment)
   uint32_t volMaxHops, volCapHits;  // VolPath shadow rays: most medium boundaries crossed by one ray / rays stopped at the cap
 };
 

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   int hops = 0;      // VOL: medium boundaries this shadow ray has crossed
   unsigned segs = 0; // VOL: shadow-ray segments traced by this lane (each is one Scene::Intersect of VisibilityTester::Tr)
   unsigned nodes = 0, tris = 0;
+  unsigned rayWork0 = 0;  // COUNT: nodes + tris at the start of the current ray (-> Counters::maxRayWork)
   while (true) {
     // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
     // (a per-warp reserve of 128 rays per atomicAdd was measured: no faster - the cursor is not a bottleneck)
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
           nt = 0;
           hops = 0;
           busy = true;
+          if (COUNT) rayWork0 = nodes + tris;
         }
       }
     }
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
       // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
       if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {
         bool again = false;
+        if (COUNT) { atomicMax(&C->maxRayWork, nodes + tris - rayWork0); rayWork0 = nodes + tris; }
         if (mode == TRACE_PATH) {
           P.ws.hit[ray] = make_float4(__int_as_float(T.hit.tri), T.hit.b0, T.hit.b1, T.hit.b2);
           // shading-queue id of this path, written in QUEUE order so that k_classify reads it coalesced

@@ -835,8 +835,17 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
           else k_trace<false, true><<<gt, kTraceBlock, 0, st>>>(P);
           if (volLog) {
             CK(cudaStreamSynchronize(st));
-            fprintf(stderr, "vol iter %d: paths %u shadow %u mis %u  k_trace %.3f ms\n", iter, s->hNCur[0], s->hNCur[2], s->hNCur[3],
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            static Counters prev{};
+            Counters hc{};
+            CK(cudaMemcpy(&hc, s->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost));
+            if (iter == 0) prev = Counters{};
+            const double rays = (double)(hc.raysClosest - prev.raysClosest);
+            fprintf(stderr, "vol iter %d: paths %u shadow %u mis %u  k_trace %.3f ms  segments %.0f nodes/seg %.2f tris/seg %.2f  max work of one ray %u\n", iter,
+                    s->hNCur[0], s->hNCur[2], s->hNCur[3], ms, rays, (hc.nodesVisited - prev.nodesVisited) / std::max(rays, 1.0),
+                    (hc.trisTested - prev.trisTested) / std::max(rays, 1.0), hc.maxRayWork);
+            prev = hc;
+            CK(cudaMemset(&s->ctr.p->maxRayWork, 0, sizeof(uint32_t)));
           }
           CK(tl.mark(T_MIS));
           if (iter > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
