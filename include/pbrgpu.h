@@ -264,6 +264,11 @@ int64_t pbrgpu_compute_perms(uint16_t* out, int64_t capacity);
  * Returns malloc'd arrays (release with pbrgpu_free); non-zero on error. */
 int pbrgpu_load_3d(const char* path, float scale, float** out_verts, int32_t* out_n_verts, int32_t** out_indices,
                    int32_t* out_n_tris);
+/* Radiance ".hdr" (RGBE, flat or run-length coded scanlines) environment map, what InfiniteAreaLight / SkyBoxLight read
+ * through stbi_loadf (Light/InfiniteAreaLight.cpp:17-18, Light/SkyBoxLight.cpp:19-22).  Returns a malloc'd
+ * width*height*3 float array, row-major, top row first unless flip_vertically (= stbi_set_flip_vertically_on_load);
+ * texels are bit-identical to stb's.  Non-zero on error (2 = cannot open, 3 = not a Radiance RGBE file, 5 = truncated). */
+int pbrgpu_load_hdr(const char* path, int flip_vertically, float** out_rgb, int32_t* out_width, int32_t* out_height);
 void pbrgpu_free(void* p);
 
 /* BVH statistics: out[0]=n_nodes, out[1]=n_leaves, out[2]=max_leaf_size, out[3]=bytes_nodes, out[4]=bytes_tris */

@@ -607,6 +607,25 @@ int ref_ply_read(const char* path, float* verts, int cap_verts, int32_t* indices
   return 0;
 }
 
+// The reference's own image loader (stb, compiled into the reference by Light/*.cpp) on a Radiance .hdr file:
+// what InfiniteAreaLight's ctor (InfiniteAreaLight.cpp:17-18) and SkyBoxLight::loadImage (SkyBoxLight.cpp:19-22) get.
+extern "C" float* stbi_loadf(char const* filename, int* x, int* y, int* channels_in_file, int desired_channels);
+extern "C" void stbi_set_flip_vertically_on_load(int flag_true_if_should_flip);
+extern "C" void stbi_image_free(void* retval_from_stbi_load);
+int ref_load_hdr(const char* path, int flip, float* out, int cap_floats, int32_t* w, int32_t* h, int32_t* comp) {
+  stbi_set_flip_vertically_on_load(flip);
+  int x = 0, y = 0, c = 0;
+  float* d = stbi_loadf(path, &x, &y, &c, 0);
+  stbi_set_flip_vertically_on_load(0);
+  if (!d) return 1;
+  *w = x; *h = y; *comp = c;
+  int rc = 0;
+  if ((long long)x * y * c > cap_floats) rc = 2;
+  else memcpy(out, d, sizeof(float) * (size_t)x * y * c);
+  stbi_image_free(d);
+  return rc;
+}
+
 // ---- known-answer hooks for the participating-media functions (pin oracle/restate.c and the GPU twins) ----
 namespace {
 // a Sampler that replays a fixed list of values (HomogeneousMedium::Sample draws two Get1D)

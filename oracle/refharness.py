@@ -42,6 +42,7 @@ def lib():
         L.ref_camera_create_lens.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.c_float, C.c_float]
         L.ref_camera_desc.argtypes = [C.c_void_p, C.POINTER(A.CameraDesc)]
+        L.ref_load_hdr.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.ref_medium_kat.argtypes = [C.POINTER(A.Medium), C.c_void_p, C.c_int, C.c_void_p]
         L.ref_hg_kat.argtypes = [C.c_float, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_camera_set_medium.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -268,3 +269,13 @@ def hg_kat(g, rows):
     out = np.zeros_like(rows)
     lib().ref_hg_kat(g, rows.ctypes.data, rows.shape[0], out.ctypes.data)
     return out
+
+
+def load_hdr(path, flip=False, cap=1 << 24):
+    """stbi_loadf of the reference on a Radiance .hdr file -> float32 [H,W,C]."""
+    out = np.zeros(cap, dtype=np.float32)
+    w, h, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    rc = lib().ref_load_hdr(str(path).encode(), int(flip), out.ctypes.data, cap, C.byref(w), C.byref(h), C.byref(c))
+    if rc != 0:
+        raise RuntimeError(f"ref_load_hdr failed ({rc})")
+    return out[: w.value * h.value * c.value].reshape(h.value, w.value, c.value).copy()

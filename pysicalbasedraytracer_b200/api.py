@@ -57,6 +57,7 @@ def lib():
         L.pbrgpu_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
         L.pbrgpu_load_3d.argtypes = [C.c_char_p, C.c_float, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
                                      C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
+        L.pbrgpu_load_hdr.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.pbrgpu_free.argtypes = [vp]
         _lib = L
     return _lib
@@ -99,6 +100,20 @@ def load_3d(path, scale=20.0):
         lib().pbrgpu_free(v)
         lib().pbrgpu_free(i)
     return verts, tris
+
+
+def load_hdr(path, flip_vertically=False):
+    """Radiance .hdr environment map as stbi_loadf returns it (Light/InfiniteAreaLight.cpp:17-18; SkyBoxLight.cpp:19-22 loads
+    with flip_vertically=True) -> float32 [H,W,3]."""
+    p = C.POINTER(C.c_float)()
+    w, h = C.c_int32(0), C.c_int32(0)
+    rc = lib().pbrgpu_load_hdr(str(path).encode(), int(flip_vertically), C.byref(p), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise PbrGpuError(f"pbrgpu_load_hdr({path}) failed with code {rc}")
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+    finally:
+        lib().pbrgpu_free(p)
 
 
 class Context:

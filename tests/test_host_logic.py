@@ -178,3 +178,64 @@ def api_camera_desc_default():
     from pysicalbasedraytracer_b200 import api
     cam = api.CreateOrthographicCamera(16, 16, api.Inverse(api.LookAt((0, 0, 5), (0, 0, 0), (0, 1, 0))), media=0)
     return cam.desc()  # Camera::medium is recorded but, as in the reference, not delivered to the rays
+
+
+def _write_hdr(path, rgbe, mode):
+    """rgbe uint8 [H,W,4] -> Radiance file.  mode: "rle" (new run-length scanlines), "flat" (plain quadruples)."""
+    h, w, _ = rgbe.shape
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\n# written by the test\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n")
+        f.write(f"-Y {h} +X {w}\n".encode())
+        if mode == "flat":
+            f.write(rgbe.tobytes())
+            return
+        for j in range(h):
+            f.write(bytes([2, 2, w >> 8, w & 255]))
+            for k in range(4):
+                row = rgbe[j, :, k]
+                i = 0
+                while i < w:
+                    run = 1
+                    while i + run < w and run < 127 and row[i + run] == row[i]:
+                        run += 1
+                    if run >= 3:
+                        f.write(bytes([128 + run, int(row[i])]))
+                        i += run
+                    else:
+                        lit = 1
+                        while i + lit < w and lit < 128 and not (i + lit + 2 < w and row[i + lit] == row[i + lit + 1] == row[i + lit + 2]):
+                            lit += 1
+                        f.write(bytes([lit]) + row[i:i + lit].tobytes())
+                        i += lit
+
+
+def test_hdr_loader_matches_reference_stb(api, ref, tmp_path):
+    """pbrgpu_load_hdr vs the reference's stbi_loadf (what InfiniteAreaLight / SkyBoxLight read): texels bit-identical,
+    run-length coded and flat files, with and without the vertical flip SkyBoxLight switches on."""
+    rng = np.random.default_rng(5)
+    for name, (w, h, mode) in {"rle": (64, 32, "rle"), "flat_small": (5, 7, "flat"), "flat_wide": (40, 9, "flat"),
+                               "rle_odd": (37, 11, "rle")}.items():
+        rgbe = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        rgbe[:, :, 3] = rng.integers(118, 140, (h, w))
+        rgbe[::3, : w // 2, :] = rgbe[0, 0, :]  # long runs
+        rgbe[1, 1, 3] = 0                        # exponent 0 -> exactly black
+        if mode == "flat" and w >= 8:
+            rgbe[0, 0, 0] = 7                    # a flat file must not start like a run-length scanline header
+        path = tmp_path / f"{name}.hdr"
+        _write_hdr(path, rgbe, mode)
+        for flip in (False, True):
+            got = api.load_hdr(path, flip_vertically=flip)
+            want = ref.load_hdr(path, flip=flip)
+            assert got.shape == (h, w, 3) and want.shape[2] == 3
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, flip)
+        assert (got[h - 2 if flip else 1, 1] == 0).all()
+    with pytest.raises(api.PbrGpuError):
+        api.load_hdr(tmp_path / "missing.hdr")
+    bad = tmp_path / "bad.hdr"
+    bad.write_bytes(b"P6\n2 2\n255\n" + bytes(12))
+    with pytest.raises(api.PbrGpuError):
+        api.load_hdr(bad)
+    trunc = tmp_path / "trunc.hdr"
+    trunc.write_bytes((tmp_path / "rle.hdr").read_bytes()[:200])
+    with pytest.raises(api.PbrGpuError):
+        api.load_hdr(trunc)
