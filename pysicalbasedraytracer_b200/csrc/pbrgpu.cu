@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "host_tables.h"
@@ -65,6 +66,8 @@ struct pbrgpu_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> pool;  // PBRGPU_RENDER_TIMERS
+  size_t l2PersistBytes = 0;      // persisting-L2 carve-out granted by the device (0 = none)
+  size_t l2WindowMax = 0;         // cudaDevAttrMaxAccessPolicyWindowSize
 };
 
 // CUDA-event timeline: mark(cat) closes the previous interval and opens one of category `cat`.
@@ -115,8 +118,8 @@ struct pbrgpu_scene {
   bool haveCamera = false, haveSampler = false;
   int64_t spp = 0;
   // device buffers
-  DevBuf<float4> tv0, tv1, tv2, tvN, tvS, tvT, tn0, tn1, tn2, tuv0, tuv1;
-  DevBuf<Bvh8Node> nodes;
+  DevBuf<float4> tvN, tvS, tvT, tn0, tn1, tn2, tuv0, tuv1;
+  DevBuf<float4> geom;  // ONE slab: Bvh8Node[] | tv0 | tv1 | tv2 - everything k_trace reads, covered by one L2 access-policy window
   DevBuf<pbrgpu_material> mats;
   DevBuf<pbrgpu_light> dlights;
   DevBuf<float> lightFunc, lightCdf;
@@ -232,6 +235,24 @@ uint32_t grid_for(const pbrgpu_ctx* c, uint64_t n, int perSm) {
   return (uint32_t)(blocks < cap ? blocks : cap);
 }
 
+// Grid of a grid-stride kernel = exactly one resident wave (SMs x the kernel's occupancy), never more blocks than work:
+// a fixed "8 blocks per SM" made 2.67 waves of the 80-register shading kernels, whose partial last wave left two thirds
+// of the SMs idle.
+template <typename K>
+uint32_t grid_occ(const pbrgpu_ctx* c, K kernel, int block, uint64_t n) {
+  static std::unordered_map<const void*, int> cache;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 4; }
+    if (const char* e = getenv("PBRGPU_SHADE_WAVES")) nb *= std::max(1, atoi(e));
+    it = cache.emplace(key, nb).first;
+  }
+  const uint64_t blocks = std::max<uint64_t>(1, (n + block - 1) / block);
+  return (uint32_t)std::min<uint64_t>(blocks, (uint64_t)c->smCount * it->second);
+}
+
 }  // namespace
 
 extern "C" {
@@ -260,6 +281,24 @@ int pbrgpu_init(int device_id, pbrgpu_ctx** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device_id));
   c->smCount = prop.multiProcessorCount;
+  {
+    // Optional L2 set-aside for the traversal data (BVH nodes + triangle vertices, ~50 MB on the dragon-class scene).
+    // OFF by default - measured on B200: k_trace does not get faster (25.4 ms either way: it is issue-bound, its L2 misses
+    // are not the limiter) while the shading kernels, which stream the wavefront state through what is left of the L2,
+    // slow down (12.7 -> 13.2 ms with 32 MB set aside, 18.7 ms with 64 MB, 22.5 ms with 96 MB).
+    size_t want = 0;
+    if (const char* e = getenv("PBRGPU_L2_PERSIST_MB")) want = (size_t)std::max(0, atoi(e)) << 20;
+    want = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
+    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+      c->l2PersistBytes = want;
+      c->l2WindowMax = (size_t)prop.accessPolicyMaxWindowSize;
+    } else {
+      cudaGetLastError();
+    }
+    if (getenv("PBRGPU_VERBOSE"))
+      fprintf(stderr, "pbrgpu: L2 %d MB, persisting max %d MB, granted %zu MB, window max %d MB\n", prop.l2CacheSize >> 20,
+              prop.persistingL2CacheMaxSize >> 20, c->l2PersistBytes >> 20, prop.accessPolicyMaxWindowSize >> 20);
+  }
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
   *out = c;
@@ -372,8 +411,18 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   CK(s->tvN.upload(vN, st)); CK(s->tvS.upload(vS, st)); CK(s->tvT.upload(vT, st));
   if (anyNormals) { CK(s->tn0.upload(vn0, st)); CK(s->tn1.upload(vn1, st)); CK(s->tn2.upload(vn2, st)); }
   if (!vuv0.empty()) { CK(s->tuv0.upload(vuv0, st)); CK(s->tuv1.upload(vuv1, st)); }
-  CK(s->tv0.upload(v0, st)); CK(s->tv1.upload(v1, st)); CK(s->tv2.upload(v2, st));
-  CK(s->nodes.upload(s->bvh.nodes, st));
+  {
+    static_assert(sizeof(Bvh8Node) == 5 * sizeof(float4), "Bvh8Node is five 16-byte words");
+    const size_t nN = s->bvh.nodes.size() * 5, nTv = (size_t)nT;
+    CK(s->geom.alloc(nN + 3 * nTv));
+    CK(cudaMemcpyAsync(s->geom.p, s->bvh.nodes.data(), nN * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->geom.p + nN, v0.data(), nTv * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->geom.p + nN + nTv, v1.data(), nTv * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->geom.p + nN + 2 * nTv, v2.data(), nTv * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // v0..v2 are locals
+    s->sc.nodes8 = s->geom.p;
+    s->sc.tv0 = s->geom.p + nN; s->sc.tv1 = s->geom.p + nN + nTv; s->sc.tv2 = s->geom.p + nN + 2 * nTv;
+  }
   // participating media + per-triangle MediumInterface (leaf order)
   if (d->n_media > 0) {
     std::vector<pbrgpu_medium> media(d->media, d->media + d->n_media);
@@ -550,10 +599,8 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
   }
   CK(s->dlights.upload(s->lights, st));
 
-  s->sc.tv0 = s->tv0.p; s->sc.tv1 = s->tv1.p; s->sc.tv2 = s->tv2.p;
   s->sc.tvN = s->tvN.p; s->sc.tvS = s->tvS.p; s->sc.tvT = s->tvT.p;
   s->sc.tn0 = s->tn0.p; s->sc.tn1 = s->tn1.p; s->sc.tn2 = s->tn2.p; s->sc.tuv0 = s->tuv0.p; s->sc.tuv1 = s->tuv1.p;
-  s->sc.nodes8 = reinterpret_cast<const float4*>(s->nodes.p);
   s->sc.mats = s->mats.p;
   s->sc.lights = s->dlights.p;
   s->sc.nTris = nT;
@@ -787,6 +834,20 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   P.countStats = count ? 1 : 0;
   P.fetchMinIdle = s->fetchMinIdle;
 
+  // traversal data persists in L2 for the duration of the render (window = the geometry slab; when the slab is larger than
+  // the carve-out, hitRatio keeps a random carve-out-sized fraction of its lines persisting instead of thrashing)
+  bool l2Window = false;
+  if (c->l2PersistBytes > 0 && s->geom.n > 0) {
+    cudaStreamAttrValue av{};
+    const size_t bytes = std::min(s->geom.n * sizeof(float4), c->l2WindowMax);
+    av.accessPolicyWindow.base_ptr = s->geom.p;
+    av.accessPolicyWindow.num_bytes = bytes;
+    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2PersistBytes / (double)bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) l2Window = true;
+    else cudaGetLastError();
+  }
   if (!(rd->flags & PBRGPU_RENDER_ACCUMULATE)) CK(cudaMemsetAsync(d_rgba_sum, 0, sizeof(float) * 4 * (size_t)W * H, st));
   CK(cudaMemsetAsync(s->ctr.p, 0, sizeof(Counters), st));  // (a memset, not a pageable H2D copy: never blocks the host)
   CK(cudaEventRecord(c->ev[0], st));
@@ -804,14 +865,13 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       P.ws.qCur = s->qA.p;
       P.ws.qNext = s->qB.p;
       uint32_t g = grid_for(c, nPaths, 8);
-      uint32_t gs = g * (kBlock / kShadeBlock);
       uint32_t gc = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths + kClassifyTile - 1) / kClassifyTile, (uint64_t)c->smCount * 8));
       // persistent traversal grid: every SM filled to the kernel's occupancy, never more blocks than rays
       uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths * (pathInteg ? 1 : 1 + raysPerHit) + kTraceBlock - 1) / kTraceBlock,
                                                                       (uint64_t)c->smCount * s->traceBlocksPerSm));
       CK(tl.mark(T_RAYGEN));
       k_wave_begin<<<1, 1, 0, st>>>(s->ctr.p);
-      k_raygen<<<g, kBlock, 0, st>>>(P);
+      k_raygen<<<grid_occ(c, k_raygen, kBlock, nPaths), kBlock, 0, st>>>(P);
       launches += 2;
       // bounce b: ONE traversal launch serves the path rays of bounce b and the shadow + MIS rays that the
       // shading of bounce b-1 emitted; then MIS resolve (b-1), classification, material-sorted shading (b).
@@ -852,12 +912,12 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
           CK(tl.mark(T_SHADE));
           if (s->sc.nMedia > 0) { k_medium_sample<<<g, kBlock, 0, st>>>(P); launches++; }
           k_classify<<<gc, kBlock, 0, st>>>(P);
-#define PBR_SHADE_V(M) if (s->hasMat[M]) { k_shade<M, true><<<gs, kShadeBlock, 0, st>>>(P, 0); launches++; }
+#define PBR_SHADE_V(M) if (s->hasMat[M]) { k_shade<M, true><<<grid_occ(c, k_shade<M, true>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, 0); launches++; }
           PBR_SHADE_V(PBRGPU_MAT_MATTE) PBR_SHADE_V(PBRGPU_MAT_MIRROR) PBR_SHADE_V(PBRGPU_MAT_GLASS)
           PBR_SHADE_V(PBRGPU_MAT_METAL) PBR_SHADE_V(PBRGPU_MAT_PLASTIC)
 #undef PBR_SHADE_V
           if (s->hasNullMat) { k_shade_null<<<g, kBlock, 0, st>>>(P); launches++; }
-          if (s->sc.nMedia > 0) { k_shade_medium<<<gs, kShadeBlock, 0, st>>>(P); launches++; }
+          if (s->sc.nMedia > 0) { k_shade_medium<<<grid_occ(c, k_shade_medium, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P); launches++; }
           if (s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, 0); launches++; }
           k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
           launches += 3;
@@ -879,7 +939,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         CK(tl.mark(T_SHADE));
         k_classify<<<gc, kBlock, 0, st>>>(P);
         // one shading launch per material type PRESENT in the scene
-#define PBR_SHADE(M) if (s->hasMat[M]) { k_shade<M><<<gs, kShadeBlock, 0, st>>>(P, bounce); launches++; }
+#define PBR_SHADE(M) if (s->hasMat[M]) { k_shade<M><<<grid_occ(c, k_shade<M, false>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, bounce); launches++; }
 #define PBR_SHADE_D(M) if (s->hasMat[M]) { k_shade_direct<M><<<g, kBlock, 0, st>>>(P, bounce); launches++; }
         if (pathInteg) {
           PBR_SHADE(PBRGPU_MAT_MATTE) PBR_SHADE(PBRGPU_MAT_MIRROR) PBR_SHADE(PBRGPU_MAT_GLASS)
@@ -911,6 +971,11 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   CK(tl.mark(T_END));
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev[1], st));
+  if (l2Window) {  // the stream may be the caller's: leave it as it was
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
   s->last = LastRender{(uint64_t)W * H * (uint64_t)nS, launches, tl};
   if (stats && fetch_stats(s, st, stats)) return 1;
   return 0;
