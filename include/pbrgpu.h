@@ -57,12 +57,26 @@ typedef struct pbrgpu_material {
   float kr[3];
   float pad0;
   float kt[3];
-  float pad1;
+  int32_t kd_texture_plus1; /* Matte / Plastic: Kd comes from textures[kd_texture_plus1 - 1] (an ImageTexture) instead of kd;
+                               0 = ConstantTexture(kd) */
   float eta[3]; /* Metal eta (RGB); Glass index of refraction in eta[0] */
   float pad2;
   float k[3]; /* Metal absorption */
   float pad3;
 } pbrgpu_material; /* 96 bytes */
+
+/* ---- image textures: ImageTexture<RGBSpectrum, Spectrum> (Texture/ImageTexture.h) = UVMapping2D + MIPMap (Texture/MIPMap.h) ---- */
+enum { PBRGPU_WRAP_REPEAT = 0, PBRGPU_WRAP_BLACK = 1, PBRGPU_WRAP_CLAMP = 2 }; /* ImageWrap */
+typedef struct pbrgpu_texture {
+  int32_t width, height;  /* powers of two (MIPMap Lanczos-resamples anything else, MIPMap.h:93-144) */
+  const float* texels;    /* width*height*3 RGB, row-major, as the MIPMap receives them, i.e. after ImageTexture::convertIn
+                             (scale, optional inverse gamma) and after the loader's vertical flip (ImageTexture.cpp:16) */
+  int32_t do_trilinear;   /* MIPMap::doTrilinear: trilinear filter instead of EWA */
+  float max_anisotropy;   /* MIPMap::maxAnisotropy (EWA) */
+  int32_t wrap;           /* PBRGPU_WRAP_* */
+  float su, sv, du, dv;   /* UVMapping2D (Texture/Texture.h) */
+  int32_t pad0;
+} pbrgpu_texture; /* 48 bytes */
 
 /* ---- participating media: Media/HomogeneousMedium.{h,cpp}, phase function Media/Medium.{h,cpp} ---- */
 enum { PBRGPU_MEDIUM_HOMOGENEOUS = 0 };
@@ -121,6 +135,10 @@ typedef struct pbrgpu_scene_desc {
   const pbrgpu_medium* media;
   const int32_t* tri_medium_inside;  /* n_tris: index into media or -1 (MediumInterface::inside);  NULL = none */
   const int32_t* tri_medium_outside; /* n_tris: index into media or -1 (MediumInterface::outside); NULL = none */
+  /* image textures referenced by pbrgpu_material::kd_texture_plus1 */
+  int32_t n_textures;
+  int32_t pad1;
+  const pbrgpu_texture* textures;
 } pbrgpu_scene_desc;
 
 /* ---- camera: Camera/Camera.h:34-54, Perspective.cpp, Orthographic.cpp ---- */
@@ -238,7 +256,9 @@ enum {
   PBRGPU_DUMP_PRIMARY_RAYS = 1, /* float[n_pix][n_samples][8] : o.xyz, tMax, d.xyz, time */
   PBRGPU_DUMP_PRIMARY_HITS = 2, /* int32 prim (caller's triangle index, -1 miss) + float t,b0,b1 : [..][4] */
   PBRGPU_DUMP_PERMS = 3,        /* uint16[n_perms] */
-  PBRGPU_DUMP_SHADOW = 4        /* int32[n] occlusion of caller-supplied rays (see pbrgpu_trace_rays) */
+  PBRGPU_DUMP_SHADOW = 4,       /* int32[n] occlusion of caller-supplied rays (see pbrgpu_trace_rays) */
+  PBRGPU_DUMP_HIT_DIFFERENTIALS = 5 /* float[n_pix][n_samples][8]: hit flag, uv, dudx, dvdx, dudy, dvdy of the camera ray's hit
+                                       (Triangle.cpp:147-170, SurfaceInteraction::ComputeDifferentials) */
 };
 typedef struct pbrgpu_dump_desc {
   int32_t what;
@@ -252,6 +272,10 @@ int pbrgpu_debug_dump(pbrgpu_scene* scene, const pbrgpu_dump_desc* dd, void* out
 /* Trace caller-supplied rays (float[n][8]: o.xyz,tMax,d.xyz,pad).  any_hit=0: closest hit ->
  * out_hits int32/float [n][4] (prim, t, b0, b1 as bit patterns); any_hit=1: out_hits int32[n]. */
 int pbrgpu_trace_rays(pbrgpu_scene* scene, const float* rays, int64_t n, int any_hit, void* out_hits);
+
+/* Parity hook: ImageTexture::Evaluate of textures[texture] for n surface points.  rows float[n][8] = u, v, dudx, dvdx, dudy,
+ * dvdy, -, - (SurfaceInteraction::uv and its screen-space derivatives); out float[n][4] = rgb, -. */
+int pbrgpu_texture_eval(pbrgpu_scene* scene, int texture, const float* rows, int64_t n, float* out);
 
 /* Halton helper mirrors (host-side integer code; Halton.cpp:40-81).  Outputs 7 ints:
  * baseScales[2], baseExponents[2], sampleStride, multInverse[2]. */

@@ -47,6 +47,7 @@
 #include "Texture/Texture.h"
 #include "Texture/ConstantTexture.h"
 #include "Texture/MIPMap.h"
+#include "Texture/ImageTexture.h"
 #include "Material/Material.h"
 #include "Material/MatteMaterial.h"
 #include "Material/Mirror.h"
@@ -125,10 +126,29 @@ std::shared_ptr<Texture<Spectrum>> ctex(const float c[3]) {
 }
 std::shared_ptr<Texture<float>> ftex(float v) { return std::make_shared<ConstantTexture<float>>(v); }
 
-std::shared_ptr<Material> makeMaterial(const pbrgpu_material& m) {
+// ImageTexture<RGBSpectrum, Spectrum> over the caller's texels.  The class only loads files (ImageTexture.cpp:10-37), so it
+// is constructed on a non-existent file (-> its 1x1 placeholder) and the placeholder MIPMap is replaced by the reference's own
+// MIPMap built from the texels (pyramid, EWA table: MIPMap.h:86-178) - the same trick as for the InfiniteAreaLight below.
+std::shared_ptr<Texture<Spectrum>> makeImageTexture(const pbrgpu_texture& t) {
+  static std::atomic<int> counter{0};
+  std::unique_ptr<TextureMapping2D> map(new UVMapping2D(t.su, t.sv, t.du, t.dv));
+  const std::string name = "/nonexistent/pbr_ref_texture_" + std::to_string(counter++);
+  const ImageWrap wrap = t.wrap == PBRGPU_WRAP_CLAMP ? ImageWrap::Clamp : (t.wrap == PBRGPU_WRAP_BLACK ? ImageWrap::Black : ImageWrap::Repeat);
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  auto tex = std::make_shared<ImageTexture<RGBSpectrum, Spectrum>>(std::move(map), name, t.do_trilinear != 0, t.max_anisotropy, wrap, 1.f, false);
+  std::cerr.rdbuf(old);
+  std::vector<RGBSpectrum> texels((size_t)t.width * t.height);
+  for (size_t k = 0; k < texels.size(); ++k)
+    for (int c = 0; c < 3; ++c) texels[k][c] = t.texels[3 * k + c];
+  tex->mipmap = new MIPMap<RGBSpectrum>(Point2i(t.width, t.height), texels.data(), t.do_trilinear != 0, t.max_anisotropy, wrap);
+  return tex;
+}
+
+std::shared_ptr<Material> makeMaterial(const pbrgpu_material& m, const pbrgpu_scene_desc* d) {
   auto bump = ftex(0.f);
+  std::shared_ptr<Texture<Spectrum>> kd = m.kd_texture_plus1 > 0 ? makeImageTexture(d->textures[m.kd_texture_plus1 - 1]) : nullptr;
   switch (m.type) {
-    case PBRGPU_MAT_MATTE: return std::make_shared<MatteMaterial>(ctex(m.kd), ftex(m.sigma), bump);
+    case PBRGPU_MAT_MATTE: return std::make_shared<MatteMaterial>(kd ? kd : ctex(m.kd), ftex(m.sigma), bump);
     case PBRGPU_MAT_MIRROR: return std::make_shared<MirrorMaterial>(ctex(m.kr), bump);
     case PBRGPU_MAT_GLASS:
       return std::make_shared<GlassMaterial>(ctex(m.kr), ctex(m.kt), ftex(m.u_rough), ftex(m.v_rough),
@@ -137,7 +157,7 @@ std::shared_ptr<Material> makeMaterial(const pbrgpu_material& m) {
       return std::make_shared<MetalMaterial>(ctex(m.eta), ctex(m.k), ftex(m.u_rough), ftex(m.u_rough),
                                              ftex(m.v_rough), bump, m.remap_roughness != 0);
     case PBRGPU_MAT_PLASTIC:
-      return std::make_shared<PlasticMaterial>(ctex(m.kd), ctex(m.kr), ftex(m.u_rough), bump,
+      return std::make_shared<PlasticMaterial>(kd ? kd : ctex(m.kd), ctex(m.kr), ftex(m.u_rough), bump,
                                                m.remap_roughness != 0);
   }
   return nullptr;
@@ -177,16 +197,27 @@ void* ref_scene_create(const pbrgpu_scene_desc* d) {
     UV.resize(d->n_verts);
     for (int i = 0; i < d->n_verts; ++i) UV[i] = Point2f(d->uvs[2 * i], d->uvs[2 * i + 1]);
   }
-  auto mesh = std::make_shared<TriangleMesh>(rs->identity, d->n_tris, d->indices, d->n_verts, P.data(), nullptr,
-                                             d->normals ? N.data() : nullptr, d->uvs ? UV.data() : nullptr, nullptr);
-  rs->meshes.push_back(mesh);
-  for (int i = 0; i < d->n_materials; ++i) rs->materials.push_back(makeMaterial(d->materials[i]));
+  // tri_flags bit2 / bit3 say whether a triangle's mesh has per-vertex normals / uvs: one TriangleMesh per combination in
+  // use (they share the vertex and index arrays), so that triangles of meshes WITHOUT uvs get Triangle::GetUVs' defaults
+  std::shared_ptr<TriangleMesh> variant[4];
+  auto meshFor = [&](int i) {
+    int key = 0;
+    if (d->tri_flags) key = ((d->tri_flags[i] & 4) && d->normals ? 1 : 0) | ((d->tri_flags[i] & 8) && d->uvs ? 2 : 0);
+    else key = (d->normals ? 1 : 0) | (d->uvs ? 2 : 0);
+    if (!variant[key]) {
+      variant[key] = std::make_shared<TriangleMesh>(rs->identity, d->n_tris, d->indices, d->n_verts, P.data(), nullptr,
+                                                    (key & 1) ? N.data() : nullptr, (key & 2) ? UV.data() : nullptr, nullptr);
+      rs->meshes.push_back(variant[key]);
+    }
+    return variant[key];
+  };
+  for (int i = 0; i < d->n_materials; ++i) rs->materials.push_back(makeMaterial(d->materials[i], d));
   for (int i = 0; i < d->n_media; ++i)
     rs->media.emplace_back(new HomogeneousMedium(rgb(d->media[i].sigma_a), rgb(d->media[i].sigma_s), d->media[i].g));
   rs->tris.reserve(d->n_tris);
   for (int i = 0; i < d->n_tris; ++i) {
     bool rev = d->tri_flags ? (d->tri_flags[i] & 1) != 0 : false;
-    rs->tris.push_back(std::make_shared<Triangle>(&rs->identity, &rs->identity, rev, mesh, i));
+    rs->tris.push_back(std::make_shared<Triangle>(&rs->identity, &rs->identity, rev, meshFor(i), i));
   }
   // lights (one entry per emissive triangle, as the reference does: Main/main.cpp:353-375)
   rs->lights.resize(d->n_lights);
@@ -605,6 +636,41 @@ int ref_ply_read(const char* path, float* verts, int cap_verts, int32_t* indices
     for (int k = 0; k < 3; ++k) verts[3 * i + k] = info.vertexArray[i][k];
   memcpy(indices, info.vertexIndices, sizeof(int32_t) * 3 * (size_t)info.nTriangles);
   return 0;
+}
+
+// Surface differentials of the camera ray of (pixel, sample s): out[16] = hit flag, uv.xy, dudx, dvdx, dudy, dvdy, dpdu.xyz, dpdv.xyz, -, -
+// (Triangle::Intersect + SurfaceInteraction::ComputeDifferentials, Core/Interaction.cpp:48-99)
+void ref_camera_hit_differentials(void* hscene, void* hc, int spp, int W, int H, int px, int py, int64_t s, float* out) {
+  auto* rs = (RefScene*)hscene;
+  auto* rc = (RefCamera*)hc;
+  HaltonSampler smp(spp, Bounds2i(Point2i(0, 0), Point2i(W, H)));
+  Point2i pixel(px, py);
+  smp.StartPixel(pixel);
+  smp.SetSampleNumber(s);
+  CameraSample cs = smp.GetCameraSample(pixel);
+  RayDifferential r;
+  rc->cam->GenerateRayDifferential(cs, &r);
+  r.ScaleDifferentials(1 / std::sqrt((float)smp.samplesPerPixel));
+  SurfaceInteraction isect;
+  memset(out, 0, 16 * sizeof(float));
+  if (!rs->scene->Intersect(r, &isect)) return;
+  isect.ComputeDifferentials(r);
+  out[0] = 1.f; out[1] = isect.uv[0]; out[2] = isect.uv[1];
+  out[3] = isect.dudx; out[4] = isect.dvdx; out[5] = isect.dudy; out[6] = isect.dvdy;
+  for (int k = 0; k < 3; ++k) { out[7 + k] = isect.dpdu[k]; out[10 + k] = isect.dpdv[k]; }
+}
+
+// ImageTexture::Evaluate known answers: in[n][8] = u, v, dudx, dvdx, dudy, dvdy, -, -  ->  out[n][4] = rgb, -
+void ref_texture_kat(const pbrgpu_texture* t, const float* in, int n, float* out) {
+  auto tex = makeImageTexture(*t);
+  for (int i = 0; i < n; ++i) {
+    const float* r = in + 8 * i;
+    SurfaceInteraction si;
+    si.uv = Point2f(r[0], r[1]);
+    si.dudx = r[2]; si.dvdx = r[3]; si.dudy = r[4]; si.dvdy = r[5];
+    Spectrum v = tex->Evaluate(si);
+    out[4 * i] = v[0]; out[4 * i + 1] = v[1]; out[4 * i + 2] = v[2]; out[4 * i + 3] = 0.f;
+  }
 }
 
 // The reference's own image loader (stb, compiled into the reference by Light/*.cpp) on a Radiance .hdr file:

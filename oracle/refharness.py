@@ -42,6 +42,8 @@ def lib():
         L.ref_camera_create_lens.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.c_float, C.c_float]
         L.ref_camera_desc.argtypes = [C.c_void_p, C.POINTER(A.CameraDesc)]
+        L.ref_camera_hit_differentials.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+        L.ref_texture_kat.argtypes = [C.POINTER(A.Texture), C.c_void_p, C.c_int, C.c_void_p]
         L.ref_load_hdr.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.ref_medium_kat.argtypes = [C.POINTER(A.Medium), C.c_void_p, C.c_int, C.c_void_p]
         L.ref_hg_kat.argtypes = [C.c_float, C.c_void_p, C.c_int, C.c_void_p]
@@ -279,3 +281,19 @@ def load_hdr(path, flip=False, cap=1 << 24):
     if rc != 0:
         raise RuntimeError(f"ref_load_hdr failed ({rc})")
     return out[: w.value * h.value * c.value].reshape(h.value, w.value, c.value).copy()
+
+
+def texture_kat(tex, rows):
+    """ImageTexture::Evaluate of the reference for rows [n,8] = u, v, dudx, dvdx, dudy, dvdy, -, - -> rgb [n,3].
+    tex: (A.Texture, texel array) as stored in SceneData.textures."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 8)
+    out = np.zeros((rows.shape[0], 4), dtype=np.float32)
+    lib().ref_texture_kat(C.byref(tex[0]), rows.ctypes.data, rows.shape[0], out.ctypes.data)
+    return out[:, :3]
+
+
+def camera_hit_differentials(scene, cam, spp, px, py, s):
+    """-> float32[16]: hit flag, uv, dudx, dvdx, dudy, dvdy, dpdu, dpdv of the camera ray of (pixel, sample)."""
+    out = np.zeros(16, dtype=np.float32)
+    lib().ref_camera_hit_differentials(scene.h, cam.h, spp, cam.W, cam.H, px, py, s, out.ctypes.data)
+    return out

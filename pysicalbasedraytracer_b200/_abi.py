@@ -9,7 +9,7 @@ INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTE
 MEDIUM_HOMOGENEOUS = 0
 LIGHTSTRATEGY_UNIFORM, LIGHTSTRATEGY_POWER = 0, 1
 RENDER_ACCUMULATE, RENDER_COUNTERS, RENDER_TIMERS = 1, 2, 4
-DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW = range(5)
+DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW, DUMP_HIT_DIFFERENTIALS = range(6)
 
 f3 = C.c_float * 3
 f16 = C.c_float * 16
@@ -17,7 +17,7 @@ f16 = C.c_float * 16
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("remap_roughness", C.c_int32), ("sigma", C.c_float), ("u_rough", C.c_float),
-                ("kd", f3), ("v_rough", C.c_float), ("kr", f3), ("pad0", C.c_float), ("kt", f3), ("pad1", C.c_float),
+                ("kd", f3), ("v_rough", C.c_float), ("kr", f3), ("pad0", C.c_float), ("kt", f3), ("kd_texture_plus1", C.c_int32),
                 ("eta", f3), ("pad2", C.c_float), ("k", f3), ("pad3", C.c_float)]
 
 
@@ -25,6 +25,15 @@ class Light(C.Structure):
     _fields_ = [("type", C.c_int32), ("tri", C.c_int32), ("two_sided", C.c_int32), ("n_samples", C.c_int32),
                 ("pos", f3), ("world_radius", C.c_float), ("L", f3), ("pad0", C.c_float),
                 ("light_to_world", f16), ("world_to_light", f16)]
+
+
+WRAP_REPEAT, WRAP_BLACK, WRAP_CLAMP = range(3)
+
+
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("texels", C.POINTER(C.c_float)), ("do_trilinear", C.c_int32),
+                ("max_anisotropy", C.c_float), ("wrap", C.c_int32), ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float),
+                ("dv", C.c_float), ("pad0", C.c_int32)]
 
 
 class Medium(C.Structure):
@@ -41,7 +50,8 @@ class SceneDesc(C.Structure):
                 ("materials", C.POINTER(Material)), ("lights", C.POINTER(Light)),
                 ("env_width", C.c_int32), ("env_height", C.c_int32), ("env_texels", C.POINTER(C.c_float)),
                 ("n_media", C.c_int32), ("pad0", C.c_int32), ("media", C.POINTER(Medium)),
-                ("tri_medium_inside", C.POINTER(C.c_int32)), ("tri_medium_outside", C.POINTER(C.c_int32))]
+                ("tri_medium_inside", C.POINTER(C.c_int32)), ("tri_medium_outside", C.POINTER(C.c_int32)),
+                ("n_textures", C.c_int32), ("pad1", C.c_int32), ("textures", C.POINTER(Texture))]
 
 
 class CameraDesc(C.Structure):
@@ -77,4 +87,4 @@ class DumpDesc(C.Structure):
                 ("s0", C.c_int64), ("s1", C.c_int64), ("n_dims", C.c_int32), ("pad", C.c_int32)]
 
 
-assert C.sizeof(Material) == 96 and C.sizeof(Light) == 176 and C.sizeof(Medium) == 32
+assert C.sizeof(Material) == 96 and C.sizeof(Light) == 176 and C.sizeof(Medium) == 32 and C.sizeof(Texture) == 48

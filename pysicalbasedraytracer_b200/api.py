@@ -57,6 +57,7 @@ def lib():
         L.pbrgpu_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
         L.pbrgpu_load_3d.argtypes = [C.c_char_p, C.c_float, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
                                      C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
+        L.pbrgpu_texture_eval.argtypes = [vp, C.c_int, vp, C.c_int64, vp]
         L.pbrgpu_load_hdr.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.pbrgpu_free.argtypes = [vp]
         _lib = L
@@ -297,6 +298,11 @@ class Scene:
         x0, y0, x1, y1 = region
         return self._dump(A.DUMP_PRIMARY_HITS, region, s0, s1, 0, ((y1 - y0) * (x1 - x0), s1 - s0, 4), np.int32)
 
+    def dump_hit_differentials(self, region, s0, s1):
+        """float32 [H,W,S,8]: hit flag, uv, dudx, dvdx, dudy, dvdy of each camera ray's surface hit."""
+        x0, y0, x1, y1 = region
+        return self._dump(A.DUMP_HIT_DIFFERENTIALS, region, s0, s1, 0, (y1 - y0, x1 - x0, s1 - s0, 8), np.float32)
+
     def dump_perms(self, n):
         out = np.zeros(n, dtype=np.uint16)
         dd = A.DumpDesc(what=A.DUMP_PERMS)
@@ -309,6 +315,13 @@ class Scene:
         out = np.zeros((n,) if any_hit else (n, 4), dtype=np.int32)
         _check(lib().pbrgpu_trace_rays(self.h, rays.ctypes.data, n, int(any_hit), out.ctypes.data))
         return out
+
+    def texture_eval(self, texture, rows):
+        """ImageTexture::Evaluate parity hook: rows [n,8] = u, v, dudx, dvdx, dudy, dvdy, -, - -> rgb [n,3]."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 8)
+        out = np.zeros((rows.shape[0], 4), dtype=np.float32)
+        _check(lib().pbrgpu_texture_eval(self.h, texture, rows.ctypes.data, rows.shape[0], out.ctypes.data))
+        return out[:, :3]
 
     # ---- render ----
     def render(self, integrator=A.INTEGRATOR_PATH, max_depth=5, rr_threshold=1.0,

@@ -49,6 +49,16 @@ struct EnvDev {
   float margInt;
 };
 
+// ImageTexture on the device: MIP pyramid (level 0 first) as float4 RGB- texels + the UVMapping2D (texture.cuh)
+struct TexDev {
+  const float4* texels;
+  int width, height, nLevels;
+  int doTrilinear, wrap;
+  float maxAnisotropy;
+  float su, sv, du, dv;
+  uint32_t levelOffset[16];
+};
+
 struct SceneDev {
   const float4* tv0;
   const float4* tv1;
@@ -68,6 +78,8 @@ struct SceneDev {
   const float4* nodes8;         // Bvh8Node[] viewed as 5 x float4 per node
   const pbrgpu_material* mats;  // roughness fields already remapped to alpha on the host (glibc logf)
   const pbrgpu_light* lights;   // AREA_TRI: .tri = LEAF-ORDER triangle index
+  const TexDev* textures;       // ImageTexture table (NULL when no material uses one)
+  const float* ewaLut;          // MIPMap::weightLut[128]
   const pbrgpu_medium* media;   // HomogeneousMedium table (VolPath)
   const uint32_t* triMedium;    // per leaf-order triangle: (inside + 1) | (outside + 1) << 16, 0 = none; NULL = no interfaces
   int nMedia;
@@ -134,6 +146,7 @@ struct RenderParams {
   int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
   int countStats;
   int fetchMinIdle;       // idle lanes of a warp that trigger a ray fetch
+  float diffScale;        // 1 / sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials of the render loop (image textures)
   int volShadowAnyHit;    // VolPath, scene without material-less surfaces: a shadow ray ends at ANY surface it finds
   int atomicL;            // several shadow / MIS rays per path and bounce (Whitted / DirectLighting): atomics on L
   // Halton offset of the pixel a global index belongs to: index = offset(pixel) + sample * stride, offset < stride

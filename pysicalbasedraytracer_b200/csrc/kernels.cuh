@@ -96,6 +96,66 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
   if (blockIdx.x == 0 && threadIdx.x == 0) P.ws.ctr->nCur = n;
 }
 
+// The offset rays of a camera sample (rxOrigin/rxDirection, ryOrigin/ryDirection of GenerateRayDifferential for a pinhole
+// camera, Perspective.cpp:72-78 / Orthographic.cpp:54-58), transformed to world space and scaled by
+// RayDifferential::ScaleDifferentials(1 / sqrt(spp)) as the render loop does (Integrator.cpp:305).
+PBR_D void camera_differentials(const RenderParams& P, float fx, float fy, V3 o, V3 d, V3* rxO, V3* rxD, V3* ryO, V3* ryD) {
+  const CameraDev& cam = P.sc.cam;
+  const V3 pCamera = xform_point(cam.r2c, V3(fx, fy, 0));
+  V3 xo, xd, yo, yd;
+  if (cam.type == PBRGPU_CAMERA_PERSPECTIVE) {
+    const V3 p00 = xform_point(cam.r2c, V3(0, 0, 0));
+    const V3 dxCamera = xform_point(cam.r2c, V3(1, 0, 0)) - p00, dyCamera = xform_point(cam.r2c, V3(0, 1, 0)) - p00;
+    xo = yo = V3(0, 0, 0);
+    xd = normalize(pCamera + dxCamera);
+    yd = normalize(pCamera + dyCamera);
+  } else {
+    const V3 dxCamera = xform_vec(cam.r2c, V3(1, 0, 0)), dyCamera = xform_vec(cam.r2c, V3(0, 1, 0));
+    xo = pCamera + dxCamera;
+    yo = pCamera + dyCamera;
+    xd = yd = V3(0, 0, 1);
+  }
+  xo = xform_point(cam.c2w, xo); yo = xform_point(cam.c2w, yo);
+  xd = xform_vec(cam.c2w, xd); yd = xform_vec(cam.c2w, yd);
+  const float s = P.diffScale;
+  *rxO = o + (xo - o) * s; *ryO = o + (yo - o) * s;
+  *rxD = d + (xd - d) * s; *ryD = d + (yd - d) * s;
+}
+
+// Kd->Evaluate(si) for a Matte / Plastic material whose Kd is an ImageTexture: uv and dpdu/dpdv of the hit
+// (Triangle.cpp:147-170), ComputeDifferentials for camera rays (every other ray has no differentials: Interaction.cpp:91-97).
+PBR_D void hit_uv_differentials(const RenderParams& P, const TriData& tri, int triId, float b0, float b1, float b2, V3 p, V3 n,
+                                bool cameraRay, int px, int py, int64_t index, V3 rayO, V3 rayD, float* u, float* v, UvDiff* dd) {
+  const SceneDev& sc = P.sc;
+  float uv[6] = {0.f, 0.f, 1.f, 0.f, 1.f, 1.f};  // Triangle::GetUVs default (Triangle.h:50-54)
+  if ((tri.w1 >> kTriFlagShift) & kTriFlagUVs) {
+    const float4 a = __ldg(sc.tuv0 + triId), b = __ldg(sc.tuv1 + triId);
+    uv[0] = a.x; uv[1] = a.y; uv[2] = a.z; uv[3] = a.w; uv[4] = b.x; uv[5] = b.y;
+  }
+  *u = (b0 * uv[0] + b1 * uv[2]) + b2 * uv[4];
+  *v = (b0 * uv[1] + b1 * uv[3]) + b2 * uv[5];
+  *dd = UvDiff{0.f, 0.f, 0.f, 0.f};
+  if (cameraRay) {
+    V3 dpdu, dpdv;
+    triangle_dpdu_dpdv(tri.p0, tri.p1, tri.p2, uv, &dpdu, &dpdv);
+    const float fx = (float)px + sampler_film_sample(index, 0, px, sc.hp);
+    const float fy = (float)py + sampler_film_sample(index, 1, py, sc.hp);
+    V3 rxO, rxD, ryO, ryD;
+    camera_differentials(P, fx, fy, rayO, rayD, &rxO, &rxD, &ryO, &ryD);
+    *dd = compute_differentials(p, n, dpdu, dpdv, rxO, rxD, ryO, ryD);
+  }
+}
+
+PBR_D Spec eval_kd_texture(const RenderParams& P, const pbrgpu_material& m, const TriData& tri, int triId, float b0, float b1, float b2,
+                           const Isect& is, bool cameraRay, uint32_t slot, int64_t index, V3 rayO, V3 rayD) {
+  int px, py; long long sIdx; uint32_t pix;
+  slot_to_pixel(P, slot, &px, &py, &sIdx, &pix);
+  float u, v;
+  UvDiff dd;
+  hit_uv_differentials(P, tri, triId, b0, b1, b2, is.p, is.n, cameraRay, px, py, index, rayO, rayD, &u, &v, &dd);
+  return tex_evaluate(P.sc.textures[m.kd_texture_plus1 - 1], P.sc.ewaLut, u, v, dd);
+}
+
 // warp-aggregated append: one atomicAdd per (warp, queue)
 PBR_D uint32_t queue_push(uint32_t* counter, bool active) {
   unsigned mask = __ballot_sync(__activemask(), active);
@@ -354,7 +414,8 @@ PBR_D uint32_t block_queue_push(uint32_t* counter, bool active, uint32_t* sCount
 // VOL = true is VolPathIntegrator::Li's surface branch (VolPathIntegrator.cpp:56-93): the bounce count comes from
 // the path (`bounce` is ignored), UniformSampleOneLight runs for every BSDF (no NumComponents guard), the shadow
 // ray carries what VisibilityTester::Tr needs, and the spawned ray takes the medium on its side of the surface.
-template <int MAT, bool VOL = false>
+// TEX = true (launched only for scenes with image textures): Matte / Plastic Kd may come from an ImageTexture.
+template <int MAT, bool VOL = false, bool TEX = false>
 __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderParams P, int bounce) {
   __shared__ uint32_t sCount, sBase;
   const uint32_t n = P.ws.ctr->nMat[MAT];
@@ -392,7 +453,24 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
       bool alive = bounce < P.maxDepth;
       if (alive) {
         Bsdf bsdf;
-        make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf);
+        Spec kdTex;
+        bool haveKdTex = false;
+        if (TEX && (MAT == PBRGPU_MAT_MATTE || MAT == PBRGPU_MAT_PLASTIC)) {
+          const pbrgpu_material& m = sc.mats[is.matId];
+          if (m.kd_texture_plus1 > 0) {
+            const float4 ro4 = P.ws.rayO[slot];
+            // Reference quirk: SurfaceInteraction::ComputeScatteringFunctions takes `const Ray&` (Interaction.h:86-89) and
+            // hands it to ComputeDifferentials(const RayDifferential&): the implicit RayDifferential(const Ray&) conversion
+            // (Geometry.h:1387) sets hasDifferentials = false, so EVERY texture lookup of a render sees zero derivatives -
+            // camera rays included.  The differential code stays reachable through PBRGPU_DUMP_HIT_DIFFERENTIALS, where it is
+            // checked against the reference's ComputeDifferentials called on the real RayDifferential.
+            const bool cameraRay = false;
+            kdTex = eval_kd_texture(P, m, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, cameraRay, slot, cur.index,
+                                    V3(ro4.x, ro4.y, ro4.z), rayD);
+            haveKdTex = true;
+          }
+        }
+        make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf, haveKdTex ? &kdTex : nullptr);
         const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
         if ((VOL || bsdf_num_components<MAT>(bsdf, nonSpec) > 0) && sc.nLights > 0) {
           // UniformSampleOneLight (Integrator.cpp:46-69)
@@ -569,7 +647,7 @@ PBR_D void estimate_direct(const RenderParams& P, const Bsdf& bsdf, const Isect&
   }
 }
 
-template <int MAT>
+template <int MAT, bool TEX = false>
 __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__ RenderParams P, int depth) {
   const uint32_t n = P.ws.ctr->nMat[MAT];
   const SceneDev& sc = P.sc;
@@ -599,7 +677,16 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
         if (!Le.is_black()) { atomicAdd(&P.ws.L[slot].x, Le.r); atomicAdd(&P.ws.L[slot].y, Le.g); atomicAdd(&P.ws.L[slot].z, Le.b); }
       }
       Bsdf bsdf;
-      make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/false, &bsdf);
+      Spec kdTex;
+      bool haveKdTex = false;
+      if (TEX && (MAT == PBRGPU_MAT_MATTE || MAT == PBRGPU_MAT_PLASTIC)) {
+        const pbrgpu_material& m = sc.mats[is.matId];
+        if (m.kd_texture_plus1 > 0) {  // zero derivatives, like every lookup of the reference (see k_shade)
+          kdTex = eval_kd_texture(P, m, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index, V3(0, 0, 0), rayD);
+          haveKdTex = true;
+        }
+      }
+      make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/false, &bsdf, haveKdTex ? &kdTex : nullptr);
       if (P.integrator == PBRGPU_INTEGRATOR_WHITTED) {
         for (int j = 0; j < sc.nLights; ++j) {
           float u0, u1;
@@ -1007,7 +1094,8 @@ __global__ void k_dump_sampler(HaltonParams hp, int x0, int y0, int w, int h, lo
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__ RenderParams P, int ns, float* outRays, int* outHits) {
+__global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__ RenderParams P, int ns, float* outRays, int* outHits,
+                                                         float* outDiff = nullptr) {
   __shared__ uint2 sstk[kBlock / 32][kSmemStack][32];
   uint2* sstack = &sstk[threadIdx.x >> 5][0][threadIdx.x & 31];
   long long n = (long long)P.w * P.h * ns;
@@ -1025,6 +1113,22 @@ __global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__
       float* r = outRays + 8 * i;
       r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = kInfinity; r[4] = d.x; r[5] = d.y; r[6] = d.z; r[7] = 0.f;
     }
+    if (outDiff) {  // hit flag, uv, dudx, dvdx, dudy, dvdy of the camera ray (SurfaceInteraction::ComputeDifferentials)
+      HitRec h;
+      unsigned a = 0, b = 0;
+      traverse<false, false>(P.sc, o, d, kInfinity, &h, sstack, &a, &b);
+      float* q = outDiff + 8 * i;
+      for (int k = 0; k < 8; ++k) q[k] = 0.f;
+      if (h.tri >= 0) {
+        const TriData tri = load_tri(P.sc, h.tri);
+        Isect is;
+        make_isect(P.sc, tri, h.tri, h.b0, h.b1, h.b2, d, &is);
+        float u, v;
+        UvDiff dd;
+        hit_uv_differentials(P, tri, h.tri, h.b0, h.b1, h.b2, is.p, is.n, true, px, py, idx, o, d, &u, &v, &dd);
+        q[0] = 1.f; q[1] = u; q[2] = v; q[3] = dd.dudx; q[4] = dd.dvdx; q[5] = dd.dudy; q[6] = dd.dvdy;
+      }
+    }
     if (outHits) {
       HitRec h;
       unsigned a = 0, b = 0;
@@ -1035,6 +1139,15 @@ __global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__
       q[2] = h.tri >= 0 ? __float_as_int(h.b0) : 0;
       q[3] = h.tri >= 0 ? __float_as_int(h.b1) : 0;
     }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_texture_eval(SceneDev sc, int tex, const float* rows, long long n, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float* r = rows + 8 * i;
+    UvDiff dd{r[2], r[3], r[4], r[5]};
+    const Spec v = tex_evaluate(sc.textures[tex], sc.ewaLut, r[0], r[1], dd);
+    out[4 * i] = v.r; out[4 * i + 1] = v.g; out[4 * i + 2] = v.b; out[4 * i + 3] = 0.f;
   }
 }
 

@@ -135,6 +135,10 @@ struct pbrgpu_scene {
   int waveLog2 = 25;
   bool hasMat[PBRGPU_MAT_COUNT] = {};  // material types present in the scene (absent ones: no shade launch)
   bool hasNullMat = false;             // some triangle has no material (medium boundary): VolPath only
+  bool hasTextures = false;            // some material takes Kd from an ImageTexture: TEX shading kernels, Path / VolPath only
+  std::vector<DevBuf<float4>> texPyramids;
+  DevBuf<TexDev> texTable;
+  DevBuf<float> ewaLut;
   DevBuf<pbrgpu_medium> media;
   DevBuf<uint32_t> triMedium;
   DevBuf<float4> shP1, shE1, shN1;     // VolPath shadow-ray endpoints (allocated on first VolPath render)
@@ -455,6 +459,72 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
       m.v_rough = host::roughness_to_alpha(m.v_rough);
     }
   }
+  // image textures: MIP pyramid per texture (MIPMap.h:146-168: each level is the 2x2 box filter of the previous one, texels
+  // fetched through the wrap mode), EWA weight table (MIPMap.h:170-176)
+  if (d->n_textures < 0 || (d->n_textures > 0 && !d->textures)) return fail("pbrgpu_scene_create: bad texture table");
+  for (auto& m : mats) {
+    if (m.kd_texture_plus1 < 0 || m.kd_texture_plus1 > d->n_textures) return fail("pbrgpu_scene_create: kd_texture_plus1 out of range");
+    if (m.kd_texture_plus1 > 0) {
+      if (m.type != PBRGPU_MAT_MATTE && m.type != PBRGPU_MAT_PLASTIC)
+        return fail("pbrgpu_scene_create: image textures are supported for the Kd of Matte and Plastic materials");
+      s->hasTextures = true;
+    }
+  }
+  if (d->n_textures > 0) {
+    std::vector<TexDev> table((size_t)d->n_textures);
+    s->texPyramids.resize((size_t)d->n_textures);
+    for (int ti = 0; ti < d->n_textures; ++ti) {
+      const pbrgpu_texture& t = d->textures[ti];
+      const int W = t.width, H = t.height;
+      if (W <= 0 || H <= 0 || !t.texels || (W & (W - 1)) || (H & (H - 1)) || W > 32768 || H > 32768)
+        return fail("pbrgpu_scene_create: texture sizes must be powers of two (MIPMap would Lanczos-resample otherwise)");
+      if (t.wrap < PBRGPU_WRAP_REPEAT || t.wrap > PBRGPU_WRAP_CLAMP) return fail("pbrgpu_scene_create: bad texture wrap mode");
+      TexDev& td = table[(size_t)ti];
+      td.width = W; td.height = H; td.doTrilinear = t.do_trilinear ? 1 : 0; td.wrap = t.wrap; td.maxAnisotropy = t.max_anisotropy;
+      td.su = t.su; td.sv = t.sv; td.du = t.du; td.dv = t.dv;
+      int nLevels = 1;
+      for (int m = std::max(W, H); m > 1; m >>= 1) ++nLevels;  // 1 + Log2Int(max(w, h))
+      td.nLevels = nLevels;
+      std::vector<float4> all;
+      std::vector<float> prev(t.texels, t.texels + (size_t)W * H * 3), cur;
+      int pw = W, ph = H;
+      for (int lv = 0; lv < nLevels; ++lv) {
+        if (lv > 0) {
+          const int sRes = std::max(1, pw / 2), tRes = std::max(1, ph / 2);
+          cur.assign((size_t)sRes * tRes * 3, 0.f);
+          auto texel = [&](int a, int b, int c) -> float {  // MIPMap::Texel on the previous level
+            if (t.wrap == PBRGPU_WRAP_REPEAT) { a = mod_i(a, pw); b = mod_i(b, ph); }
+            else if (t.wrap == PBRGPU_WRAP_CLAMP) { a = std::min(std::max(a, 0), pw - 1); b = std::min(std::max(b, 0), ph - 1); }
+            else if (a < 0 || a >= pw || b < 0 || b >= ph) return 0.f;
+            return prev[3 * ((size_t)b * pw + a) + c];
+          };
+          for (int tt = 0; tt < tRes; ++tt)
+            for (int u = 0; u < sRes; ++u)
+              for (int c = 0; c < 3; ++c)
+                cur[3 * ((size_t)tt * sRes + u) + c] =
+                    .25f * (((texel(2 * u, 2 * tt, c) + texel(2 * u + 1, 2 * tt, c)) + texel(2 * u, 2 * tt + 1, c)) + texel(2 * u + 1, 2 * tt + 1, c));
+          prev.swap(cur);
+          pw = sRes; ph = tRes;
+        }
+        td.levelOffset[lv] = (uint32_t)all.size();
+        for (size_t k = 0; k < (size_t)pw * ph; ++k) all.push_back(make_float4(prev[3 * k], prev[3 * k + 1], prev[3 * k + 2], 0.f));
+      }
+      CK(s->texPyramids[(size_t)ti].upload(all, st));
+      CK(cudaStreamSynchronize(st));
+      td.texels = s->texPyramids[(size_t)ti].p;
+    }
+    CK(s->texTable.upload(table, st));
+    std::vector<float> lut(kWeightLutSize);
+    for (int i = 0; i < kWeightLutSize; ++i) {
+      float alpha = 2;
+      float r2 = float(i) / float(kWeightLutSize - 1);
+      lut[i] = std::exp(-alpha * r2) - std::exp(-alpha);
+    }
+    CK(s->ewaLut.upload(lut, st));
+    CK(cudaStreamSynchronize(st));
+    s->sc.textures = s->texTable.p;
+    s->sc.ewaLut = s->ewaLut.p;
+  }
   CK(s->mats.upload(mats, st));
 
   // scene bound -> InfiniteAreaLight::Preprocess (BoundingSphere, Geometry.h)
@@ -720,6 +790,22 @@ int pbrgpu_sampler_set(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
   return 0;
 }
 
+int pbrgpu_texture_eval(pbrgpu_scene* s, int texture, const float* rows, int64_t n, float* out) {
+  if (!s || !rows || !out || n < 0) return fail("pbrgpu_texture_eval: bad argument");
+  if (texture < 0 || (size_t)texture >= s->texPyramids.size()) return fail("pbrgpu_texture_eval: texture index out of range");
+  if (n == 0) return 0;
+  pbrgpu_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  DevBuf<float> din, dout;
+  CK(din.alloc((size_t)n * 8)); CK(dout.alloc((size_t)n * 4));
+  CK(cudaMemcpyAsync(din.p, rows, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  k_texture_eval<<<grid_for(c, (uint64_t)n, 8), kBlock, 0, c->stream>>>(s->sc, texture, din.p, n, dout.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout.p, sizeof(float) * 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int pbrgpu_scene_info(pbrgpu_scene* s, int64_t out[8]) {
   if (!s || !out) return fail("pbrgpu_scene_info: NULL argument");
   memset(out, 0, sizeof(int64_t) * 8);
@@ -831,6 +917,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) P.arrayEndDim = 5 + 2 * (2 * (int)s->lights.size() * rd->max_depth);
   P.atomicL = (pathInteg || volInteg) ? 0 : 1;
   P.volShadowAnyHit = s->hasNullMat ? 0 : 1;
+  P.diffScale = 1 / std::sqrt((float)s->spp);
   P.countStats = count ? 1 : 0;
   P.fetchMinIdle = s->fetchMinIdle;
 
@@ -912,7 +999,14 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
           CK(tl.mark(T_SHADE));
           if (s->sc.nMedia > 0) { k_medium_sample<<<g, kBlock, 0, st>>>(P); launches++; }
           k_classify<<<gc, kBlock, 0, st>>>(P);
-#define PBR_SHADE_V(M) if (s->hasMat[M]) { k_shade<M, true><<<grid_occ(c, k_shade<M, true>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, 0); launches++; }
+#define PBR_SHADE_V(M)                                                                                                            \
+  if (s->hasMat[M]) {                                                                                                             \
+    if (s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC))                                                     \
+      k_shade<M, true, true><<<grid_occ(c, k_shade<M, true, true>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, 0);              \
+    else                                                                                                                          \
+      k_shade<M, true><<<grid_occ(c, k_shade<M, true, false>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, 0);                  \
+    launches++;                                                                                                                   \
+  }
           PBR_SHADE_V(PBRGPU_MAT_MATTE) PBR_SHADE_V(PBRGPU_MAT_MIRROR) PBR_SHADE_V(PBRGPU_MAT_GLASS)
           PBR_SHADE_V(PBRGPU_MAT_METAL) PBR_SHADE_V(PBRGPU_MAT_PLASTIC)
 #undef PBR_SHADE_V
@@ -939,8 +1033,22 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
         CK(tl.mark(T_SHADE));
         k_classify<<<gc, kBlock, 0, st>>>(P);
         // one shading launch per material type PRESENT in the scene
-#define PBR_SHADE(M) if (s->hasMat[M]) { k_shade<M><<<grid_occ(c, k_shade<M, false>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, bounce); launches++; }
-#define PBR_SHADE_D(M) if (s->hasMat[M]) { k_shade_direct<M><<<g, kBlock, 0, st>>>(P, bounce); launches++; }
+#define PBR_SHADE(M)                                                                                                              \
+  if (s->hasMat[M]) {                                                                                                             \
+    if (s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC))                                                     \
+      k_shade<M, false, true><<<grid_occ(c, k_shade<M, false, true>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, bounce);       \
+    else                                                                                                                          \
+      k_shade<M><<<grid_occ(c, k_shade<M, false, false>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, bounce);                  \
+    launches++;                                                                                                                   \
+  }
+#define PBR_SHADE_D(M)                                                                                  \
+  if (s->hasMat[M]) {                                                                                   \
+    if (s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC))                           \
+      k_shade_direct<M, true><<<g, kBlock, 0, st>>>(P, bounce);                                         \
+    else                                                                                                \
+      k_shade_direct<M><<<g, kBlock, 0, st>>>(P, bounce);                                               \
+    launches++;                                                                                         \
+  }
         if (pathInteg) {
           PBR_SHADE(PBRGPU_MAT_MATTE) PBR_SHADE(PBRGPU_MAT_MIRROR) PBR_SHADE(PBRGPU_MAT_GLASS)
           PBR_SHADE(PBRGPU_MAT_METAL) PBR_SHADE(PBRGPU_MAT_PLASTIC)
@@ -1101,18 +1209,21 @@ int pbrgpu_debug_dump(pbrgpu_scene* s, const pbrgpu_dump_desc* dd, void* out, si
     CK(cudaStreamSynchronize(c->stream));
     return 0;
   }
-  if (dd->what == PBRGPU_DUMP_PRIMARY_RAYS || dd->what == PBRGPU_DUMP_PRIMARY_HITS) {
+  if (dd->what == PBRGPU_DUMP_PRIMARY_RAYS || dd->what == PBRGPU_DUMP_PRIMARY_HITS || dd->what == PBRGPU_DUMP_HIT_DIFFERENTIALS) {
     if (!s->haveCamera) return fail("pbrgpu_debug_dump: camera not set");
     bool rays = dd->what == PBRGPU_DUMP_PRIMARY_RAYS;
+    const bool diff = dd->what == PBRGPU_DUMP_HIT_DIFFERENTIALS;
     size_t n = (size_t)W * H * ns;
-    size_t bytes = n * (rays ? 8 * sizeof(float) : 4 * sizeof(int));
+    size_t bytes = n * ((rays || diff) ? 8 * sizeof(float) : 4 * sizeof(int));
     if (out_bytes < bytes) return fail("pbrgpu_debug_dump: output too small");
     DevBuf<unsigned char> d;
     CK(d.alloc(bytes));
     RenderParams P{};
     P.sc = s->sc;
     P.x0 = dd->x0; P.y0 = dd->y0; P.w = W; P.h = H; P.sBegin = dd->s0;
-    k_dump_primary<<<grid_for(c, n, 8), kBlock, 0, c->stream>>>(P, (int)ns, rays ? (float*)d.p : nullptr, rays ? nullptr : (int*)d.p);
+    P.diffScale = 1 / std::sqrt((float)s->spp);
+    k_dump_primary<<<grid_for(c, n, 8), kBlock, 0, c->stream>>>(P, (int)ns, rays ? (float*)d.p : nullptr,
+                                                                 (rays || diff) ? nullptr : (int*)d.p, diff ? (float*)d.p : nullptr);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -11,6 +11,7 @@
 #include "bsdf.cuh"
 #include "device_types.cuh"
 #include "trace.cuh"
+#include "texture.cuh"
 
 namespace pbr {
 
@@ -45,6 +46,19 @@ PBR_HD V3 triangle_dpdu(V3 p0, V3 p1, V3 p2, float u0x, float u0y, float u1x, fl
     dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
   }
   return dpdu;
+}
+
+// dpdu AND dpdv (Triangle.cpp:147-160), needed by SurfaceInteraction::ComputeDifferentials for image textures
+PBR_D void triangle_dpdu_dpdv(V3 p0, V3 p1, V3 p2, const float uv[6], V3* dpdu, V3* dpdv) {
+  V3 dp02 = p0 - p2, dp12 = p1 - p2;
+  const float duv02x = uv[0] - uv[4], duv02y = uv[1] - uv[5], duv12x = uv[2] - uv[4], duv12y = uv[3] - uv[5];
+  float determinant = duv02x * duv12y - duv02y * duv12x;
+  *dpdu = V3(0, 0, 0); *dpdv = V3(0, 0, 0);
+  if (!(fabsf(determinant) < 1e-8)) {
+    float invdet = 1 / determinant;
+    *dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+    *dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+  }
 }
 
 // Host + device: the per-triangle frame of a FLAT-shaded triangle exactly as the reference computes it per hit
@@ -128,8 +142,9 @@ PBR_D Lobe make_lobe(int kind, int flags, Spec R) {
 
 // Material::ComputeScatteringFunctions for the five materials.  `mats[...]` roughness values were
 // already passed through RoughnessToAlpha on the host when remap_roughness was set (Microfacet.h:78-83).
+// kdTex: Kd->Evaluate(si) of an ImageTexture (Matte / Plastic), or NULL for the ConstantTexture in the material record.
 template <int MAT>
-PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobes, Bsdf* b) {
+PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobes, Bsdf* b, const Spec* kdTex = nullptr) {
   const pbrgpu_material& m = sc.mats[is.matId];
   b->eta = 1.f;
   b->ns = is.ns;
@@ -139,7 +154,7 @@ PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobe
   b->n = 0;
   switch (MAT) {  // == m.type: the shading queues are sorted by material type
     case PBRGPU_MAT_MATTE: {
-      Spec r = spec_clamp0(Spec(m.kd[0], m.kd[1], m.kd[2]));
+      Spec r = spec_clamp0(kdTex ? *kdTex : Spec(m.kd[0], m.kd[1], m.kd[2]));
       float sig = clampf(m.sigma, 0.f, 90.f);
       if (!r.is_black()) {
         if (sig == 0) b->lobes[b->n++] = make_lobe(LOBE_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE, r);
@@ -199,7 +214,7 @@ PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobe
       break;
     }
     case PBRGPU_MAT_PLASTIC: {
-      Spec kd = spec_clamp0(Spec(m.kd[0], m.kd[1], m.kd[2]));
+      Spec kd = spec_clamp0(kdTex ? *kdTex : Spec(m.kd[0], m.kd[1], m.kd[2]));
       if (!kd.is_black()) b->lobes[b->n++] = make_lobe(LOBE_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE, kd);
       Spec ks = spec_clamp0(Spec(m.kr[0], m.kr[1], m.kr[2]));
       if (!ks.is_black()) {

@@ -52,6 +52,7 @@
 #include "Texture/Texture.h"
 #include "Texture/ConstantTexture.h"
 #include "Texture/MIPMap.h"
+#include "Texture/ImageTexture.h"
 #include "Material/Material.h"
 #include "Material/MatteMaterial.h"
 #include "Material/Mirror.h"
@@ -83,6 +84,9 @@ struct Flat {
   std::vector<uint8_t> triFlags;
   std::vector<pbrgpu_material> materials;
   std::vector<pbrgpu_light> lights;
+  std::vector<pbrgpu_texture> textures;          // ImageTexture objects used as Kd (texels point into texelStore)
+  std::vector<std::vector<float>> texelStore;
+  std::unordered_map<const void*, int> textureId;
   std::vector<pbrgpu_medium> media;              // distinct HomogeneousMedium objects met on the primitives
   std::vector<int32_t> triMediumIn, triMediumOut;  // MediumInterface::inside / ::outside per triangle (-1 = none)
   std::vector<float> env;
@@ -106,11 +110,45 @@ inline bool constFloat(const std::shared_ptr<Texture<float>>& t, float* out, std
   return true;
 }
 
-inline bool flattenMaterial(const Material* m, pbrgpu_material* o, std::string* err) {
+// Kd of Matte / Plastic: a ConstantTexture, or an ImageTexture<RGBSpectrum, Spectrum> with a UVMapping2D whose MIPMap level 0
+// (already converted by ImageTexture::convertIn) becomes a pbrgpu_texture
+inline bool flattenKd(const std::shared_ptr<Texture<Spectrum>>& t, pbrgpu_material* o, Flat* f) {
+  auto* img = dynamic_cast<const ImageTexture<RGBSpectrum, Spectrum>*>(t.get());
+  if (!img) return constSpectrum(t, o->kd, &f->error);
+  auto it = f->textureId.find(img);
+  if (it == f->textureId.end()) {
+    auto* map = dynamic_cast<const UVMapping2D*>(img->mapping.get());
+    if (!map) { f->error = "ImageTexture with a mapping other than UVMapping2D"; return false; }
+    const MIPMap<RGBSpectrum>* mm = img->mipmap;
+    const auto& lvl0 = *mm->pyramid[0];
+    pbrgpu_texture pt;
+    std::memset(&pt, 0, sizeof(pt));
+    pt.width = lvl0.uSize(); pt.height = lvl0.vSize();
+    pt.do_trilinear = mm->doTrilinear ? 1 : 0;
+    pt.max_anisotropy = mm->maxAnisotropy;
+    pt.wrap = mm->wrapMode == ImageWrap::Clamp ? PBRGPU_WRAP_CLAMP : (mm->wrapMode == ImageWrap::Black ? PBRGPU_WRAP_BLACK : PBRGPU_WRAP_REPEAT);
+    pt.su = map->su; pt.sv = map->sv; pt.du = map->du; pt.dv = map->dv;
+    f->texelStore.emplace_back((size_t)pt.width * pt.height * 3);
+    std::vector<float>& tx = f->texelStore.back();
+    for (int v = 0; v < pt.height; ++v)
+      for (int u = 0; u < pt.width; ++u) {
+        const RGBSpectrum& s = lvl0(u, v);
+        float* d = &tx[3 * ((size_t)v * pt.width + u)];
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+      }
+    it = f->textureId.emplace(img, (int)f->textures.size()).first;
+    f->textures.push_back(pt);  // .texels is filled in once texelStore stops growing (flattenScene's caller)
+  }
+  o->kd_texture_plus1 = it->second + 1;
+  return true;
+}
+
+inline bool flattenMaterial(const Material* m, pbrgpu_material* o, Flat* f) {
+  std::string* err = &f->error;
   std::memset(o, 0, sizeof(*o));
   if (auto* p = dynamic_cast<const MatteMaterial*>(m)) {
     o->type = PBRGPU_MAT_MATTE;
-    return constSpectrum(p->Kd, o->kd, err) && constFloat(p->sigma, &o->sigma, err);
+    return flattenKd(p->Kd, o, f) && constFloat(p->sigma, &o->sigma, err);
   }
   if (auto* p = dynamic_cast<const MirrorMaterial*>(m)) {
     o->type = PBRGPU_MAT_MIRROR;
@@ -138,7 +176,7 @@ inline bool flattenMaterial(const Material* m, pbrgpu_material* o, std::string* 
   if (auto* p = dynamic_cast<const PlasticMaterial*>(m)) {
     o->type = PBRGPU_MAT_PLASTIC;
     o->remap_roughness = p->remapRoughness ? 1 : 0;
-    bool ok = constSpectrum(p->Kd, o->kd, err) && constSpectrum(p->Ks, o->kr, err) && constFloat(p->roughness, &o->u_rough, err);
+    bool ok = flattenKd(p->Kd, o, f) && constSpectrum(p->Ks, o->kr, err) && constFloat(p->roughness, &o->u_rough, err);
     o->v_rough = o->u_rough;
     return ok;
   }
@@ -225,7 +263,7 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
       auto it = matId.find(gp->material.get());
       if (it == matId.end()) {
         pbrgpu_material m;
-        if (!flattenMaterial(gp->material.get(), &m, &f->error)) return false;
+        if (!flattenMaterial(gp->material.get(), &m, f)) return false;
         it = matId.emplace(gp->material.get(), (int)f->materials.size()).first;
         f->materials.push_back(m);
       }
@@ -315,6 +353,9 @@ class GpuSamplerIntegrator : public Integrator {
       d.n_materials = (int32_t)f.materials.size(); d.materials = f.materials.data();
       d.n_lights = (int32_t)f.lights.size(); d.lights = f.lights.data();
       d.env_width = f.envW; d.env_height = f.envH; d.env_texels = f.env.empty() ? nullptr : f.env.data();
+      for (size_t k = 0; k < f.textures.size(); ++k) f.textures[k].texels = f.texelStore[k].data();
+      d.n_textures = (int32_t)f.textures.size();
+      d.textures = f.textures.empty() ? nullptr : f.textures.data();
       if (!f.media.empty()) {
         d.n_media = (int32_t)f.media.size(); d.media = f.media.data();
         d.tri_medium_inside = f.triMediumIn.data(); d.tri_medium_outside = f.triMediumOut.data();

@@ -18,8 +18,9 @@ def _f3(v):
     return (C.c_float * 3)(*[float(F(x)) for x in v])
 
 
-def matte(kd, sigma=0.0):
-    return A.Material(type=A.MAT_MATTE, kd=_f3(kd), sigma=sigma)
+def matte(kd, sigma=0.0, kd_texture=None):
+    """kd_texture: id from SceneData.add_texture - Kd becomes that ImageTexture (kd is then ignored)."""
+    return A.Material(type=A.MAT_MATTE, kd=_f3(kd), sigma=sigma, kd_texture_plus1=0 if kd_texture is None else kd_texture + 1)
 
 
 def mirror(kr):
@@ -36,9 +37,9 @@ def metal(eta, k, u_rough, v_rough, remap=False):
                       remap_roughness=int(remap))
 
 
-def plastic(kd, ks, rough, remap=True):
+def plastic(kd, ks, rough, remap=True, kd_texture=None):
     return A.Material(type=A.MAT_PLASTIC, kd=_f3(kd), kr=_f3(ks), u_rough=rough, v_rough=rough,
-                      remap_roughness=int(remap))
+                      remap_roughness=int(remap), kd_texture_plus1=0 if kd_texture is None else kd_texture + 1)
 
 
 class SceneData:
@@ -55,6 +56,7 @@ class SceneData:
         self._tri_med_in = []
         self._tri_med_out = []
         self.media = []
+        self.textures = []  # (A.Texture, texel array) pairs
         self.materials = []
         self.lights = []
         self.env = None  # (H, W, 3) float32
@@ -67,6 +69,16 @@ class SceneData:
     def add_material(self, m):
         self.materials.append(m)
         return len(self.materials) - 1
+
+    def add_texture(self, texels, do_trilinear=False, max_anisotropy=8.0, wrap=A.WRAP_REPEAT, su=1.0, sv=1.0, du=0.0, dv=0.0):
+        """ImageTexture<RGBSpectrum, Spectrum>(UVMapping2D(su, sv, du, dv), ..., doTrilinear, maxAniso, wrap) over the RGB
+        image `texels` [H,W,3] (power-of-two sizes; the values the MIPMap receives, Texture/ImageTexture.cpp:88-95) -> id."""
+        tx = np.ascontiguousarray(texels, dtype=F)
+        assert tx.ndim == 3 and tx.shape[2] == 3
+        t = A.Texture(width=tx.shape[1], height=tx.shape[0], texels=tx.ctypes.data_as(C.POINTER(C.c_float)),
+                      do_trilinear=int(do_trilinear), max_anisotropy=max_anisotropy, wrap=wrap, su=su, sv=sv, du=du, dv=dv)
+        self.textures.append((t, tx))
+        return len(self.textures) - 1
 
     def add_medium(self, sigma_a, sigma_s, g):
         """HomogeneousMedium(sigma_a, sigma_s, g)  (Media/HomogeneousMedium.h:12-16) -> medium id."""
@@ -190,6 +202,11 @@ class SceneData:
             d.env_height, d.env_width = self.env.shape[0], self.env.shape[1]
             d.env_texels = self.env.ctypes.data_as(C.POINTER(C.c_float))
             keep.append(self.env)
+        if self.textures:
+            tex = (A.Texture * len(self.textures))(*[t for t, _ in self.textures])
+            d.n_textures = len(self.textures)
+            d.textures = tex
+            keep += [tex, self.textures]
         if self.media:
             media = (A.Medium * len(self.media))(*self.media)
             mi = np.ascontiguousarray(np.concatenate(self._tri_med_in), dtype=np.int32)

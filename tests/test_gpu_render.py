@@ -445,3 +445,130 @@ def test_volpath_error_behaviour(api, gpu_ctx):
     bad._tri_med_in[-1][:] = 7
     with pytest.raises(api.PbrGpuError, match="medium index"):
         api.Scene(bad)
+
+
+# ---------------------------------------------------------------------------------------------
+# ImageTexture (UVMapping2D + MIPMap: EWA / trilinear, wrap modes) as Kd of Matte and Plastic
+# ---------------------------------------------------------------------------------------------
+def _textured_scene(variant):
+    rng = np.random.default_rng(3)
+    H, W = 32, 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    checker = (((xx // 8) + (yy // 4)) % 2).astype(np.float32)
+    img = np.stack([0.15 + 0.7 * checker, 0.2 + 0.5 * (1 - checker), 0.1 + 0.8 * (xx / W)], -1).astype(np.float32)
+    img += rng.uniform(0, 0.1, img.shape).astype(np.float32)
+    s = scenes.SceneData()
+    kw = dict(ewa_repeat=dict(), trilinear_clamp=dict(do_trilinear=True, wrap=A.WRAP_CLAMP, su=2.5, sv=1.5, du=0.1, dv=-0.2),
+              ewa_black=dict(wrap=A.WRAP_BLACK, su=1.7, sv=2.2, du=-0.3, dv=0.15, max_anisotropy=4.0))[variant]
+    t0 = s.add_texture(img, **kw)
+    t1 = s.add_texture(img[::2, ::2] * np.float32(0.9), su=4.0, sv=2.0)  # 32 x 16
+    white = s.add_material(scenes.matte([1, 1, 1], kd_texture=t0))
+    red = s.add_material(scenes.matte([0.9, 0.1, 0.17]))
+    blue = s.add_material(scenes.matte([0.14, 0.21, 0.87], sigma=20.0, kd_texture=t1))
+    plast = s.add_material(scenes.plastic([0.3, 0.3, 0.3], [0.5, 0.5, 0.5], 0.1, kd_texture=t1))
+    mir = s.add_material(scenes.mirror([0.9, 0.9, 0.9]))
+    lightmat = s.add_material(scenes.matte([1, 1, 1]))
+    scenes.cornell_walls(s, white, red, blue)   # no mesh uvs: every triangle gets (0,0),(1,0),(1,1)  (Triangle.h:50-54)
+    scenes.cornell_area_light(s, lightmat)
+    n_lat, n_lon = 12, 24
+    v, t = scenes.uv_sphere([-1.0, -1.5, 0.3], 1.0, n_lat, n_lon)
+    th, ph = np.meshgrid(np.arange(n_lat + 1) / n_lat, np.arange(n_lon + 1) / n_lon, indexing="ij")
+    uv = np.stack([ph, th], -1).reshape(-1, 2).astype(np.float32)
+    s.add_mesh(v, t, plast, uvs=uv)
+    v, t = scenes.uv_sphere([1.2, -1.7, 0.9], 0.8, n_lat, n_lon)
+    s.add_mesh(v, t, mir)
+    return s
+
+
+@pytest.mark.parametrize("variant", ["ewa_repeat", "trilinear_clamp", "ewa_black"])
+def test_image_textures_match_reference(api, ref, gpu_ctx, variant):
+    """ImageTexture::Evaluate (Texture/ImageTexture.h:53-61): UV mapping + MIPMap lookup.  In a render the reference always
+    looks textures up with ZERO derivatives: ComputeScatteringFunctions(const Ray&) slices the RayDifferential
+    (Interaction.h:86-91, Geometry.h:1387), so hasDifferentials is false even for camera rays.  The filtered lookups
+    (EWA / trilinear) are pinned by test_texture_lookup_known_answers, the derivatives by test_hit_differentials."""
+    data = _textured_scene(variant)
+    p = Pair(api, ref, data, 96, 96, 4)
+    got, want = _direct_check(p, ref, max_depth=1, spp=4, frac_ok=0.995, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.96, rr_threshold=0.8)
+    # the texture is visible: the floor is not a flat colour
+    floor = got[80:, 20:76] / 4
+    assert floor.std(axis=(0, 1)).max() > 0.02
+    # VolPath, Whitted and DirectLighting evaluate textures the same way
+    _vol_check(p, ref, max_depth=3, spp=2, frac_ok=0.97, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=3, spp=2, frac_ok=0.99, integrator=A.INTEGRATOR_WHITTED)
+    _direct_check(p, ref, max_depth=3, spp=2, frac_ok=0.99, integrator=A.INTEGRATOR_DIRECT_ONE)
+
+
+def test_image_texture_error_behaviour(api, gpu_ctx):
+    bad = scenes.SceneData()
+    t = bad.add_texture(np.zeros((24, 64, 3), dtype=np.float32))  # 24 is not a power of two
+    m = bad.add_material(scenes.matte([1, 1, 1], kd_texture=t))
+    scenes.cornell_walls(bad, m, m, m)
+    with pytest.raises(api.PbrGpuError, match="powers of two"):
+        api.Scene(bad)
+    bad2 = scenes.SceneData()
+    m = bad2.add_material(scenes.matte([1, 1, 1], kd_texture=3))
+    scenes.cornell_walls(bad2, m, m, m)
+    with pytest.raises(api.PbrGpuError, match="kd_texture"):
+        api.Scene(bad2)
+    bad3 = scenes.SceneData()
+    t = bad3.add_texture(np.zeros((8, 8, 3), dtype=np.float32))
+    mm = scenes.mirror([1, 1, 1])
+    mm.kd_texture_plus1 = t + 1
+    m = bad3.add_material(mm)
+    scenes.cornell_walls(bad3, m, m, m)
+    with pytest.raises(api.PbrGpuError, match="Matte and Plastic"):
+        api.Scene(bad3)
+
+
+def test_hit_differentials(api, ref, gpu_ctx):
+    """uv and du/dx, dv/dx, du/dy, dv/dy of camera-ray hits (Triangle.cpp:147-170, SurfaceInteraction::ComputeDifferentials
+    Interaction.cpp:48-99, camera offset rays + ScaleDifferentials) against the reference called on the real RayDifferential."""
+    data = _textured_scene("ewa_repeat")
+    for cam_type in (A.CAMERA_PERSPECTIVE, A.CAMERA_ORTHOGRAPHIC):
+        p = Pair(api, ref, data, 48, 48, 4, cam_type=cam_type, eye=(0.2, 0.1, 2.3 if cam_type else 5.0), look=(0.0, -0.1, 0.0))
+        g = p.scene.dump_hit_differentials((0, 0, 48, 48), 0, 2)
+        worst = 0.0
+        for (y, x, s) in [(5, 40, 0), (32, 5, 1), (40, 30, 0), (24, 24, 1), (46, 2, 0), (20, 12, 1), (30, 36, 0)]:
+            want = ref.camera_hit_differentials(p.rscene, p.rcam, 4, x, y, s)[:7]
+            got = g[y, x, s, :7]
+            assert got[0] == want[0] == 1.0
+            scale = max(np.abs(want[3:7]).max(), 1e-6)
+            worst = max(worst, np.abs(got[1:3] - want[1:3]).max(), np.abs(got[3:7] - want[3:7]).max() / scale)
+        print("camera type", cam_type, "worst uv / derivative error", worst)
+        assert worst < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["ewa_repeat", "trilinear_clamp", "ewa_black"])
+def test_texture_lookup_known_answers(api, ref, gpu_ctx, variant):
+    """Device MIPMap lookups against the reference's ImageTexture::Evaluate on random (uv, derivative) rows: isotropic and
+    very anisotropic footprints, zero derivatives (bilinear on level 0), footprints larger than the texture."""
+    data = _textured_scene(variant)
+    sc = api.Scene(data)
+    rng = np.random.default_rng(17)
+    n = 4096
+    rows = np.zeros((n, 8), dtype=np.float32)
+    rows[:, 0:2] = rng.uniform(-0.5, 1.5, (n, 2))
+    scale = 10.0 ** rng.uniform(-4, 0.3, (n, 1))
+    rows[:, 2:6] = rng.normal(size=(n, 4)) * scale
+    rows[: n // 8, 2:6] = 0
+    rows[n // 8: n // 4, 4:6] *= 1e-3   # needle-shaped footprints: anisotropy clamp
+    for t in range(len(data.textures)):
+        got = sc.texture_eval(t, rows)
+        want = ref.texture_kat(data.textures[t], rows)
+        err = np.abs(got - want).max(axis=1) / np.maximum(np.abs(want).max(axis=1), 1e-3)
+        print(variant, "texture", t, "max rel err", err.max(), "fraction > 1e-4:", (err > 1e-4).mean())
+        assert np.isfinite(got).all() and (err <= 1e-4).mean() >= 0.999 and err.max() < 5e-2
+
+
+def test_cpp_dropin_with_image_textures(api, ref, gpu_ctx):
+    """GpuPathIntegrator's flattener reads ImageTexture objects (MIPMap level 0, filter settings, UVMapping2D) out of the
+    reference's materials; the FrameBuffer matches the reference's own PathIntegrator::Render."""
+    data = _textured_scene("ewa_black")
+    rsc = ref.RefScene(data)
+    rc = ref.RefCamera(A.CAMERA_PERSPECTIVE, 64, 64, (0, 0, 5), (0, 0, 0), (0, 1, 0))
+    rgba, _, sec = ref.gpu_dropin_render(rsc, rc, 2, 64, 64, 4, 0.8, "uniform")
+    want, _, _ = ref.render_shipped(rsc, rc, 2, 64, 64, 4, 0.8)
+    diff = np.abs(rgba.astype(int) - want.astype(int))
+    print("drop-in with textures: bytes equal", (diff == 0).mean(), "max diff", diff.max())
+    assert (diff <= 1).mean() >= 0.995
