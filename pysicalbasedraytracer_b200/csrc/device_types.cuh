@@ -14,10 +14,11 @@ constexpr int kQueueNull = PBRGPU_MAT_COUNT + 1;    // 6: GeometricPrimitive wit
 constexpr int kQueueMedium = PBRGPU_MAT_COUNT + 2;  // 7: MediumInteraction sampled on this segment
 constexpr int kNumQueues = PBRGPU_MAT_COUNT + 3;
 constexpr uint32_t kQueueDead = 15u;                // path ended before shading (beta went black in Medium::Sample)
-// per-path word `meta`: sampler dimension (bits 0-15) | specularBounce (bit 16) | VolPath: bounces (bits 17-23)
+// per-path word `meta`: sampler dimension (bits 0-15) | specularBounce (bit 16) | VolPath: bounces (bits 17-23), in-medium (24)
 constexpr int kMetaSpecBit = 16;
 constexpr int kMetaBounceShift = 17;
 constexpr uint32_t kMetaBounceMask = 0x7fu;
+constexpr int kMetaInMediumBit = 24;  // VolPath: Ray::medium != nullptr (lets the medium kernels skip a path after one 4-byte read)
 
 // ---- triangle record (leaf order): three float4 = three 16-byte loads ----
 //   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-23), material type (24-27), flags (28-31)

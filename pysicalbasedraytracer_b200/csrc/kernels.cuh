@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
     P.ws.beta[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
     P.ws.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     P.ws.hidx[slot] = make_uint2((uint32_t)((uint64_t)idx & 0xffffffffu), (uint32_t)((uint64_t)idx >> 32));
-    P.ws.meta[slot] = 5u;  // next dimension; specularBounce = false
+    // next dimension; specularBounce = false; VolPath: bounces = 0, in-medium flag
+    P.ws.meta[slot] = 5u | ((P.integrator == PBRGPU_INTEGRATOR_VOLPATH && P.sc.cam.medium >= 0) ? (1u << kMetaInMediumBit) : 0u);
     P.ws.qCur[slot] = slot;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) P.ws.ctr->nCur = n;
@@ -556,10 +557,11 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
           }
           if (alive) {
             P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
-            P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, VOL ? __int_as_float(dot(wi, is.n) > 0 ? medOut : medIn) : 0.f);
+            const int nextMedium = VOL ? (dot(wi, is.n) > 0 ? medOut : medIn) : -1;
+            P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, VOL ? __int_as_float(nextMedium) : 0.f);
             P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, etaScale);
             P.ws.meta[slot] = (uint32_t)cur.dim | (specularBounce ? (1u << kMetaSpecBit) : 0u) |
-                              (VOL ? ((uint32_t)(bounce + 1) << kMetaBounceShift) : 0u);
+                              (VOL ? ((uint32_t)(bounce + 1) << kMetaBounceShift) | (nextMedium >= 0 ? (1u << kMetaInMediumBit) : 0u) : 0u);
             pushNext = true;
           }
         }
@@ -777,10 +779,10 @@ __global__ void __launch_bounds__(kBlock) k_medium_presample(const __grid_consta
   const uint32_t n = P.ws.ctr->nCur;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = P.ws.qCur[i];
+    const uint32_t meta = P.ws.meta[slot];
+    if (!((meta >> kMetaInMediumBit) & 1u)) continue;  // vacuum: nothing to sample (4 bytes read)
     const float4 rd4 = P.ws.rayD[slot];
     const int med = __float_as_int(rd4.w);
-    if (med < 0) continue;
-    const uint32_t meta = P.ws.meta[slot];
     SamplerCursor cur = load_cursor(P, slot, meta);
     const float u0 = cur.get1D(P.sc.hp);
     const float u1 = cur.get1D(P.sc.hp);
@@ -793,9 +795,9 @@ __global__ void __launch_bounds__(kBlock) k_medium_sample(const __grid_constant_
   const uint32_t n = P.ws.ctr->nCur;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = P.ws.qCur[i];
+    if (!((P.ws.meta[slot] >> kMetaInMediumBit) & 1u)) continue;
     const float4 rd4 = P.ws.rayD[slot];
     const int med = __float_as_int(rd4.w);
-    if (med < 0) continue;
     const bool hit = __float_as_int(P.ws.hit[slot].x) >= 0;
     const float t = P.ws.rayO[slot].w;           // k_trace: hit distance, or the sampled distance when nothing was hit
     const bool sampled = !hit && t < kInfinity;  // t < ray.tMax
@@ -842,7 +844,9 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const __grid_constant__ R
         isect_media(sc, tri, __float_as_int(rd4.w), &mIn, &mOut);
         const V3 o = offset_ray_origin(is.p, is.pError, is.n, rayD);
         P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
-        P.ws.rayD[slot] = make_float4(rayD.x, rayD.y, rayD.z, __int_as_float(dot(rayD, is.n) > 0 ? mOut : mIn));
+        const int nextMedium = dot(rayD, is.n) > 0 ? mOut : mIn;
+        P.ws.rayD[slot] = make_float4(rayD.x, rayD.y, rayD.z, __int_as_float(nextMedium));
+        P.ws.meta[slot] = (meta & ~(1u << kMetaInMediumBit)) | (nextMedium >= 0 ? (1u << kMetaInMediumBit) : 0u);
         pushNext = true;
       }
     }
@@ -945,7 +949,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_const
           P.ws.rayO[slot] = make_float4(p.x, p.y, p.z, kInfinity);
           P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, __int_as_float(med));
           P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, etaScale);
-          P.ws.meta[slot] = (uint32_t)cur.dim | ((uint32_t)(bounce + 1) << kMetaBounceShift);
+          P.ws.meta[slot] = (uint32_t)cur.dim | ((uint32_t)(bounce + 1) << kMetaBounceShift) | (1u << kMetaInMediumBit);
           pushNext = true;
         }
       }
