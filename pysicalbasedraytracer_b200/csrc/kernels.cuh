@@ -202,18 +202,18 @@ constexpr int kNodeStepsPerIter = PBR_NODE_STEPS;
 // ray continues behind a medium boundary (state re-initialised in T), false when it is done (blocked, or arrived and
 // its contribution x transmittance added to L).
 constexpr int kMaxShadowCrossings = 256;
-PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T, int* hops) {
+PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T, const HitRec& hit, int* hops) {
   const SceneDev& sc = P.sc;
-  if (T.hit.tri >= 0 && ((T.hit.w1 >> kTriTypeShift) & 0xfu) != (uint32_t)kQueueNull) return false;  // opaque surface: Tr = 0
+  if (hit.tri >= 0 && ((hit.w1 >> kTriTypeShift) & 0xfu) != (uint32_t)kQueueNull) return false;  // opaque surface: Tr = 0
   float4 c = P.ws.shC[ray];
   const float4 p1m = P.ws.shP1[ray], dd = P.ws.shD[ray];
   const int med = __float_as_int(p1m.w);
   const V3 d(dd.x, dd.y, dd.z);
   if (med >= 0) {  // ray.medium->Tr(ray): ray.tMax is the hit distance after Intersect, else 1 - ShadowEpsilon
-    const Spec tr = medium_Tr(sc.media[med], T.hit.t, length(d));
+    const Spec tr = medium_Tr(sc.media[med], hit.t, length(d));
     c.x *= tr.r; c.y *= tr.g; c.z *= tr.b;
   }
-  if (T.hit.tri < 0) {
+  if (hit.tri < 0) {
     const uint32_t slot = __float_as_uint(dd.w);
     atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
     return false;
@@ -221,16 +221,16 @@ PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T,
   if (++*hops > kMaxShadowCrossings) { atomicAdd(&P.ws.ctr->volCapHits, 1u); return false; }
   if (P.countStats) atomicMax(&P.ws.ctr->volMaxHops, (uint32_t)*hops);
   // ray = isect.SpawnRayTo(p1)   (Interaction.h:38-43; isect.mediumInterface from GeometricPrimitive::Intersect)
-  const TriData tri = load_tri(sc, T.hit.tri);
+  const TriData tri = load_tri(sc, hit.tri);
   Isect is;
-  make_isect(sc, tri, T.hit.tri, T.hit.b0, T.hit.b1, T.hit.b2, d, &is);
+  make_isect(sc, tri, hit.tri, hit.b0, hit.b1, hit.b2, d, &is);
   const float4 e1 = P.ws.shE1[ray], n1 = P.ws.shN1[ray];
   const V3 p1(p1m.x, p1m.y, p1m.z);
   const V3 origin = offset_ray_origin(is.p, is.pError, is.n, p1 - is.p);
   const V3 target = offset_ray_origin(p1, V3(e1.x, e1.y, e1.z), V3(n1.x, n1.y, n1.z), origin - p1);
   const V3 nd = target - origin;
   int mIn, mOut;
-  isect_media(sc, T.hit.tri, med, &mIn, &mOut);
+  isect_media(sc, hit.tri, med, &mIn, &mOut);
   const int nmed = dot(nd, is.n) > 0 ? mOut : mIn;
   P.ws.shC[ray] = c;
   P.ws.shP1[ray].w = __int_as_float(nmed);
@@ -243,6 +243,8 @@ template <bool COUNT, bool VOL = false>
 __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
   __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
   __shared__ uint2 stri[kTraceBlock / 32][kTriQueue][32];
+  __shared__ HitRec shit[kTraceBlock];  // closest hit so far of each lane's ray (see cw_tri_step)
+  HitRec& hit = shit[threadIdx.x];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint2* sstack = &sstk[warp][0][lane];
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
           nt = 0;
           hops = 0;
           busy = true;
+          hit.tri = -1;
           if (COUNT) rayWork0 = nodes + tris;
         }
       }
@@ -308,23 +311,25 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         if (COUNT) tris++;
         // any-hit exit for shadow rays; VolPath shadow rays need the CLOSEST surface (it may be a medium boundary)
         // (unless the scene has no such boundary at all: then the first surface found ends the ray either way)
-        if (cw_tri_step(P.sc, T) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+        if (cw_tri_step(P.sc, T, &hit) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
       }
       // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
       if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {
         bool again = false;
         if (COUNT) { atomicMax(&C->maxRayWork, nodes + tris - rayWork0); rayWork0 = nodes + tris; }
         if (mode == TRACE_PATH) {
-          P.ws.hit[ray] = make_float4(__int_as_float(T.hit.tri), T.hit.b0, T.hit.b1, T.hit.b2);
+          P.ws.hit[ray] = make_float4(__int_as_float(hit.tri), hit.b0, hit.b1, hit.b2);
           // shading-queue id of this path, written in QUEUE order so that k_classify reads it coalesced
-          P.ws.qType[qi] = T.hit.tri >= 0 ? ((T.hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
-          if (VOL) P.ws.rayO[ray].w = T.hit.t;  // ray.tMax after Scene::Intersect, read by Medium::Sample
+          P.ws.qType[qi] = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
+          if (VOL) P.ws.rayO[ray].w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
         } else if (mode == TRACE_MIS) {
-          P.ws.miO[ray].w = __int_as_float(T.hit.tri);
+          P.ws.miO[ray].w = __int_as_float(hit.tri);
         } else if (VOL) {
           segs++;
-          again = vol_shadow_next_segment(P, ray, T, &hops);  // true: next segment, same lane
-        } else if (T.hit.tri < 0) {  // unoccluded: add the light-sampling contribution
+          hit.t = T.tMax;
+          again = vol_shadow_next_segment(P, ray, T, hit, &hops);  // true: next segment, same lane
+          if (again) hit.tri = -1;
+        } else if (hit.tri < 0) {  // unoccluded: add the light-sampling contribution
           const uint32_t slot = __float_as_uint(P.ws.shD[ray].w);
           const float4 c = P.ws.shC[ray];
           if (P.atomicL) {

@@ -119,7 +119,6 @@ constexpr int kLocalStack = 36;
 struct Trav {
   V3 o;
   float idx, idy, idz;        // reciprocal direction (|d| clamped away from 0)
-  float jdx, jdy, jdz;        // 32768 * reciprocal direction
   unsigned octinv4;           // inverse octant replicated in 4 bytes
   unsigned f32one;            // 0x3F800000, from RenderParams::f32one (see q2f)
   RayPrep rp;
@@ -144,7 +143,6 @@ PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax, unsigned f32one) {
   T.o = o;
   T.f32one = f32one;
   T.idx = safe_rcp(d.x); T.idy = safe_rcp(d.y); T.idz = safe_rcp(d.z);
-  T.jdx = T.idx * 32768.f; T.jdy = T.idy * 32768.f; T.jdz = T.idz * 32768.f;
   T.octinv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
   T.rp = prep_ray(o, d);
   T.tMax = tMax;
@@ -189,10 +187,10 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
   const unsigned ei = __float_as_uint(n0.w);
   T.ngroup.x = __float_as_uint(n1.x);
   T.tgroup.x = __float_as_uint(n1.y);
-  // A = 32768 * 2^e / d (exact scalings of 1/d), B = (origin - o) / d
-  const float Ax = __uint_as_float((ei & 0xffu) << 23) * T.jdx;
-  const float Ay = __uint_as_float(((ei >> 8) & 0xffu) << 23) * T.jdy;
-  const float Az = __uint_as_float(((ei >> 16) & 0xffu) << 23) * T.jdz;
+  // A = 32768 * 2^e / d (exact scalings of 1/d: the factor 2^15 is added to the exponent byte), B = (origin - o) / d
+  const float Ax = __uint_as_float(((ei & 0xffu) + 15u) << 23) * T.idx;
+  const float Ay = __uint_as_float((((ei >> 8) & 0xffu) + 15u) << 23) * T.idy;
+  const float Az = __uint_as_float((((ei >> 16) & 0xffu) + 15u) << 23) * T.idz;
   const float Bx = (n0.x - T.o.x) * T.idx, By = (n0.y - T.o.y) * T.idy, Bz = (n0.z - T.o.z) * T.idz;
   const float ex = 4e-7f * (fabsf(Bx) + fabsf(Ax)), ey = 4e-7f * (fabsf(By) + fabsf(Ay)), ez = 4e-7f * (fabsf(Bz) + fabsf(Az));
   const float Bnx = (Bx - Ax) - ex, Bfx = (Bx - Ax) + ex;
@@ -233,7 +231,9 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
 }
 
 // One triangle of the triangle group: the reference's watertight test, bit-exact (t, b0, b1, b2).
-PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T) {
+// `store`: where the hit record goes (k_trace keeps it in shared memory: it is written once or twice per ray and read once,
+// and six registers less let a ninth block fit on the SM); NULL = T.hit.
+PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T, HitRec* store = nullptr) {
   const int bit = 31 - __clz(T.tgroup.y);
   T.tgroup.y &= ~(1u << bit);
   const int ti = (int)T.tgroup.x + bit;
@@ -242,8 +242,9 @@ PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T) {
   float t, b0, b1, b2;
   if (intersect_triangle(T.rp, T.tMax, p0, p1, p2, &t, &b0, &b1, &b2)) {
     T.tMax = t;
-    T.hit.tri = ti; T.hit.t = t; T.hit.b0 = b0; T.hit.b1 = b1; T.hit.b2 = b2;
-    T.hit.w1 = __float_as_uint(v1.w);
+    HitRec& h = store ? *store : T.hit;
+    h.tri = ti; h.t = t; h.b0 = b0; h.b1 = b1; h.b2 = b2;
+    h.w1 = __float_as_uint(v1.w);
     return true;
   }
   return false;
