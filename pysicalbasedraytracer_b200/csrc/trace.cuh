@@ -111,7 +111,7 @@ PBR_D V3 ld3(const float4* p, int i) {
 // lane ([level][lane] -> conflict-free), deeper levels spill to a small local array.
 // ---------------------------------------------------------------------------------------------
 #ifndef PBR_SMEM_STACK
-#define PBR_SMEM_STACK 12
+#define PBR_SMEM_STACK 8
 #endif
 constexpr int kSmemStack = PBR_SMEM_STACK;
 constexpr int kLocalStack = 36;
