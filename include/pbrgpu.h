@@ -242,7 +242,9 @@ int pbrgpu_render(pbrgpu_scene* scene, const pbrgpu_render_desc* rd, float* out_
 
 /* Same, but the sums stay in HBM: d_rgb_sum is a DEVICE pointer ((x1-x0)*(y1-y0)*4 floats, RGBA with
  * A = number of samples) on the context's device, e.g. a torch tensor's data_ptr() so that the
- * multi-GPU driver can NCCL-reduce it.  `stream` is a cudaStream_t (0 = the context's stream). */
+ * multi-GPU driver can NCCL-reduce it.  `stream` is a cudaStream_t; 0 means the context's own stream, which is created
+ * with cudaStreamNonBlocking and is therefore NOT ordered against the legacy default stream: a caller that fills
+ * d_rgb_sum on another stream (or on the default stream) must pass that stream, or synchronise before the call. */
 int pbrgpu_render_device(pbrgpu_scene* scene, const pbrgpu_render_desc* rd, float* d_rgb_sum,
                          void* stream, pbrgpu_stats* stats);
 
@@ -257,6 +259,9 @@ enum {
   PBRGPU_DUMP_PRIMARY_HITS = 2, /* int32 prim (caller's triangle index, -1 miss) + float t,b0,b1 : [..][4] */
   PBRGPU_DUMP_PERMS = 3,        /* uint16[n_perms] */
   PBRGPU_DUMP_SHADOW = 4,       /* int32[n] occlusion of caller-supplied rays (see pbrgpu_trace_rays) */
+  PBRGPU_DUMP_WAVE_HITS = 6,    /* same layout as PRIMARY_HITS, but produced by the PRODUCTION kernels of a render: k_wave_begin ->
+                                   k_raygen -> k_trace (persistent warps, parked triangle groups, shared-memory hit record);
+                                   PRIMARY_HITS uses the one-thread-per-ray helper loop.  region x samples <= 2^25 */
   PBRGPU_DUMP_HIT_DIFFERENTIALS = 5 /* float[n_pix][n_samples][8]: hit flag, uv, dudx, dvdx, dudy, dvdy of the camera ray's hit
                                        (Triangle.cpp:147-170, SurfaceInteraction::ComputeDifferentials) */
 };
@@ -270,7 +275,11 @@ typedef struct pbrgpu_dump_desc {
 int pbrgpu_debug_dump(pbrgpu_scene* scene, const pbrgpu_dump_desc* dd, void* out, size_t out_bytes);
 
 /* Trace caller-supplied rays (float[n][8]: o.xyz,tMax,d.xyz,pad).  any_hit=0: closest hit ->
- * out_hits int32/float [n][4] (prim, t, b0, b1 as bit patterns); any_hit=1: out_hits int32[n]. */
+ * out_hits int32/float [n][4] (prim, t, b0, b1 as bit patterns); any_hit=1: out_hits int32[n].
+ * any_hit | PBRGPU_TRACE_VIA_WAVE_KERNEL: the rays go through the production traversal kernel k_trace (closest-hit rays
+ * through its path AND MIS queues - the call fails if the two disagree -, any-hit rays through its shadow queue) instead
+ * of the one-thread-per-ray helper loop; n <= 2^25. */
+enum { PBRGPU_TRACE_VIA_WAVE_KERNEL = 2 };
 int pbrgpu_trace_rays(pbrgpu_scene* scene, const float* rays, int64_t n, int any_hit, void* out_hits);
 
 /* Parity hook: ImageTexture::Evaluate of textures[texture] for n surface points.  rows float[n][8] = u, v, dudx, dvdx, dudy,

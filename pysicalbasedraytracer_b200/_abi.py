@@ -9,7 +9,8 @@ INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTE
 MEDIUM_HOMOGENEOUS = 0
 LIGHTSTRATEGY_UNIFORM, LIGHTSTRATEGY_POWER = 0, 1
 RENDER_ACCUMULATE, RENDER_COUNTERS, RENDER_TIMERS = 1, 2, 4
-DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW, DUMP_HIT_DIFFERENTIALS = range(6)
+DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW, DUMP_HIT_DIFFERENTIALS, DUMP_WAVE_HITS = range(7)
+TRACE_VIA_WAVE_KERNEL = 2
 
 f3 = C.c_float * 3
 f16 = C.c_float * 16

@@ -298,6 +298,11 @@ class Scene:
         x0, y0, x1, y1 = region
         return self._dump(A.DUMP_PRIMARY_HITS, region, s0, s1, 0, ((y1 - y0) * (x1 - x0), s1 - s0, 4), np.int32)
 
+    def dump_wave_hits(self, region, s0, s1):
+        """Primary hits as the PRODUCTION kernels of a render find them (k_raygen -> k_trace): int32 [pix, S, 4]."""
+        x0, y0, x1, y1 = region
+        return self._dump(A.DUMP_WAVE_HITS, region, s0, s1, 0, ((y1 - y0) * (x1 - x0), s1 - s0, 4), np.int32)
+
     def dump_hit_differentials(self, region, s0, s1):
         """float32 [H,W,S,8]: hit flag, uv, dudx, dvdx, dudy, dvdy of each camera ray's surface hit."""
         x0, y0, x1, y1 = region
@@ -309,11 +314,14 @@ class Scene:
         _check(lib().pbrgpu_debug_dump(self.h, C.byref(dd), out.ctypes.data, out.nbytes))
         return out
 
-    def trace(self, rays, any_hit=False):
+    def trace(self, rays, any_hit=False, via_wave_kernel=False):
+        """Closest / any-hit queries for caller-supplied rays.  via_wave_kernel: through k_trace's own queues (the kernel
+        a render launches) instead of the one-thread-per-ray helper loop."""
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
         n = rays.shape[0]
         out = np.zeros((n,) if any_hit else (n, 4), dtype=np.int32)
-        _check(lib().pbrgpu_trace_rays(self.h, rays.ctypes.data, n, int(any_hit), out.ctypes.data))
+        mode = int(any_hit) | (A.TRACE_VIA_WAVE_KERNEL if via_wave_kernel else 0)
+        _check(lib().pbrgpu_trace_rays(self.h, rays.ctypes.data, n, mode, out.ctypes.data))
         return out
 
     def texture_eval(self, texture, rows):

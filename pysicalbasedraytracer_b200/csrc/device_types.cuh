@@ -149,6 +149,7 @@ struct RenderParams {
   int fetchMinIdle;       // idle lanes of a warp that trigger a ray fetch
   float diffScale;        // 1 / sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials of the render loop (image textures)
   int volShadowAnyHit;    // VolPath, scene without material-less surfaces: a shadow ray ends at ANY surface it finds
+  int storeHitT;          // parity hooks: k_trace also stores the hit distance of path rays (rayO.w), like the VOL build
   int atomicL;            // several shadow / MIS rays per path and bounce (Whitted / DirectLighting): atomics on L
   // Halton offset of the pixel a global index belongs to: index = offset(pixel) + sample * stride, offset < stride
   PBR_D int64_t pixelOffsetOf(int64_t index) const { return index % sc.hp.sampleStride; }

@@ -1,0 +1,194 @@
+// k_trace.cuh - the persistent traversal kernel (BVHAccel::Intersect / IntersectP, Accelerator/BVHAccel.cpp:285-366).
+#pragma once
+#include "kcommon.cuh"
+
+namespace pbr {
+
+// K2/K3/K6: the traversal kernel.  Persistent warps; each lane owns one ray at a time.  When at least
+// P.fetchMinIdle lanes of a warp have finished their rays, the idle lanes fetch new ones with a single
+// warp-aggregated atomicAdd on the queue cursor (__ballot_sync / __shfl_sync), so a warp is not held
+// hostage by its longest ray.  Per iteration a lane performs one node step (80-byte node, 8 child
+// boxes) and then drains the triangle group that step produced.
+// One launch per bounce serves three queues at once: the path rays of bounce b and the shadow / MIS
+// rays emitted by the shading of bounce b-1 (independent work, so the machine stays full).
+enum { TRACE_PATH = 0, TRACE_SHADOW = 1, TRACE_MIS = 2 };
+constexpr int kTraceBlock = 128;
+
+// Triangle batching: a node step leaves a lane with 0..24 candidate triangles.  Draining them right away
+// (a while loop) would run the long watertight test with only the few lanes that happen to have several
+// candidates, so a lane parks unfinished triangle groups in a small shared-memory list and keeps
+// descending; every loop iteration tests at most ONE triangle per lane.
+#ifndef PBR_TRI_QUEUE
+#define PBR_TRI_QUEUE 6
+#endif
+constexpr int kTriQueue = PBR_TRI_QUEUE;
+#ifndef PBR_NODE_STEPS
+#define PBR_NODE_STEPS 1
+#endif
+constexpr int kNodeStepsPerIter = PBR_NODE_STEPS;
+
+#ifndef PBR_TRACE_MIN_BLOCKS
+#define PBR_TRACE_MIN_BLOCKS 8
+#endif
+// VisibilityTester::Tr (Light/Light.cpp:31-47) for one finished segment of a VolPath shadow ray: returns true when the
+// ray continues behind a medium boundary (state re-initialised in T), false when it is done (blocked, or arrived and
+// its contribution x transmittance added to L).
+constexpr int kMaxShadowCrossings = 256;
+PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T, const HitRec& hit, int* hops) {
+  const SceneDev& sc = P.sc;
+  if (hit.tri >= 0 && ((hit.w1 >> kTriTypeShift) & 0xfu) != (uint32_t)kQueueNull) return false;  // opaque surface: Tr = 0
+  float4 c = P.ws.shC[ray];
+  const float4 p1m = P.ws.shP1[ray], dd = P.ws.shD[ray];
+  const int med = __float_as_int(p1m.w);
+  const V3 d(dd.x, dd.y, dd.z);
+  if (med >= 0) {  // ray.medium->Tr(ray): ray.tMax is the hit distance after Intersect, else 1 - ShadowEpsilon
+    const Spec tr = medium_Tr(sc.media[med], hit.t, length(d));
+    c.x *= tr.r; c.y *= tr.g; c.z *= tr.b;
+  }
+  if (hit.tri < 0) {
+    const uint32_t slot = __float_as_uint(dd.w);
+    atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
+    return false;
+  }
+  if (++*hops > kMaxShadowCrossings) { atomicAdd(&P.ws.ctr->volCapHits, 1u); return false; }
+  if (P.countStats) atomicMax(&P.ws.ctr->volMaxHops, (uint32_t)*hops);
+  // ray = isect.SpawnRayTo(p1)   (Interaction.h:38-43; isect.mediumInterface from GeometricPrimitive::Intersect)
+  const TriData tri = load_tri(sc, hit.tri);
+  Isect is;
+  make_isect(sc, tri, hit.tri, hit.b0, hit.b1, hit.b2, d, &is);
+  const float4 e1 = P.ws.shE1[ray], n1 = P.ws.shN1[ray];
+  const V3 p1(p1m.x, p1m.y, p1m.z);
+  const V3 origin = offset_ray_origin(is.p, is.pError, is.n, p1 - is.p);
+  const V3 target = offset_ray_origin(p1, V3(e1.x, e1.y, e1.z), V3(n1.x, n1.y, n1.z), origin - p1);
+  const V3 nd = target - origin;
+  int mIn, mOut;
+  isect_media(sc, hit.tri, med, &mIn, &mOut);
+  const int nmed = dot(nd, is.n) > 0 ? mOut : mIn;
+  P.ws.shC[ray] = c;
+  P.ws.shP1[ray].w = __int_as_float(nmed);
+  P.ws.shD[ray] = make_float4(nd.x, nd.y, nd.z, dd.w);
+  trav_init(T, origin, nd, 1 - kShadowEpsilon, sc.f32one);
+  return true;
+}
+
+template <bool COUNT, bool VOL = false>
+__global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
+  __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
+  __shared__ uint2 stri[kTraceBlock / 32][kTriQueue][32];
+  __shared__ HitRec shit[kTraceBlock];  // closest hit so far of each lane's ray (see cw_tri_step)
+  HitRec& hit = shit[threadIdx.x];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2* sstack = &sstk[warp][0][lane];
+  uint2* tq = &stri[warp][0][lane];
+  Counters* C = P.ws.ctr;
+  const uint32_t nPath = C->nCur, nShadow = C->nShadow, nMis = C->nMis;
+  const uint32_t n = nPath + nShadow + nMis;
+  Trav T;
+  TravSpill S;
+  T.ngroup = make_uint2(0u, 0u); T.tgroup = make_uint2(0u, 0u); T.sp = 0;
+  int nt = 0;  // parked triangle groups
+  bool busy = false, exhausted = false;
+  int mode = TRACE_PATH;
+  uint32_t ray = 0;  // PATH: wavefront slot; SHADOW / MIS: index in that queue
+  uint32_t qi = 0;   // PATH: position in the path queue
+  int hops = 0;      // VOL: medium boundaries this shadow ray has crossed
+  unsigned segs = 0; // VOL: shadow-ray segments traced by this lane (each is one Scene::Intersect of VisibilityTester::Tr)
+  unsigned nodes = 0, tris = 0;
+  unsigned rayWork0 = 0;  // COUNT: nodes + tris at the start of the current ray (-> Counters::maxRayWork)
+  while (true) {
+    // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
+    // (a per-warp reserve of 128 rays per atomicAdd was measured: no faster - the cursor is not a bottleneck)
+    const unsigned idle = __ballot_sync(full, !busy);
+    if (idle != 0u && !exhausted && (idle == full || __popc(idle) >= P.fetchMinIdle)) {
+      const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&C->cursor[0], (uint32_t)nIdle);
+      base = __shfl_sync(full, base, leader);
+      exhausted = base + (uint32_t)nIdle >= n;
+      if (!busy) {
+        uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+        if (i < n) {
+          float4 ro, rd;
+          if (i < nPath) { mode = TRACE_PATH; qi = i; ray = P.ws.qCur[i]; ro = P.ws.rayO[ray]; rd = P.ws.rayD[ray]; }
+          else if (i < nPath + nShadow) { mode = TRACE_SHADOW; ray = i - nPath; ro = P.ws.shO[ray]; rd = P.ws.shD[ray]; }
+          else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
+          trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, P.sc.f32one);
+          nt = 0;
+          hops = 0;
+          busy = true;
+          hit.tri = -1;
+          if (COUNT) rayWork0 = nodes + tris;
+        }
+      }
+    }
+    if (exhausted && __ballot_sync(full, busy) == 0u) break;
+    // ---- node phase: kNodeStepsPerIter x (pop if the node group is exhausted, then one node step).  More than one
+    // node step per triangle round was measured (2: +4 % time, 3: +19 %): the extra speculative node visits cost more
+    // than the fuller triangle rounds save, so kNodeStepsPerIter = 1 ----
+    if (busy) {
+#pragma unroll 1
+      for (int rep = 0; rep < kNodeStepsPerIter; ++rep) {
+        if (T.ngroup.y <= 0x00FFFFFFu && T.sp > 0) T.ngroup = trav_pop(T, sstack, S);
+        if (T.ngroup.y > 0x00FFFFFFu && (T.tgroup.y == 0u || nt < kTriQueue)) {
+          if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }  // park the unfinished triangle group
+          cw_node_step(P.sc.nodes8, T, sstack, S);
+          if (COUNT) nodes++;
+        }
+      }
+      // ---- triangle round: ONE candidate triangle per lane (a threshold on the number of lanes with candidates
+      // was measured: lanes always have a backlog, so the round runs every iteration anyway) ----
+      if (T.tgroup.y != 0u || nt > 0) {
+        if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
+        if (COUNT) tris++;
+        // any-hit exit for shadow rays; VolPath shadow rays need the CLOSEST surface (it may be a medium boundary)
+        // (unless the scene has no such boundary at all: then the first surface found ends the ray either way)
+        if (cw_tri_step(P.sc, T, &hit) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+      }
+      // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
+      if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {
+        bool again = false;
+        if (COUNT) { atomicMax(&C->maxRayWork, nodes + tris - rayWork0); rayWork0 = nodes + tris; }
+        if (mode == TRACE_PATH) {
+          P.ws.hit[ray] = make_float4(__int_as_float(hit.tri), hit.b0, hit.b1, hit.b2);
+          // shading-queue id of this path, written in QUEUE order so that k_classify reads it coalesced
+          P.ws.qType[qi] = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
+          if (VOL || P.storeHitT) P.ws.rayO[ray].w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
+        } else if (mode == TRACE_MIS) {
+          P.ws.miO[ray].w = __int_as_float(hit.tri);
+        } else if (VOL) {
+          segs++;
+          hit.t = T.tMax;
+          again = vol_shadow_next_segment(P, ray, T, hit, &hops);  // true: next segment, same lane
+          if (again) hit.tri = -1;
+        } else if (hit.tri < 0) {  // unoccluded: add the light-sampling contribution
+          const uint32_t slot = __float_as_uint(P.ws.shD[ray].w);
+          const float4 c = P.ws.shC[ray];
+          if (P.atomicL) {
+            atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
+          } else {
+            float4 L = P.ws.L[slot];
+            P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
+          }
+        }
+        busy = again;
+      }
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&C->nodesVisited, (unsigned long long)nodes);
+    atomicAdd(&C->trisTested, (unsigned long long)tris);
+  }
+  if (VOL) {  // VolPath has no IntersectP queries: every shadow segment is a closest-hit query
+    segs = __reduce_add_sync(full, segs);
+    if (lane == 0 && segs) atomicAdd(&C->raysClosest, (unsigned long long)segs);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!VOL) atomicAdd(&C->raysShadow, (unsigned long long)nShadow);
+    atomicAdd(&C->raysClosest, (unsigned long long)(nPath + nMis));
+    atomicAdd(&C->raysPath, (unsigned long long)nPath);
+  }
+}
+
+
+}  // namespace pbr

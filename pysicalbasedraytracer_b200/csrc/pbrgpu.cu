@@ -19,7 +19,8 @@
 #include <vector>
 
 #include "host_tables.h"
-#include "kernels.cuh"
+#include "kmisc.cuh"
+#include "launch.h"
 
 using namespace pbr;
 
@@ -255,6 +256,18 @@ uint32_t grid_occ(const pbrgpu_ctx* c, K kernel, int block, uint64_t n) {
   }
   const uint64_t blocks = std::max<uint64_t>(1, (n + block - 1) / block);
   return (uint32_t)std::min<uint64_t>(blocks, (uint64_t)c->smCount * it->second);
+}
+
+// one resident wave of k_shade<mat, vol, tex>
+uint32_t shade_grid(const pbrgpu_ctx* c, int mat, bool vol, bool tex, uint64_t n) {
+  static int cache[PBRGPU_MAT_COUNT][2][2] = {};
+  int& nb = cache[mat][vol ? 1 : 0][tex ? 1 : 0];
+  if (nb == 0) {
+    nb = std::max(1, shade_blocks_per_sm(mat, vol, tex));
+    if (const char* e = getenv("PBRGPU_SHADE_WAVES")) nb *= std::max(1, atoi(e));
+  }
+  const uint64_t blocks = std::max<uint64_t>(1, (n + kShadeBlock - 1) / kShadeBlock);
+  return (uint32_t)std::min<uint64_t>(blocks, (uint64_t)c->smCount * nb);
 }
 
 }  // namespace
@@ -872,8 +885,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : c->stream;
   if (build_light_distribution(s, rd->light_strategy)) return 1;
   if (s->traceBlocksPerSm <= 0) {
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false>, kTraceBlock, 0));
+    int nb = trace_blocks_per_sm();
     if (const char* e = getenv("PBRGPU_TRACE_BLOCKS_PER_SM")) nb = atoi(e);
     s->traceBlocksPerSm = std::max(1, nb);
     if (const char* e = getenv("PBRGPU_FETCH_MIN_IDLE")) s->fetchMinIdle = std::max(1, std::min(32, atoi(e)));
@@ -954,7 +966,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       uint32_t g = grid_for(c, nPaths, 8);
       uint32_t gc = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths + kClassifyTile - 1) / kClassifyTile, (uint64_t)c->smCount * 8));
       // persistent traversal grid: every SM filled to the kernel's occupancy, never more blocks than rays
-      uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths * (pathInteg ? 1 : 1 + raysPerHit) + kTraceBlock - 1) / kTraceBlock,
+      uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths * (pathInteg ? 1 : 1 + raysPerHit) + kTraceBlockThreads - 1) / kTraceBlockThreads,
                                                                       (uint64_t)c->smCount * s->traceBlocksPerSm));
       CK(tl.mark(T_RAYGEN));
       k_wave_begin<<<1, 1, 0, st>>>(s->ctr.p);
@@ -978,8 +990,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
           CK(tl.mark(T_SHADE));
           if (s->sc.nMedia > 0) { k_medium_presample<<<g, kBlock, 0, st>>>(P); launches++; }
           CK(tl.mark(T_CLOSEST));
-          if (count) k_trace<true, true><<<gt, kTraceBlock, 0, st>>>(P);
-          else k_trace<false, true><<<gt, kTraceBlock, 0, st>>>(P);
+          launch_trace(count, true, gt, st, P);
           if (volLog) {
             CK(cudaStreamSynchronize(st));
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -999,17 +1010,12 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
           CK(tl.mark(T_SHADE));
           if (s->sc.nMedia > 0) { k_medium_sample<<<g, kBlock, 0, st>>>(P); launches++; }
           k_classify<<<gc, kBlock, 0, st>>>(P);
-#define PBR_SHADE_V(M)                                                                                                            \
-  if (s->hasMat[M]) {                                                                                                             \
-    if (s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC))                                                     \
-      k_shade<M, true, true><<<grid_occ(c, k_shade<M, true, true>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, 0);              \
-    else                                                                                                                          \
-      k_shade<M, true><<<grid_occ(c, k_shade<M, true, false>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, 0);                  \
-    launches++;                                                                                                                   \
-  }
-          PBR_SHADE_V(PBRGPU_MAT_MATTE) PBR_SHADE_V(PBRGPU_MAT_MIRROR) PBR_SHADE_V(PBRGPU_MAT_GLASS)
-          PBR_SHADE_V(PBRGPU_MAT_METAL) PBR_SHADE_V(PBRGPU_MAT_PLASTIC)
-#undef PBR_SHADE_V
+          for (int M = 0; M < PBRGPU_MAT_COUNT; ++M)
+            if (s->hasMat[M]) {
+              const bool tex = s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC);
+              launch_shade(M, true, tex, shade_grid(c, M, true, tex, nPaths), st, P, 0);
+              launches++;
+            }
           if (s->hasNullMat) { k_shade_null<<<g, kBlock, 0, st>>>(P); launches++; }
           if (s->sc.nMedia > 0) { k_shade_medium<<<grid_occ(c, k_shade_medium, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P); launches++; }
           if (s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, 0); launches++; }
@@ -1026,38 +1032,19 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       const int lastBounce = volInteg ? -1 : (pathInteg ? rd->max_depth : std::max(rd->max_depth - 1, 0));
       for (int bounce = 0; bounce <= lastBounce; ++bounce) {
         CK(tl.mark(T_CLOSEST));
-        if (count) k_trace<true><<<gt, kTraceBlock, 0, st>>>(P);
-        else k_trace<false><<<gt, kTraceBlock, 0, st>>>(P);
+        launch_trace(count, false, gt, st, P);
         CK(tl.mark(T_MIS));
         if (bounce > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
         CK(tl.mark(T_SHADE));
         k_classify<<<gc, kBlock, 0, st>>>(P);
         // one shading launch per material type PRESENT in the scene
-#define PBR_SHADE(M)                                                                                                              \
-  if (s->hasMat[M]) {                                                                                                             \
-    if (s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC))                                                     \
-      k_shade<M, false, true><<<grid_occ(c, k_shade<M, false, true>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, bounce);       \
-    else                                                                                                                          \
-      k_shade<M><<<grid_occ(c, k_shade<M, false, false>, kShadeBlock, nPaths), kShadeBlock, 0, st>>>(P, bounce);                  \
-    launches++;                                                                                                                   \
-  }
-#define PBR_SHADE_D(M)                                                                                  \
-  if (s->hasMat[M]) {                                                                                   \
-    if (s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC))                           \
-      k_shade_direct<M, true><<<g, kBlock, 0, st>>>(P, bounce);                                         \
-    else                                                                                                \
-      k_shade_direct<M><<<g, kBlock, 0, st>>>(P, bounce);                                               \
-    launches++;                                                                                         \
-  }
-        if (pathInteg) {
-          PBR_SHADE(PBRGPU_MAT_MATTE) PBR_SHADE(PBRGPU_MAT_MIRROR) PBR_SHADE(PBRGPU_MAT_GLASS)
-          PBR_SHADE(PBRGPU_MAT_METAL) PBR_SHADE(PBRGPU_MAT_PLASTIC)
-        } else {
-          PBR_SHADE_D(PBRGPU_MAT_MATTE) PBR_SHADE_D(PBRGPU_MAT_MIRROR) PBR_SHADE_D(PBRGPU_MAT_GLASS)
-          PBR_SHADE_D(PBRGPU_MAT_METAL) PBR_SHADE_D(PBRGPU_MAT_PLASTIC)
-        }
-#undef PBR_SHADE_D
-#undef PBR_SHADE
+        for (int M = 0; M < PBRGPU_MAT_COUNT; ++M)
+          if (s->hasMat[M]) {
+            const bool tex = s->hasTextures && (M == PBRGPU_MAT_MATTE || M == PBRGPU_MAT_PLASTIC);
+            if (pathInteg) launch_shade(M, false, tex, shade_grid(c, M, false, tex, nPaths), st, P, bounce);
+            else launch_shade_direct(M, tex, g, st, P, bounce);
+            launches++;
+          }
         if (!pathInteg || s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce); launches++; }
         k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
         launches += 3;
@@ -1065,8 +1052,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
       }
       if (!pathInteg && !volInteg) {  // shadow / MIS rays of the last shaded depth
         CK(tl.mark(T_CLOSEST));
-        if (count) k_trace<true><<<gt, kTraceBlock, 0, st>>>(P);
-        else k_trace<false><<<gt, kTraceBlock, 0, st>>>(P);
+        launch_trace(count, false, gt, st, P);
         CK(tl.mark(T_MIS));
         k_resolve_mis<<<g, kBlock, 0, st>>>(P);
         launches += 2;
@@ -1229,6 +1215,38 @@ int pbrgpu_debug_dump(pbrgpu_scene* s, const pbrgpu_dump_desc* dd, void* out, si
     CK(cudaStreamSynchronize(c->stream));
     return 0;
   }
+  if (dd->what == PBRGPU_DUMP_WAVE_HITS) {
+    // the PRODUCTION kernels: k_wave_begin -> k_raygen -> k_trace<false, false>, then ws.hit in caller order
+    if (!s->haveCamera) return fail("pbrgpu_debug_dump: camera not set");
+    const uint64_t n = (uint64_t)W * H * ns;
+    if (n > (1u << 25)) return fail("pbrgpu_debug_dump: region x samples exceeds one wave (2^25 paths)");
+    if (out_bytes < n * 4 * sizeof(int)) return fail("pbrgpu_debug_dump: output too small");
+    if (s->bvh.maxDepth >= kSmemStack + kLocalStack) return fail("pbrgpu_debug_dump: BVH deeper than the traversal stack");
+    if (ensure_wave(s, (uint32_t)n, 1, false)) return 1;
+    if (s->traceBlocksPerSm <= 0) s->traceBlocksPerSm = std::max(1, trace_blocks_per_sm());
+    DevBuf<int> d;
+    CK(d.alloc(n * 4));
+    RenderParams P{};
+    P.sc = s->sc;
+    fill_wave(s, &P.ws);
+    P.integrator = PBRGPU_INTEGRATOR_PATH;
+    P.x0 = dd->x0; P.y0 = dd->y0; P.w = W; P.h = H; P.sBegin = dd->s0; P.nsWave = (int)ns;
+    P.arrayEndDim = 5;
+    P.fetchMinIdle = s->fetchMinIdle;
+    P.storeHitT = 1;
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(s->ctr.p, 0, sizeof(Counters), st));
+    k_wave_begin<<<1, 1, 0, st>>>(s->ctr.p);
+    k_raygen<<<grid_for(c, n, 8), kBlock, 0, st>>>(P);
+    const uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + kTraceBlockThreads - 1) / kTraceBlockThreads,
+                                                                            (uint64_t)c->smCount * s->traceBlocksPerSm));
+    launch_trace(false, false, gt, st, P);
+    k_collect_wave_hits<<<grid_for(c, n, 8), kBlock, 0, st>>>(P, (int)ns, d.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d.p, n * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+  }
   return fail("pbrgpu_debug_dump: unknown dump kind");
 }
 
@@ -1239,11 +1257,40 @@ int pbrgpu_trace_rays(pbrgpu_scene* s, const float* rays, int64_t n, int any_hit
   DevBuf<float> dr;
   DevBuf<int> dh;
   CK(dr.alloc((size_t)n * 8));
-  CK(dh.alloc((size_t)n * (any_hit ? 1 : 4)));
+  CK(dh.alloc((size_t)n * ((any_hit & 1) ? 1 : 4)));
   CK(cudaMemcpyAsync(dr.p, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   RenderParams P{};
   P.sc = s->sc;
-  k_trace_user<<<grid_for(c, (uint64_t)n, 8), kBlock, 0, c->stream>>>(P, dr.p, n, any_hit, dh.p);
+  if (any_hit & PBRGPU_TRACE_VIA_WAVE_KERNEL) {
+    // through the production kernel k_trace and its three queues (path + MIS for closest hits, shadow for any-hit)
+    const bool anyHit = (any_hit & 1) != 0;
+    if (n > (1 << 25)) return fail("pbrgpu_trace_rays: more rays than one wave holds (2^25)");
+    if (s->bvh.maxDepth >= kSmemStack + kLocalStack) return fail("pbrgpu_trace_rays: BVH deeper than the traversal stack");
+    if (ensure_wave(s, (uint32_t)n, 1, false)) return 1;
+    if (s->traceBlocksPerSm <= 0) s->traceBlocksPerSm = std::max(1, trace_blocks_per_sm());
+    fill_wave(s, &P.ws);
+    P.fetchMinIdle = s->fetchMinIdle;
+    P.storeHitT = 1;
+    DevBuf<int> dis;
+    CK(dis.alloc(1));
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(dis.p, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(s->ctr.p, 0, sizeof(Counters), st));
+    k_wave_begin<<<1, 1, 0, st>>>(s->ctr.p);
+    k_feed_rays<<<grid_for(c, (uint64_t)n, 8), kBlock, 0, st>>>(P, dr.p, (uint32_t)n, anyHit ? 1 : 0);
+    const uint32_t gt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((2 * (uint64_t)n + kTraceBlockThreads - 1) / kTraceBlockThreads,
+                                                                            (uint64_t)c->smCount * s->traceBlocksPerSm));
+    launch_trace(false, false, gt, st, P);
+    k_collect_rays<<<grid_for(c, (uint64_t)n, 8), kBlock, 0, st>>>(P, (uint32_t)n, anyHit ? 1 : 0, dh.p, dis.p);
+    CK(cudaGetLastError());
+    int nDis = 0;
+    CK(cudaMemcpyAsync(out_hits, dh.p, dh.n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&nDis, dis.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nDis) return fail("pbrgpu_trace_rays: k_trace's path queue and MIS queue found different triangles for " + std::to_string(nDis) + " rays");
+    return 0;
+  }
+  k_trace_user<<<grid_for(c, (uint64_t)n, 8), kBlock, 0, c->stream>>>(P, dr.p, n, any_hit & 1, dh.p);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_hits, dh.p, dh.n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));

@@ -112,7 +112,9 @@ PBR_D float radical_inverse(int baseIndex, uint64_t a, const HaltonParams& hp) {
     // ReverseBits64(a) * 5.4210108624275222e-20 : uint64 -> double product, narrowed on return
     return (float)((double)__brevll(a) * 5.4210108624275222e-20);
   }
-  if (baseIndex >= 1024) return 0.f;  // LowDiscrepancy.cpp:2279-2280 (table itself has 1000 primes)
+  // LowDiscrepancy.cpp:2279-2280 returns 0 from 1024 on, but Primes[] / PrimeSums[] have 1000 entries: dimensions 1000..1023 read
+  // past the tables in the reference (undefined).  Here every dimension beyond the tables yields 0.
+  if (baseIndex >= kPrimeTableSize) return 0.f;
   uint32_t base = (uint32_t)hp.primes[baseIndex];
   float invBase = __ldg(hp.dimConst + baseIndex).x;
   float invBaseN;
@@ -121,7 +123,7 @@ PBR_D float radical_inverse(int baseIndex, uint64_t a, const HaltonParams& hp) {
 }
 
 PBR_D float scrambled_radical_inverse(int baseIndex, uint64_t a, const HaltonParams& hp) {
-  if (baseIndex >= 1024) return 0.f;
+  if (baseIndex >= kPrimeTableSize) return 0.f;  // see radical_inverse
   uint32_t base = (uint32_t)hp.primes[baseIndex];
   const uint16_t* perm = hp.perms + hp.primeSums[baseIndex];
   const float2 dc = __ldg(hp.dimConst + baseIndex);  // invBase, invBase * perm[0] / (1 - invBase)

@@ -17,13 +17,20 @@ class ProgressiveFilm:
         self.scene, self.W, self.H = scene, width, height
         self.kw = render_kwargs  # integrator, max_depth, rr_threshold, light_strategy
         self.accum = torch.zeros((height, width, 4), dtype=torch.float32, device=torch.device("cuda", device))
+        self.stream = torch.cuda.Stream(self.accum.device)
         self.next_sample = 0
 
     def render(self, n_samples):
         """Add samples [next_sample, next_sample + n_samples) of every pixel."""
         s0, s1 = self.next_sample, self.next_sample + int(n_samples)
-        self.scene.render_device(self.accum.data_ptr(), stream=0, region=(0, 0, self.W, self.H), s0=s0, s1=s1,
+        # The accumulator is produced on torch's current stream (zero fill, checkpoint upload) and the C-ABI treats
+        # stream 0 as "the library's private non-blocking stream", so the render runs on a stream of our own that is
+        # ordered after torch's current stream, and torch's stream is ordered after the render.
+        cur = torch.cuda.current_stream(self.accum.device)
+        self.stream.wait_stream(cur)
+        self.scene.render_device(self.accum.data_ptr(), stream=self.stream.cuda_stream, region=(0, 0, self.W, self.H), s0=s0, s1=s1,
                                  flags=A.RENDER_ACCUMULATE, **self.kw)
+        cur.wait_stream(self.stream)
         self.next_sample = s1
         return self
 

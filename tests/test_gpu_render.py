@@ -304,20 +304,30 @@ def test_full_size_dragon_class_properties(api, ref, gpu_ctx):
     # ray queries against the reference on the full mesh (a strip of primary rays + random rays)
     region = (900, 500, 1028, 516)
     want = ref.primary_hits(p.rscene, p.rcam, p.rsmp, region, 0, 1)
-    got = p.scene.dump_primary_hits(region, 0, 1)
-    assert (got[..., 0] != want[..., 0]).mean() < 1e-4
-    same = got[..., 0] == want[..., 0]
-    assert np.array_equal(got[..., 1][same], want[..., 1][same])
+    for got in (p.scene.dump_wave_hits(region, 0, 1),      # the production kernel k_trace (north-star check 1)
+                p.scene.dump_primary_hits(region, 0, 1)):  # the helper loop, second pin
+        assert (got[..., 0] != want[..., 0]).mean() < 1e-4
+        same = got[..., 0] == want[..., 0]
+        assert np.array_equal(got[..., 1][same], want[..., 1][same])  # t bit-identical
+    # the whole 1080p wave of the production kernel against the helper loop (2 M primary rays at tess 467)
+    full = (0, 0, W, H)
+    assert np.array_equal(p.scene.dump_wave_hits(full, 3, 4), p.scene.dump_primary_hits(full, 3, 4))
     rng = np.random.default_rng(4)
     rays = np.zeros((50_000, 8), dtype=np.float32)
     rays[:, 0:3] = rng.uniform(-2.4, 2.4, (50_000, 3))
     dd = rng.normal(size=(50_000, 3))
     rays[:, 4:7] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
     rays[:, 3] = np.inf
-    wr, gr = p.rscene.trace(rays), p.scene.trace(rays)
-    assert (wr[:, 0] != gr[:, 0]).mean() < 1e-4
+    wr = p.rscene.trace(rays)
+    for via in (True, False):
+        gr = p.scene.trace(rays, via_wave_kernel=via)
+        assert (wr[:, 0] != gr[:, 0]).mean() < 1e-4
+        same = wr[:, 0] == gr[:, 0]
+        assert np.array_equal(gr[:, 1][same], wr[:, 1][same])
     rays[:, 3] = rng.uniform(0.05, 3.0, 50_000)
-    assert (p.rscene.trace(rays, any_hit=True) != p.scene.trace(rays, any_hit=True)).mean() < 1e-4
+    wa = p.rscene.trace(rays, any_hit=True)
+    for via in (True, False):
+        assert (wa != p.scene.trace(rays, any_hit=True, via_wave_kernel=via)).mean() < 1e-4
 
 
 # ---------------------------------------------------------------------------------------------

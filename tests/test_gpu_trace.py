@@ -28,13 +28,35 @@ def _compare_hits(got, want):
     return frac
 
 
-def test_primary_hits(cornell, ref):
+# Every hit-id check runs twice: on the PRODUCTION kernel of a render (k_wave_begin -> k_raygen -> k_trace: persistent warps,
+# parked triangle groups, mid-warp refetch, shared-memory hit record; PBRGPU_DUMP_WAVE_HITS / PBRGPU_TRACE_VIA_WAVE_KERNEL) and
+# on the one-thread-per-ray helper loop (PBRGPU_DUMP_PRIMARY_HITS / plain pbrgpu_trace_rays) as a second, independent pin.
+KERNELS = ["k_trace", "helper_loop"]
+
+
+def _primary(scene, region, s0, s1, kernel):
+    return scene.dump_wave_hits(region, s0, s1) if kernel == "k_trace" else scene.dump_primary_hits(region, s0, s1)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_primary_hits(cornell, ref, kernel):
     region = (0, 0, 256, 256)
     want = ref.primary_hits(cornell.rscene, cornell.rcam, cornell.rsmp, region, 0, 2)
-    got = cornell.scene.dump_primary_hits(region, 0, 2)
+    got = _primary(cornell.scene, region, 0, 2, kernel)
     frac = _compare_hits(got, want)
-    print("primary-hit mismatch fraction", frac)
+    print(kernel, "primary-hit mismatch fraction", frac)
     assert frac < MAX_MISMATCH
+    # barycentrics bit-identical where the primitive agrees
+    same = got[..., 0] == want[..., 0]
+    assert np.array_equal(got[..., 2:4][same], want[..., 2:4][same])
+
+
+def test_wave_kernel_equals_helper_loop(cornell):
+    """The two device paths share the node / triangle steps; their answers must be identical."""
+    region = (13, 40, 256, 211)
+    a = cornell.scene.dump_wave_hits(region, 1, 4)
+    b = cornell.scene.dump_primary_hits(region, 1, 4)
+    assert np.array_equal(a, b)
 
 
 def _random_rays(n, seed, tmax=np.inf):
@@ -49,22 +71,26 @@ def _random_rays(n, seed, tmax=np.inf):
     return rays
 
 
-def test_random_closest_hits(cornell):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_random_closest_hits(cornell, kernel):
+    # k_trace: the rays go through its path queue AND its MIS queue in one launch (the call fails if the two disagree)
     rays = _random_rays(200_000, 1)
     want = cornell.rscene.trace(rays)
-    got = cornell.scene.trace(rays)
+    got = cornell.scene.trace(rays, via_wave_kernel=kernel == "k_trace")
     frac = _compare_hits(got, want)
-    print("random closest mismatch fraction", frac)
+    print(kernel, "random closest mismatch fraction", frac)
     assert frac < MAX_MISMATCH
 
 
-def test_random_any_hits(cornell):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_random_any_hits(cornell, kernel):
+    # k_trace: through its shadow queue (any-hit early-out, contribution added when unoccluded)
     rays = _random_rays(200_000, 2)
     rays[:, 3] = np.random.default_rng(3).uniform(0.05, 3.0, rays.shape[0]).astype(np.float32)
     want = cornell.rscene.trace(rays, any_hit=True)
-    got = cornell.scene.trace(rays, any_hit=True)
+    got = cornell.scene.trace(rays, any_hit=True, via_wave_kernel=kernel == "k_trace")
     frac = (want != got).mean()
-    print("random any-hit mismatch fraction", frac)
+    print(kernel, "random any-hit mismatch fraction", frac)
     assert frac < MAX_MISMATCH
     assert 0.05 < want.mean() < 0.95  # the test exercises both outcomes
 
@@ -82,15 +108,18 @@ def test_axis_aligned_and_degenerate_rays(cornell):
     assert np.array_equal(got[:, 1], want[:, 1])
 
 
-def test_dragon_class_primary_hits(api, ref, gpu_ctx):
-    # reduced tessellation of the BASELINE config-2 mesh (full size is exercised by bench.py)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_dragon_class_primary_hits(api, ref, gpu_ctx, kernel):
+    # reduced tessellation of the BASELINE config-2 mesh (the full 872 k-triangle mesh: test_gpu_render.py::test_full_size_*)
     p = Pair(api, ref, scenes.dragon_class(tess=96), 192, 108, 2)
     region = (0, 0, 192, 108)
     want = ref.primary_hits(p.rscene, p.rcam, p.rsmp, region, 0, 2)
-    got = p.scene.dump_primary_hits(region, 0, 2)
+    got = _primary(p.scene, region, 0, 2, kernel)
     frac = _compare_hits(got, want)
-    print("dragon-class primary-hit mismatch fraction", frac, "bvh", p.scene.info())
+    print(kernel, "dragon-class primary-hit mismatch fraction", frac, "bvh", p.scene.info())
     assert frac < MAX_MISMATCH
+    rays = _random_rays(100_000, 7)
+    assert _compare_hits(p.scene.trace(rays, via_wave_kernel=kernel == "k_trace"), p.rscene.trace(rays)) < MAX_MISMATCH
 
 
 def test_tiny_scenes_and_edge_cases(api, ref, gpu_ctx):
