@@ -13,8 +13,10 @@ Metric: Msamples/s (camera samples = PathIntegrator::Li calls), with Mrays/s bes
            launching stream, barrier + synchronize on both sides, max over ranks.
   e2e    - the same step through the host-buffer C-ABI call pbrgpu_render (what Integrator::Render does):
            descriptors host->device, radiance image device->host every step, wall-clock around the call.
-  N > 1  - scene replicated per GPU, sample ranges sharded across ranks (weak scaling: every rank renders
-           SPP_PER_STEP samples per pixel per step), per-step NCCL reduce(sum) of the fp32 accumulators to rank 0.
+  N > 1  - scene replicated per GPU; every rank attaches its context to one NCCL communicator (pbrgpu_comm_attach) and
+           makes the SAME pbrgpu_render(_device) call: the library shards the sample range, reduces the fp32 sum films
+           to rank 0 (ncclReduce) and resolves there.  `value` is weak scaling (SPP_PER_STEP samples per pixel per rank per
+           step); `strong` is the fixed 1024-spp job end to end; `multi_gpu_check` compares the N-rank film with rank 0 alone.
 """
 import argparse
 import json
@@ -37,6 +39,14 @@ RR_THRESHOLD = 1.0
 TESS = 467
 SPP_PER_STEP = 16
 EYE, LOOK, UP = (0.0, 0.0, 5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)
+def config_dict():
+    """Identical on both arms (the driver compares it): the workload, not how an arm runs it."""
+    return {"workload": WORKLOAD, "sampler": "Halton", "max_depth": MAX_DEPTH, "rr_threshold": RR_THRESHOLD, "resolution": [W, H],
+            "spp_job": SPP_TOTAL,
+            "l2_policy": "GPU arm: the working set of a step (wave state 7.5 GB + 54 MB scene) exceeds the 126 MB L2, no explicit "
+                         "flush; reference arm: host caches, not applicable"}
+
+
 WORKLOAD = "dragon-class 872368-tri mesh in Cornell walls, Matte+Mirror, Halton, 1920x1080, PathIntegrator maxDepth 8 (configs[1])"
 
 
@@ -156,7 +166,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Msamples/s", "value": r["value"], "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sampler": "Halton", "max_depth": MAX_DEPTH, "resolution": [W, H]},
+        "config": config_dict(),
         "mrays_per_s": r["mrays_per_s"],
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -165,7 +175,32 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def cpu_as_shipped(data):
+    """The reference's own SamplerIntegrator::Render exactly as shipped - its hard-coded 4 OpenMP threads
+    (Integrator/Integrator.cpp:282-288) - on a square crop (its pixel loop is only correct for square images)."""
+    from oracle import refharness as R
+    from pysicalbasedraytracer_b200 import _abi as A
+    if not R.available():
+        return None
+    side, spp = 384, 1
+    rs = R.RefScene(data)
+    rc = R.RefCamera(A.CAMERA_PERSPECTIVE, side, side, EYE, LOOK, UP)
+    _, st, sec = R.render_shipped(rs, rc, spp, side, side, MAX_DEPTH, RR_THRESHOLD)
+    return dict(value=side * side * spp / max(sec, 1e-9) / 1e6, unit="Msamples/s", cores=4, kind="reference",
+                sample=f"{side}x{side} image of the same scene, {spp} spp, the reference's SamplerIntegrator::Render as shipped "
+                       f"(omp_set_num_threads(4), Integrator.cpp:282-288), wall time of the call {sec:.2f} s")
+
+
+def _load_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def run_gpu(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from pysicalbasedraytracer_b200 import api
@@ -177,53 +212,62 @@ def run_gpu(args):
     if api.device_count() == 0:
         raise RuntimeError("bench.py: no CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = api.Context(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+        # torch.distributed is the launcher-side plumbing only (rendezvous, barriers, max over ranks).  The data path - sample
+        # sharding and the ncclReduce of the films - is INSIDE the C-ABI: rank 0 creates the NCCL id, every rank attaches its
+        # context (pbrgpu_comm_attach), and from here on every rank makes the same pbrgpu_render(_device) call.
+        uid = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.attach(world, rank, uid[0])
 
     data = build_scene_data()
-    ctx = api.Context(local)
     scene = api.Scene(data, ctx)
+    scene_build_s = scene.build_seconds
     cam = api.CreatePerspectiveCamera(W, H, api.Inverse(api.LookAt(EYE, LOOK, UP)))
     scene.set_camera(cam)
-    scene.set_sampler(api.HaltonSampler(SPP_TOTAL, (0, 0, W, H)))
+    halton = api.HaltonSampler(SPP_TOTAL, (0, 0, W, H))
+    scene.set_sampler(halton)
     kw = dict(integrator=A.INTEGRATOR_PATH, max_depth=MAX_DEPTH, rr_threshold=RR_THRESHOLD)
 
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    # one explicit stream carries the render launches, the NCCL reduce and the timing events
-    stream = torch.cuda.Stream(dev)
+    stream = torch.cuda.Stream(dev)  # carries the render launches, the reduce and the timing events
     torch.cuda.synchronize(dev)
+    spp_step = SPP_PER_STEP * world  # weak scaling: every rank renders SPP_PER_STEP samples per pixel per step
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def sample_range(step):
-        # consecutive slices of the 1024-spp job; ranks take disjoint sub-ranges of each slice
-        base = (step * world + rank) * SPP_PER_STEP
-        base %= max(SPP_TOTAL - SPP_PER_STEP, 1)
-        return base, base + SPP_PER_STEP
+        # consecutive slices of the 1024-spp job; the library splits each slice into one disjoint sub-range per rank
+        base = (step * spp_step) % max(SPP_TOTAL - spp_step + 1, 1)
+        return base, base + spp_step
 
     def step_device(step, flags=0, want_stats=False):
         s0, s1 = sample_range(step)
-        st = scene.render_device(accum.data_ptr(), stream=stream.cuda_stream, s0=s0, s1=s1, flags=flags,
-                                 want_stats=want_stats, **kw)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-        return st
+        return scene.render_device(accum.data_ptr(), stream=stream.cuda_stream, s0=s0, s1=s1, flags=flags,
+                                   want_stats=want_stats, **kw)
 
     # ---- warm-up ----
     for i in range(args.warmup):
         step_device(i)
     barrier()
 
-    # ---- timed region: exactly K steps, device-resident ----
+    # ---- timed region: exactly K steps, film resident in HBM (reduce to rank 0 included at N > 1) ----
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -234,16 +278,12 @@ def run_gpu(args):
         step_device(args.warmup + i)
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms_max = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    samples_per_step = W * H * SPP_PER_STEP * world
+    samples_per_step = W * H * spp_step
     value = samples_per_step * args.steps / (ms_max * 1e-3) / 1e6
 
-    # ---- per-kernel timeline + counters (separate passes, same steps; not part of `value`) ----
+    # ---- per-kernel timeline + counters (separate passes over the same steps; not part of `value`) ----
     barrier()
     tsum = dict(closest=0.0, shade=0.0, shadow=0.0, mis=0.0, raygen=0.0, film=0.0, total=0.0, n_closest=0,
                 rays_closest=0, rays_shadow=0, rays_path=0)
@@ -260,30 +300,82 @@ def run_gpu(args):
     nodes_per_ray = stc.nodes_visited / max(rays_c, 1)
     tris_per_ray = stc.tris_tested / max(rays_c, 1)
 
-    # ---- e2e: host-buffer C-ABI call, wall clock, H2D descriptors + D2H image inside the timed region ----
+    # ---- e2e: the host-buffer C-ABI call (what Integrator::Render makes): descriptors H2D, at N > 1 the NCCL reduce, the
+    #      image D2H on rank 0; wall clock, max over ranks ----
+    def e2e_leg(host_film):
+        for i in range(2):
+            s0, s1 = sample_range(i)
+            scene.render(s0=s0, s1=s1, out=host_film, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            s0, s1 = sample_range(args.warmup + i)
+            scene.render(s0=s0, s1=s1, out=host_film, **kw)
+        torch.cuda.synchronize(dev)
+        return samples_per_step * args.steps / max_over_ranks(time.perf_counter() - t0) / 1e6
+
     barrier()
     # the application's frame buffer: allocated once, reused; page-locked so that the image leaves the GPU in one DMA
-    host_film = torch.zeros((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()
-    for i in range(2):
-        s0, s1 = sample_range(i)
-        scene.render(s0=s0, s1=s1, out=host_film, **kw)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        s0, s1 = sample_range(args.warmup + i)
-        rgb, _, _ = scene.render(s0=s0, s1=s1, out=host_film, **kw)
-    torch.cuda.synchronize(dev)
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = samples_per_step * args.steps / float(te.item()) / 1e6
-    import ctypes as C
+    e2e_value = e2e_leg(torch.zeros((H, W, 3), dtype=torch.float32, pin_memory=True).numpy())
+    # the same with a pageable film (a std::vector / numpy array, what host/GpuIntegrator.h passes)
+    e2e_pageable = e2e_leg(np.zeros((H, W, 3), dtype=np.float32))
     h2d = C.sizeof(A.RenderDesc) + C.sizeof(A.Stats)
     d2h = W * H * 3 * 4 + C.sizeof(A.Stats)
 
+    # ---- multi-GPU check: the reduced film of N ranks == rank 0 rendering the same sample range alone ----
+    multi_gpu_check = None
+    if world > 1:
+        barrier()
+        s0, s1 = 0, 4 * world
+        scene.render_device(accum.data_ptr(), stream=stream.cuda_stream, s0=s0, s1=s1, want_stats=False, **kw)
+        barrier()
+        if rank == 0:
+            alone = torch.zeros_like(accum)
+            scene.render_device(alone.data_ptr(), stream=stream.cuda_stream, s0=s0, s1=s1, flags=A.RENDER_LOCAL_ONLY,
+                                want_stats=False, **kw)
+            torch.cuda.synchronize(dev)
+            den = alone[..., :3].abs().amax(dim=-1).clamp_min(1e-3)
+            rel = ((accum[..., :3] - alone[..., :3]).abs().amax(dim=-1) / den).max().item()
+            multi_gpu_check = {"max_rel_err": rel, "samples_equal": bool(torch.equal(accum[..., 3], alone[..., 3])),
+                               "sample_range": [s0, s1], "tolerance": 2e-6, "ok": bool(rel <= 2e-6)}
+        barrier()
+
+    # ---- strong scaling record: the WHOLE config job (1024 spp) as ONE host-buffer call at N ranks: sharding, render,
+    #      NCCL reduce, film resolve (tone map) and D2H of both images included; wall clock, max over ranks ----
+    barrier()
+    host_rgb = np.zeros((H, W, 3), dtype=np.float32)
+    t0 = time.perf_counter()
+    scene.render(s0=0, s1=SPP_TOTAL, out=host_rgb, want_rgba8=True, **kw)
+    torch.cuda.synchronize(dev)
+    strong_s = max_over_ranks(time.perf_counter() - t0)
+    strong = {"job": f"{SPP_TOTAL} spp of the {W}x{H} frame in one pbrgpu_render call", "seconds": strong_s, "n_gpus": world,
+              "msamples_per_s": W * H * SPP_TOTAL / strong_s / 1e6,
+              "includes": "sample sharding, render, ncclReduce to rank 0, film resolve + 8-bit tone map, D2H of both images"}
+
+    # ---- Sobol' sampler, config 2 as written (N = 1 extras; parity unpinned: the reference has no Sobol sampler) ----
+    sobol_msamples = None
+    if world == 1:
+        tp = os.path.join(ROOT, "tests", "golden", "sobol_tables_1080p.npz")
+        if os.path.exists(tp):
+            t = np.load(tp)
+            scene.set_sampler(api.SobolSampler(SPP_TOTAL, (0, 0, W, H), t["matrices32"], t["vdc"], t["vdc_inv"]))
+            for i in range(2):
+                step_device(i)
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            for i in range(args.steps):
+                step_device(args.warmup + i)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            sobol_msamples = samples_per_step * args.steps / (e0.elapsed_time(e1) * 1e-3) / 1e6
+            scene.set_sampler(halton)
+
     if rank == 0:
         info = scene.info()
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        # measured L2-resident and HBM read bandwidth of this GPU (traversal is bounded by the L2, not by HBM)
+        l2_peak = ctx.read_bandwidth(48 << 20, 40)
+        hbm_read = ctx.read_bandwidth(4 << 30, 1)
         # roofline of the dominant kernel (k_trace: path + shadow + MIS rays of a bounce): algorithmic bytes per ray
         #   B_ray = 32 (ray record) + 16 (hit record) + nodes/ray * S_node + tris/ray * S_tri   
         S_NODE, S_TRI = 80, 48
@@ -292,38 +384,71 @@ def run_gpu(args):
         avg_ms = tsum["closest"] / max(tsum["n_closest"], 1)
         achieved = rays_per_launch * b_ray / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         peak, peak_src = _peaks()
-        # DRAM traffic of the same kernel from the committed ncu --set full capture (per ray, scaled to the mean launch)
+        trace_rays_per_s = rays_per_launch / (avg_ms * 1e-3) if avg_ms > 0 else 0.0
+        # instruction / DRAM counters per ray of the same kernel on the same workload: scripts/ncu_counters.py writes them
+        # from a fresh `ncu` pass of THIS code (the file records the commit it was captured at); times are live
+        ctrs = _load_json("r02_k_trace_counters.json")
+        issue = None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_k_trace_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = float(json.load(f)["dram_bytes_per_ray"]) * rays_per_launch
+        dram = None
+        if ctrs:
+            sm_hz = (clk["sm_mhz"] if clk and clk.get("sm_mhz") else 1965.0) * 1e6
+            warp_inst_s = ctrs["warp_inst_per_ray"] * trace_rays_per_s
+            slot_util = warp_inst_s / (sm_hz * sm_count * 4)  # 4 schedulers per SM, one warp instruction per cycle each
+            lanes = ctrs["thread_inst_per_ray"] / ctrs["warp_inst_per_ray"]
+            issue = {"issue_slot_util": slot_util, "lanes_per_inst": lanes, "thread_inst_frac_of_peak": slot_util * lanes / 32,
+                     "warp_inst_per_ray": ctrs["warp_inst_per_ray"], "thread_inst_per_ray": ctrs["thread_inst_per_ray"],
+                     "sm_mhz": sm_hz / 1e6, "source": "instructions per ray: profiles/r02_k_trace_counters.json (ncu, commit "
+                     + str(ctrs.get("commit")) + "); rays/s: this run"}
+            traffic = ctrs["dram_bytes_per_ray"] * rays_per_launch
+            dram_gbs = ctrs["dram_bytes_per_ray"] * trace_rays_per_s / 1e9
+            dram = {"achieved_gbs": dram_gbs, "peak_gbs": peak, "frac": dram_gbs / peak}
+        l2_gbs = (nodes_per_ray * S_NODE + tris_per_ray * S_TRI) * trace_rays_per_s / 1e9
         rays_total = tsum["rays_closest"] + tsum["rays_shadow"]
         launches_per_step = int(stc.kernel_launches)
         cpu = cpu_reference_steps(data, 4, 1, budget_s=25.0) if world == 1 and not args.no_cpu else None
+        shipped = cpu_as_shipped(data) if world == 1 and not args.no_cpu else None
+        mrays = rays_total / max(tsum["total"], 1e-9) / 1e3 * world
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sampler": "Halton", "max_depth": MAX_DEPTH, "resolution": [W, H],
-                       "spp_per_step_per_gpu": SPP_PER_STEP, "spp_job": SPP_TOTAL, "sharding": f"sample-range x{world}",
-                       "l2_policy": "working set per step (wave state 7.5 GB + 54 MB scene) exceeds the 126 MB L2; no explicit flush"},
-            "mrays_per_s": rays_total / max(tsum["total"], 1e-9) / 1e3 * world,
+            "config": config_dict(),
+            "run": {"spp_per_step_per_gpu": SPP_PER_STEP,
+                    "sharding": f"sample-range x{world} inside pbrgpu_render_device (pbrgpu_comm_attach) + ncclReduce to rank 0"},
+            "mrays_per_s": mrays,
+            "rays_per_s_per_sm": mrays * 1e6 / (sm_count * world),
             "rays_per_sample": rays_total / (W * H * SPP_PER_STEP * args.steps),
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "includes_reduce": world > 1},
+            "e2e_pageable": {"value": e2e_pageable, "unit": "Msamples/s",
+                             "note": "same call with a pageable host film (what host/GpuIntegrator.h passes): staged through pinned chunks"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "issue", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "issue": issue,
+                         "l2": {"achieved_gbs": l2_gbs, "peak_gbs": l2_peak, "frac": l2_gbs / l2_peak if l2_peak else None,
+                                "peak_source": "measured in this run: 48 MB buffer re-read 40x with 16-byte ld.global.cg"},
+                         "dram": dram, "hbm_read_gbs_measured": hbm_read,
                          "bytes_per_ray": b_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_ms,
-                         "note": "k_trace serves path + shadow + MIS rays of one bounce in one launch; the scene (12 MB compressed 8-wide nodes + 42 MB triangles) is L2-resident, so the algorithmic node/triangle bytes are served by L1/L2 (measured DRAM traffic is ~95 B/ray, profiles/r01_k_trace_traffic.json); ncu shows the kernel issue-slot bound (0.73 issue/cycle/SMSP, 17 of 32 lanes per instruction), not bandwidth bound"},
+                         "note": "achieved/peak/frac: algorithmic bytes per ray (SURVEY 8(d)) x rays/s against the HBM peak, as the contract asks - but the kernel is NOT HBM bound: the scene (8.5 MB of 8-wide nodes + 42 MB of triangles) is L2-resident, DRAM carries only the ray / hit records, and ncu shows the issue slots as the limiter.  `issue` = warp instructions issued per scheduler cycle and the active lanes per instruction; `l2` = node + triangle bytes per second against the L2 bandwidth measured in this run; `dram` = measured DRAM bytes per ray x rays/s against the HBM peak."},
             "kernel_ms_per_step": {k: tsum[k] / args.steps for k in ("raygen", "closest", "shade", "mis", "film", "total")},
             "bvh": info,
+            "scene_build_s": scene_build_s,
+            "strong": strong,
         }
+        if sobol_msamples is not None:
+            line["sobol_msamples_per_s"] = sobol_msamples
+        if multi_gpu_check is not None:
+            line["multi_gpu_check"] = multi_gpu_check
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["mrays_per_s"] = cpu["mrays_per_s"]
+            line["cpu_baseline"]["bvh_build_s"] = cpu["bvh_build_s"]
+        if shipped is not None:
+            line["cpu_baseline_as_shipped"] = shipped
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-typedef struct pbrgpu_ctx pbrgpu_ctx;     /* one CUDA device + stream */
+typedef struct pbrgpu_ctx pbrgpu_ctx;     /* one CUDA device + stream, or a group of them (pbrgpu_init_multi) */
 typedef struct pbrgpu_scene pbrgpu_scene; /* flattened Scene + Camera + Sampler resident in HBM */
 
 /* ---- materials: Material/{MatteMaterial,Mirror,GlassMaterial,MetalMaterial,PlasticMaterial}.cpp ---- */
@@ -200,7 +200,8 @@ typedef struct pbrgpu_render_desc {
 enum {
   PBRGPU_RENDER_ACCUMULATE = 1, /* add into the output sums instead of overwriting */
   PBRGPU_RENDER_COUNTERS = 2,   /* count nodes visited / triangles tested (slower) */
-  PBRGPU_RENDER_TIMERS = 4      /* CUDA events around every kernel group -> pbrgpu_stats.ms_* */
+  PBRGPU_RENDER_TIMERS = 4,     /* CUDA events around every kernel group -> pbrgpu_stats.ms_* */
+  PBRGPU_RENDER_LOCAL_ONLY = 8  /* multi-GPU context: do NOT shard / reduce - this device renders [s0,s1) alone (parity checks) */
 };
 
 typedef struct pbrgpu_stats {
@@ -227,6 +228,22 @@ int pbrgpu_init(int device_id, pbrgpu_ctx** out);
 void pbrgpu_shutdown(pbrgpu_ctx* ctx);
 const char* pbrgpu_last_error(void);
 int pbrgpu_device_count(void);
+
+/* ---- multi-GPU: scene replicated per GPU, the sample range [s0,s1) of a render sharded across the GPUs,
+ *      ONE ncclReduce(sum, fp32, root 0) of the RGBA sum films over NVLink, film resolve on the root.  The application still
+ *      makes the single call Integrator::Render -> pbrgpu_render (Integrator/Integrator.h:14, Main/main.cpp:413). ----
+ * (a) one process, N devices: a GROUP context.  device_ids == NULL: devices 0..n_devices-1; n_devices <= 0: all devices.
+ *     Every entry point that takes this context / its scenes behaves as on one GPU; pbrgpu_render(_device) shards.
+ *     With pbrgpu_render_device the accumulator lives on the FIRST device of the group. */
+int pbrgpu_init_multi(int n_devices, const int* device_ids, pbrgpu_ctx** out);
+/* (b) one process per GPU (torchrun, MPI): rank 0 obtains a 128-byte id, the launcher broadcasts it, every rank attaches its
+ *     ordinary single-device context.  Afterwards every rank calls pbrgpu_render(_device) with the SAME arguments: each renders
+ *     its share of [s0,s1), the films are reduced to rank 0, and only rank 0's output buffers are written (the other ranks may
+ *     pass NULL).  PBRGPU_RENDER_ACCUMULATE is honoured on rank 0's accumulator. */
+int pbrgpu_comm_unique_id(void* out128);
+int pbrgpu_comm_attach(pbrgpu_ctx* ctx, int nranks, int rank, const void* unique_id128);
+/* out[0] = devices driven by this context, out[1] = rank, out[2] = nranks, out[3] = NCCL version code (0 = NCCL not in use) */
+int pbrgpu_ctx_info(pbrgpu_ctx* ctx, int32_t out[4]);
 
 int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* desc, pbrgpu_scene** out);
 void pbrgpu_scene_destroy(pbrgpu_scene* scene);
@@ -303,6 +320,14 @@ int pbrgpu_load_3d(const char* path, float scale, float** out_verts, int32_t* ou
  * texels are bit-identical to stb's.  Non-zero on error (2 = cannot open, 3 = not a Radiance RGBE file, 5 = truncated). */
 int pbrgpu_load_hdr(const char* path, int flip_vertically, float** out_rgb, int32_t* out_width, int32_t* out_height);
 void pbrgpu_free(void* p);
+
+/* Host-only helper: the sample sub-range rank `rank` of `world` renders for [s0,s1) (contiguous, balanced; what
+ * pbrgpu_render applies on a multi-GPU context). */
+int pbrgpu_shard_samples(int64_t s0, int64_t s1, int rank, int world, int64_t out2[2]);
+/* Measurement helper (bench.py): read bandwidth in GB/s of a `bytes`-sized device buffer re-read `iters` times
+ * with 16-byte loads that bypass the L1.  bytes << L2 size (e.g. 48 MB on B200's 126 MB): L2 -> SM bandwidth, the bound of
+ * the traversal kernel's node / triangle fetches; bytes >> L2: HBM read bandwidth. */
+int pbrgpu_measure_read_bandwidth(pbrgpu_ctx* ctx, size_t bytes, int iters, double* out_gb_per_s);
 
 /* BVH statistics: out[0]=n_nodes, out[1]=n_leaves, out[2]=max_leaf_size, out[3]=bytes_nodes, out[4]=bytes_tris */
 int pbrgpu_scene_info(pbrgpu_scene* scene, int64_t out[8]);

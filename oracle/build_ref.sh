@@ -72,6 +72,13 @@ cat srcs.txt | xargs -P "$JOBS" -I{} sh -c 'o=obj/$(echo {} | tr "/" "_").o; g++
 # harness (ours) - compiled against the staged reference headers and our C-ABI header
 PKG="$HERE/../pysicalbasedraytracer_b200"
 g++ $CXXFLAGS -I"$HERE/../include" -I"$PKG/host" -c "$HERE/ref_harness.cpp" -o obj/ref_harness.o
-# the harness also hosts the C++ drop-in test (GpuPathIntegrator), so it links the product library
-g++ -shared -fopenmp -o "$OUT/libpbr_ref.so" obj/*.o -L"$PKG" -lpbrgpu -Wl,-rpath,'$ORIGIN/../../pysicalbasedraytracer_b200'
+# libpbr_ref.so = the reference + the harness: NO product code (the reference arm of bench.py loads only this)
+g++ -shared -fopenmp -o "$OUT/libpbr_ref.so" obj/*.o
 echo "built $OUT/libpbr_ref.so"
+# libdropin_test.so = the C++ drop-in test: the ONLY oracle-side object that links the product library
+if [ -f "$PKG/libpbrgpu.so" ]; then
+  g++ $CXXFLAGS -I"$HERE/../include" -I"$PKG/host" -c "$HERE/dropin_test.cpp" -o dropin_test.o
+  g++ -shared -fopenmp -o "$OUT/libdropin_test.so" dropin_test.o -L"$OUT" -lpbr_ref -L"$PKG" -lpbrgpu \
+      -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../pysicalbasedraytracer_b200'
+  echo "built $OUT/libdropin_test.so"
+fi

@@ -13,9 +13,6 @@
 // It does NOT use SamplerIntegrator::Render for parity dumps (quirk Q1: swapped loop bounds); its own
 // pixel loop iterates x in [x0,x1), y in [y0,y1) and returns linear-float sums.  ref_render_shipped()
 // calls the reference's Render() verbatim (4 threads, square images) for the as-shipped CPU baseline.
-// The C++ drop-in under test (flattener + GpuPathIntegrator); must precede every reference header.
-#include "GpuIntegrator.h"
-#include "SobolSampler.h"  // our CPU twin of the GPU Sobol sampler (the reference has only the tables)
 
 #include <atomic>
 #include <cstdio>
@@ -71,6 +68,7 @@
 #undef private
 #undef protected
 
+#include "SobolSampler.h"  // our CPU twin of the GPU Sobol sampler (the reference has only the tables)
 #include "pbrgpu.h"
 
 namespace PBR {
@@ -739,36 +737,10 @@ void ref_hg_kat(float g, const float* in, int n, float* out) {
   }
 }
 
-// Drop-in test: the reference's OWN object graph (Scene / BVHAccel / GeometricPrimitive / Triangle / Material /
-// Light / PerspectiveCamera / HaltonSampler) rendered through PBR::GpuPathIntegrator::Render, i.e. through the
-// flattener of pysicalbasedraytracer_b200/host/GpuIntegrator.h and the C-ABI of libpbrgpu.so.  Needs a GPU.
-int ref_gpu_dropin_render(void* hscene, void* hc, int integrator, int spp, int W, int H, int max_depth, float rr, const char* strategy,
-                          unsigned char* rgba8, float* rgb_sum, double* seconds) {
-  auto* rs = (RefScene*)hscene;
-  auto* rc = (RefCamera*)hc;
-  Scene raw(rs->bvh, rs->lights);  // the app's Scene: aggregate = BVHAccel (no counting wrapper)
-  Bounds2i b(Point2i(0, 0), Point2i(W, H));
-  std::shared_ptr<Sampler> sampler = std::make_shared<HaltonSampler>(spp, b);
-  FrameBuffer fb;
-  fb.InitBuffer(W, H, 4);
-  std::unique_ptr<GpuSamplerIntegrator> integ;
-  switch (integrator) {
-    case PBRGPU_INTEGRATOR_PATH: integ.reset(new GpuPathIntegrator(max_depth, rc->cam, sampler, b, rr, strategy, &fb)); break;
-    case PBRGPU_INTEGRATOR_VOLPATH: integ.reset(new GpuVolPathIntegrator(max_depth, rc->cam, sampler, b, rr, strategy, &fb)); break;
-    case PBRGPU_INTEGRATOR_WHITTED: integ.reset(new GpuWhittedIntegrator(max_depth, rc->cam, sampler, b, &fb)); break;
-    case PBRGPU_INTEGRATOR_DIRECT_ONE:
-      integ.reset(new GpuDirectLightingIntegrator(LightStrategy::UniformSampleOne, max_depth, rc->cam, sampler, b, &fb)); break;
-    case PBRGPU_INTEGRATOR_DIRECT_ALL:
-      integ.reset(new GpuDirectLightingIntegrator(LightStrategy::UniformSampleAll, max_depth, rc->cam, sampler, b, &fb)); break;
-    default: return 2;
-  }
-  double t = -1;
-  integ->Render(raw, t);
-  if (seconds) *seconds = t;
-  if (t < 0) return 1;
-  if (rgba8) memcpy(rgba8, fb.getUCbuffer(), (size_t)W * H * 4);
-  if (rgb_sum) memcpy(rgb_sum, integ->rgbSum.data(), sizeof(float) * (size_t)W * H * 3);
-  return 0;
-}
+// Accessors for oracle/dropin_test.cpp (the C++ drop-in test lives in its own library, libdropin_test.so, which links the
+// product; this library never does): the application-side objects of a harness scene / camera.
+const void* ref_scene_bvh_shared(void* hscene) { return &((RefScene*)hscene)->bvh; }        // std::shared_ptr<BVHAccel>*
+const void* ref_scene_lights_vector(void* hscene) { return &((RefScene*)hscene)->lights; }  // std::vector<std::shared_ptr<Light>>*
+const void* ref_camera_shared(void* hc) { return &((RefCamera*)hc)->cam; }                  // std::shared_ptr<Camera>*
 
 }  // extern "C"

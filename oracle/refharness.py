@@ -78,8 +78,6 @@ def lib():
         L.ref_sobol_tables.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_render_typed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(A.RenderDesc),
                                        C.c_int, C.c_void_p, C.POINTER(RefRenderStats)]
-        L.ref_gpu_dropin_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                            C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_render_shipped_integrator.restype = C.c_double
         L.ref_render_shipped_integrator.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                                     C.c_void_p, C.POINTER(RefRenderStats)]
@@ -233,13 +231,29 @@ def tonemap(rgb_mean):
     return out
 
 
-def gpu_dropin_render(scene, cam, spp, W, H, max_depth, rr, strategy="uniform", integrator=A.INTEGRATOR_PATH):
-    """The reference's own object graph rendered through the C++ drop-in GpuPathIntegrator (needs a GPU)."""
+_dropin = None
+
+
+def dropin_lib():
+    """oracle/_ref/libdropin_test.so: the C++ drop-in test (the only oracle-side object that links libpbrgpu.so)."""
+    global _dropin
+    if _dropin is None:
+        lib()  # libpbr_ref.so first (libdropin_test.so needs its symbols)
+        D = C.CDLL(os.path.join(os.path.dirname(LIB_PATH), "libdropin_test.so"))
+        D.ref_gpu_dropin_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                            C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        _dropin = D
+    return _dropin
+
+
+def gpu_dropin_render(scene, cam, spp, W, H, max_depth, rr, strategy="uniform", integrator=A.INTEGRATOR_PATH, n_devices=1):
+    """The reference's own object graph rendered through the C++ drop-in GpuPathIntegrator (needs a GPU).
+    n_devices > 1: GpuPathIntegrator::setDevices({0..n-1}) - one process driving several GPUs (pbrgpu_init_multi)."""
     rgba = np.zeros((H, W, 4), dtype=np.uint8)
     rgb_sum = np.zeros((H, W, 3), dtype=np.float32)
     sec = C.c_double(0)
-    rc = lib().ref_gpu_dropin_render(scene.h, cam.h, integrator, spp, W, H, max_depth, rr, strategy.encode(), rgba.ctypes.data,
-                                     rgb_sum.ctypes.data, C.byref(sec))
+    rc = dropin_lib().ref_gpu_dropin_render(scene.h, cam.h, integrator, spp, W, H, max_depth, rr, strategy.encode(), rgba.ctypes.data,
+                                            rgb_sum.ctypes.data, C.byref(sec), n_devices)
     if rc != 0:
         raise RuntimeError("GpuPathIntegrator::Render failed (see stderr)")
     return rgba, rgb_sum, sec.value

@@ -8,7 +8,7 @@ SAMPLER_HALTON, SAMPLER_SOBOL = 0, 1
 INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED, INTEGRATOR_VOLPATH = range(5)
 MEDIUM_HOMOGENEOUS = 0
 LIGHTSTRATEGY_UNIFORM, LIGHTSTRATEGY_POWER = 0, 1
-RENDER_ACCUMULATE, RENDER_COUNTERS, RENDER_TIMERS = 1, 2, 4
+RENDER_ACCUMULATE, RENDER_COUNTERS, RENDER_TIMERS, RENDER_LOCAL_ONLY = 1, 2, 4, 8
 DUMP_SAMPLER, DUMP_PRIMARY_RAYS, DUMP_PRIMARY_HITS, DUMP_PERMS, DUMP_SHADOW, DUMP_HIT_DIFFERENTIALS, DUMP_WAVE_HITS = range(7)
 TRACE_VIA_WAVE_KERNEL = 2
 

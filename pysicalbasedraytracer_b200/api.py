@@ -60,6 +60,12 @@ def lib():
         L.pbrgpu_texture_eval.argtypes = [vp, C.c_int, vp, C.c_int64, vp]
         L.pbrgpu_load_hdr.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.pbrgpu_free.argtypes = [vp]
+        L.pbrgpu_init_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+        L.pbrgpu_comm_unique_id.argtypes = [vp]
+        L.pbrgpu_comm_attach.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.pbrgpu_ctx_info.argtypes = [vp, C.POINTER(C.c_int32)]
+        L.pbrgpu_shard_samples.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.pbrgpu_measure_read_bandwidth.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -117,13 +123,51 @@ def load_hdr(path, flip_vertically=False):
         lib().pbrgpu_free(p)
 
 
-class Context:
-    """One CUDA device + stream (pbrgpu_ctx)."""
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 creates it, the launcher broadcasts it, every rank passes it to Context.attach)."""
+    buf = (C.c_ubyte * 128)()
+    _check(lib().pbrgpu_comm_unique_id(buf))
+    return bytes(buf)
 
-    def __init__(self, device=0):
+
+def shard_samples(s0, s1, rank, world):
+    """The sample sub-range of [s0, s1) that rank `rank` of `world` renders on a multi-GPU context (host-only helper)."""
+    out = (C.c_int64 * 2)()
+    _check(lib().pbrgpu_shard_samples(s0, s1, rank, world, out))
+    return int(out[0]), int(out[1])
+
+
+class Context:
+    """One CUDA device + stream (pbrgpu_ctx), or - `devices` given - a GROUP of devices driven by this process
+    (pbrgpu_init_multi): scenes are replicated, Scene.render shards the sample range and reduces the films with NCCL."""
+
+    def __init__(self, device=0, devices=None):
         self.h = C.c_void_p()
-        _check(lib().pbrgpu_init(device, C.byref(self.h)))
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*devices) if len(devices) else None
+            _check(lib().pbrgpu_init_multi(len(devices), ids, C.byref(self.h)))
+            device = devices[0] if len(devices) else 0
+        else:
+            _check(lib().pbrgpu_init(device, C.byref(self.h)))
         self.device = device
+
+    def attach(self, nranks, rank, unique_id):
+        """One process per GPU: join rank `rank` of `nranks` (pbrgpu_comm_attach).  Afterwards every rank calls Scene.render /
+        render_device with the same arguments; the reduced film arrives on rank 0."""
+        assert len(unique_id) == 128
+        _check(lib().pbrgpu_comm_attach(self.h, nranks, rank, C.c_char_p(unique_id)))
+        return self
+
+    def read_bandwidth(self, nbytes, iters):
+        """GB/s of re-reading an nbytes device buffer `iters` times (L2-resident when nbytes is well below the L2 size)."""
+        out = C.c_double(0)
+        _check(lib().pbrgpu_measure_read_bandwidth(self.h, nbytes, iters, C.byref(out)))
+        return out.value
+
+    def info(self):
+        out = (C.c_int32 * 4)()
+        _check(lib().pbrgpu_ctx_info(self.h, out))
+        return dict(n_devices=out[0], rank=out[1], nranks=out[2], nccl_version=out[3])
 
     def close(self):
         if self.h:

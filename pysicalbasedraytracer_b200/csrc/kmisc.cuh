@@ -481,6 +481,26 @@ __global__ void __launch_bounds__(kBlock) k_trace_user(const __grid_constant__ R
 }
 
 
+// Read bandwidth of a buffer that is re-read `iters` times (pbrgpu_measure_read_bandwidth): with a buffer smaller than the
+// L2 this is the L2 -> SM bandwidth the traversal kernel's node / triangle fetches are bounded by (SURVEY 8(d) regime (i));
+// with a multi-GB buffer it is the HBM read bandwidth.  16-byte loads that bypass the L1 (ld.global.cg), 8 in flight per thread.
+__global__ void __launch_bounds__(256) k_read_bandwidth(const float4* __restrict__ p, size_t n, int iters, float* sink) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; ++it) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n; i += 8 * stride) {
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(p + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+    for (; i < n; i += stride) { const float4 v = __ldcg(p + i); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 123456.789f) *sink = acc.x;  // never true: keeps the loads alive
+}
+
 // ---- parity hooks on the PRODUCTION traversal kernel (k_trace) ----
 // PBRGPU_DUMP_WAVE_HITS: after k_wave_begin -> k_raygen -> k_trace, the hit records of the wave in the layout of
 // PBRGPU_DUMP_PRIMARY_HITS ([pixel][sample][prim, t, b0, b1]).

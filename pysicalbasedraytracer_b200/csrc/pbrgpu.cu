@@ -15,12 +15,14 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include "host_tables.h"
 #include "kmisc.cuh"
 #include "launch.h"
+#include "nccl_dyn.h"
 
 using namespace pbr;
 
@@ -69,6 +71,13 @@ struct pbrgpu_ctx {
   std::vector<cudaEvent_t> pool;  // PBRGPU_RENDER_TIMERS
   size_t l2PersistBytes = 0;      // persisting-L2 carve-out granted by the device (0 = none)
   size_t l2WindowMax = 0;         // cudaDevAttrMaxAccessPolicyWindowSize
+  // ---- multi-GPU (scene replicated, sample range sharded, ONE ncclReduce(sum) of the RGBA film to rank 0) ----
+  // (a) pbrgpu_init_multi: this context is a GROUP - it owns one ordinary context per device and one communicator each
+  std::vector<pbrgpu_ctx*> subs;
+  std::vector<NcclApi::Comm> comms;
+  // (b) pbrgpu_comm_attach: one process per GPU (torchrun / MPI); this ordinary context is rank `rank` of `nranks`
+  NcclApi::Comm comm = nullptr;
+  int nranks = 1, rank = 0;
 };
 
 // CUDA-event timeline: mark(cat) closes the previous interval and opens one of category `cat`.
@@ -160,6 +169,7 @@ struct pbrgpu_scene {
   DevBuf<unsigned char> d8;
   void* hstage = nullptr;
   size_t hstageBytes = 0;
+  std::vector<pbrgpu_scene*> replicas;  // scene of a GROUP context: one ordinary scene per device (this object holds nothing else)
   ~pbrgpu_scene() { if (hstage) cudaFreeHost(hstage); if (hNCur) cudaFreeHost(hNCur); }
 };
 
@@ -324,6 +334,11 @@ int pbrgpu_init(int device_id, pbrgpu_ctx** out) {
 
 void pbrgpu_shutdown(pbrgpu_ctx* c) {
   if (!c) return;
+  if (const NcclApi* api = (c->comm || !c->comms.empty()) ? nccl_api(nullptr) : nullptr) {
+    if (c->comm) api->CommDestroy(c->comm);
+    for (NcclApi::Comm m : c->comms) if (m) api->CommDestroy(m);
+  }
+  for (pbrgpu_ctx* sub : c->subs) pbrgpu_shutdown(sub);
   cudaSetDevice(c->device);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->pool) cudaEventDestroy(ev);
@@ -344,7 +359,7 @@ int64_t pbrgpu_compute_perms(uint16_t* out, int64_t capacity) {
   return (int64_t)p.size();
 }
 
-int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scene** out) {
+static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, const BuiltBvh8* prebuilt, pbrgpu_scene** out) {
   if (!ctx || !d || !out) return fail("pbrgpu_scene_create: NULL argument");
   *out = nullptr;
   if (d->n_tris <= 0 || d->n_verts <= 0 || !d->verts || !d->indices || !d->tri_material)
@@ -371,7 +386,8 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
 
   int maxLeaf = 3;
   if (const char* e = getenv("PBRGPU_MAX_LEAF")) maxLeaf = std::max(1, std::min(3, atoi(e)));
-  build_bvh8(d->verts, d->indices, d->n_tris, maxLeaf, &s->bvh);
+  if (prebuilt) s->bvh = *prebuilt;  // group context: built once, uploaded to every device
+  else build_bvh8(d->verts, d->indices, d->n_tris, maxLeaf, &s->bvh);
   const int nT = d->n_tris;
   s->leafOf.assign((size_t)nT, -1);
   std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT), vN((size_t)nT), vS((size_t)nT), vT((size_t)nT);
@@ -708,11 +724,13 @@ int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scen
 
 void pbrgpu_scene_destroy(pbrgpu_scene* s) {
   if (!s) return;
+  for (pbrgpu_scene* r : s->replicas) pbrgpu_scene_destroy(r);
+  s->replicas.clear();
   cudaSetDevice(s->ctx->device);
   delete s;
 }
 
-int pbrgpu_camera_set(pbrgpu_scene* s, const pbrgpu_camera_desc* c) {
+static int camera_set_single(pbrgpu_scene* s, const pbrgpu_camera_desc* c) {
   if (!s || !c) return fail("pbrgpu_camera_set: NULL argument");
   if (c->type != PBRGPU_CAMERA_PERSPECTIVE && c->type != PBRGPU_CAMERA_ORTHOGRAPHIC) return fail("pbrgpu_camera_set: bad type");
   if (c->width <= 0 || c->height <= 0) return fail("pbrgpu_camera_set: bad resolution");
@@ -727,7 +745,7 @@ int pbrgpu_camera_set(pbrgpu_scene* s, const pbrgpu_camera_desc* c) {
   return 0;
 }
 
-int pbrgpu_sampler_set(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
+static int sampler_set_single(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
   if (!s || !d) return fail("pbrgpu_sampler_set: NULL argument");
   if (d->samples_per_pixel <= 0) return fail("pbrgpu_sampler_set: samples_per_pixel <= 0");
   CK(cudaSetDevice(s->ctx->device));
@@ -804,6 +822,7 @@ int pbrgpu_sampler_set(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
 }
 
 int pbrgpu_texture_eval(pbrgpu_scene* s, int texture, const float* rows, int64_t n, float* out) {
+  if (s && !s->replicas.empty()) s = s->replicas[0];  // group scene: the hooks run on the first device
   if (!s || !rows || !out || n < 0) return fail("pbrgpu_texture_eval: bad argument");
   if (texture < 0 || (size_t)texture >= s->texPyramids.size()) return fail("pbrgpu_texture_eval: texture index out of range");
   if (n == 0) return 0;
@@ -820,6 +839,7 @@ int pbrgpu_texture_eval(pbrgpu_scene* s, int texture, const float* rows, int64_t
 }
 
 int pbrgpu_scene_info(pbrgpu_scene* s, int64_t out[8]) {
+  if (s && !s->replicas.empty()) s = s->replicas[0];  // group scene: the hooks run on the first device
   if (!s || !out) return fail("pbrgpu_scene_info: NULL argument");
   memset(out, 0, sizeof(int64_t) * 8);
   out[0] = (int64_t)s->bvh.nodes.size();
@@ -877,7 +897,7 @@ static int fetch_stats(pbrgpu_scene* s, cudaStream_t st, pbrgpu_stats* stats) {
   return 0;
 }
 
-int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d_rgba_sum, void* stream_, pbrgpu_stats* stats) {
+static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d_rgba_sum, void* stream_, pbrgpu_stats* stats) {
   if (check_render_args(s, rd)) return 1;
   if (!d_rgba_sum) return fail("pbrgpu_render_device: NULL accumulator");
   pbrgpu_ctx* c = s->ctx;
@@ -1078,6 +1098,7 @@ int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d
 int pbrgpu_resolve_film(pbrgpu_ctx* c, const float* d_rgba_sum, int width, int height, float inv_spp, float* out_rgb_mean,
                         unsigned char* out_rgba8) {
   if (!c || !d_rgba_sum || width <= 0 || height <= 0) return fail("pbrgpu_resolve_film: bad argument");
+  if (!c->subs.empty()) c = c->subs[0];  // group context: the film lives on its first device
   CK(cudaSetDevice(c->device));
   size_t n = (size_t)width * height;
   DevBuf<float> drgb;
@@ -1143,33 +1164,331 @@ static int staged_d2h(pbrgpu_scene* s, void* dst, const void* dsrc, size_t bytes
   return 0;
 }
 
-int pbrgpu_render(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* out_rgb_sum, unsigned char* out_rgba8, pbrgpu_stats* stats) {
-  if (check_render_args(s, rd)) return 1;
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU.  Every (pixel, sample index) is independent and addressable in O(1)
+// (HaltonSampler::GetIndexForSample, Sampler/Halton.cpp:61-81), so a render shards by SAMPLE RANGE: the scene is
+// replicated, device g of G renders [s0 + g*n/G, s0 + (g+1)*n/G) of every pixel into a private fp32 RGBA sum film
+// (A = sample count), and ONE ncclReduce(sum, root 0) over NVLink adds the films; rank 0 resolves.  There is no other
+// exchange.  Two ways to get there behind the same pbrgpu_render call:
+//   pbrgpu_init_multi      one process, N devices (what a C++ application does: Main/main.cpp:413 stays one call)
+//   pbrgpu_comm_attach     one process per device (torchrun): every rank calls pbrgpu_render with the same arguments
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+// contiguous, balanced split of [s0, s1): the first (n % world) ranks take one extra sample (== shard.py)
+void shard_samples(int64_t s0, int64_t s1, int rank, int world, int64_t* lo, int64_t* hi) {
+  const int64_t n = s1 - s0, base = n / world, extra = n % world;
+  *lo = s0 + rank * base + std::min<int64_t>(rank, extra);
+  *hi = *lo + base + (rank < extra ? 1 : 0);
+}
+
+int nccl_fail(const NcclApi* api, const char* what, int rc) {
+  return fail(std::string(what) + ": NCCL error " + std::to_string(rc) + " (" + (api->GetErrorString ? api->GetErrorString(rc) : "?") + ")");
+}
+
+void add_stats(pbrgpu_stats* a, const pbrgpu_stats& b) {
+  a->camera_samples += b.camera_samples; a->rays_closest += b.rays_closest; a->rays_shadow += b.rays_shadow;
+  a->nodes_visited += b.nodes_visited; a->tris_tested += b.tris_tested; a->kernel_launches += b.kernel_launches;
+  a->rays_path += b.rays_path; a->n_trace_closest_launches += b.n_trace_closest_launches;
+  a->ms_total = std::max(a->ms_total, b.ms_total);  // the devices run concurrently
+  a->ms_raygen = std::max(a->ms_raygen, b.ms_raygen); a->ms_trace_closest = std::max(a->ms_trace_closest, b.ms_trace_closest);
+  a->ms_shade = std::max(a->ms_shade, b.ms_shade); a->ms_trace_shadow = std::max(a->ms_trace_shadow, b.ms_trace_shadow);
+  a->ms_trace_mis = std::max(a->ms_trace_mis, b.ms_trace_mis); a->ms_film = std::max(a->ms_film, b.ms_film);
+}
+
+// RGBA sum film on the scene's device -> the caller's host buffers (RGB sums and / or the tone-mapped 8-bit image)
+int film_to_host(pbrgpu_scene* s, const float* d_rgba, int W, int H, float* out_rgb_sum, unsigned char* out_rgba8, bool accumulate) {
   pbrgpu_ctx* c = s->ctx;
-  CK(cudaSetDevice(c->device));
-  const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
-  size_t n = (size_t)W * H;
-  if (s->accumPix < n) { CK(s->accum.alloc(n * 4)); s->accumPix = n; }
-  pbrgpu_render_desc r2 = *rd;
-  r2.flags &= ~PBRGPU_RENDER_ACCUMULATE;  // PBRGPU_RENDER_ACCUMULATE on host buffers: the caller's sums are added after the render
-  if (pbrgpu_render_device(s, &r2, s->accum.p, c->stream, nullptr)) return 1;
+  const size_t n = (size_t)W * H;
   if (out_rgb_sum) {
     if (s->drgb.n < n * 3) CK(s->drgb.alloc(n * 3));
-    k_rgba_to_rgb<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)s->accum.p, n, s->drgb.p);
+    k_rgba_to_rgb<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)d_rgba, n, s->drgb.p);
     CK(cudaGetLastError());
-    if (staged_d2h(s, out_rgb_sum, s->drgb.p, n * 3 * sizeof(float), (rd->flags & PBRGPU_RENDER_ACCUMULATE) != 0)) return 1;
+    if (staged_d2h(s, out_rgb_sum, s->drgb.p, n * 3 * sizeof(float), accumulate)) return 1;
   }
   if (out_rgba8) {
     if (s->d8.n < n * 4) CK(s->d8.alloc(n * 4));
-    k_resolve_film<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)s->accum.p, W, H, 0.f, 1, nullptr, s->d8.p);
+    k_resolve_film<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float4*)d_rgba, W, H, 0.f, 1, nullptr, s->d8.p);
     CK(cudaGetLastError());
     if (staged_d2h(s, out_rgba8, s->d8.p, n * 4, false)) return 1;
   }
-  if (stats && fetch_stats(s, c->stream, stats)) return 1;
+  return 0;
+}
+
+// GROUP scene: every replica renders its shard on its own device (one host thread each: the VolPath loop reads counters
+// back, and nothing should serialise the devices), then one grouped ncclReduce into `d_root` on device 0.
+// d_root: the root's film (device 0).  rootStream: the stream the root renders / reduces on.
+int render_group_device(pbrgpu_scene* g, const pbrgpu_render_desc* rd, float* d_root, cudaStream_t rootStream, pbrgpu_stats* stats) {
+  const int N = (int)g->replicas.size();
+  const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
+  const size_t n = (size_t)W * H;
+  std::vector<int> rc((size_t)N, 0);
+  std::vector<std::string> err((size_t)N);
+  std::vector<pbrgpu_stats> st((size_t)N);
+  std::vector<float*> film((size_t)N, nullptr);
+  std::vector<std::thread> th;
+  for (int i = 0; i < N; ++i) {
+    th.emplace_back([&, i] {
+      pbrgpu_scene* r = g->replicas[i];
+      pbrgpu_render_desc r2 = *rd;
+      shard_samples(rd->s0, rd->s1, i, N, &r2.s0, &r2.s1);
+      float* dst = d_root;
+      cudaStream_t stream = rootStream;
+      if (i > 0) {  // private film, never accumulating
+        r2.flags &= ~PBRGPU_RENDER_ACCUMULATE;
+        if (cudaSetDevice(r->ctx->device) != cudaSuccess) { rc[i] = 1; err[i] = "cudaSetDevice failed"; return; }
+        if (r->accumPix < n) {
+          if (r->accum.alloc(n * 4) != cudaSuccess) { rc[i] = 1; err[i] = "out of device memory for the film"; return; }
+          r->accumPix = n;
+        }
+        dst = r->accum.p;
+        stream = r->ctx->stream;
+      }
+      film[i] = dst;
+      rc[i] = render_device_single(r, &r2, dst, stream, stats ? &st[i] : nullptr);
+      if (rc[i]) err[i] = g_err;
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < N; ++i) if (rc[i]) return fail("device " + std::to_string(g->replicas[i]->ctx->device) + ": " + err[i]);
+  if (N > 1) {
+    std::string e;
+    const NcclApi* api = nccl_api(&e);
+    if (!api) return fail(e);
+    int r = api->GroupStart();
+    if (r) return nccl_fail(api, "ncclGroupStart", r);
+    for (int i = 0; i < N; ++i) {
+      r = api->Reduce(film[i], film[0], n * 4, NcclApi::kFloat32, NcclApi::kSum, 0, g->ctx->comms[i], i == 0 ? rootStream : g->replicas[i]->ctx->stream);
+      if (r) { api->GroupEnd(); return nccl_fail(api, "ncclReduce", r); }
+    }
+    r = api->GroupEnd();
+    if (r) return nccl_fail(api, "ncclGroupEnd", r);
+  }
+  CK(cudaSetDevice(g->replicas[0]->ctx->device));
+  if (stats) {
+    *stats = st[0];
+    for (int i = 1; i < N; ++i) add_stats(stats, st[i]);
+  }
+  return 0;
+}
+
+// ATTACHED context (one process per GPU): render this rank's shard, reduce to rank 0.
+int render_rank_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d_film, cudaStream_t st, pbrgpu_stats* stats) {
+  pbrgpu_ctx* c = s->ctx;
+  pbrgpu_render_desc r2 = *rd;
+  shard_samples(rd->s0, rd->s1, c->rank, c->nranks, &r2.s0, &r2.s1);
+  if (c->rank != 0) r2.flags &= ~PBRGPU_RENDER_ACCUMULATE;  // only the root's film carries earlier sums
+  if (render_device_single(s, &r2, d_film, st, stats)) return 1;
+  std::string e;
+  const NcclApi* api = nccl_api(&e);
+  if (!api) return fail(e);
+  const size_t n = (size_t)(rd->x1 - rd->x0) * (rd->y1 - rd->y0);
+  const int r = api->Reduce(d_film, d_film, n * 4, NcclApi::kFloat32, NcclApi::kSum, 0, c->comm, st);
+  if (r) return nccl_fail(api, "ncclReduce", r);
+  return 0;
+}
+
+inline bool is_group(const pbrgpu_scene* s) { return !s->replicas.empty(); }
+inline bool sharded(const pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
+  if (rd->flags & PBRGPU_RENDER_LOCAL_ONLY) return false;
+  return is_group(s) ? s->replicas.size() > 1 : (s->ctx->comm != nullptr && s->ctx->nranks > 1);
+}
+
+}  // namespace
+
+int pbrgpu_render_device(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* d_rgba_sum, void* stream_, pbrgpu_stats* stats) {
+  if (!s) return fail("pbrgpu_render_device: NULL scene");
+  pbrgpu_scene* s0 = is_group(s) ? s->replicas[0] : s;
+  if (check_render_args(s0, rd)) return 1;
+  if (!d_rgba_sum) return fail("pbrgpu_render_device: NULL accumulator");
+  if (!sharded(s, rd)) return render_device_single(s0, rd, d_rgba_sum, stream_, stats);
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : s0->ctx->stream;
+  if (is_group(s)) return render_group_device(s, rd, d_rgba_sum, st, stats);
+  return render_rank_device(s, rd, d_rgba_sum, st, stats);
+}
+
+int pbrgpu_render(pbrgpu_scene* s, const pbrgpu_render_desc* rd, float* out_rgb_sum, unsigned char* out_rgba8, pbrgpu_stats* stats) {
+  if (!s) return fail("pbrgpu_render: NULL scene");
+  pbrgpu_scene* s0 = is_group(s) ? s->replicas[0] : s;  // the scene on the root device
+  if (check_render_args(s0, rd)) return 1;
+  pbrgpu_ctx* c = s0->ctx;
+  CK(cudaSetDevice(c->device));
+  const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
+  size_t n = (size_t)W * H;
+  if (s0->accumPix < n) { CK(s0->accum.alloc(n * 4)); s0->accumPix = n; }
+  pbrgpu_render_desc r2 = *rd;
+  r2.flags &= ~PBRGPU_RENDER_ACCUMULATE;  // PBRGPU_RENDER_ACCUMULATE on host buffers: the caller's sums are added after the render
+  bool root = true;
+  if (!sharded(s, rd)) {
+    if (render_device_single(s0, &r2, s0->accum.p, c->stream, nullptr)) return 1;
+  } else if (is_group(s)) {
+    if (render_group_device(s, &r2, s0->accum.p, c->stream, stats)) return 1;
+  } else {
+    if (render_rank_device(s, &r2, s0->accum.p, c->stream, nullptr)) return 1;
+    root = c->rank == 0;
+  }
+  // the reduced film leaves the GPU on the root only; the other ranks of a process-per-GPU job return once their
+  // shard has been handed to the reduce (their output buffers are not touched and may be NULL)
+  if (root && film_to_host(s0, s0->accum.p, W, H, out_rgb_sum, out_rgba8, (rd->flags & PBRGPU_RENDER_ACCUMULATE) != 0)) return 1;
+  if (!root) CK(cudaStreamSynchronize(c->stream));
+  if (stats && !(is_group(s) && sharded(s, rd)) && fetch_stats(s0, c->stream, stats)) return 1;
+  return 0;
+}
+
+int pbrgpu_scene_create(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, pbrgpu_scene** out) {
+  if (!ctx || !d || !out) return fail("pbrgpu_scene_create: NULL argument");
+  *out = nullptr;
+  if (ctx->subs.empty()) return scene_create_single(ctx, d, nullptr, out);
+  // GROUP context: validate + build on the first device, then replicate with the same BVH on the others (in parallel)
+  std::unique_ptr<pbrgpu_scene> g(new pbrgpu_scene);
+  g->ctx = ctx;
+  const int N = (int)ctx->subs.size();
+  g->replicas.assign((size_t)N, nullptr);
+  auto destroy_all = [&] { for (auto*& r : g->replicas) { if (r) pbrgpu_scene_destroy(r); r = nullptr; } };
+  if (scene_create_single(ctx->subs[0], d, nullptr, &g->replicas[0])) { destroy_all(); g->replicas.clear(); return 1; }
+  std::vector<int> rc((size_t)N, 0);
+  std::vector<std::string> err((size_t)N);
+  std::vector<std::thread> th;
+  for (int i = 1; i < N; ++i)
+    th.emplace_back([&, i] {
+      rc[i] = scene_create_single(ctx->subs[i], d, &g->replicas[0]->bvh, &g->replicas[i]);
+      if (rc[i]) err[i] = g_err;
+    });
+  for (auto& t : th) t.join();
+  for (int i = 1; i < N; ++i)
+    if (rc[i]) { destroy_all(); g->replicas.clear(); return fail("device " + std::to_string(ctx->subs[i]->device) + ": " + err[i]); }
+  CK(cudaSetDevice(ctx->subs[0]->device));
+  *out = g.release();
+  return 0;
+}
+
+int pbrgpu_camera_set(pbrgpu_scene* s, const pbrgpu_camera_desc* c) {
+  if (!s || !c) return fail("pbrgpu_camera_set: NULL argument");
+  if (!is_group(s)) return camera_set_single(s, c);
+  for (pbrgpu_scene* r : s->replicas) if (camera_set_single(r, c)) return 1;
+  return 0;
+}
+
+int pbrgpu_sampler_set(pbrgpu_scene* s, const pbrgpu_sampler_desc* d) {
+  if (!s || !d) return fail("pbrgpu_sampler_set: NULL argument");
+  if (!is_group(s)) return sampler_set_single(s, d);
+  for (pbrgpu_scene* r : s->replicas) if (sampler_set_single(r, d)) return 1;
+  return cudaSetDevice(s->replicas[0]->ctx->device) == cudaSuccess ? 0 : fail("cudaSetDevice failed");
+}
+
+int pbrgpu_init_multi(int n_devices, const int* device_ids, pbrgpu_ctx** out) {
+  if (!out) return fail("pbrgpu_init_multi: out == NULL");
+  *out = nullptr;
+  const int avail = pbrgpu_device_count();
+  if (avail == 0) return fail("pbrgpu_init_multi: no CUDA device available (this library has no CPU fallback)");
+  if (n_devices <= 0) n_devices = avail;  // "all devices"
+  if (n_devices > avail && !device_ids) return fail("pbrgpu_init_multi: more devices requested than present");
+  std::vector<int> ids((size_t)n_devices);
+  for (int i = 0; i < n_devices; ++i) {
+    ids[i] = device_ids ? device_ids[i] : i;
+    if (ids[i] < 0 || ids[i] >= avail) return fail("pbrgpu_init_multi: bad device id");
+    for (int j = 0; j < i; ++j) if (ids[j] == ids[i]) return fail("pbrgpu_init_multi: duplicate device id");
+  }
+  std::unique_ptr<pbrgpu_ctx> g(new pbrgpu_ctx);
+  auto cleanup = [&] { for (pbrgpu_ctx* c : g->subs) pbrgpu_shutdown(c); g->subs.clear(); };
+  for (int i = 0; i < n_devices; ++i) {
+    pbrgpu_ctx* c = nullptr;
+    if (pbrgpu_init(ids[i], &c)) { cleanup(); return 1; }
+    g->subs.push_back(c);
+  }
+  g->device = ids[0];
+  g->smCount = g->subs[0]->smCount;
+  if (n_devices > 1) {
+    std::string e;
+    const NcclApi* api = nccl_api(&e);
+    if (!api) { cleanup(); return fail("pbrgpu_init_multi: " + e); }
+    g->comms.assign((size_t)n_devices, nullptr);
+    const int r = api->CommInitAll(g->comms.data(), n_devices, ids.data());
+    if (r) { g->comms.clear(); cleanup(); return nccl_fail(api, "ncclCommInitAll", r); }
+  }
+  cudaSetDevice(ids[0]);
+  *out = g.release();
+  return 0;
+}
+
+int pbrgpu_comm_unique_id(void* out128) {
+  if (!out128) return fail("pbrgpu_comm_unique_id: NULL argument");
+  std::string e;
+  const NcclApi* api = nccl_api(&e);
+  if (!api) return fail("pbrgpu_comm_unique_id: " + e);
+  NcclApi::UniqueId id;
+  const int r = api->GetUniqueId(&id);
+  if (r) return nccl_fail(api, "ncclGetUniqueId", r);
+  memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+
+int pbrgpu_comm_attach(pbrgpu_ctx* c, int nranks, int rank, const void* unique_id128) {
+  if (!c || !unique_id128) return fail("pbrgpu_comm_attach: NULL argument");
+  if (!c->subs.empty()) return fail("pbrgpu_comm_attach: a pbrgpu_init_multi context already owns its devices");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("pbrgpu_comm_attach: bad rank / nranks");
+  if (c->comm) return fail("pbrgpu_comm_attach: already attached");
+  std::string e;
+  const NcclApi* api = nccl_api(&e);
+  if (!api) return fail("pbrgpu_comm_attach: " + e);
+  CK(cudaSetDevice(c->device));
+  NcclApi::UniqueId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  const int r = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (r) { c->comm = nullptr; return nccl_fail(api, "ncclCommInitRank", r); }
+  c->nranks = nranks;
+  c->rank = rank;
+  return 0;
+}
+
+int pbrgpu_shard_samples(int64_t s0, int64_t s1, int rank, int world, int64_t out2[2]) {
+  if (!out2 || world < 1 || rank < 0 || rank >= world || s1 < s0) return fail("pbrgpu_shard_samples: bad argument");
+  shard_samples(s0, s1, rank, world, &out2[0], &out2[1]);
+  return 0;
+}
+
+int pbrgpu_measure_read_bandwidth(pbrgpu_ctx* c, size_t bytes, int iters, double* out_gb_per_s) {
+  if (!c || !out_gb_per_s || bytes < (1u << 20) || iters < 1) return fail("pbrgpu_measure_read_bandwidth: bad argument");
+  if (!c->subs.empty()) c = c->subs[0];
+  CK(cudaSetDevice(c->device));
+  DevBuf<float4> buf;
+  DevBuf<float> sink;
+  const size_t n = bytes / sizeof(float4);
+  CK(buf.alloc(n));
+  CK(sink.alloc(1));
+  CK(cudaMemsetAsync(buf.p, 0, n * sizeof(float4), c->stream));
+  const unsigned grid = (unsigned)c->smCount * 8;
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms the L2 (and the clocks)
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    k_read_bandwidth<<<grid, 256, 0, c->stream>>>(buf.p, n, iters, sink.p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    CK(cudaEventSynchronize(c->ev[6]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]));
+    if (rep > 0 && ms > 0) best = std::max(best, (double)n * sizeof(float4) * iters / (ms * 1e-3) / 1e9);
+  }
+  *out_gb_per_s = best;
+  return 0;
+}
+
+int pbrgpu_ctx_info(pbrgpu_ctx* c, int32_t out[4]) {
+  if (!c || !out) return fail("pbrgpu_ctx_info: NULL argument");
+  out[0] = c->subs.empty() ? 1 : (int32_t)c->subs.size();
+  out[1] = c->rank;
+  out[2] = c->nranks;
+  out[3] = 0;
+  if (!c->subs.empty() || c->comm) {
+    const NcclApi* api = nccl_api(nullptr);
+    int v = 0;
+    if (api && api->GetVersion && api->GetVersion(&v) == 0) out[3] = v;
+  }
   return 0;
 }
 
 int pbrgpu_debug_dump(pbrgpu_scene* s, const pbrgpu_dump_desc* dd, void* out, size_t out_bytes) {
+  if (s && !s->replicas.empty()) s = s->replicas[0];  // group scene: the hooks run on the first device
   if (!s || !dd || !out) return fail("pbrgpu_debug_dump: NULL argument");
   pbrgpu_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));
@@ -1251,6 +1570,7 @@ int pbrgpu_debug_dump(pbrgpu_scene* s, const pbrgpu_dump_desc* dd, void* out, si
 }
 
 int pbrgpu_trace_rays(pbrgpu_scene* s, const float* rays, int64_t n, int any_hit, void* out_hits) {
+  if (s && !s->replicas.empty()) s = s->replicas[0];  // group scene: the hooks run on the first device
   if (!s || !rays || !out_hits || n <= 0) return fail("pbrgpu_trace_rays: bad argument");
   pbrgpu_ctx* c = s->ctx;
   CK(cudaSetDevice(c->device));

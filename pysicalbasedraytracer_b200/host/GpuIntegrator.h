@@ -337,7 +337,10 @@ class GpuSamplerIntegrator : public Integrator {
   void Render(const Scene& scene, double& timeConsume) override {
     auto t0 = std::chrono::steady_clock::now();
     timeConsume = -1;
-    if (!ctx && pbrgpu_init(device, &ctx)) return fail("pbrgpu_init");
+    if (!ctx) {  // one GPU (pbrgpu_init) or a group of GPUs driven by this process (pbrgpu_init_multi)
+      if (devices.size() > 1 ? pbrgpu_init_multi((int)devices.size(), devices.data(), &ctx) : pbrgpu_init(devices.empty() ? device : devices[0], &ctx))
+        return fail("pbrgpu_init");
+    }
     if (!gscene || flattenedScene != &scene) {  // flatten once per Scene object
       if (gscene) { pbrgpu_scene_destroy(gscene); gscene = nullptr; }
       gpu_detail::Flat f;
@@ -433,6 +436,11 @@ class GpuSamplerIntegrator : public Integrator {
   pbrgpu_stats stats{};
   std::vector<float> rgbSum;  // linear per-pixel SUM of Li over the samples (the reference's colObj before /= spp)
 
+  // Multi-GPU: call before the first Render().  The scene is replicated on these devices, every Render()
+  // shards the samples of each pixel across them and sums the per-GPU films with one ncclReduce; the application still makes
+  // the single Integrator::Render call of Main/main.cpp:413.
+  void setDevices(const std::vector<int>& ids) { devices = ids; }
+
  protected:
   virtual void fillRenderDesc(pbrgpu_render_desc* rd) const = 0;
   void fail(const char* what) { std::cerr << "GpuIntegrator: " << what << " failed: " << pbrgpu_last_error() << std::endl; }
@@ -441,6 +449,7 @@ class GpuSamplerIntegrator : public Integrator {
   const Bounds2i pixelBounds;
   FrameBuffer* m_FrameBuffer;
   int device;
+  std::vector<int> devices;  // setDevices(): more than one -> pbrgpu_init_multi
   pbrgpu_ctx* ctx = nullptr;
   pbrgpu_scene* gscene = nullptr;
   const Scene* flattenedScene = nullptr;

@@ -4,18 +4,18 @@ addressable in O(1): HaltonSampler::GetIndexForSample, Sampler/Halton.cpp:61-81)
 a private fp32 RGBA *sum* film (A = sample count) and the films are summed by ONE reduce to rank 0.
 There is no other data-path exchange: path tracing has no cross-sample dependency.
 
-Plumbing only (torch.distributed: NCCL on GPUs, gloo in the CPU tests); no rendering happens here."""
+On the GPUs all of this happens INSIDE the C-ABI (pbrgpu_init_multi / pbrgpu_comm_attach: sharding + ncclReduce + resolve,
+csrc/pbrgpu.cu); this module is the host-side twin used by launchers that keep the films in torch tensors (film.py) and by
+the world_size-2 gloo tests that cover the N > 1 logic on CPU.  Plumbing only; no rendering happens here."""
 import torch
 import torch.distributed as dist
 
 
 def shard_samples(s0, s1, rank, world):
-    """Contiguous, balanced split of [s0, s1): the first (n % world) ranks get one extra sample."""
-    n = s1 - s0
-    base, extra = divmod(n, world)
-    lo = s0 + rank * base + min(rank, extra)
-    hi = lo + base + (1 if rank < extra else 0)
-    return lo, hi
+    """Contiguous, balanced split of [s0, s1): the first (n % world) ranks get one extra sample.  This IS the split the
+    library applies inside pbrgpu_render on a multi-GPU context (pbrgpu_shard_samples, csrc/pbrgpu.cu): one definition."""
+    from . import api
+    return api.shard_samples(s0, s1, rank, world)
 
 
 def reduce_film(accum, dst=0, group=None):

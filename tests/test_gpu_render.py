@@ -15,6 +15,19 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-3
 
 
+def assert_diverged_is_discrete(err, frac_ok=0.999):
+    """The mismatch budget of north_star is a COUNTED fraction of paths that took a different discrete decision (a tie /
+    float-epsilon hit, a light pick or Russian-roulette outcome flipped by a libm ulp), not drift.  Observed on B200: 0 - 2
+    pixels per image (>= 0.9995).  Count them, and require every pixel that does not diverge to sit far inside the
+    tolerance: drift would fill the band just below 1e-3, a flipped decision does not."""
+    n_div = int((err > REL_TOL).sum())
+    budget = max(2, int(np.ceil((1 - frac_ok) * err.size)))
+    near = int(((err > 0.2 * REL_TOL) & (err <= REL_TOL)).sum())
+    print(f"  diverged pixels {n_div} of {err.size} (budget {budget}); within tolerance but above 2e-4: {near}")
+    assert n_div <= budget
+    assert near <= max(4, int(0.005 * err.size)), "errors pile up just below the tolerance: drift, not discrete divergence"
+
+
 def _direct_check(p, ref, max_depth, spp, frac_ok=0.999, integrator=A.INTEGRATOR_PATH, **kw):
     want, rst = ref.render(p.rscene, p.rcam, p.spp, (0, 0, p.W, p.H), integrator=integrator,
                            max_depth=max_depth, s1=spp, sampler_type=p.sampler_type, **kw)
@@ -24,6 +37,7 @@ def _direct_check(p, ref, max_depth, spp, frac_ok=0.999, integrator=A.INTEGRATOR
     print(f"depth {max_depth}: pixels within {REL_TOL}: {ok:.5f}, median err {np.median(err):.2e}, "
           f"rays gpu {st.rays_closest}+{st.rays_shadow} ref {rst.rays_closest}+{rst.rays_shadow}")
     assert ok >= frac_ok
+    assert_diverged_is_discrete(err, frac_ok)
     # ray counts identical up to diverged paths
     assert abs(int(st.rays_closest) - int(rst.rays_closest)) <= 1e-3 * rst.rays_closest + 8
     assert abs(int(st.rays_shadow) - int(rst.rays_shadow)) <= 1e-3 * rst.rays_shadow + 8
@@ -45,7 +59,7 @@ def test_cornell_path_matched_samples_mostly_agree(api, ref, gpu_ctx):
     # full paths: libm ulps after the first diffuse bounce can flip a discrete decision (light pick,
     # RR) on a few paths, so only a high fraction of pixels is required to agree at 1e-3.
     p = Pair(api, ref, scenes.cornell(sphere_tess=24), 96, 96, 2)
-    _direct_check(p, ref, max_depth=5, spp=2, frac_ok=0.97, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=5, spp=2, rr_threshold=0.8)
 
 
 def test_point_light_and_power_strategy(api, ref, gpu_ctx):
@@ -60,15 +74,15 @@ def test_materials_under_infinite_light(api, ref, gpu_ctx):
     env = scenes.procedural_env(128, 64)
     data = scenes.bsdf_stress(sphere_tess=12, env=env)
     p = Pair(api, ref, data, 96, 64, 2, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
-    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.995)
-    _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.93)
+    _direct_check(p, ref, max_depth=1, spp=2)
+    _direct_check(p, ref, max_depth=4, spp=2)
 
 
 def test_materials_under_skybox(api, ref, gpu_ctx):
     env = scenes.procedural_env(128, 64, sun=50.0)
     data = scenes.bsdf_stress(sphere_tess=12, env=env, skybox=True)
     p = Pair(api, ref, data, 96, 64, 2, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
-    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.995)
+    _direct_check(p, ref, max_depth=1, spp=2)
 
 
 def test_path_rmse_vs_reference_high_spp(api, ref, gpu_ctx):
@@ -123,10 +137,10 @@ def test_cpp_dropin_integrator_matches_reference_render(api, ref, gpu_ctx):
     assert (diff <= 1).mean() >= 0.995
     assert rgba[..., 3].min() == 255
     want_lin, _ = ref.render(rsc, rc, 4, (0, 0, 64, 64), integrator=A.INTEGRATOR_PATH, max_depth=5, rr_threshold=0.8)
-    assert (rel_err(rgb_sum / 4, want_lin / 4) <= REL_TOL).mean() >= 0.97
+    assert (rel_err(rgb_sum / 4, want_lin / 4) <= REL_TOL).mean() >= 0.999
 
 
-@pytest.mark.parametrize("fixture,depth,frac", [("cornell64_direct.npz", 1, 0.999), ("cornell64_path5.npz", 5, 0.97)])
+@pytest.mark.parametrize("fixture,depth,frac", [("cornell64_direct.npz", 1, 0.999), ("cornell64_path5.npz", 5, 0.999)])
 def test_cornell_vs_golden_fixture(api, gpu_ctx, fixture, depth, frac):
     """Same check without the compiled reference: committed fixtures (tests/golden/make_golden.py)."""
     from tests.util import golden
@@ -145,7 +159,7 @@ def test_stress_direct_vs_golden_fixture(api, gpu_ctx):
     data = scenes.bsdf_stress(sphere_tess=12, env=scenes.procedural_env(128, 64))
     p = Pair(api, None, data, 96, 64, 2, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
     got, _, _ = p.scene.render(integrator=A.INTEGRATOR_PATH, max_depth=1)
-    assert (rel_err(got / 2, g["rgb_mean"]) <= REL_TOL).mean() >= 0.995
+    assert (rel_err(got / 2, g["rgb_mean"]) <= REL_TOL).mean() >= 0.999
 
 
 @pytest.mark.parametrize("integ", [A.INTEGRATOR_WHITTED, A.INTEGRATOR_DIRECT_ONE, A.INTEGRATOR_DIRECT_ALL])
@@ -156,7 +170,7 @@ def test_whitted_and_direct_lighting_integrators(api, ref, gpu_ctx, integ):
     data = scenes.cornell(sphere_tess=16, floor_mirror=True)
     data.add_point_light([0.5, 1.5, 0.5], [20.0, 18.0, 15.0])
     p = Pair(api, ref, data, 96, 96, 2)
-    _direct_check(p, ref, max_depth=5, spp=2, frac_ok=0.995, integrator=integ)
+    _direct_check(p, ref, max_depth=5, spp=2, integrator=integ)
     # rays that escape pick up Light::Le = 0.8 per light (quirk Q3): open scene, camera looking past the geometry
     open_scene = scenes.SceneData()
     m = open_scene.add_material(scenes.matte([0.6, 0.6, 0.6]))
@@ -165,7 +179,7 @@ def test_whitted_and_direct_lighting_integrators(api, ref, gpu_ctx, integ):
     open_scene.add_point_light([3.0, 3.0, 3.0], [30.0, 30.0, 30.0])
     open_scene.add_point_light([-3.0, 2.0, 3.0], [10.0, 20.0, 30.0])
     p2 = Pair(api, ref, open_scene, 64, 64, 2)
-    got, want = _direct_check(p2, ref, max_depth=3, spp=2, frac_ok=0.995, integrator=integ)
+    got, want = _direct_check(p2, ref, max_depth=3, spp=2, integrator=integ)
     assert abs(want[0, 0, 0] / 2 - 1.6) < 1e-5  # corner pixel escapes: 2 lights x 0.8
 
 
@@ -176,7 +190,7 @@ def test_sobol_path_render_vs_reference_with_cpu_twin(api, ref, gpu_ctx):
     p = Pair(api, ref, scenes.cornell(sphere_tess=16), 96, 96, 4, eye=(0.3, 0.2, 5.0), look=(0.1, -0.2, 0.0),
              sampler_type=A.SAMPLER_SOBOL)
     _direct_check(p, ref, max_depth=1, spp=4, rr_threshold=0.8)
-    _direct_check(p, ref, max_depth=5, spp=4, frac_ok=0.97, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=5, spp=4, rr_threshold=0.8)
 
 
 def test_power_strategy_with_infinite_light(api, ref, gpu_ctx):
@@ -186,7 +200,7 @@ def test_power_strategy_with_infinite_light(api, ref, gpu_ctx):
     data = scenes.bsdf_stress(sphere_tess=8, env=env)
     data.add_point_light([0.0, 4.0, 0.0], [40.0, 40.0, 40.0])
     p = Pair(api, ref, data, 64, 48, 2, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
-    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.99, light_strategy=A.LIGHTSTRATEGY_POWER)
+    _direct_check(p, ref, max_depth=1, spp=2, light_strategy=A.LIGHTSTRATEGY_POWER)
 
 
 def test_oren_nayar_two_sided_light_and_reversed_orientation(api, ref, gpu_ctx):
@@ -206,8 +220,8 @@ def test_oren_nayar_two_sided_light_and_reversed_orientation(api, ref, gpu_ctx):
     flags[0:2] = 1                   # floor too
     s.tri_flags = flags
     p = Pair(api, ref, s, 96, 96, 2, eye=(0.4, 0.3, 5.0), look=(0.0, -0.3, 0.0))
-    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.998)
-    _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.97, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=1, spp=2)
+    _direct_check(p, ref, max_depth=4, spp=2, rr_threshold=0.8)
 
 
 def test_thin_lens_and_orthographic_cameras(api, ref, gpu_ctx):
@@ -218,9 +232,9 @@ def test_thin_lens_and_orthographic_cameras(api, ref, gpu_ctx):
     got = p.scene.dump_primary_rays((10, 10, 20, 12), 0, 4)
     # cosf/sinf of the lens disk differ from glibc by ulps: rays agree to 1e-6, not bit for bit
     np.testing.assert_allclose(got[..., [0, 1, 2, 4, 5, 6]], want[..., [0, 1, 2, 4, 5, 6]], rtol=0, atol=2e-6)
-    _direct_check(p, ref, max_depth=1, spp=4, frac_ok=0.99)
+    _direct_check(p, ref, max_depth=1, spp=4)
     po = Pair(api, ref, data, 64, 64, 2, eye=(0.0, 0.0, 4.0), cam_type=A.CAMERA_ORTHOGRAPHIC)
-    _direct_check(po, ref, max_depth=2, spp=2, frac_ok=0.995)
+    _direct_check(po, ref, max_depth=2, spp=2)
 
 
 def test_progressive_film_checkpoint_resume(api, gpu_ctx, tmp_path):
@@ -277,8 +291,8 @@ def test_smooth_shading_normals_and_uvs(api, ref, gpu_ctx):
     s.add_point_light([0.0, 4.0, 3.0], [60.0, 55.0, 50.0])
     s.add_point_light([-3.0, 2.0, -1.0], [15.0, 20.0, 30.0])
     p = Pair(api, ref, s, 96, 72, 2, eye=(0.0, 1.5, 5.0), look=(0.0, -0.2, 0.0))
-    _direct_check(p, ref, max_depth=1, spp=2, frac_ok=0.995)
-    _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.97)
+    _direct_check(p, ref, max_depth=1, spp=2)
+    _direct_check(p, ref, max_depth=4, spp=2)
 
 
 def test_full_size_dragon_class_properties(api, ref, gpu_ctx):
@@ -333,12 +347,13 @@ def test_full_size_dragon_class_properties(api, ref, gpu_ctx):
 # ---------------------------------------------------------------------------------------------
 # VolPathIntegrator (Integrator/VolPathIntegrator.cpp) + HomogeneousMedium: the integrator Main/main.cpp:399 runs
 # ---------------------------------------------------------------------------------------------
-def _vol_check(p, ref, max_depth, spp, frac_ok, **kw):
+def _vol_check(p, ref, max_depth, spp, frac_ok=0.999, **kw):
     V = A.INTEGRATOR_VOLPATH
     want, rst = ref.render(p.rscene, p.rcam, p.spp, (0, 0, p.W, p.H), integrator=V, max_depth=max_depth, s1=spp, **kw)
     got, _, st = p.scene.render(integrator=V, max_depth=max_depth, s1=spp, **kw)
     err = rel_err(got / spp, want / spp)
     ok = (err <= REL_TOL).mean()
+    assert_diverged_is_discrete(err, frac_ok)
     print(f"volpath depth {max_depth}: pixels within {REL_TOL}: {ok:.5f}, median err {np.median(err):.2e}, "
           f"mean gpu {got.mean() / spp:.5f} ref {want.mean() / spp:.5f}, rays gpu {st.rays_closest}+{st.rays_shadow} "
           f"ref {rst.rays_closest}+{rst.rays_shadow}")
@@ -357,7 +372,7 @@ def test_volpath_without_media_matches_reference(api, ref, gpu_ctx):
     data.add_point_light([0.5, 1.5, 0.5], [20.0, 18.0, 15.0])
     p = Pair(api, ref, data, 96, 96, 2)
     _vol_check(p, ref, max_depth=1, spp=2, frac_ok=0.999, rr_threshold=0.8)
-    _vol_check(p, ref, max_depth=5, spp=2, frac_ok=0.97, rr_threshold=0.8)
+    _vol_check(p, ref, max_depth=5, spp=2, rr_threshold=0.8)
 
 
 @pytest.mark.parametrize("kind", ["smoke", "glass"])
@@ -365,8 +380,8 @@ def test_volpath_medium_in_a_sphere(api, ref, gpu_ctx, kind):
     data, _ = scenes.cornell_media(kind, sphere_tess=16)
     data.add_point_light([0.5, 1.5, 0.5], [20.0, 18.0, 15.0])
     p = Pair(api, ref, data, 96, 96, 2)
-    _vol_check(p, ref, max_depth=1, spp=2, frac_ok=0.995, rr_threshold=0.8)
-    got, want = _vol_check(p, ref, max_depth=6, spp=2, frac_ok=0.93, rr_threshold=0.8)
+    _vol_check(p, ref, max_depth=1, spp=2, rr_threshold=0.8)
+    got, want = _vol_check(p, ref, max_depth=6, spp=2, rr_threshold=0.8)
     # the medium matters: same scene without it renders differently
     plain, _, _ = p.scene.render(integrator=A.INTEGRATOR_VOLPATH, max_depth=0, s1=1)
     assert np.isfinite(got).all() and np.isfinite(plain).all()
@@ -384,8 +399,8 @@ def test_volpath_camera_medium(api, ref, gpu_ctx):
         p = Pair(api, ref, data, 64, 64, 2, cam_type=cam_type, camera_medium=med, **views)
         clear, _ = _vol_check(p, ref, max_depth=1, spp=2, frac_ok=0.999)  # as shipped: no fog on either side
         q = Pair(api, ref, data, 64, 64, 2, cam_type=cam_type, camera_medium=med, honour_camera_medium=True, **views)
-        _vol_check(q, ref, max_depth=1, spp=2, frac_ok=0.99)
-        fog, _ = _vol_check(q, ref, max_depth=4, spp=2, frac_ok=0.90, rr_threshold=0.8)
+        _vol_check(q, ref, max_depth=1, spp=2)
+        fog, _ = _vol_check(q, ref, max_depth=4, spp=2, rr_threshold=0.8)
         assert abs(fog.mean() - clear.mean()) > 0.02 * clear.mean()
 
 
@@ -416,7 +431,7 @@ def test_volpath_vs_golden_fixture(api, gpu_ctx, kind):
     got, _, st = p.scene.render(integrator=A.INTEGRATOR_VOLPATH, max_depth=5, rr_threshold=0.8)
     ok = (rel_err(got / 4, g["rgb_mean"]) <= REL_TOL).mean()
     print("volpath fixture", kind, "pixels within 1e-3:", ok)
-    assert ok >= 0.95
+    assert ok >= 0.999
     assert abs(int(st.rays_closest) - int(g["rays_closest"])) <= 5e-3 * int(g["rays_closest"]) + 8
 
 
@@ -498,15 +513,15 @@ def test_image_textures_match_reference(api, ref, gpu_ctx, variant):
     (EWA / trilinear) are pinned by test_texture_lookup_known_answers, the derivatives by test_hit_differentials."""
     data = _textured_scene(variant)
     p = Pair(api, ref, data, 96, 96, 4)
-    got, want = _direct_check(p, ref, max_depth=1, spp=4, frac_ok=0.995, rr_threshold=0.8)
-    _direct_check(p, ref, max_depth=4, spp=2, frac_ok=0.96, rr_threshold=0.8)
+    got, want = _direct_check(p, ref, max_depth=1, spp=4, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=4, spp=2, rr_threshold=0.8)
     # the texture is visible: the floor is not a flat colour
     floor = got[80:, 20:76] / 4
     assert floor.std(axis=(0, 1)).max() > 0.02
     # VolPath, Whitted and DirectLighting evaluate textures the same way
-    _vol_check(p, ref, max_depth=3, spp=2, frac_ok=0.97, rr_threshold=0.8)
-    _direct_check(p, ref, max_depth=3, spp=2, frac_ok=0.99, integrator=A.INTEGRATOR_WHITTED)
-    _direct_check(p, ref, max_depth=3, spp=2, frac_ok=0.99, integrator=A.INTEGRATOR_DIRECT_ONE)
+    _vol_check(p, ref, max_depth=3, spp=2, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=3, spp=2, integrator=A.INTEGRATOR_WHITTED)
+    _direct_check(p, ref, max_depth=3, spp=2, integrator=A.INTEGRATOR_DIRECT_ONE)
 
 
 def test_image_texture_error_behaviour(api, gpu_ctx):

@@ -73,6 +73,32 @@ def _free_port():
     return p
 
 
+def test_shard_samples_partition_properties(api):
+    """pbrgpu_shard_samples (the split pbrgpu_render applies on a multi-GPU context): the shards tile [s0, s1) without gaps
+    or overlap, in rank order, sizes differ by at most one; ranks beyond the sample count get empty ranges."""
+    for s0, s1 in [(0, 1024), (0, 4096), (7, 8), (5, 5), (100, 111), (0, 3), (16, 16 + 128)]:
+        for world in (1, 2, 3, 4, 8):
+            cuts = [api.shard_samples(s0, s1, r, world) for r in range(world)]
+            assert cuts[0][0] == s0 and cuts[-1][1] == s1
+            sizes = [hi - lo for lo, hi in cuts]
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1 and sum(sizes) == s1 - s0
+            assert sizes == sorted(sizes, reverse=True)  # the first (n % world) ranks take the extra sample
+            for r, (lo, hi) in enumerate(cuts):
+                assert (lo, hi) == shard.shard_samples(s0, s1, r, world)
+    with pytest.raises(api.PbrGpuError):
+        api.shard_samples(0, 8, 2, 2)
+    with pytest.raises(api.PbrGpuError):
+        api.shard_samples(9, 8, 0, 2)
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_gpu(api):
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.PbrGpuError, match="no CUDA device"):
+        api.Context(devices=[0, 1])
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
