@@ -1,0 +1,85 @@
+"""Parity at the BASELINE.json configurations' OWN parameters (resolution, spp, depth, Russian roulette, env-map size,
+mesh size).  Full-size jobs are hours of CPU time, so each config is compared with the compiled reference on a crop of its
+frame that the oracle renders in seconds - same camera, same sampler (sample bounds = the full frame, so the Halton
+offsets are those of the full job), same scene - at matched sample indices, per pixel within 1e-3 relative, with the
+diverged pixels counted (tests/test_gpu_render.py::assert_diverged_is_discrete).
+  config 1  Cornell 512x512, 16 spp, PathIntegrator maxDepth 10, rr 0.8                 (whole frame: as main.cpp runs it)
+  config 2  dragon-class 872 368 triangles, 1920x1080, 1024 spp, maxDepth 8             (128x16 strip, Halton + Sobol)
+  config 3  Glass / Metal / Plastic spheres, 2048x1024 procedural HDR, 1080p            (256x128 crop, InfiniteAreaLight + SkyBox)
+  config 4  Whitted / DirectLighting on the dragon scene with point + area lights       (192x108 crop)
+  config 5  3840x2160, 4096 spp, dragon + SkyBox                                        (crop, late sample indices)"""
+import numpy as np
+import pytest
+
+from pysicalbasedraytracer_b200 import _abi as A
+from pysicalbasedraytracer_b200 import scenes
+from tests.test_gpu_render import REL_TOL, assert_diverged_is_discrete
+from tests.util import Pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(p, ref, region, s0, s1, frac_ok=0.999, **kw):
+    want, rst = ref.render(p.rscene, p.rcam, p.spp, (0, 0, p.W, p.H), region=region, s0=s0, s1=s1,
+                           sampler_type=p.sampler_type, **kw)
+    got, _, st = p.scene.render(region=region, s0=s0, s1=s1, **kw)
+    n = s1 - s0
+    err = rel_err(got / n, want / n)
+    ok = (err <= REL_TOL).mean()
+    print(f"region {region} samples [{s0},{s1}): pixels within {REL_TOL}: {ok:.5f}, median err {np.median(err):.2e}, "
+          f"rays gpu {st.rays_closest}+{st.rays_shadow} ref {rst.rays_closest}+{rst.rays_shadow}, "
+          f"gpu {st.ms_total:.1f} ms, reference {rst.seconds:.1f} s on {rst.threads} threads")
+    assert np.isfinite(got).all() and want.max() > 0
+    assert ok >= frac_ok
+    assert_diverged_is_discrete(err, frac_ok)
+    assert abs(int(st.rays_closest) - int(rst.rays_closest)) <= 1e-3 * rst.rays_closest + 8
+    assert abs(int(st.rays_shadow) - int(rst.rays_shadow)) <= 1e-3 * rst.rays_shadow + 8
+    return got, want
+
+
+def test_config1_cornell_512_16spp_depth10_rr08(api, ref, gpu_ctx):
+    """configs[0] exactly as Main/main.cpp:401-403 runs it: the whole 512x512 frame, all 16 samples."""
+    p = Pair(api, ref, scenes.cornell(sphere_tess=48), 512, 512, 16)
+    got, want = _check(p, ref, (0, 0, 512, 512), 0, 16, integrator=A.INTEGRATOR_PATH, max_depth=10, rr_threshold=0.8)
+    # and the 8-bit film the application would save
+    _, rgba8, _ = p.scene.render(integrator=A.INTEGRATOR_PATH, max_depth=10, rr_threshold=0.8, want_rgba8=True)
+    ref8 = ref.tonemap(want / np.float32(16)).reshape(512, 512, 4)[::-1]
+    diff = np.abs(rgba8.astype(int) - ref8.astype(int))
+    print("8-bit film: bytes differing", (diff > 0).mean(), "max", diff.max())
+    assert (diff <= 1).mean() >= 0.9995
+
+
+@pytest.fixture(scope="module")
+def dragon(api, ref, gpu_ctx):
+    data = scenes.dragon_class(tess=467, with_point_light=True)  # config 4's lights; config 2 = the same mesh with the area light only
+    assert data.n_tris == 872368
+    return data
+
+
+@pytest.mark.parametrize("sampler", [A.SAMPLER_HALTON, A.SAMPLER_SOBOL])
+def test_config2_dragon_class_radiance_strip(api, ref, gpu_ctx, sampler):
+    p = Pair(api, ref, scenes.dragon_class(tess=467), 1920, 1080, 1024, sampler_type=sampler)
+    # a strip across the silhouette of the mesh (matte / mirror blocks, walls behind), late samples of the 1024-spp job
+    _check(p, ref, (896, 532, 1024, 548), 1000, 1002, integrator=A.INTEGRATOR_PATH, max_depth=8, rr_threshold=1.0)
+
+
+@pytest.mark.parametrize("skybox", [False, True])
+def test_config3_bsdf_stress_2048x1024_env_1080p(api, ref, gpu_ctx, skybox):
+    env = scenes.procedural_env(2048, 1024)
+    data = scenes.bsdf_stress(sphere_tess=64, env=env, skybox=skybox)
+    p = Pair(api, ref, data, 1920, 1080, 1024, eye=(0.0, 3.0, 7.0), look=(0.0, -0.3, 0.0))
+    _check(p, ref, (832, 476, 1088, 604), 500, 501, integrator=A.INTEGRATOR_PATH, max_depth=8, rr_threshold=1.0)
+
+
+@pytest.mark.parametrize("integ", [A.INTEGRATOR_WHITTED, A.INTEGRATOR_DIRECT_ONE, A.INTEGRATOR_DIRECT_ALL])
+def test_config4_shadow_ray_integrators_on_the_dragon_mesh(api, ref, gpu_ctx, dragon, integ):
+    p = Pair(api, ref, dragon, 1920, 1080, 8)
+    _check(p, ref, (864, 486, 1056, 594), 0, 2, integrator=integ, max_depth=5)
+
+
+def test_config5_4k_dragon_skybox_late_samples(api, ref, gpu_ctx):
+    data = scenes.dragon_class(tess=467)
+    data.add_skybox_light(scenes.procedural_env(2048, 1024), world_radius=20.0, n_samples=1)
+    p = Pair(api, ref, data, 3840, 2160, 4096)
+    # sample 4000 of 4096 at 4K: Halton indices ~1.2e8 (still the 32-bit digit path), crop across the mesh silhouette
+    _check(p, ref, (1800, 1060, 2056, 1092), 4000, 4001, integrator=A.INTEGRATOR_PATH, max_depth=8, rr_threshold=1.0)

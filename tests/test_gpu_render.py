@@ -25,7 +25,7 @@ def assert_diverged_is_discrete(err, frac_ok=0.999):
     near = int(((err > 0.2 * REL_TOL) & (err <= REL_TOL)).sum())
     print(f"  diverged pixels {n_div} of {err.size} (budget {budget}); within tolerance but above 2e-4: {near}")
     assert n_div <= budget
-    assert near <= max(4, int(0.005 * err.size)), "errors pile up just below the tolerance: drift, not discrete divergence"
+    assert near <= 2, "errors pile up just below the tolerance: drift, not discrete divergence"  # observed on B200: 0 everywhere
 
 
 def _direct_check(p, ref, max_depth, spp, frac_ok=0.999, integrator=A.INTEGRATOR_PATH, **kw):
