@@ -106,15 +106,29 @@ struct Counters {
   uint32_t volMaxHops, volCapHits;  // VolPath shadow rays: most medium boundaries crossed by one ray / rays stopped at the cap
 };
 
-// SoA wavefront state, `capacity` slots.  slot = j*nPix + pixel (j = sample within the wave).
+// One live path of the current bounce: a 64-byte record = two full 32-byte sectors.  Records live in QUEUE ORDER: position i
+// of `cur` is the i-th live path of this bounce, the shading kernels write the survivors compacted into `nxt` (ping-pong), so
+//   * k_trace reads its rays with coalesced 32-byte loads (record offset 0..31) and writes hit[i] / qType[i] at the same index,
+//   * the shading kernels gather whole records through the material queues (positions in a material queue are ascending up
+//     to the tile-local order of k_classify) - every fetched sector is used completely.
+// (Round 1 kept five separate 16-byte arrays indexed by a fixed per-path slot: after a few bounces the live slots were
+// scattered, every 16-byte access pulled a half-used sector and k_shade moved ~430 bytes of DRAM per path.)
+struct alignas(16) PathRec {
+  float4 o;      // ray origin, tMax (VolPath: k_trace stores the hit distance here for Medium::Sample)
+  float4 d;      // ray direction, time (VolPath: as_float(Ray::medium id or -1))
+  float4 beta;   // beta.rgb, etaScale
+  uint32_t idxLo, idxHi;  // Halton / Sobol index of the camera sample
+  uint32_t meta;          // dim (bits 0-15) | specularBounce (bit 16) | VolPath: bounces (bits 17-23), in-medium (24)
+  uint32_t slot;          // j * nPix + pixel (j = sample within the wave): where this path's radiance accumulates (L[slot])
+};
+static_assert(sizeof(PathRec) == 64, "PathRec is two 32-byte sectors");
+
+// Wavefront state.  `capacity` paths per wave.
 struct WaveDev {
-  float4* rayO;     // o.xyz, tMax (VolPath: k_trace stores the hit distance here for Medium::Sample)
-  float4* rayD;     // d.xyz, time (VolPath: as_float(Ray::medium id or -1))
-  float4* hit;      // as_float(leaf tri index or -1), b0, b1, b2
-  float4* beta;     // beta.rgb, etaScale
-  float4* L;        // L.rgb (per-path radiance, summed in launch order => deterministic)
-  uint2* hidx;      // Halton index (lo, hi)
-  uint32_t* meta;   // dim (bits 0-15) | specularBounce (bit 16) | VolPath: bounces (bits 17-23)
+  PathRec* cur;     // live paths of this bounce, queue order
+  PathRec* nxt;     // survivors, written compacted by the shading kernels (the host swaps cur / nxt after every bounce)
+  float4* hit;      // [position in cur] as_float(leaf tri index or -1), b0, b1, b2
+  float4* L;        // [slot] L.rgb (per-path radiance, summed in launch order => deterministic)
   // shadow-ray queue (EstimateDirect light-sampling strategy)
   float4* shO;      // o.xyz, tMax
   float4* shD;      // d.xyz, as_float(slot)
@@ -128,10 +142,8 @@ struct WaveDev {
   float4* miO;      // o.xyz, tMax -> after k_trace<MIS>: as_float(hit triangle or -1)
   float4* miD;      // d.xyz, as_float(slot)
   float4* miC;      // throughput rgb, as_float(light id)
-  uint32_t* qCur;
-  uint32_t* qNext;
-  uint32_t* qMat;   // [kNumQueues][capacity]
-  uint32_t* qType;  // shading-queue id per entry of qCur (written by k_trace, read by k_classify)
+  uint32_t* qMat;   // [kNumQueues][capacity] positions in `cur`, one queue per shading kernel
+  uint32_t* qType;  // [position in cur] shading-queue id (written by k_trace, read by k_classify)
   Counters* ctr;
   uint32_t capacity;
 };

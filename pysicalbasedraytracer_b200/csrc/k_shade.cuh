@@ -25,11 +25,14 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
     bool pushShadow = false, pushMis = false, pushNext = false;
     uint32_t slot = 0;
     float4 shO, shD, shC, miO, miD, miC, shP1, shE1, shN1;
+    float4 nxO, nxD, nxB;              // the continuation ray's record, written at its compacted position after the queue push
+    uint32_t nxMeta = 0, idxLo = 0, idxHi = 0;
     if (active) {
-      slot = queue[i];
-      float4 rd4 = P.ws.rayD[slot], h4 = P.ws.hit[slot], be4 = P.ws.beta[slot];
-      uint2 hi = P.ws.hidx[slot];
-      uint32_t meta = P.ws.meta[slot];
+      const uint32_t pos = queue[i];   // position of this path in ws.cur
+      const PathRegs rec = load_path(P.ws.cur + pos);  // 64 bytes = two full sectors
+      const float4 rd4 = rec.d, h4 = P.ws.hit[pos], be4 = rec.beta;
+      const uint32_t meta = rec.meta;
+      slot = rec.slot; idxLo = rec.idxLo; idxHi = rec.idxHi;
       if (VOL) bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
       int medIn = -1, medOut = -1;
       if (VOL) isect_media(sc, __float_as_int(h4.x), __float_as_int(rd4.w), &medIn, &medOut);
@@ -37,10 +40,7 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
       Spec beta(be4.x, be4.y, be4.z);
       float etaScale = be4.w;
       bool specularBounce = (meta >> 16) & 1u;
-      SamplerCursor cur;
-      cur.index = (int64_t)(((uint64_t)hi.y << 32) | hi.x);
-      cur.dim = (int)(meta & 0xffffu);
-      cur.arrayEndDim = P.arrayEndDim;
+      SamplerCursor cur = load_cursor(P, rec);
       TriData tri = load_tri(sc, __float_as_int(h4.x));
       Isect is;
       make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is);
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
         if (TEX && (MAT == PBRGPU_MAT_MATTE || MAT == PBRGPU_MAT_PLASTIC)) {
           const pbrgpu_material& m = sc.mats[is.matId];
           if (m.kd_texture_plus1 > 0) {
-            const float4 ro4 = P.ws.rayO[slot];
+            const float4 ro4 = rec.o;
             // Reference quirk: SurfaceInteraction::ComputeScatteringFunctions takes `const Ray&` (Interaction.h:86-89) and
             // hands it to ComputeDifferentials(const RayDifferential&): the implicit RayDifferential(const Ray&) conversion
             // (Geometry.h:1387) sets hasDifferentials = false, so EVERY texture lookup of a render sees zero derivatives -
@@ -153,12 +153,12 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
             else beta = beta / (1 - q);
           }
           if (alive) {
-            P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
+            nxO = make_float4(o.x, o.y, o.z, kInfinity);
             const int nextMedium = VOL ? (dot(wi, is.n) > 0 ? medOut : medIn) : -1;
-            P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, VOL ? __int_as_float(nextMedium) : 0.f);
-            P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, etaScale);
-            P.ws.meta[slot] = (uint32_t)cur.dim | (specularBounce ? (1u << kMetaSpecBit) : 0u) |
-                              (VOL ? ((uint32_t)(bounce + 1) << kMetaBounceShift) | (nextMedium >= 0 ? (1u << kMetaInMediumBit) : 0u) : 0u);
+            nxD = make_float4(wi.x, wi.y, wi.z, VOL ? __int_as_float(nextMedium) : 0.f);
+            nxB = make_float4(beta.r, beta.g, beta.b, etaScale);
+            nxMeta = (uint32_t)cur.dim | (specularBounce ? (1u << kMetaSpecBit) : 0u) |
+                     (VOL ? ((uint32_t)(bounce + 1) << kMetaBounceShift) | (nextMedium >= 0 ? (1u << kMetaInMediumBit) : 0u) : 0u);
             pushNext = true;
           }
         }
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
       if (VOL) { P.ws.shP1[pos] = shP1; P.ws.shE1[pos] = shE1; P.ws.shN1[pos] = shN1; }
     }
     if (pushMis) { P.ws.miO[posMis] = miO; P.ws.miD[posMis] = miD; P.ws.miC[posMis] = miC; }
-    if (pushNext) P.ws.qNext[posNext] = slot;
+    if (pushNext) store_path(P.ws.nxt + posNext, nxO, nxD, nxB, idxLo, idxHi, nxMeta, slot);  // compacted: 64 contiguous bytes per lane
   }
 }
 

@@ -79,18 +79,16 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
     uint32_t i = base + threadIdx.x;
     bool active = i < n;
     bool pushNext = false;
-    uint32_t slot = 0;
+    uint32_t slot = 0, idxLo = 0, idxHi = 0, nxMeta = 0;
+    float4 nxO, nxD, nxB;
     if (active) {
-      slot = queue[i];
-      float4 rd4 = P.ws.rayD[slot], h4 = P.ws.hit[slot], be4 = P.ws.beta[slot];
-      uint2 hi = P.ws.hidx[slot];
-      uint32_t meta = P.ws.meta[slot];
+      const uint32_t qpos = queue[i];  // position of this path in ws.cur
+      const PathRegs rec = load_path(P.ws.cur + qpos);
+      const float4 rd4 = rec.d, h4 = P.ws.hit[qpos], be4 = rec.beta;
+      slot = rec.slot; idxLo = rec.idxLo; idxHi = rec.idxHi;
       V3 rayD(rd4.x, rd4.y, rd4.z);
       Spec beta(be4.x, be4.y, be4.z);
-      SamplerCursor cur;
-      cur.index = (int64_t)(((uint64_t)hi.y << 32) | hi.x);
-      cur.dim = (int)(meta & 0xffffu);
-      cur.arrayEndDim = P.arrayEndDim;
+      SamplerCursor cur = load_cursor(P, rec);
       TriData tri = load_tri(sc, __float_as_int(h4.x));
       Isect is;
       make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is);
@@ -166,16 +164,16 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
         if (pdf > 0.f && !f.is_black() && absdot(wi, is.ns) != 0.f) {
           beta = beta * (f * absdot(wi, is.ns) / pdf);
           V3 o = offset_ray_origin(is.p, is.pError, is.n, wi);
-          P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
-          P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, 0.f);
-          P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, 1.f);
-          P.ws.meta[slot] = (uint32_t)cur.dim;
+          nxO = make_float4(o.x, o.y, o.z, kInfinity);
+          nxD = make_float4(wi.x, wi.y, wi.z, 0.f);
+          nxB = make_float4(beta.r, beta.g, beta.b, 1.f);
+          nxMeta = (uint32_t)cur.dim;
           pushNext = true;
         }
       }
     }
     uint32_t pos = queue_push(&P.ws.ctr->nNext, pushNext);
-    if (pushNext) P.ws.qNext[pos] = slot;
+    if (pushNext) store_path(P.ws.nxt + pos, nxO, nxD, nxB, idxLo, idxHi, nxMeta, slot);
   }
 }
 

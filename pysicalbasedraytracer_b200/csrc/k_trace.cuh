@@ -90,8 +90,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   int nt = 0;  // parked triangle groups
   bool busy = false, exhausted = false;
   int mode = TRACE_PATH;
-  uint32_t ray = 0;  // PATH: wavefront slot; SHADOW / MIS: index in that queue
-  uint32_t qi = 0;   // PATH: position in the path queue
+  uint32_t ray = 0;  // index in the queue of `mode`: PATH = position in ws.cur, SHADOW / MIS = position in that ray queue
   int hops = 0;      // VOL: medium boundaries this shadow ray has crossed
   unsigned segs = 0; // VOL: shadow-ray segments traced by this lane (each is one Scene::Intersect of VisibilityTester::Tr)
   unsigned nodes = 0, tris = 0;
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
         if (i < n) {
           float4 ro, rd;
-          if (i < nPath) { mode = TRACE_PATH; qi = i; ray = P.ws.qCur[i]; ro = P.ws.rayO[ray]; rd = P.ws.rayD[ray]; }
+          if (i < nPath) { mode = TRACE_PATH; ray = i; ro = P.ws.cur[i].o; rd = P.ws.cur[i].d; }  // coalesced: records are in queue order
           else if (i < nPath + nShadow) { mode = TRACE_SHADOW; ray = i - nPath; ro = P.ws.shO[ray]; rd = P.ws.shD[ray]; }
           else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
           trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, P.sc.f32one);
@@ -151,9 +150,9 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         if (COUNT) { atomicMax(&C->maxRayWork, nodes + tris - rayWork0); rayWork0 = nodes + tris; }
         if (mode == TRACE_PATH) {
           P.ws.hit[ray] = make_float4(__int_as_float(hit.tri), hit.b0, hit.b1, hit.b2);
-          // shading-queue id of this path, written in QUEUE order so that k_classify reads it coalesced
-          P.ws.qType[qi] = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
-          if (VOL || P.storeHitT) P.ws.rayO[ray].w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
+          // hit record and shading-queue id at the path's queue position
+          P.ws.qType[ray] = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
+          if (VOL || P.storeHitT) P.ws.cur[ray].o.w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
         } else if (mode == TRACE_MIS) {
           P.ws.miO[ray].w = __int_as_float(hit.tri);
         } else if (VOL) {

@@ -190,11 +190,29 @@ PBR_D void block_queue_push3(uint32_t* c0, uint32_t* c1, uint32_t* c2, bool a0, 
   *p2 = sBase3[2] + w2 + __popc(m2 & below);
 }
 
-PBR_D SamplerCursor load_cursor(const RenderParams& P, uint32_t slot, uint32_t meta) {
-  const uint2 hi = P.ws.hidx[slot];
+// A path record as four 16-byte loads (the fourth word holds the sampler index, meta and the film slot)
+struct PathRegs {
+  float4 o, d, beta;
+  uint32_t idxLo, idxHi, meta, slot;
+};
+PBR_D PathRegs load_path(const PathRec* rec) {
+  const float4* p = reinterpret_cast<const float4*>(rec);
+  PathRegs r;
+  r.o = p[0]; r.d = p[1]; r.beta = p[2];
+  const float4 w = p[3];
+  r.idxLo = __float_as_uint(w.x); r.idxHi = __float_as_uint(w.y); r.meta = __float_as_uint(w.z); r.slot = __float_as_uint(w.w);
+  return r;
+}
+PBR_D void store_path(PathRec* rec, float4 o, float4 d, float4 beta, uint32_t idxLo, uint32_t idxHi, uint32_t meta, uint32_t slot) {
+  float4* p = reinterpret_cast<float4*>(rec);
+  p[0] = o; p[1] = d; p[2] = beta;
+  p[3] = make_float4(__uint_as_float(idxLo), __uint_as_float(idxHi), __uint_as_float(meta), __uint_as_float(slot));
+}
+
+PBR_D SamplerCursor load_cursor(const RenderParams& P, const PathRegs& r) {
   SamplerCursor cur;
-  cur.index = (int64_t)(((uint64_t)hi.y << 32) | hi.x);
-  cur.dim = (int)(meta & 0xffffu);
+  cur.index = (int64_t)(((uint64_t)r.idxHi << 32) | r.idxLo);
+  cur.dim = (int)(r.meta & 0xffffu);
   cur.arrayEndDim = P.arrayEndDim;
   return cur;
 }

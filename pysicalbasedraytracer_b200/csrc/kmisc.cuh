@@ -21,14 +21,12 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
     }
     V3 o, d;
     generate_ray(P.sc.cam, (float)px + u0, (float)py + u1, lu, lv, &o, &d);
-    P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
-    P.ws.rayD[slot] = make_float4(d.x, d.y, d.z, P.integrator == PBRGPU_INTEGRATOR_VOLPATH ? __int_as_float(P.sc.cam.medium) : 0.f);
-    P.ws.beta[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
     P.ws.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    P.ws.hidx[slot] = make_uint2((uint32_t)((uint64_t)idx & 0xffffffffu), (uint32_t)((uint64_t)idx >> 32));
-    // next dimension; specularBounce = false; VolPath: bounces = 0, in-medium flag
-    P.ws.meta[slot] = 5u | ((P.integrator == PBRGPU_INTEGRATOR_VOLPATH && P.sc.cam.medium >= 0) ? (1u << kMetaInMediumBit) : 0u);
-    P.ws.qCur[slot] = slot;
+    // camera paths: queue position == slot.  meta: next dimension 5; specularBounce = false; VolPath: bounces = 0, in-medium flag
+    store_path(P.ws.cur + slot, make_float4(o.x, o.y, o.z, kInfinity),
+               make_float4(d.x, d.y, d.z, P.integrator == PBRGPU_INTEGRATOR_VOLPATH ? __int_as_float(P.sc.cam.medium) : 0.f),
+               make_float4(1.f, 1.f, 1.f, 1.f), (uint32_t)((uint64_t)idx & 0xffffffffu), (uint32_t)((uint64_t)idx >> 32),
+               5u | ((P.integrator == PBRGPU_INTEGRATOR_VOLPATH && P.sc.cam.medium >= 0) ? (1u << kMetaInMediumBit) : 0u), slot);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) P.ws.ctr->nCur = n;
 }
@@ -58,7 +56,7 @@ __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ Ren
       const uint32_t i = tile + k * kBlock + threadIdx.x;
       q[k] = -1;
       if (i < n) {
-        slot[k] = P.ws.qCur[i];
+        slot[k] = i;  // position in ws.cur
         q[k] = (int)P.ws.qType[i];
         if (q[k] >= kNumQueues) q[k] = -1;  // kQueueDead: the path ended in k_medium_sample
         else rank[k] = atomicAdd(&cnt[q[k]], 1u);  // shared-memory atomic: rank inside this block's tile
@@ -82,34 +80,35 @@ __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ Ren
 __global__ void __launch_bounds__(kBlock) k_medium_presample(const __grid_constant__ RenderParams P) {
   const uint32_t n = P.ws.ctr->nCur;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t slot = P.ws.qCur[i];
-    const uint32_t meta = P.ws.meta[slot];
+    PathRec* rec = P.ws.cur + i;
+    const uint32_t meta = rec->meta;
     if (!((meta >> kMetaInMediumBit) & 1u)) continue;  // vacuum: nothing to sample (4 bytes read)
-    const float4 rd4 = P.ws.rayD[slot];
+    const PathRegs r = load_path(rec);
+    const float4 rd4 = r.d;
     const int med = __float_as_int(rd4.w);
-    SamplerCursor cur = load_cursor(P, slot, meta);
+    SamplerCursor cur = load_cursor(P, r);
     const float u0 = cur.get1D(P.sc.hp);
     const float u1 = cur.get1D(P.sc.hp);
-    P.ws.rayO[slot].w = medium_sample_distance(P.sc.media[med], u0, u1, length(V3(rd4.x, rd4.y, rd4.z)));
-    P.ws.meta[slot] = (meta & ~0xffffu) | (uint32_t)cur.dim;
+    rec->o.w = medium_sample_distance(P.sc.media[med], u0, u1, length(V3(rd4.x, rd4.y, rd4.z)));
+    rec->meta = (meta & ~0xffffu) | (uint32_t)cur.dim;
   }
 }
 
 __global__ void __launch_bounds__(kBlock) k_medium_sample(const __grid_constant__ RenderParams P) {
   const uint32_t n = P.ws.ctr->nCur;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t slot = P.ws.qCur[i];
-    if (!((P.ws.meta[slot] >> kMetaInMediumBit) & 1u)) continue;
-    const float4 rd4 = P.ws.rayD[slot];
+    PathRec* rec = P.ws.cur + i;
+    if (!((rec->meta >> kMetaInMediumBit) & 1u)) continue;
+    const float4 rd4 = rec->d;
     const int med = __float_as_int(rd4.w);
-    const bool hit = __float_as_int(P.ws.hit[slot].x) >= 0;
-    const float t = P.ws.rayO[slot].w;           // k_trace: hit distance, or the sampled distance when nothing was hit
+    const bool hit = __float_as_int(P.ws.hit[i].x) >= 0;
+    const float t = rec->o.w;                    // k_trace: hit distance, or the sampled distance when nothing was hit
     const bool sampled = !hit && t < kInfinity;  // t < ray.tMax
     const Spec w = medium_sample_weight(P.sc.media[med], t, sampled, length(V3(rd4.x, rd4.y, rd4.z)));
-    const float4 be4 = P.ws.beta[slot];
+    const float4 be4 = rec->beta;
     const Spec beta = Spec(be4.x, be4.y, be4.z) * w;
     if (beta.is_black()) { P.ws.qType[i] = kQueueDead; continue; }
-    P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, be4.w);
+    rec->beta = make_float4(beta.r, beta.g, beta.b, be4.w);
     if (sampled) P.ws.qType[i] = (uint32_t)kQueueMedium;  // mi.p = ray(t), t stays in rayO.w
   }
 }
@@ -123,11 +122,15 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const __grid_constant__ R
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const uint32_t i = base + threadIdx.x;
     bool pushNext = false;
-    uint32_t slot = 0;
+    PathRegs rec;
+    float4 nxO, nxD;
+    uint32_t nxMeta = 0;
     if (i < n) {
-      slot = queue[i];
-      const float4 rd4 = P.ws.rayD[slot], h4 = P.ws.hit[slot];
-      const uint32_t meta = P.ws.meta[slot];
+      const uint32_t qpos = queue[i];
+      rec = load_path(P.ws.cur + qpos);
+      const uint32_t slot = rec.slot;
+      const float4 rd4 = rec.d, h4 = P.ws.hit[qpos];
+      const uint32_t meta = rec.meta;
       const int bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
       const bool specularBounce = (meta >> kMetaSpecBit) & 1u;
       const V3 rayD(rd4.x, rd4.y, rd4.z);
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const __grid_constant__ R
       Isect is;
       make_isect(sc, td, tri, h4.y, h4.z, h4.w, rayD, &is);
       if ((bounce == 0 || specularBounce) && is.lightId >= 0) {
-        const float4 be4 = P.ws.beta[slot];
+        const float4 be4 = rec.beta;
         const Spec Ladd = Spec(be4.x, be4.y, be4.z) * area_light_L(sc.lights[is.lightId], is.n, -rayD);
         if (!Ladd.is_black()) {
           const float4 L = P.ws.L[slot];
@@ -147,15 +150,15 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const __grid_constant__ R
         int mIn, mOut;
         isect_media(sc, tri, __float_as_int(rd4.w), &mIn, &mOut);
         const V3 o = offset_ray_origin(is.p, is.pError, is.n, rayD);
-        P.ws.rayO[slot] = make_float4(o.x, o.y, o.z, kInfinity);
+        nxO = make_float4(o.x, o.y, o.z, kInfinity);
         const int nextMedium = dot(rayD, is.n) > 0 ? mOut : mIn;
-        P.ws.rayD[slot] = make_float4(rayD.x, rayD.y, rayD.z, __int_as_float(nextMedium));
-        P.ws.meta[slot] = (meta & ~(1u << kMetaInMediumBit)) | (nextMedium >= 0 ? (1u << kMetaInMediumBit) : 0u);
+        nxD = make_float4(rayD.x, rayD.y, rayD.z, __int_as_float(nextMedium));
+        nxMeta = (meta & ~(1u << kMetaInMediumBit)) | (nextMedium >= 0 ? (1u << kMetaInMediumBit) : 0u);
         pushNext = true;
       }
     }
     const uint32_t pos = queue_push(&P.ws.ctr->nNext, pushNext);
-    if (pushNext) P.ws.qNext[pos] = slot;
+    if (pushNext) store_path(P.ws.nxt + pos, nxO, nxD, rec.beta, rec.idxLo, rec.idxHi, nxMeta, rec.slot);
   }
 }
 
@@ -169,12 +172,13 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_const
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const uint32_t i = base + threadIdx.x;
     bool pushShadow = false, pushMis = false, pushNext = false;
-    uint32_t slot = 0;
-    float4 shO, shD, shC, miO, miD, miC, shP1, shE1, shN1;
+    uint32_t slot = 0, idxLo = 0, idxHi = 0, nxMeta = 0;
+    float4 shO, shD, shC, miO, miD, miC, shP1, shE1, shN1, nxO, nxD, nxB;
     if (i < n) {
-      slot = queue[i];
-      const float4 ro4 = P.ws.rayO[slot], rd4 = P.ws.rayD[slot], be4 = P.ws.beta[slot];
-      const uint32_t meta = P.ws.meta[slot];
+      const PathRegs rec = load_path(P.ws.cur + queue[i]);
+      slot = rec.slot; idxLo = rec.idxLo; idxHi = rec.idxHi;
+      const float4 ro4 = rec.o, rd4 = rec.d, be4 = rec.beta;
+      const uint32_t meta = rec.meta;
       const int bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
       if (bounce < P.maxDepth) {
         const int med = __float_as_int(rd4.w);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_const
         const V3 zero(0, 0, 0);
         Spec beta(be4.x, be4.y, be4.z);
         const float etaScale = be4.w;
-        SamplerCursor cur = load_cursor(P, slot, meta);
+        SamplerCursor cur = load_cursor(P, rec);
         if (sc.nLights > 0) {
           float pickPdf;
           const int lightNum = sample_discrete(sc.lightFunc, sc.lightCdf, sc.lightFuncInt, sc.nLights, cur.get1D(sc.hp), &pickPdf);
@@ -250,10 +254,10 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_const
           else beta = beta / (1 - q);
         }
         if (alive) {
-          P.ws.rayO[slot] = make_float4(p.x, p.y, p.z, kInfinity);
-          P.ws.rayD[slot] = make_float4(wi.x, wi.y, wi.z, __int_as_float(med));
-          P.ws.beta[slot] = make_float4(beta.r, beta.g, beta.b, etaScale);
-          P.ws.meta[slot] = (uint32_t)cur.dim | ((uint32_t)(bounce + 1) << kMetaBounceShift) | (1u << kMetaInMediumBit);
+          nxO = make_float4(p.x, p.y, p.z, kInfinity);
+          nxD = make_float4(wi.x, wi.y, wi.z, __int_as_float(med));
+          nxB = make_float4(beta.r, beta.g, beta.b, etaScale);
+          nxMeta = (uint32_t)cur.dim | ((uint32_t)(bounce + 1) << kMetaBounceShift) | (1u << kMetaInMediumBit);
           pushNext = true;
         }
       }
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_const
     pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nMis, pushMis, &sCount, &sBase);
     if (pushMis) { P.ws.miO[pos] = miO; P.ws.miD[pos] = miD; P.ws.miC[pos] = miC; }
     pos = block_queue_push<kShadeBlock>(&P.ws.ctr->nNext, pushNext, &sCount, &sBase);
-    if (pushNext) P.ws.qNext[pos] = slot;
+    if (pushNext) store_path(P.ws.nxt + pos, nxO, nxD, nxB, idxLo, idxHi, nxMeta, slot);
   }
 }
 
@@ -278,12 +282,13 @@ __global__ void __launch_bounds__(kBlock) k_shade_miss(const __grid_constant__ R
   const bool pathInteg = P.integrator == PBRGPU_INTEGRATOR_PATH || volInteg;
   if (pathInteg && P.sc.nInfinite == 0) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint32_t slot = queue[i];
-    const uint32_t meta = P.ws.meta[slot];
+    const PathRec* rec = P.ws.cur + queue[i];
+    const uint32_t meta = rec->meta;
+    const uint32_t slot = rec->slot;
     bool specularBounce = (meta >> kMetaSpecBit) & 1u;
     if (volInteg) bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
     if (pathInteg && !(bounce == 0 || specularBounce)) continue;
-    float4 rd = P.ws.rayD[slot], be = P.ws.beta[slot];
+    float4 rd = rec->d, be = rec->beta;
     Spec beta(be.x, be.y, be.z);
     Spec Ladd(0.f);
     if (pathInteg) {
@@ -513,7 +518,7 @@ __global__ void __launch_bounds__(kBlock) k_collect_wave_hits(const __grid_const
     const int tri = __float_as_int(h.x);
     int* q = out + 4 * ((size_t)p * ns + j);
     q[0] = tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[tri].w)) : -1;
-    q[1] = __float_as_int(P.ws.rayO[slot].w);  // k_trace stored the hit distance (RenderParams::storeHitT), tMax on a miss
+    q[1] = __float_as_int(P.ws.cur[slot].o.w);  // k_trace stored the hit distance (RenderParams::storeHitT), tMax on a miss
     q[2] = tri >= 0 ? __float_as_int(h.y) : 0;
     q[3] = tri >= 0 ? __float_as_int(h.z) : 0;
   }
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(kBlock) k_feed_rays(const __grid_constant__ Re
       P.ws.shD[i] = make_float4(d.x, d.y, d.z, __uint_as_float(i));
       P.ws.shC[i] = make_float4(1.f, 0.f, 0.f, 0.f);
     } else {
-      P.ws.rayO[i] = o; P.ws.rayD[i] = d; P.ws.qCur[i] = i;
+      store_path(P.ws.cur + i, o, d, make_float4(1.f, 1.f, 1.f, 1.f), 0u, 0u, 5u, i);
       P.ws.miO[i] = o;
       P.ws.miD[i] = make_float4(d.x, d.y, d.z, __uint_as_float(i));
       P.ws.miC[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
@@ -551,7 +556,7 @@ __global__ void __launch_bounds__(kBlock) k_collect_rays(const __grid_constant__
     if (__float_as_int(P.ws.miO[i].w) != tri) atomicAdd(nDisagree, 1);  // the MIS queue must find the same triangle
     int* q = out + 4 * (size_t)i;
     q[0] = tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[tri].w)) : -1;
-    q[1] = __float_as_int(P.ws.rayO[i].w);
+    q[1] = __float_as_int(P.ws.cur[i].o.w);
     q[2] = tri >= 0 ? __float_as_int(h.y) : 0;
     q[3] = tri >= 0 ? __float_as_int(h.z) : 0;
   }

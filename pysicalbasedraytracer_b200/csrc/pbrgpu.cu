@@ -157,9 +157,9 @@ struct pbrgpu_scene {
   // wavefront state
   uint32_t capacity = 0;
   size_t rayCapacity = 0;
-  DevBuf<float4> rayO, rayD, hit, beta, L, shO, shD, shC, miO, miD, miC;
-  DevBuf<uint2> hidx;
-  DevBuf<uint32_t> meta, qA, qB, qMat, qType;
+  DevBuf<PathRec> recA, recB;  // live paths in queue order, ping-pong (WaveDev::cur / nxt)
+  DevBuf<float4> hit, L, shO, shD, shC, miO, miD, miC;
+  DevBuf<uint32_t> qMat, qType;
   DevBuf<Counters> ctr;
   DevBuf<float> accum;
   size_t accumPix = 0;
@@ -189,8 +189,7 @@ int ensure_wave(pbrgpu_scene* s, uint32_t cap, uint32_t raysPerHit, bool vol) {
     s->rayCapacity = rcap;
   }
   if (s->capacity >= cap) return 0;
-  CK(s->rayO.alloc(cap)); CK(s->rayD.alloc(cap)); CK(s->hit.alloc(cap)); CK(s->beta.alloc(cap)); CK(s->L.alloc(cap));
-  CK(s->hidx.alloc(cap)); CK(s->meta.alloc(cap)); CK(s->qA.alloc(cap)); CK(s->qB.alloc(cap));
+  CK(s->recA.alloc(cap)); CK(s->recB.alloc(cap)); CK(s->hit.alloc(cap)); CK(s->L.alloc(cap));
   CK(s->qMat.alloc((size_t)cap * kNumQueues));
   CK(s->qType.alloc(cap));
   if (!s->ctr.p) CK(s->ctr.alloc(1));
@@ -199,12 +198,11 @@ int ensure_wave(pbrgpu_scene* s, uint32_t cap, uint32_t raysPerHit, bool vol) {
 }
 
 void fill_wave(pbrgpu_scene* s, WaveDev* w) {
-  w->rayO = s->rayO.p; w->rayD = s->rayD.p; w->hit = s->hit.p; w->beta = s->beta.p; w->L = s->L.p;
-  w->hidx = s->hidx.p; w->meta = s->meta.p;
+  w->cur = s->recA.p; w->nxt = s->recB.p; w->hit = s->hit.p; w->L = s->L.p;
   w->shO = s->shO.p; w->shD = s->shD.p; w->shC = s->shC.p;
   w->shP1 = s->shP1.p; w->shE1 = s->shE1.p; w->shN1 = s->shN1.p;
   w->miO = s->miO.p; w->miD = s->miD.p; w->miC = s->miC.p;
-  w->qCur = s->qA.p; w->qNext = s->qB.p; w->qMat = s->qMat.p; w->qType = s->qType.p;
+  w->qMat = s->qMat.p; w->qType = s->qType.p;
   w->ctr = s->ctr.p;
   w->capacity = s->capacity;
 }
@@ -981,8 +979,8 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
       P.sBegin = sb;
       P.nsWave = ns;
       uint64_t nPaths = (uint64_t)rows * W * ns;
-      P.ws.qCur = s->qA.p;
-      P.ws.qNext = s->qB.p;
+      P.ws.cur = s->recA.p;
+      P.ws.nxt = s->recB.p;
       uint32_t g = grid_for(c, nPaths, 8);
       uint32_t gc = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((nPaths + kClassifyTile - 1) / kClassifyTile, (uint64_t)c->smCount * 8));
       // persistent traversal grid: every SM filled to the kernel's occupancy, never more blocks than rays
@@ -1041,7 +1039,7 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
           if (s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, 0); launches++; }
           k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
           launches += 3;
-          std::swap(P.ws.qCur, P.ws.qNext);
+          std::swap(P.ws.cur, P.ws.nxt);
           if (iter >= rd->max_depth) {
             CK(cudaMemcpyAsync(s->hNCur, s->ctr.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));  // nCur, nNext, nShadow, nMis
             CK(cudaStreamSynchronize(st));
@@ -1068,7 +1066,7 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
         if (!pathInteg || s->sc.nInfinite > 0) { k_shade_miss<<<g, kBlock, 0, st>>>(P, bounce); launches++; }
         k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
         launches += 3;
-        std::swap(P.ws.qCur, P.ws.qNext);
+        std::swap(P.ws.cur, P.ws.nxt);
       }
       if (!pathInteg && !volInteg) {  // shadow / MIS rays of the last shaded depth
         CK(tl.mark(T_CLOSEST));
