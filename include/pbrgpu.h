@@ -92,7 +92,9 @@ enum {
   PBRGPU_LIGHT_POINT = 0,    /* pos, L = intensity I */
   PBRGPU_LIGHT_AREA_TRI = 1, /* DiffuseAreaLight over ONE triangle (the reference creates one light per Triangle) */
   PBRGPU_LIGHT_INFINITE = 2, /* InfiniteAreaLight: env map * L, importance sampled, light_to_world */
-  PBRGPU_LIGHT_SKYBOX = 3    /* SkyBoxLight: env map, uniform sphere sampling, tone-mapped texels */
+  PBRGPU_LIGHT_SKYBOX = 3,   /* SkyBoxLight: env map, uniform sphere sampling, tone-mapped texels */
+  PBRGPU_LIGHT_AREA_SPHERE = 4 /* DiffuseAreaLight over ONE analytic sphere (pbrgpu_sphere): .tri = index into spheres; sampled by
+                                  solid angle (uniform cone outside, uniform area inside: host/AnalyticSphere.h) */
 };
 typedef struct pbrgpu_light {
   int32_t type;
@@ -106,6 +108,19 @@ typedef struct pbrgpu_light {
   float light_to_world[16]; /* INFINITE, row-major Matrix4x4::m */
   float world_to_light[16]; /* INFINITE, row-major inverse */
 } pbrgpu_light; /* 176 bytes */
+
+/* ---- analytic spheres.  The reference's PBR::Sphere is a stub (Shape/Sphere.cpp:8-37: no hit record, IntersectP
+ *      false); Shape/README.md section 3 documents the intended quadratic.  CPU twin: host/AnalyticSphere.h (a subclass of the
+ *      reference's Shape) - PARITY UNPINNED by the reference, pins are twin == GPU.  Optional: a scene without spheres never
+ *      runs this code (separate kernel instantiation).  Sphere k is primitive n_tris + k in the parity hooks. ---- */
+typedef struct pbrgpu_sphere {
+  float center[3];   /* ObjectToWorld must be a pure translation */
+  float radius;
+  int32_t material;  /* index into materials */
+  int32_t light;     /* index into lights (PBRGPU_LIGHT_AREA_SPHERE) or -1 */
+  int32_t reverse_orientation;
+  int32_t pad0;
+} pbrgpu_sphere; /* 32 bytes */
 
 /* ---- scene: Core/Scene.h:13-30 + Accelerator/BVHAccel.h + Shape/Triangle.h ---- */
 typedef struct pbrgpu_scene_desc {
@@ -139,6 +154,10 @@ typedef struct pbrgpu_scene_desc {
   int32_t n_textures;
   int32_t pad1;
   const pbrgpu_texture* textures;
+  /* analytic spheres (optional) */
+  int32_t n_spheres;
+  int32_t pad2;
+  const pbrgpu_sphere* spheres;
 } pbrgpu_scene_desc;
 
 /* ---- camera: Camera/Camera.h:34-54, Perspective.cpp, Orthographic.cpp ---- */
@@ -302,6 +321,10 @@ int pbrgpu_trace_rays(pbrgpu_scene* scene, const float* rays, int64_t n, int any
 /* Parity hook: ImageTexture::Evaluate of textures[texture] for n surface points.  rows float[n][8] = u, v, dudx, dvdx, dudy,
  * dvdy, -, - (SurfaceInteraction::uv and its screen-space derivatives); out float[n][4] = rgb, -. */
 int pbrgpu_texture_eval(pbrgpu_scene* scene, int texture, const float* rows, int64_t n, float* out);
+
+/* Parity hook: Light::Sample_Li / Pdf_Li of lights[light] for n reference points.  rows float[n][16] = ref.p, ref.pError, ref.n,
+ * u0, u1, query wi, -, -;  out float[n][16] = Li.rgb, pdf, wi, p1, n1, Pdf_Li(ref, query wi), -, -. */
+int pbrgpu_light_eval(pbrgpu_scene* scene, int light, const float* rows, int64_t n, float* out);
 
 /* Halton helper mirrors (host-side integer code; Halton.cpp:40-81).  Outputs 7 ints:
  * baseScales[2], baseExponents[2], sampleStride, multInverse[2]. */

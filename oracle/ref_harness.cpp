@@ -69,6 +69,7 @@
 #undef protected
 
 #include "SobolSampler.h"  // our CPU twin of the GPU Sobol sampler (the reference has only the tables)
+#include "AnalyticSphere.h"  // our CPU twin of the GPU analytic sphere (the reference's Sphere is a stub)
 #include "pbrgpu.h"
 
 namespace PBR {
@@ -102,6 +103,8 @@ struct RefScene {
   Transform identity;
   std::vector<std::shared_ptr<TriangleMesh>> meshes;
   std::vector<std::shared_ptr<Shape>> tris;
+  std::vector<std::shared_ptr<Shape>> spheres;                // AnalyticSphere twins (pbrgpu_sphere)
+  std::vector<std::unique_ptr<Transform>> sphereXf;            // their ObjectToWorld / WorldToObject (translations)
   std::vector<std::shared_ptr<Material>> materials;
   std::vector<std::unique_ptr<HomogeneousMedium>> media;
   std::vector<std::shared_ptr<Light>> lights;
@@ -217,6 +220,13 @@ void* ref_scene_create(const pbrgpu_scene_desc* d) {
     bool rev = d->tri_flags ? (d->tri_flags[i] & 1) != 0 : false;
     rs->tris.push_back(std::make_shared<Triangle>(&rs->identity, &rs->identity, rev, meshFor(i), i));
   }
+  for (int i = 0; i < d->n_spheres; ++i) {
+    const pbrgpu_sphere& sp = d->spheres[i];
+    rs->sphereXf.emplace_back(new Transform(Translate(Vector3f(sp.center[0], sp.center[1], sp.center[2]))));
+    Transform* o2w = rs->sphereXf.back().get();
+    rs->sphereXf.emplace_back(new Transform(Inverse(*o2w)));
+    rs->spheres.push_back(std::make_shared<AnalyticSphere>(o2w, rs->sphereXf.back().get(), sp.reverse_orientation != 0, sp.radius));
+  }
   // lights (one entry per emissive triangle, as the reference does: Main/main.cpp:353-375)
   rs->lights.resize(d->n_lights);
   std::vector<std::shared_ptr<AreaLight>> areaOfLight(d->n_lights);
@@ -230,6 +240,13 @@ void* ref_scene_create(const pbrgpu_scene_desc* d) {
       case PBRGPU_LIGHT_AREA_TRI: {
         auto a = std::make_shared<DiffuseAreaLight>(rs->identity, MediumInterface(), rgb(L.L), L.n_samples,
                                                     rs->tris[L.tri], L.two_sided != 0);
+        areaOfLight[i] = a;
+        rs->lights[i] = a;
+        break;
+      }
+      case PBRGPU_LIGHT_AREA_SPHERE: {
+        auto a = std::make_shared<DiffuseAreaLight>(rs->identity, MediumInterface(), rgb(L.L), L.n_samples,
+                                                    rs->spheres[L.tri], L.two_sided != 0);
         areaOfLight[i] = a;
         rs->lights[i] = a;
         break;
@@ -288,6 +305,13 @@ void* ref_scene_create(const pbrgpu_scene_desc* d) {
     std::shared_ptr<Material> mat = d->tri_material[i] >= 0 ? rs->materials[d->tri_material[i]] : nullptr;
     auto gp = std::make_shared<GeometricPrimitive>(rs->tris[i], mat, al, MediumInterface(mIn, mOut));
     rs->primIndex[gp.get()] = i;
+    rs->prims.push_back(gp);
+  }
+  for (int i = 0; i < d->n_spheres; ++i) {  // primitive ids n_tris .. n_tris + n_spheres - 1
+    const pbrgpu_sphere& sp = d->spheres[i];
+    std::shared_ptr<AreaLight> al = sp.light >= 0 ? areaOfLight[sp.light] : nullptr;
+    auto gp = std::make_shared<GeometricPrimitive>(rs->spheres[i], rs->materials[sp.material], al, MediumInterface());
+    rs->primIndex[gp.get()] = d->n_tris + i;
     rs->prims.push_back(gp);
   }
   double t0 = omp_get_wtime();
@@ -734,6 +758,30 @@ void ref_hg_kat(float g, const float* in, int n, float* out) {
     o[0] = wi.x; o[1] = wi.y; o[2] = wi.z; o[3] = p;
     o[4] = hg.p(wo, Vector3f(r[5], r[6], r[7]));
     o[5] = o[6] = o[7] = 0.f;
+  }
+}
+
+// Light::Sample_Li / Pdf_Li of lights[light] for n reference points (same row layout as pbrgpu_light_eval)
+void ref_light_eval(void* hscene, int light, const float* rows, int n, float* out) {
+  auto* rs = (RefScene*)hscene;
+  const Light& L = *rs->lights[light];
+  for (int i = 0; i < n; ++i) {
+    const float* r = rows + 16 * i;
+    Interaction ref;
+    ref.p = Point3f(r[0], r[1], r[2]);
+    ref.pError = Vector3f(r[3], r[4], r[5]);
+    ref.n = Normal3f(r[6], r[7], r[8]);
+    Vector3f wi(0, 0, 0);
+    float pdf = 0;
+    VisibilityTester vis;
+    Spectrum Li = L.Sample_Li(ref, Point2f(r[9], r[10]), &wi, &pdf, &vis);
+    const float pq = L.Pdf_Li(ref, Vector3f(r[11], r[12], r[13]));
+    float* o = out + 16 * i;
+    o[0] = Li[0]; o[1] = Li[1]; o[2] = Li[2]; o[3] = pdf;
+    o[4] = wi.x; o[5] = wi.y; o[6] = wi.z;
+    o[7] = vis.P1().p.x; o[8] = vis.P1().p.y; o[9] = vis.P1().p.z;
+    o[10] = vis.P1().n.x; o[11] = vis.P1().n.y; o[12] = vis.P1().n.z;
+    o[13] = pq; o[14] = o[15] = 0.f;
   }
 }
 

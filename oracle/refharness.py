@@ -102,6 +102,13 @@ class RefScene:
         lib().ref_scene_bound(self.h, out)
         return np.array(out[:], dtype=np.float32)
 
+    def light_eval(self, light, rows):
+        """The reference's Light::Sample_Li / Pdf_Li (row layout of pbrgpu_light_eval)."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 16)
+        out = np.zeros_like(rows)
+        lib().ref_light_eval(C.c_void_p(self.h), light, rows.ctypes.data, rows.shape[0], out.ctypes.data)
+        return out
+
     def trace(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
         n = rays.shape[0]

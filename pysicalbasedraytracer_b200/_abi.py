@@ -2,7 +2,7 @@
 import ctypes as C
 
 MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_METAL, MAT_PLASTIC = range(5)
-LIGHT_POINT, LIGHT_AREA_TRI, LIGHT_INFINITE, LIGHT_SKYBOX = range(4)
+LIGHT_POINT, LIGHT_AREA_TRI, LIGHT_INFINITE, LIGHT_SKYBOX, LIGHT_AREA_SPHERE = range(5)
 CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC = 0, 1
 SAMPLER_HALTON, SAMPLER_SOBOL = 0, 1
 INTEGRATOR_PATH, INTEGRATOR_DIRECT_ONE, INTEGRATOR_DIRECT_ALL, INTEGRATOR_WHITTED, INTEGRATOR_VOLPATH = range(5)
@@ -41,6 +41,11 @@ class Medium(C.Structure):
     _fields_ = [("type", C.c_int32), ("g", C.c_float), ("sigma_a", f3), ("sigma_s", f3)]
 
 
+class Sphere(C.Structure):
+    _fields_ = [("center", f3), ("radius", C.c_float), ("material", C.c_int32), ("light", C.c_int32),
+                ("reverse_orientation", C.c_int32), ("pad0", C.c_int32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("n_verts", C.c_int32), ("n_tris", C.c_int32),
                 ("verts", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_int32)),
@@ -52,7 +57,8 @@ class SceneDesc(C.Structure):
                 ("env_width", C.c_int32), ("env_height", C.c_int32), ("env_texels", C.POINTER(C.c_float)),
                 ("n_media", C.c_int32), ("pad0", C.c_int32), ("media", C.POINTER(Medium)),
                 ("tri_medium_inside", C.POINTER(C.c_int32)), ("tri_medium_outside", C.POINTER(C.c_int32)),
-                ("n_textures", C.c_int32), ("pad1", C.c_int32), ("textures", C.POINTER(Texture))]
+                ("n_textures", C.c_int32), ("pad1", C.c_int32), ("textures", C.POINTER(Texture)),
+                ("n_spheres", C.c_int32), ("pad2", C.c_int32), ("spheres", C.POINTER(Sphere))]
 
 
 class CameraDesc(C.Structure):
@@ -88,4 +94,4 @@ class DumpDesc(C.Structure):
                 ("s0", C.c_int64), ("s1", C.c_int64), ("n_dims", C.c_int32), ("pad", C.c_int32)]
 
 
-assert C.sizeof(Material) == 96 and C.sizeof(Light) == 176 and C.sizeof(Medium) == 32 and C.sizeof(Texture) == 48
+assert C.sizeof(Sphere) == 32 and C.sizeof(Material) == 96 and C.sizeof(Light) == 176 and C.sizeof(Medium) == 32 and C.sizeof(Texture) == 48

@@ -60,6 +60,7 @@ def lib():
         L.pbrgpu_texture_eval.argtypes = [vp, C.c_int, vp, C.c_int64, vp]
         L.pbrgpu_load_hdr.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.pbrgpu_free.argtypes = [vp]
+        L.pbrgpu_light_eval.argtypes = [vp, C.c_int, vp, C.c_int64, vp]
         L.pbrgpu_init_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
         L.pbrgpu_comm_unique_id.argtypes = [vp]
         L.pbrgpu_comm_attach.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -374,6 +375,14 @@ class Scene:
         out = np.zeros((rows.shape[0], 4), dtype=np.float32)
         _check(lib().pbrgpu_texture_eval(self.h, texture, rows.ctypes.data, rows.shape[0], out.ctypes.data))
         return out[:, :3]
+
+    def light_eval(self, light, rows):
+        """Light::Sample_Li / Pdf_Li parity hook: rows [n,16] = ref.p, ref.pError, ref.n, u0, u1, query wi, -, - ->
+        [n,16] = Li.rgb, pdf, wi, p1, n1, Pdf_Li(ref, query wi), -, -."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 16)
+        out = np.zeros_like(rows)
+        _check(lib().pbrgpu_light_eval(self.h, light, rows.ctypes.data, rows.shape[0], out.ctypes.data))
+        return out
 
     # ---- render ----
     def render(self, integrator=A.INTEGRATOR_PATH, max_depth=5, rr_threshold=1.0,

@@ -40,7 +40,9 @@ struct BuiltBvh8 {
   int maxDepth = 0;               // wide-tree depth = upper bound on traversal stack entries
 };
 
-// verts: float[nVerts*3], indices: int[nTris*3].  Deterministic binned-SAH build.
-void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh8* out);
+// verts: float[nVerts*3], indices: int[nTris*3].  Deterministic binned-SAH build.  `extra` / nExtra: bounds of further
+// primitives (analytic spheres), which get the primitive ids nTris .. nTris + nExtra - 1.
+void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh8* out,
+                const Aabb* extra = nullptr, int64_t nExtra = 0);
 
 }  // namespace pbr

@@ -50,18 +50,23 @@ namespace {
 struct BinaryStats { int maxLeafSize = 0; int64_t nLeaves = 0; int maxDepth = 0; };
 
 // Binned-SAH binary tree over triangle bounds; `order` = leaf-order permutation of triangle ids.
-void build_binary(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, std::vector<TmpNode>& tmp,
-                  std::vector<int32_t>& order, BinaryStats* out) {
+void build_binary(const float* verts, const int32_t* indices, int64_t nTriangles, const Aabb* extra, int64_t nExtra, int maxLeaf,
+                  std::vector<TmpNode>& tmp, std::vector<int32_t>& order, BinaryStats* out) {
+  const int64_t nTris = nTriangles + nExtra;  // primitives: triangles, then the caller's extra boxes
   std::vector<Aabb> tb((size_t)nTris);
   std::vector<float> cen((size_t)nTris * 3);
   for (int64_t i = 0; i < nTris; ++i) {
     Aabb b = empty_box();
-    for (int v = 0; v < 3; ++v) {
-      const float* p = verts + 3 * (int64_t)indices[3 * i + v];
-      for (int k = 0; k < 3; ++k) {
-        b.lo[k] = std::min(b.lo[k], p[k]);
-        b.hi[k] = std::max(b.hi[k], p[k]);
+    if (i < nTriangles) {
+      for (int v = 0; v < 3; ++v) {
+        const float* p = verts + 3 * (int64_t)indices[3 * i + v];
+        for (int k = 0; k < 3; ++k) {
+          b.lo[k] = std::min(b.lo[k], p[k]);
+          b.hi[k] = std::max(b.hi[k], p[k]);
+        }
       }
+    } else {
+      b = extra[i - nTriangles];
     }
     tb[i] = b;
     for (int k = 0; k < 3; ++k) cen[3 * i + k] = 0.5f * b.lo[k] + 0.5f * b.hi[k];
@@ -243,12 +248,14 @@ void collect_forest(const std::vector<TmpNode>& tmp, const Widening& w, int32_t 
 }
 }  // namespace
 
-void build_bvh8(const float* verts, const int32_t* indices, int64_t nTris, int maxLeaf, BuiltBvh8* out) {
+void build_bvh8(const float* verts, const int32_t* indices, int64_t nTriangles, int maxLeaf, BuiltBvh8* out, const Aabb* extra,
+                int64_t nExtra) {
   maxLeaf = std::max(1, std::min(3, maxLeaf));
   std::vector<TmpNode> tmp;
   std::vector<int32_t> order;
   BinaryStats bs;
-  build_binary(verts, indices, nTris, 1, tmp, order, &bs);  // one triangle per binary leaf: the widening forms the leaves
+  const int64_t nTris = nTriangles + nExtra;
+  build_binary(verts, indices, nTriangles, extra, nExtra, 1, tmp, order, &bs);  // one triangle per binary leaf: the widening forms the leaves
   Widening wd;
   if (const char* e = std::getenv("PBRGPU_PRIM_COST")) kPrimCost = (float)std::atof(e);
   compute_widening(tmp, maxLeaf, &wd);

@@ -21,9 +21,10 @@ constexpr uint32_t kMetaBounceMask = 0x7fu;
 constexpr int kMetaInMediumBit = 24;  // VolPath: Ray::medium != nullptr (lets the medium kernels skip a path after one 4-byte read)
 
 // ---- triangle record (leaf order): three float4 = three 16-byte loads ----
-//   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-23), material type (24-27), flags (28-31)
+//   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-22), sphere (23), material type (24-27), flags (28-31)
 //   tv2 = p2.xyz | area-light id or -1
-constexpr uint32_t kTriMatMask = 0x00ffffffu;
+constexpr uint32_t kTriMatMask = 0x007fffffu;
+constexpr uint32_t kPrimSphereBit = 0x00800000u;  // the record is an analytic sphere (sphere.cuh): tv0 = centre | id, tv1.x = radius
 constexpr int kTriTypeShift = 24;
 constexpr int kTriFlagShift = 28;
 constexpr uint32_t kTriFlagFlipNormal = 1u;  // reverseOrientation ^ transformSwapsHandedness
@@ -84,7 +85,8 @@ struct SceneDev {
   const pbrgpu_medium* media;   // HomogeneousMedium table (VolPath)
   const uint32_t* triMedium;    // per leaf-order triangle: (inside + 1) | (outside + 1) << 16, 0 = none; NULL = no interfaces
   int nMedia;
-  int nTris, nLights, nInfinite;
+  int nTris, nLights, nInfinite;  // nTris: primitives in the leaf arrays (triangles + analytic spheres)
+  int nSpheres;                   // analytic spheres among them (0: the sphere code is never instantiated)
   unsigned f32one;              // 0x3F800000 (opaque to ptxas: keeps the PRMT selector an immediate, trace.cuh q2f)
   int infinite[4];              // indices of infinite lights (Scene::infiniteLights)
   const float* lightFunc;       // Distribution1D of the active light-sampling strategy
@@ -159,6 +161,8 @@ struct RenderParams {
   int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
   int countStats;
   int fetchMinIdle;       // idle lanes of a warp that trigger a ray fetch
+  int triMinLanes;        // k_trace: lanes with a candidate triangle that trigger a triangle round (1 = every iteration)
+  int stallMin;           // k_trace: ... or this many lanes that cannot progress without a triangle round
   float diffScale;        // 1 / sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials of the render loop (image textures)
   int volShadowAnyHit;    // VolPath, scene without material-less surfaces: a shadow ray ends at ANY surface it finds
   int storeHitT;          // parity hooks: k_trace also stores the hit distance of path rays (rayO.w), like the VOL build

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
       SamplerCursor cur = load_cursor(P, rec);
       TriData tri = load_tri(sc, __float_as_int(h4.x));
       Isect is;
-      make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is);
+      make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is, V3(rec.o.x, rec.o.y, rec.o.z));
       Spec Ladd(0.f);
       // emitted light for camera rays / after specular bounces
       if ((bounce == 0 || specularBounce) && is.lightId >= 0)
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
             const pbrgpu_light& light = sc.lights[lightNum];
             // EstimateDirect (Integrator.cpp:71-177), strategy 1: sample the light
             LightSample ls;
-            sample_light(sc, light, is.p, uL0, uL1, &ls);
+            sample_light(sc, light, is.p, uL0, uL1, &ls, is.pError, is.n);
             if (ls.pdf > 0 && !ls.Li.is_black()) {
               Spec f = bsdf_f<MAT>(bsdf, is.wo, ls.wi, nonSpec) * absdot(ls.wi, is.ns);
               float scatteringPdf = bsdf_pdf<MAT>(bsdf, is.wo, ls.wi, nonSpec);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
                 float weight = 1;
                 bool ok = true;
                 if (!(sampledType & BSDF_SPECULAR)) {
-                  float lightPdf = light_pdf_li(sc, light, origin, is.p, wi);
+                  float lightPdf = light_pdf_li(sc, light, origin, is.p, wi, is.pError, is.n);
                   if (lightPdf == 0) ok = false;
                   else weight = power_heuristic(1, scatteringPdf, 1, lightPdf);
                 }

@@ -37,7 +37,7 @@ PBR_D void estimate_direct(const RenderParams& P, const Bsdf& bsdf, const Isect&
   const pbrgpu_light& light = sc.lights[lightNum];
   const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
   LightSample ls;
-  sample_light(sc, light, is.p, uL0, uL1, &ls);
+  sample_light(sc, light, is.p, uL0, uL1, &ls, is.pError, is.n);
   if (ls.pdf > 0 && !ls.Li.is_black()) {
     Spec f = bsdf_f<MAT>(bsdf, is.wo, ls.wi, nonSpec) * absdot(ls.wi, is.ns);
     float scatteringPdf = bsdf_pdf<MAT>(bsdf, is.wo, ls.wi, nonSpec);
@@ -61,7 +61,7 @@ PBR_D void estimate_direct(const RenderParams& P, const Bsdf& bsdf, const Isect&
       float weight = 1;
       bool ok = true;
       if (!(sampledType & BSDF_SPECULAR)) {
-        float lightPdf = light_pdf_li(sc, light, origin, is.p, wi);
+        float lightPdf = light_pdf_li(sc, light, origin, is.p, wi, is.pError, is.n);
         if (lightPdf == 0) ok = false;
         else weight = power_heuristic(1, scatteringPdf, 1, lightPdf);
       }
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
       SamplerCursor cur = load_cursor(P, rec);
       TriData tri = load_tri(sc, __float_as_int(h4.x));
       Isect is;
-      make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is);
+      make_isect(sc, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, rayD, &is, V3(rec.o.x, rec.o.y, rec.o.z));
       // L += isect.Le(wo) at every depth (WhittedIntegrator.cpp:33, DirectLightingIntegrator.cpp:41)
       if (is.lightId >= 0) {
         Spec Le = beta * area_light_L(sc.lights[is.lightId], is.n, is.wo);
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
           float u0, u1;
           cur.get2D(sc.hp, &u0, &u1);
           LightSample ls;
-          sample_light(sc, sc.lights[j], is.p, u0, u1, &ls);
+          sample_light(sc, sc.lights[j], is.p, u0, u1, &ls, is.pError, is.n);
           if (ls.Li.is_black() || ls.pdf == 0) continue;
           Spec f = bsdf_f<MAT>(bsdf, is.wo, ls.wi, BSDF_ALL);
           if (f.is_black()) continue;

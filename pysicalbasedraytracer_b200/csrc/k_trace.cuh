@@ -55,7 +55,8 @@ PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T,
   // ray = isect.SpawnRayTo(p1)   (Interaction.h:38-43; isect.mediumInterface from GeometricPrimitive::Intersect)
   const TriData tri = load_tri(sc, hit.tri);
   Isect is;
-  make_isect(sc, tri, hit.tri, hit.b0, hit.b1, hit.b2, d, &is);
+  const float4 so = P.ws.shO[ray];  // origin of the segment just traced (an analytic-sphere boundary needs it)
+  make_isect(sc, tri, hit.tri, hit.b0, hit.b1, hit.b2, d, &is, V3(so.x, so.y, so.z));
   const float4 e1 = P.ws.shE1[ray], n1 = P.ws.shN1[ray];
   const V3 p1(p1m.x, p1m.y, p1m.z);
   const V3 origin = offset_ray_origin(is.p, is.pError, is.n, p1 - is.p);
@@ -67,11 +68,12 @@ PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T,
   P.ws.shC[ray] = c;
   P.ws.shP1[ray].w = __int_as_float(nmed);
   P.ws.shD[ray] = make_float4(nd.x, nd.y, nd.z, dd.w);
+  P.ws.shO[ray] = make_float4(origin.x, origin.y, origin.z, 1 - kShadowEpsilon);
   trav_init(T, origin, nd, 1 - kShadowEpsilon, sc.f32one);
   return true;
 }
 
-template <bool COUNT, bool VOL = false>
+template <bool COUNT, bool VOL = false, bool SPH = false>
 __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
   __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
   __shared__ uint2 stri[kTraceBlock / 32][kTriQueue][32];
@@ -135,14 +137,25 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
           if (COUNT) nodes++;
         }
       }
-      // ---- triangle round: ONE candidate triangle per lane (a threshold on the number of lanes with candidates
-      // was measured: lanes always have a backlog, so the round runs every iteration anyway) ----
-      if (T.tgroup.y != 0u || nt > 0) {
+    }
+    // ---- triangle round: ONE candidate triangle per lane.  The round is SKIPPED while fewer than P.triMinLanes lanes have a
+    // candidate, unless P.stallMin lanes cannot make progress without it (traversal finished with candidates pending, or the
+    // parked-group list is full) or no lane has node work left: the long watertight test then runs with fuller warps ----
+    bool triRound = true;
+    if (P.triMinLanes > 1) {
+      const bool wantTri = busy && (T.tgroup.y != 0u || nt > 0);
+      const bool canNode = busy && (T.ngroup.y > 0x00FFFFFFu || T.sp > 0) && (T.tgroup.y == 0u || nt < kTriQueue);
+      const unsigned mWant = __ballot_sync(full, wantTri), mStall = __ballot_sync(full, wantTri && !canNode);
+      const unsigned mNode = __ballot_sync(full, canNode);
+      triRound = __popc(mWant) >= P.triMinLanes || __popc(mStall) >= P.stallMin || mNode == 0u;
+    }
+    if (busy) {
+      if (triRound && (T.tgroup.y != 0u || nt > 0)) {
         if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
         if (COUNT) tris++;
         // any-hit exit for shadow rays; VolPath shadow rays need the CLOSEST surface (it may be a medium boundary)
         // (unless the scene has no such boundary at all: then the first surface found ends the ray either way)
-        if (cw_tri_step(P.sc, T, &hit) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+        if (cw_tri_step<SPH>(P.sc, T, &hit) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
       }
       // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
       if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {

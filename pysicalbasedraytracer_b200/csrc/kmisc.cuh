@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_null(const __grid_constant__ R
       const int tri = __float_as_int(h4.x);
       const TriData td = load_tri(sc, tri);
       Isect is;
-      make_isect(sc, td, tri, h4.y, h4.z, h4.w, rayD, &is);
+      make_isect(sc, td, tri, h4.y, h4.z, h4.w, rayD, &is, V3(rec.o.x, rec.o.y, rec.o.z));
       if ((bounce == 0 || specularBounce) && is.lightId >= 0) {
         const float4 be4 = rec.beta;
         const Spec Ladd = Spec(be4.x, be4.y, be4.z) * area_light_L(sc.lights[is.lightId], is.n, -rayD);
@@ -318,8 +318,15 @@ __global__ void __launch_bounds__(kBlock) k_resolve_mis(const __grid_constant__ 
     Spec Li(0.f);
     if (tri >= 0) {
       if (__float_as_int(__ldg(&P.sc.tv2[tri].w)) == lightId) {
-        const float4 n4 = __ldg(P.sc.tvN + tri);
-        Li = area_light_L(light, V3(n4.x, n4.y, n4.z), -wi);
+        if (light.type == PBRGPU_LIGHT_AREA_SPHERE) {  // the hit normal of the analytic sphere along this ray
+          const V3 c(light.pos[0], light.pos[1], light.pos[2]), ro(o.x, o.y, o.z);
+          float t;
+          if (sphere_solve(ro - c, wi, light.world_radius, kInfinity, &t))
+            Li = area_light_L(light, sphere_hit(c, light.world_radius, light.light_to_world[0] != 0.f, ro, wi, t).n, -wi);
+        } else {
+          const float4 n4 = __ldg(P.sc.tvN + tri);
+          Li = area_light_L(light, V3(n4.x, n4.y, n4.z), -wi);
+        }
       }
     } else {
       Li = light_Le(P.sc, light, wi);
@@ -429,13 +436,13 @@ __global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__
     if (outDiff) {  // hit flag, uv, dudx, dvdx, dudy, dvdy of the camera ray (SurfaceInteraction::ComputeDifferentials)
       HitRec h;
       unsigned a = 0, b = 0;
-      traverse<false, false>(P.sc, o, d, kInfinity, &h, sstack, &a, &b);
+      traverse<false, false, true>(P.sc, o, d, kInfinity, &h, sstack, &a, &b);
       float* q = outDiff + 8 * i;
       for (int k = 0; k < 8; ++k) q[k] = 0.f;
       if (h.tri >= 0) {
         const TriData tri = load_tri(P.sc, h.tri);
         Isect is;
-        make_isect(P.sc, tri, h.tri, h.b0, h.b1, h.b2, d, &is);
+        make_isect(P.sc, tri, h.tri, h.b0, h.b1, h.b2, d, &is, o);
         float u, v;
         UvDiff dd;
         hit_uv_differentials(P, tri, h.tri, h.b0, h.b1, h.b2, is.p, is.n, true, px, py, idx, o, d, &u, &v, &dd);
@@ -445,7 +452,7 @@ __global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__
     if (outHits) {
       HitRec h;
       unsigned a = 0, b = 0;
-      traverse<false, false>(P.sc, o, d, kInfinity, &h, sstack, &a, &b);
+      traverse<false, false, true>(P.sc, o, d, kInfinity, &h, sstack, &a, &b);
       int* q = outHits + 4 * i;
       q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
       q[1] = __float_as_int(h.t);
@@ -473,9 +480,9 @@ __global__ void __launch_bounds__(kBlock) k_trace_user(const __grid_constant__ R
     unsigned a = 0, b = 0;
     V3 o(r[0], r[1], r[2]), d(r[4], r[5], r[6]);
     if (anyHit) {
-      out[i] = traverse<true, false>(P.sc, o, d, r[3], &h, sstack, &a, &b) ? 1 : 0;
+      out[i] = traverse<true, false, true>(P.sc, o, d, r[3], &h, sstack, &a, &b) ? 1 : 0;
     } else {
-      traverse<false, false>(P.sc, o, d, r[3], &h, sstack, &a, &b);
+      traverse<false, false, true>(P.sc, o, d, r[3], &h, sstack, &a, &b);
       int* q = out + 4 * i;
       q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
       q[1] = __float_as_int(h.t);
@@ -504,6 +511,27 @@ __global__ void __launch_bounds__(256) k_read_bandwidth(const float4* __restrict
     for (; i < n; i += stride) { const float4 v = __ldcg(p + i); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
   }
   if (acc.x + acc.y + acc.z + acc.w == 123456.789f) *sink = acc.x;  // never true: keeps the loads alive
+}
+
+// Parity hook: Light::Sample_Li / Pdf_Li of one light for n reference points.  rows float[n][16] = ref.p, ref.pError, ref.n,
+// u0, u1, query wi, -, -;  out float[n][16] = Li.rgb, pdf, wi, p1, n1, Pdf_Li(ref, query wi), -, -.
+__global__ void __launch_bounds__(kBlock) k_light_eval(SceneDev sc, int light, const float* rows, long long n, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float* r = rows + 16 * i;
+    const V3 p(r[0], r[1], r[2]), pe(r[3], r[4], r[5]), nn(r[6], r[7], r[8]), wq(r[11], r[12], r[13]);
+    const pbrgpu_light& l = sc.lights[light];
+    LightSample ls;
+    ls.wi = V3(0, 0, 0); ls.p1 = V3(0, 0, 0);
+    sample_light(sc, l, p, r[9], r[10], &ls, pe, nn);
+    const V3 spawnO = offset_ray_origin(p, pe, nn, wq);  // ref.SpawnRay(wi).o
+    const float pq = light_pdf_li(sc, l, spawnO, p, wq, pe, nn);
+    float* o = out + 16 * i;
+    o[0] = ls.Li.r; o[1] = ls.Li.g; o[2] = ls.Li.b; o[3] = ls.pdf;
+    o[4] = ls.wi.x; o[5] = ls.wi.y; o[6] = ls.wi.z;
+    o[7] = ls.p1.x; o[8] = ls.p1.y; o[9] = ls.p1.z;
+    o[10] = ls.n1.x; o[11] = ls.n1.y; o[12] = ls.n1.z;
+    o[13] = pq; o[14] = o[15] = 0.f;
+  }
 }
 
 // ---- parity hooks on the PRODUCTION traversal kernel (k_trace) ----

@@ -13,6 +13,7 @@ constexpr int kDirectBlockThreads = 256;  // == kBlock
 
 // k_trace<COUNT, VOL>: resident blocks per SM (occupancy of the plain build), launch
 int trace_blocks_per_sm();
+// (P.sc.nSpheres > 0 selects the instantiations that know the analytic-sphere primitive)
 void launch_trace(bool count, bool vol, unsigned grid, cudaStream_t st, const RenderParams& P);
 
 // k_shade<MAT, VOL, TEX>: resident blocks per SM of that instantiation (0 = no such instantiation), launch

@@ -142,6 +142,7 @@ struct pbrgpu_scene {
   int lightStrategyBuilt = -1;
   int traceBlocksPerSm = 0;
   int fetchMinIdle = 8;
+  int triMinLanes = 1, stallMin = 32;
   int waveLog2 = 25;
   bool hasMat[PBRGPU_MAT_COUNT] = {};  // material types present in the scene (absent ones: no shade launch)
   bool hasNullMat = false;             // some triangle has no material (medium boundary): VolPath only
@@ -360,8 +361,16 @@ int64_t pbrgpu_compute_perms(uint16_t* out, int64_t capacity) {
 static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, const BuiltBvh8* prebuilt, pbrgpu_scene** out) {
   if (!ctx || !d || !out) return fail("pbrgpu_scene_create: NULL argument");
   *out = nullptr;
-  if (d->n_tris <= 0 || d->n_verts <= 0 || !d->verts || !d->indices || !d->tri_material)
+  if (d->n_spheres < 0 || (d->n_spheres > 0 && !d->spheres)) return fail("pbrgpu_scene_create: bad sphere table");
+  if (d->n_tris < 0 || (d->n_tris == 0 && d->n_spheres == 0) || (d->n_tris > 0 && (d->n_verts <= 0 || !d->verts || !d->indices || !d->tri_material)))
     return fail("pbrgpu_scene_create: empty scene");
+  for (int i = 0; i < d->n_spheres; ++i) {
+    const pbrgpu_sphere& sp = d->spheres[i];
+    if (!(sp.radius > 0)) return fail("pbrgpu_scene_create: sphere radius must be positive");
+    if (sp.material < 0 || sp.material >= d->n_materials) return fail("pbrgpu_scene_create: sphere material out of range");
+    if (sp.light >= d->n_lights) return fail("pbrgpu_scene_create: sphere light out of range");
+    if (d->materials[sp.material].kd_texture_plus1 > 0) return fail("pbrgpu_scene_create: image textures on analytic spheres are not supported");
+  }
   if (d->n_tris >= (1 << 29)) return fail("pbrgpu_scene_create: too many triangles");
   if (d->n_materials < 0 || d->n_materials > (int)kTriMatMask || (d->n_materials > 0 && !d->materials))
     return fail("pbrgpu_scene_create: bad material count");
@@ -371,6 +380,8 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   for (int64_t i = 0; i < (int64_t)d->n_tris * 3; ++i)
     if (d->indices[i] < 0 || d->indices[i] >= d->n_verts) return fail("pbrgpu_scene_create: vertex index out of range");
   for (int i = 0; i < d->n_tris; ++i) {
+    if (d->tri_light && d->tri_light[i] >= 0 && d->lights[d->tri_light[i]].type != PBRGPU_LIGHT_AREA_TRI)
+      return fail("pbrgpu_scene_create: tri_light must name an AREA_TRI light");
     if (d->tri_material[i] < -1 || d->tri_material[i] >= d->n_materials)
       return fail("pbrgpu_scene_create: tri_material out of range");
     for (const int32_t* tm : {d->tri_medium_inside, d->tri_medium_outside})
@@ -384,9 +395,18 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
 
   int maxLeaf = 3;
   if (const char* e = getenv("PBRGPU_MAX_LEAF")) maxLeaf = std::max(1, std::min(3, atoi(e)));
+  const int nTriangles = d->n_tris;
+  const int nT = d->n_tris + d->n_spheres;  // primitives in the leaf arrays: triangles, then analytic spheres
   if (prebuilt) s->bvh = *prebuilt;  // group context: built once, uploaded to every device
-  else build_bvh8(d->verts, d->indices, d->n_tris, maxLeaf, &s->bvh);
-  const int nT = d->n_tris;
+  else {
+    std::vector<Aabb> sb((size_t)d->n_spheres);  // WorldBound() = ObjectToWorld(ObjectBound()): centre -/+ radius per axis
+    for (int i = 0; i < d->n_spheres; ++i)
+      for (int a = 0; a < 3; ++a) {
+        sb[i].lo[a] = -d->spheres[i].radius + d->spheres[i].center[a];
+        sb[i].hi[a] = d->spheres[i].radius + d->spheres[i].center[a];
+      }
+    build_bvh8(d->verts, d->indices, nTriangles, maxLeaf, &s->bvh, sb.data(), d->n_spheres);
+  }
   s->leafOf.assign((size_t)nT, -1);
   std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT), vN((size_t)nT), vS((size_t)nT), vT((size_t)nT);
   std::vector<float4> vn0, vn1, vn2, vuv0, vuv1;  // only when some mesh has shading normals / uvs
@@ -394,6 +414,16 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   for (int k = 0; k < nT; ++k) {
     int ti = s->bvh.triOrder[k];
     s->leafOf[ti] = k;
+    if (ti >= nTriangles) {  // analytic sphere (sphere.cuh): tv0 = centre | id, tv1 = radius | material word, tv2 = - | light
+      const pbrgpu_sphere& sp = d->spheres[ti - nTriangles];
+      const uint32_t flags = sp.reverse_orientation ? (kTriFlagFlipNormal | kTriFlagReverse) : 0u;
+      const uint32_t w1 = (uint32_t)sp.material | kPrimSphereBit | ((uint32_t)d->materials[sp.material].type << kTriTypeShift) | (flags << kTriFlagShift);
+      v0[k] = make_float4(sp.center[0], sp.center[1], sp.center[2], u2f((uint32_t)ti));
+      v1[k] = make_float4(sp.radius, 0.f, 0.f, u2f(w1));
+      v2[k] = make_float4(0.f, 0.f, 0.f, u2f((uint32_t)sp.light));
+      vN[k] = vS[k] = vT[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     const float* a = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti];
     const float* b = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti + 1];
     const float* c = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti + 2];
@@ -464,8 +494,9 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
       std::vector<uint32_t> tm((size_t)nT);
       for (int k = 0; k < nT; ++k) {
         const int ti = s->bvh.triOrder[k];
-        const int in = d->tri_medium_inside ? d->tri_medium_inside[ti] : -1;
-        const int out = d->tri_medium_outside ? d->tri_medium_outside[ti] : -1;
+        const bool isTri = ti < nTriangles;  // analytic spheres carry no MediumInterface
+        const int in = isTri && d->tri_medium_inside ? d->tri_medium_inside[ti] : -1;
+        const int out = isTri && d->tri_medium_outside ? d->tri_medium_outside[ti] : -1;
         tm[k] = (uint32_t)(in + 1) | ((uint32_t)(out + 1) << 16);
       }
       CK(s->triMedium.upload(tm, st));
@@ -577,7 +608,7 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
         break;
       }
       case PBRGPU_LIGHT_AREA_TRI: {
-        if (l.tri < 0 || l.tri >= nT) return fail("pbrgpu_scene_create: area light triangle out of range");
+        if (l.tri < 0 || l.tri >= nTriangles) return fail("pbrgpu_scene_create: area light triangle out of range");
         if (!d->tri_light || d->tri_light[l.tri] != i) return fail("pbrgpu_scene_create: tri_light / light.tri mismatch");
         const float* a = d->verts + 3 * (size_t)d->indices[3 * (size_t)l.tri];
         const float* b = d->verts + 3 * (size_t)d->indices[3 * (size_t)l.tri + 1];
@@ -597,6 +628,19 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
         l.light_to_world[0] = nS.x; l.light_to_world[1] = nS.y; l.light_to_world[2] = nS.z; l.light_to_world[3] = area;
         l.light_to_world[4] = nI.x; l.light_to_world[5] = nI.y; l.light_to_world[6] = nI.z;
         l.tri = s->leafOf[l.tri];
+        break;
+      }
+      case PBRGPU_LIGHT_AREA_SPHERE: {
+        if (l.tri < 0 || l.tri >= d->n_spheres) return fail("pbrgpu_scene_create: sphere light index out of range");
+        const pbrgpu_sphere& sp = d->spheres[l.tri];
+        if (sp.light != i) return fail("pbrgpu_scene_create: sphere.light / light.tri mismatch");
+        const float area = 4 * kPi * sp.radius * sp.radius;  // Sphere::Area (Sphere.cpp:31)
+        Spec p = ((l.two_sided ? 2.f : 1.f) * Spec(l.L[0], l.L[1], l.L[2])) * area * kPi;  // DiffuseAreaLight::Power
+        s->lightPower[i] = p.y();
+        l.pos[0] = sp.center[0]; l.pos[1] = sp.center[1]; l.pos[2] = sp.center[2];
+        l.world_radius = sp.radius;
+        l.light_to_world[0] = sp.reverse_orientation ? 1.f : 0.f;
+        l.tri = s->leafOf[nTriangles + l.tri];
         break;
       }
       case PBRGPU_LIGHT_INFINITE:
@@ -701,6 +745,7 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   s->sc.mats = s->mats.p;
   s->sc.lights = s->dlights.p;
   s->sc.nTris = nT;
+  s->sc.nSpheres = d->n_spheres;
   s->sc.f32one = 0x3F800000u;
   s->sc.nLights = d->n_lights;
 
@@ -836,6 +881,24 @@ int pbrgpu_texture_eval(pbrgpu_scene* s, int texture, const float* rows, int64_t
   return 0;
 }
 
+int pbrgpu_light_eval(pbrgpu_scene* s, int light, const float* rows, int64_t n, float* out) {
+  if (s && !s->replicas.empty()) s = s->replicas[0];
+  if (!s || !rows || !out || n < 0) return fail("pbrgpu_light_eval: bad argument");
+  if (light < 0 || light >= s->sc.nLights) return fail("pbrgpu_light_eval: light index out of range");
+  if (n == 0) return 0;
+  pbrgpu_ctx* c = s->ctx;
+  CK(cudaSetDevice(c->device));
+  if (build_light_distribution(s, PBRGPU_LIGHTSTRATEGY_UNIFORM)) return 1;
+  DevBuf<float> din, dout;
+  CK(din.alloc((size_t)n * 16)); CK(dout.alloc((size_t)n * 16));
+  CK(cudaMemcpyAsync(din.p, rows, sizeof(float) * 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  k_light_eval<<<grid_for(c, (uint64_t)n, 8), kBlock, 0, c->stream>>>(s->sc, light, din.p, n, dout.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout.p, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int pbrgpu_scene_info(pbrgpu_scene* s, int64_t out[8]) {
   if (s && !s->replicas.empty()) s = s->replicas[0];  // group scene: the hooks run on the first device
   if (!s || !out) return fail("pbrgpu_scene_info: NULL argument");
@@ -908,6 +971,8 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
     s->traceBlocksPerSm = std::max(1, nb);
     if (const char* e = getenv("PBRGPU_FETCH_MIN_IDLE")) s->fetchMinIdle = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("PBRGPU_WAVE_LOG2")) s->waveLog2 = std::max(14, std::min(25, atoi(e)));
+    if (const char* e = getenv("PBRGPU_TRI_MIN_LANES")) s->triMinLanes = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("PBRGPU_STALL_MIN")) s->stallMin = std::max(1, std::min(32, atoi(e)));
   }
 
   const int W = rd->x1 - rd->x0, H = rd->y1 - rd->y0;
@@ -950,6 +1015,8 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
   P.diffScale = 1 / std::sqrt((float)s->spp);
   P.countStats = count ? 1 : 0;
   P.fetchMinIdle = s->fetchMinIdle;
+  P.triMinLanes = s->triMinLanes;
+  P.stallMin = s->stallMin;
 
   // traversal data persists in L2 for the duration of the render (window = the geometry slab; when the slab is larger than
   // the carve-out, hitRatio keeps a random carve-out-sized fraction of its lines persisting instead of thrashing)
@@ -1550,6 +1617,8 @@ int pbrgpu_debug_dump(pbrgpu_scene* s, const pbrgpu_dump_desc* dd, void* out, si
     P.x0 = dd->x0; P.y0 = dd->y0; P.w = W; P.h = H; P.sBegin = dd->s0; P.nsWave = (int)ns;
     P.arrayEndDim = 5;
     P.fetchMinIdle = s->fetchMinIdle;
+    P.triMinLanes = s->triMinLanes;
+    P.stallMin = s->stallMin;
     P.storeHitT = 1;
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(s->ctr.p, 0, sizeof(Counters), st));
@@ -1588,6 +1657,8 @@ int pbrgpu_trace_rays(pbrgpu_scene* s, const float* rays, int64_t n, int any_hit
     if (s->traceBlocksPerSm <= 0) s->traceBlocksPerSm = std::max(1, trace_blocks_per_sm());
     fill_wave(s, &P.ws);
     P.fetchMinIdle = s->fetchMinIdle;
+    P.triMinLanes = s->triMinLanes;
+    P.stallMin = s->stallMin;
     P.storeHitT = 1;
     DevBuf<int> dis;
     CK(dis.alloc(1));

@@ -75,7 +75,27 @@ PBR_HD void triangle_frame(V3 p0, V3 p1, V3 p2, const float uv[6], bool flip, V3
   *ts = cross(nn, *ss);
 }
 
-PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, float b1, float b2, V3 rayD, Isect* is) {
+// SurfaceInteraction of a hit on an analytic sphere (host/AnalyticSphere.h::Intersect); kept out of line: scenes without
+// spheres never call it and the shading kernels stay as compact as before.
+static __device__ __noinline__ void make_isect_sphere(const TriData& t, V3 rayO, V3 rayD, float tHit, Isect* is) {
+  const uint32_t fl = t.w1 >> kTriFlagShift;
+  const SphereHit h = sphere_hit(t.p0, t.p1.x, (fl & kTriFlagFlipNormal) != 0, rayO, rayD, tHit);
+  is->p = h.p;
+  is->pError = h.pError;
+  is->n = h.n;
+  is->ns = h.n;
+  is->ss = normalize(h.dpdu);   // BSDF ctor (Reflection.h:105-110): ss = Normalize(shading.dpdu), ts = Cross(ns, ss)
+  is->ts = cross(h.n, is->ss);
+  is->wo = normalize(-rayD);
+  is->matId = (int)(t.w1 & kTriMatMask);
+  is->matType = (int)((t.w1 >> kTriTypeShift) & 0xf);
+  is->lightId = (int)t.w2;
+}
+
+// rayO: origin of the ray that produced the hit; read for analytic spheres only (their hit record is the ray parameter in b0)
+PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, float b1, float b2, V3 rayD, Isect* is,
+                      V3 rayO = V3(0.f, 0.f, 0.f)) {
+  if (t.w1 & kPrimSphereBit) { make_isect_sphere(t, rayO, rayD, b0, is); return; }
   const V3 p0 = t.p0, p1 = t.p1, p2 = t.p2;
   float xAbsSum = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x) + fabsf(b2 * p2.x));
   float yAbsSum = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y) + fabsf(b2 * p2.y));
@@ -361,7 +381,90 @@ PBR_D float area_light_pdf(const SceneDev& sc, const pbrgpu_light& l, V3 rayO, V
   return pdf;
 }
 
-PBR_D void sample_light(const SceneDev& sc, const pbrgpu_light& l, V3 refP, float u0, float u1, LightSample* ls) {
+// DiffuseAreaLight over an analytic sphere: AnalyticSphere::Sample(ref, u) (uniform cone outside the sphere, uniform area
+// inside) and ::Pdf(ref, wi).  Out of line for the same reason as make_isect_sphere.
+static __device__ __noinline__ void sample_sphere_light(const pbrgpu_light& l, V3 refP, V3 refPError, V3 refN, float u0, float u1, LightSample* ls) {
+  const V3 pCenter(l.pos[0], l.pos[1], l.pos[2]);
+  const float radius = l.world_radius;
+  const bool reverse = l.light_to_world[0] != 0.f;
+  const V3 pOrigin = offset_ray_origin(refP, refPError, refN, pCenter - refP);
+  V3 p, n, pErr;
+  float pdf;
+  if (dist_sq(pOrigin, pCenter) <= radius * radius) {
+    // Sample(u): uniform by area
+    const float z = 1 - 2 * u0;
+    const float r = sqrtf(stdmax(0.f, 1.f - z * z));
+    const float phi = 2 * kPi * u1;
+    V3 pObj = radius * V3(r * cosf(phi), r * sinf(phi), z);
+    n = normalize(pObj);
+    if (reverse) n = -n;
+    const float f = radius / sqrtf(pObj.x * pObj.x + pObj.y * pObj.y + pObj.z * pObj.z);
+    pObj = V3(pObj.x * f, pObj.y * f, pObj.z * f);
+    p = pObj + pCenter;
+    pErr = gamma_f(5) * (vabs(pObj) + vabs(p));
+    pdf = 1 / (4 * kPi * radius * radius);
+    V3 wi = p - refP;
+    if (length_sq(wi) == 0) pdf = 0;
+    else {
+      wi = normalize(wi);
+      pdf *= dist_sq(refP, p) / absdot(n, -wi);
+    }
+    if (isinf(pdf)) pdf = 0.f;
+  } else {
+    const float dc = sqrtf(dist_sq(refP, pCenter));
+    const float invDc = 1 / dc;
+    const V3 wc = (pCenter - refP) * invDc;
+    V3 wcX, wcY;
+    coordinate_system(wc, &wcX, &wcY);
+    const float sinThetaMax = radius * invDc;
+    const float sinThetaMax2 = sinThetaMax * sinThetaMax;
+    const float invSinThetaMax = 1 / sinThetaMax;
+    const float cosThetaMax = sqrtf(stdmax(0.f, 1 - sinThetaMax2));
+    float cosTheta = (cosThetaMax - 1) * u0 + 1;
+    float sinTheta2 = 1 - cosTheta * cosTheta;
+    if (sinThetaMax2 < 0.00068523f) {
+      sinTheta2 = sinThetaMax2 * u0;
+      cosTheta = sqrtf(1 - sinTheta2);
+    }
+    const float cosAlpha = sinTheta2 * invSinThetaMax + cosTheta * sqrtf(stdmax(0.f, 1.f - sinTheta2 * invSinThetaMax * invSinThetaMax));
+    const float sinAlpha = sqrtf(stdmax(0.f, 1.f - cosAlpha * cosAlpha));
+    const float phi = u1 * 2 * kPi;
+    // SphericalDirection(sinAlpha, cosAlpha, phi, -wcX, -wcY, -wc)
+    const V3 nWorld = sinAlpha * cosf(phi) * (-wcX) + sinAlpha * sinf(phi) * (-wcY) + cosAlpha * (-wc);
+    p = pCenter + radius * nWorld;
+    pErr = gamma_f(5) * vabs(p);
+    n = nWorld;
+    if (reverse) n = -n;
+    pdf = 1 / (2 * kPi * (1 - cosThetaMax));
+  }
+  ls->p1 = p; ls->n1 = n; ls->pErr1 = pErr;
+  // DiffuseAreaLight::Sample_Li (DiffuseLight.cpp:25-38)
+  if (pdf == 0 || length_sq(p - refP) == 0) { ls->pdf = 0; ls->Li = Spec(0.f); return; }
+  ls->wi = normalize(p - refP);
+  ls->pdf = pdf;
+  ls->Li = area_light_L(l, n, -ls->wi);
+}
+static __device__ __noinline__ float sphere_light_pdf(const pbrgpu_light& l, V3 spawnO, V3 refP, V3 refPError, V3 refN, V3 wi) {
+  const V3 pCenter(l.pos[0], l.pos[1], l.pos[2]);
+  const float radius = l.world_radius;
+  const V3 pOrigin = offset_ray_origin(refP, refPError, refN, pCenter - refP);
+  if (dist_sq(pOrigin, pCenter) <= radius * radius) {
+    // Shape::Pdf (Shape.cpp:31-42): intersect the light's own shape along ref.SpawnRay(wi)
+    float t;
+    if (!sphere_solve(spawnO - pCenter, wi, radius, kInfinity, &t)) return 0;
+    const SphereHit h = sphere_hit(pCenter, radius, l.light_to_world[0] != 0.f, spawnO, wi, t);
+    float pdf = dist_sq(refP, h.p) / (absdot(h.n, -wi) * (4 * kPi * radius * radius));
+    if (isinf(pdf)) pdf = 0.f;
+    return pdf;
+  }
+  const float sinThetaMax2 = radius * radius / dist_sq(refP, pCenter);
+  const float cosThetaMax = sqrtf(stdmax(0.f, 1 - sinThetaMax2));
+  return 1 / (2 * kPi * (1 - cosThetaMax));
+}
+
+// refPError / refN: the reference point's error bound and normal (zero for a point inside a medium); read by sphere lights only
+PBR_D void sample_light(const SceneDev& sc, const pbrgpu_light& l, V3 refP, float u0, float u1, LightSample* ls,
+                        V3 refPError = V3(0.f, 0.f, 0.f), V3 refN = V3(0.f, 0.f, 0.f)) {
   ls->pdf = 0;  // EstimateDirect initialises lightPdf = 0 (Integrator.cpp:77)
   ls->Li = Spec(0.f);
   ls->n1 = V3(0, 0, 0);
@@ -376,6 +479,7 @@ PBR_D void sample_light(const SceneDev& sc, const pbrgpu_light& l, V3 refP, floa
       break;
     }
     case PBRGPU_LIGHT_AREA_TRI: sample_area_light(sc, l, refP, u0, u1, ls); break;
+    case PBRGPU_LIGHT_AREA_SPHERE: sample_sphere_light(l, refP, refPError, refN, u0, u1, ls); break;
     case PBRGPU_LIGHT_INFINITE: {
       const EnvDev& e = sc.env;
       float pdf1, pdf0;
@@ -411,9 +515,11 @@ PBR_D void sample_light(const SceneDev& sc, const pbrgpu_light& l, V3 refP, floa
 }
 
 // Light::Pdf_Li
-PBR_D float light_pdf_li(const SceneDev& sc, const pbrgpu_light& l, V3 spawnO, V3 refP, V3 wi) {
+PBR_D float light_pdf_li(const SceneDev& sc, const pbrgpu_light& l, V3 spawnO, V3 refP, V3 wi, V3 refPError = V3(0.f, 0.f, 0.f),
+                         V3 refN = V3(0.f, 0.f, 0.f)) {
   switch (l.type) {
     case PBRGPU_LIGHT_AREA_TRI: return area_light_pdf(sc, l, spawnO, refP, wi);
+    case PBRGPU_LIGHT_AREA_SPHERE: return sphere_light_pdf(l, spawnO, refP, refPError, refN, wi);
     case PBRGPU_LIGHT_INFINITE: {
       V3 w = xform_vec(l.world_to_light, wi);
       float theta = spherical_theta(w), phi = spherical_phi(w);

@@ -6,6 +6,7 @@
 //   widening, ours is widened, so the set of triangles we test is a superset of what the reference tests).
 #pragma once
 #include "device_types.cuh"
+#include "sphere.cuh"
 
 namespace pbr {
 
@@ -117,6 +118,7 @@ constexpr int kSmemStack = PBR_SMEM_STACK;
 constexpr int kLocalStack = 36;
 
 struct Trav {
+  V3 dir;                     // ray direction: read by the analytic-sphere test only (dead in every other instantiation)
   V3 o;
   float idx, idy, idz;        // reciprocal direction (|d| clamped away from 0)
   unsigned octinv4;           // inverse octant replicated in 4 bytes
@@ -141,6 +143,7 @@ PBR_D float safe_rcp(float d) {
 
 PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax, unsigned f32one) {
   T.o = o;
+  T.dir = d;
   T.f32one = f32one;
   T.idx = safe_rcp(d.x); T.idy = safe_rcp(d.y); T.idz = safe_rcp(d.z);
   T.octinv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
@@ -233,11 +236,23 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
 // One triangle of the triangle group: the reference's watertight test, bit-exact (t, b0, b1, b2).
 // `store`: where the hit record goes (k_trace keeps it in shared memory: it is written once or twice per ray and read once,
 // and six registers less let a ninth block fit on the SM); NULL = T.hit.
+// SPH: the leaf arrays may hold analytic spheres (kPrimSphereBit); their hit record is (prim, t, b0 = t, 0, 0).
+template <bool SPH = false>
 PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T, HitRec* store = nullptr) {
   const int bit = 31 - __clz(T.tgroup.y);
   T.tgroup.y &= ~(1u << bit);
   const int ti = (int)T.tgroup.x + bit;
   const float4 v1 = __ldg(sc.tv1 + ti);
+  if (SPH && (__float_as_uint(v1.w) & kPrimSphereBit)) {
+    const V3 center = ld3(sc.tv0, ti);
+    float ts;
+    if (!sphere_solve(T.rp.o - center, T.dir, v1.x, T.tMax, &ts)) return false;
+    T.tMax = ts;
+    HitRec& h = store ? *store : T.hit;
+    h.tri = ti; h.t = ts; h.b0 = ts; h.b1 = 0.f; h.b2 = 0.f;
+    h.w1 = __float_as_uint(v1.w);
+    return true;
+  }
   V3 p0 = ld3(sc.tv0, ti), p1(v1.x, v1.y, v1.z), p2 = ld3(sc.tv2, ti);
   float t, b0, b1, b2;
   if (intersect_triangle(T.rp, T.tMax, p0, p1, p2, &t, &b0, &b1, &b2)) {
@@ -252,7 +267,7 @@ PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T, HitRec* store = nullptr) {
 
 // Whole-ray traversal by one thread (parity hooks and small queries).  `sstack` = this lane's column
 // of the warp's shared-memory stack.
-template <bool ANY_HIT, bool COUNT>
+template <bool ANY_HIT, bool COUNT, bool SPH = false>
 PBR_D bool traverse(const SceneDev& sc, V3 o, V3 d, float tMax, HitRec* hit, uint2* sstack, unsigned* nNodes, unsigned* nTris) {
   Trav T;
   TravSpill S;
@@ -268,7 +283,7 @@ PBR_D bool traverse(const SceneDev& sc, V3 o, V3 d, float tMax, HitRec* hit, uin
     }
     while (T.tgroup.y != 0u) {
       if (COUNT) (*nTris)++;
-      if (cw_tri_step(sc, T) && ANY_HIT) { T.tgroup.y = 0u; T.ngroup.y = 0u; T.sp = 0; }
+      if (cw_tri_step<SPH>(sc, T) && ANY_HIT) { T.tgroup.y = 0u; T.ngroup.y = 0u; T.sp = 0; }
     }
     if (T.ngroup.y <= 0x00FFFFFFu) {
       if (T.sp > 0) T.ngroup = trav_pop(T, sstack, S);

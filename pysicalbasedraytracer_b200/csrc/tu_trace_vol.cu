@@ -4,7 +4,7 @@
 
 namespace pbr {
 void launch_trace_vol(bool count, unsigned grid, cudaStream_t st, const RenderParams& P) {
-  if (count) k_trace<true, true><<<grid, kTraceBlock, 0, st>>>(P);
-  else k_trace<false, true><<<grid, kTraceBlock, 0, st>>>(P);
+  if (count) k_trace<true, true, false><<<grid, kTraceBlock, 0, st>>>(P);
+  else k_trace<false, true, false><<<grid, kTraceBlock, 0, st>>>(P);
 }
 }  // namespace pbr

@@ -72,6 +72,7 @@
 
 #include "pbrgpu.h"
 #include "SobolSampler.h"
+#include "AnalyticSphere.h"
 
 namespace PBR {
 
@@ -89,6 +90,7 @@ struct Flat {
   std::unordered_map<const void*, int> textureId;
   std::vector<pbrgpu_medium> media;              // distinct HomogeneousMedium objects met on the primitives
   std::vector<int32_t> triMediumIn, triMediumOut;  // MediumInterface::inside / ::outside per triangle (-1 = none)
+  std::vector<pbrgpu_sphere> spheres;            // AnalyticSphere shapes (host/AnalyticSphere.h)
   std::vector<float> env;
   int envW = 0, envH = 0;
   std::string error;
@@ -216,23 +218,58 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
   const size_t n = prims.size();
   f->verts.reserve(n * 9);
   f->indices.reserve(n * 3);
-  f->triMaterial.resize(n);
-  f->triLight.assign(n, -1);
-  f->triFlags.assign(n, 0);
-  f->triMediumIn.assign(n, -1);
-  f->triMediumOut.assign(n, -1);
+  f->triMaterial.reserve(n);
   std::unordered_map<const Medium*, int> mediumId;
   std::unordered_map<const Material*, int> matId;
   std::unordered_map<const Light*, int> lightId;
   for (size_t i = 0; i < scene.lights.size(); ++i) lightId[scene.lights[i].get()] = (int)i;
   f->lights.resize(scene.lights.size());
-  std::vector<int> lightTri(scene.lights.size(), -1);
-  for (size_t i = 0; i < n; ++i) {
-    auto* gp = dynamic_cast<const GeometricPrimitive*>(prims[i].get());
+  std::vector<int> lightTri(scene.lights.size(), -1), lightSphere(scene.lights.size(), -1);
+  auto materialOf = [&](const GeometricPrimitive* gp, int* out) {
+    if (!gp->material) { *out = -1; return true; }  // medium boundary: rendered by GpuVolPathIntegrator only
+    auto it = matId.find(gp->material.get());
+    if (it == matId.end()) {
+      pbrgpu_material m;
+      if (!flattenMaterial(gp->material.get(), &m, f)) return false;
+      it = matId.emplace(gp->material.get(), (int)f->materials.size()).first;
+      f->materials.push_back(m);
+    }
+    *out = it->second;
+    return true;
+  };
+  for (size_t pi = 0; pi < n; ++pi) {
+    auto* gp = dynamic_cast<const GeometricPrimitive*>(prims[pi].get());
     if (!gp) { f->error = "primitive is not a GeometricPrimitive"; return false; }
+    if (auto* sph = dynamic_cast<const AnalyticSphere*>(gp->shape.get())) {
+      // analytic sphere (the reference's own Sphere is a stub: Shape/Sphere.cpp:8-37); ObjectToWorld must be a translation
+      const Matrix4x4& m = sph->ObjectToWorld->m;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+          if (m.m[r][c] != (r == c ? 1.f : 0.f)) { f->error = "AnalyticSphere: ObjectToWorld must be a pure translation"; return false; }
+      if (gp->mediumInterface.inside || gp->mediumInterface.outside) { f->error = "AnalyticSphere with a MediumInterface is not supported"; return false; }
+      pbrgpu_sphere o;
+      std::memset(&o, 0, sizeof(o));
+      o.center[0] = m.m[0][3]; o.center[1] = m.m[1][3]; o.center[2] = m.m[2][3];
+      o.radius = sph->radius;
+      o.reverse_orientation = sph->reverseOrientation ? 1 : 0;
+      o.light = -1;
+      if (!gp->material) { f->error = "AnalyticSphere without a material is not supported"; return false; }
+      if (!materialOf(gp, &o.material)) return false;
+      if (gp->areaLight) {
+        auto li = lightId.find(gp->areaLight.get());
+        if (li == lightId.end()) { f->error = "area light of a primitive is not in scene.lights"; return false; }
+        o.light = li->second;
+        lightSphere[li->second] = (int)f->spheres.size();
+      }
+      f->spheres.push_back(o);
+      continue;
+    }
     auto* tri = dynamic_cast<const Triangle*>(gp->shape.get());
-    if (!tri) { f->error = "shape is not a Triangle (the reference's Sphere is a stub, SURVEY Q4)"; return false; }
+    if (!tri) { f->error = "shape is neither a Triangle nor an AnalyticSphere (the reference's Sphere is a stub, SURVEY Q4)"; return false; }
     if (tri->mesh->s) { f->error = "per-vertex tangents (TriangleMesh::s) are not supported on the GPU path"; return false; }
+    const size_t i = f->triMaterial.size();  // triangle index (analytic spheres are numbered separately)
+    f->triMaterial.push_back(-1); f->triLight.push_back(-1); f->triFlags.push_back(0);
+    f->triMediumIn.push_back(-1); f->triMediumOut.push_back(-1);
     if (!flattenMedium(gp->mediumInterface.inside, &mediumId, f, &f->triMediumIn[i]) ||
         !flattenMedium(gp->mediumInterface.outside, &mediumId, f, &f->triMediumOut[i]))
       return false;
@@ -257,18 +294,7 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
     }
     f->triFlags[i] = (uint8_t)(((tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0) | (tri->reverseOrientation ? 2 : 0) |
                                (tri->mesh->n ? 4 : 0) | (tri->mesh->uv ? 8 : 0));
-    if (!gp->material) {
-      f->triMaterial[i] = -1;  // medium boundary: rendered by GpuVolPathIntegrator only
-    } else {
-      auto it = matId.find(gp->material.get());
-      if (it == matId.end()) {
-        pbrgpu_material m;
-        if (!flattenMaterial(gp->material.get(), &m, f)) return false;
-        it = matId.emplace(gp->material.get(), (int)f->materials.size()).first;
-        f->materials.push_back(m);
-      }
-      f->triMaterial[i] = it->second;
-    }
+    if (!materialOf(gp, &f->triMaterial[i])) return false;
     if (gp->areaLight) {
       auto li = lightId.find(gp->areaLight.get());
       if (li == lightId.end()) { f->error = "area light of a primitive is not in scene.lights"; return false; }
@@ -287,8 +313,8 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
       o.pos[0] = p->pLight.x; o.pos[1] = p->pLight.y; o.pos[2] = p->pLight.z;
       o.L[0] = p->I[0]; o.L[1] = p->I[1]; o.L[2] = p->I[2];
     } else if (auto* p = dynamic_cast<const DiffuseAreaLight*>(l)) {
-      o.type = PBRGPU_LIGHT_AREA_TRI;
-      o.tri = lightTri[i];
+      o.type = lightSphere[i] >= 0 ? PBRGPU_LIGHT_AREA_SPHERE : PBRGPU_LIGHT_AREA_TRI;
+      o.tri = lightSphere[i] >= 0 ? lightSphere[i] : lightTri[i];
       if (o.tri < 0) { f->error = "DiffuseAreaLight whose shape is not a scene primitive"; return false; }
       o.two_sided = p->twoSided ? 1 : 0;
       o.L[0] = p->Lemit[0]; o.L[1] = p->Lemit[1]; o.L[2] = p->Lemit[2];
@@ -363,6 +389,8 @@ class GpuSamplerIntegrator : public Integrator {
         d.n_media = (int32_t)f.media.size(); d.media = f.media.data();
         d.tri_medium_inside = f.triMediumIn.data(); d.tri_medium_outside = f.triMediumOut.data();
       }
+      d.n_spheres = (int32_t)f.spheres.size();
+      d.spheres = f.spheres.empty() ? nullptr : f.spheres.data();
       if (pbrgpu_scene_create(ctx, &d, &gscene)) return fail("pbrgpu_scene_create");
       flattenedScene = &scene;
     }

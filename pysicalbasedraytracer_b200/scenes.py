@@ -56,6 +56,7 @@ class SceneData:
         self._tri_med_in = []
         self._tri_med_out = []
         self.media = []
+        self.spheres = []   # analytic spheres (A.Sphere); primitive ids n_tris .. n_tris + len(spheres) - 1
         self.textures = []  # (A.Texture, texel array) pairs
         self.materials = []
         self.lights = []
@@ -118,6 +119,18 @@ class SceneData:
         self._ntris += n
         self._frozen = None
 
+    def add_sphere(self, center, radius, material, emit=None, two_sided=False, n_samples=1, reverse_orientation=False):
+        """Analytic sphere (pbrgpu_sphere; CPU twin host/AnalyticSphere.h - the reference's own Sphere is a stub).
+        emit: RGB Lemit -> a DiffuseAreaLight over the sphere, sampled by solid angle."""
+        light = -1
+        if emit is not None:
+            light = len(self.lights)
+            self.lights.append(A.Light(type=A.LIGHT_AREA_SPHERE, tri=len(self.spheres), two_sided=int(two_sided),
+                                       n_samples=n_samples, L=_f3(emit)))
+        self.spheres.append(A.Sphere(center=_f3(center), radius=float(radius), material=int(material), light=light,
+                                     reverse_orientation=int(reverse_orientation)))
+        return len(self.spheres) - 1
+
     def add_point_light(self, pos, intensity):
         self.lights.append(A.Light(type=A.LIGHT_POINT, tri=-1, n_samples=1, pos=_f3(pos), L=_f3(intensity)))
 
@@ -137,11 +150,11 @@ class SceneData:
     # ---- flattened arrays ----
     def _freeze(self):
         if self._frozen is None:
+            cat = lambda parts, shape, dt: (np.ascontiguousarray(np.concatenate(parts), dtype=dt) if parts
+                                            else np.zeros(shape, dtype=dt))  # a scene of analytic spheres only has no mesh
             self._frozen = dict(
-                verts=np.ascontiguousarray(np.concatenate(self._verts), dtype=F),
-                indices=np.ascontiguousarray(np.concatenate(self._tris), dtype=np.int32),
-                tri_material=np.ascontiguousarray(np.concatenate(self._tri_mat), dtype=np.int32),
-                tri_light=np.ascontiguousarray(np.concatenate(self._tri_light), dtype=np.int32),
+                verts=cat(self._verts, (0, 3), F), indices=cat(self._tris, (0, 3), np.int32),
+                tri_material=cat(self._tri_mat, (0,), np.int32), tri_light=cat(self._tri_light, (0,), np.int32),
             )
         return self._frozen
 
@@ -182,7 +195,13 @@ class SceneData:
         d.materials = mats
         d.lights = lights
         keep = [fz, mats, lights]
-        fl = np.ascontiguousarray(np.concatenate(self._mesh_flags), dtype=np.uint8)
+        if self.spheres:
+            sph = (A.Sphere * len(self.spheres))(*self.spheres)
+            d.n_spheres = len(self.spheres)
+            d.spheres = sph
+            keep.append(sph)
+        fl = (np.ascontiguousarray(np.concatenate(self._mesh_flags), dtype=np.uint8) if self._mesh_flags
+              else np.zeros(0, dtype=np.uint8))
         if self.tri_flags is not None:  # caller-supplied bit0: reverseOrientation (identity transforms: bit1 = bit0)
             user = np.ascontiguousarray(self.tri_flags, dtype=np.uint8)
             assert user.shape[0] == d.n_tris
@@ -284,6 +303,29 @@ def cornell(sphere_tess=48, floor_mirror=False):
         s.add_mesh(v, t, green)
         v, t = uv_sphere([1.0, -1.6, 0.7], 0.9, sphere_tess, 2 * sphere_tess)
         s.add_mesh(v, t, mir)
+    return s
+
+
+def cornell_analytic(light_sphere=True, floor_mirror=False):
+    """The Cornell box of `cornell()` with ANALYTIC spheres (pbrgpu_sphere / host/AnalyticSphere.h) instead of tessellated
+    ones: a Matte, a Mirror, a Glass and a Plastic sphere, and (light_sphere) a small emissive sphere next to the ceiling
+    light.  The reference's own Sphere is a stub, so the CPU side of the comparison is the twin."""
+    s = SceneData()
+    white = s.add_material(matte([0.73, 0.73, 0.73]))
+    red = s.add_material(matte([0.9, 0.1, 0.17]))
+    blue = s.add_material(matte([0.14, 0.21, 0.87]))
+    cornell_walls(s, white, red, blue)
+    cornell_area_light(s, white)
+    m_matte = s.add_material(matte([0.2, 0.7, 0.3], sigma=20.0))
+    m_mirror = s.add_material(mirror([0.9, 0.9, 0.9]))
+    m_glass = s.add_material(glass([0.98, 0.98, 0.98], [0.98, 0.98, 0.98], 1.5))
+    m_plastic = s.add_material(plastic([0.35, 0.12, 0.48], [0.65, 0.88, 0.52], 0.1))
+    s.add_sphere([-1.2, -1.6, -0.6], 0.9, m_matte)
+    s.add_sphere([1.1, -1.7, -1.0], 0.8, m_mirror)
+    s.add_sphere([0.2, -1.9, 1.0], 0.6, m_glass)
+    s.add_sphere([-0.4, 0.3, -1.4], 0.55, m_plastic)
+    if light_sphere:
+        s.add_sphere([1.4, 1.3, 0.4], 0.3, white, emit=[9.0, 7.0, 4.0], n_samples=2)
     return s
 
 
