@@ -135,8 +135,8 @@ typedef struct pbrgpu_scene_desc {
                                   with PBRGPU_INTEGRATOR_VOLPATH only */
   const int32_t* tri_light;    /* n_tris: index into lights for emissive triangles, else -1 */
   const uint8_t* tri_flags;    /* optional n_tris: bit0 = reverseOrientation ^ transformSwapsHandedness, bit1 = reverseOrientation,
-                                  bit2 / bit3 = the triangle's mesh has per-vertex normals / uvs (when NULL: no flips, and
-                                  every triangle uses whichever of `normals` / `uvs` is given) */
+                                  bit2 / bit3 / bit4 = the triangle's mesh has per-vertex normals / uvs / tangents (when NULL: no
+                                  flips, and every triangle uses whichever of `normals` / `uvs` / `tangents` is given) */
   int32_t n_materials;
   int32_t n_lights;
   const pbrgpu_material* materials;
@@ -158,6 +158,8 @@ typedef struct pbrgpu_scene_desc {
   int32_t n_spheres;
   int32_t pad2;
   const pbrgpu_sphere* spheres;
+  const float* tangents;       /* optional n_verts*3 world-space per-vertex tangents (mesh->s, Triangle.cpp:204-213) or NULL;
+                                  tri_flags bit4 = this triangle's mesh has them (NULL tri_flags: every triangle uses them) */
 } pbrgpu_scene_desc;
 
 /* ---- camera: Camera/Camera.h:34-54, Perspective.cpp, Orthographic.cpp ---- */

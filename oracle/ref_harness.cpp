@@ -198,15 +198,21 @@ void* ref_scene_create(const pbrgpu_scene_desc* d) {
     UV.resize(d->n_verts);
     for (int i = 0; i < d->n_verts; ++i) UV[i] = Point2f(d->uvs[2 * i], d->uvs[2 * i + 1]);
   }
-  // tri_flags bit2 / bit3 say whether a triangle's mesh has per-vertex normals / uvs: one TriangleMesh per combination in
-  // use (they share the vertex and index arrays), so that triangles of meshes WITHOUT uvs get Triangle::GetUVs' defaults
-  std::shared_ptr<TriangleMesh> variant[4];
+  std::vector<Vector3f> TG;
+  if (d->tangents) {
+    TG.resize(d->n_verts);
+    for (int i = 0; i < d->n_verts; ++i) TG[i] = Vector3f(d->tangents[3 * i], d->tangents[3 * i + 1], d->tangents[3 * i + 2]);
+  }
+  // tri_flags bit2 / bit3 / bit4 say whether a triangle's mesh has per-vertex normals / uvs / tangents: one TriangleMesh per
+  // combination in use (they share the vertex and index arrays), so that triangles of meshes WITHOUT uvs get Triangle::GetUVs' defaults
+  std::shared_ptr<TriangleMesh> variant[8];
   auto meshFor = [&](int i) {
     int key = 0;
-    if (d->tri_flags) key = ((d->tri_flags[i] & 4) && d->normals ? 1 : 0) | ((d->tri_flags[i] & 8) && d->uvs ? 2 : 0);
-    else key = (d->normals ? 1 : 0) | (d->uvs ? 2 : 0);
+    if (d->tri_flags) key = ((d->tri_flags[i] & 4) && d->normals ? 1 : 0) | ((d->tri_flags[i] & 8) && d->uvs ? 2 : 0) |
+                            ((d->tri_flags[i] & 16) && d->tangents ? 4 : 0);
+    else key = (d->normals ? 1 : 0) | (d->uvs ? 2 : 0) | (d->tangents ? 4 : 0);
     if (!variant[key]) {
-      variant[key] = std::make_shared<TriangleMesh>(rs->identity, d->n_tris, d->indices, d->n_verts, P.data(), nullptr,
+      variant[key] = std::make_shared<TriangleMesh>(rs->identity, d->n_tris, d->indices, d->n_verts, P.data(), (key & 4) ? TG.data() : nullptr,
                                                     (key & 1) ? N.data() : nullptr, (key & 2) ? UV.data() : nullptr, nullptr);
       rs->meshes.push_back(variant[key]);
     }

@@ -58,7 +58,8 @@ class SceneDesc(C.Structure):
                 ("n_media", C.c_int32), ("pad0", C.c_int32), ("media", C.POINTER(Medium)),
                 ("tri_medium_inside", C.POINTER(C.c_int32)), ("tri_medium_outside", C.POINTER(C.c_int32)),
                 ("n_textures", C.c_int32), ("pad1", C.c_int32), ("textures", C.POINTER(Texture)),
-                ("n_spheres", C.c_int32), ("pad2", C.c_int32), ("spheres", C.POINTER(Sphere))]
+                ("n_spheres", C.c_int32), ("pad2", C.c_int32), ("spheres", C.POINTER(Sphere)),
+                ("tangents", C.POINTER(C.c_float))]
 
 
 class CameraDesc(C.Structure):

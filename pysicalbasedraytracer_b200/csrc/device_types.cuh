@@ -21,9 +21,10 @@ constexpr uint32_t kMetaBounceMask = 0x7fu;
 constexpr int kMetaInMediumBit = 24;  // VolPath: Ray::medium != nullptr (lets the medium kernels skip a path after one 4-byte read)
 
 // ---- triangle record (leaf order): three float4 = three 16-byte loads ----
-//   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-22), sphere (23), material type (24-27), flags (28-31)
+//   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-21), tangents (22), sphere (23), material type (24-27), flags (28-31)
 //   tv2 = p2.xyz | area-light id or -1
-constexpr uint32_t kTriMatMask = 0x007fffffu;
+constexpr uint32_t kTriMatMask = 0x003fffffu;
+constexpr uint32_t kTriTangentBit = 0x00400000u;  // the triangle's mesh has per-vertex tangents (TriangleMesh::s)
 constexpr uint32_t kPrimSphereBit = 0x00800000u;  // the record is an analytic sphere (sphere.cuh): tv0 = centre | id, tv1.x = radius
 constexpr int kTriTypeShift = 24;
 constexpr int kTriFlagShift = 28;
@@ -75,6 +76,9 @@ struct SceneDev {
   const float4* tn0;   // normal of vertex 0 | -          (triangles of meshes with TriangleMesh::n)
   const float4* tn1;
   const float4* tn2;
+  const float4* ts0;   // tangent of vertex 0 | -         (triangles of meshes with TriangleMesh::s; NULL when no mesh has them)
+  const float4* ts1;
+  const float4* ts2;
   const float4* tuv0;  // uv0.xy, uv1.xy
   const float4* tuv1;  // uv2.xy, -, -
   const float4* nodes8;         // Bvh8Node[] viewed as 5 x float4 per node

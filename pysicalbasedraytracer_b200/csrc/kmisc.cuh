@@ -325,7 +325,20 @@ __global__ void __launch_bounds__(kBlock) k_resolve_mis(const __grid_constant__ 
             Li = area_light_L(light, sphere_hit(c, light.world_radius, light.light_to_world[0] != 0.f, ro, wi, t).n, -wi);
         } else {
           const float4 n4 = __ldg(P.sc.tvN + tri);
-          Li = area_light_L(light, V3(n4.x, n4.y, n4.z), -wi);
+          V3 nh(n4.x, n4.y, n4.z);
+          const TriData td = load_tri(P.sc, tri);
+          if (((td.w1 >> kTriFlagShift) & kTriFlagNormals) || (td.w1 & kTriTangentBit)) {
+            // emissive mesh with shading normals / tangents: the hit normal is face-forwarded by the interpolated shading
+            // normal (SetShadingGeometry), which needs the barycentrics of this hit
+            const RayPrep rp = prep_ray(V3(o.x, o.y, o.z), wi);
+            float th, b0, b1, b2;
+            if (intersect_triangle(rp, kInfinity, td.p0, td.p1, td.p2, &th, &b0, &b1, &b2)) {
+              Isect il;
+              make_isect(P.sc, td, tri, b0, b1, b2, wi, &il);
+              nh = il.n;
+            }
+          }
+          Li = area_light_L(light, nh, -wi);
         }
       }
     } else {

@@ -128,7 +128,7 @@ struct pbrgpu_scene {
   bool haveCamera = false, haveSampler = false;
   int64_t spp = 0;
   // device buffers
-  DevBuf<float4> tvN, tvS, tvT, tn0, tn1, tn2, tuv0, tuv1;
+  DevBuf<float4> tvN, tvS, tvT, tn0, tn1, tn2, ts0, ts1, ts2, tuv0, tuv1;
   DevBuf<float4> geom;  // ONE slab: Bvh8Node[] | tv0 | tv1 | tv2 - everything k_trace reads, covered by one L2 access-policy window
   DevBuf<pbrgpu_material> mats;
   DevBuf<pbrgpu_light> dlights;
@@ -409,7 +409,7 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   }
   s->leafOf.assign((size_t)nT, -1);
   std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT), vN((size_t)nT), vS((size_t)nT), vT((size_t)nT);
-  std::vector<float4> vn0, vn1, vn2, vuv0, vuv1;  // only when some mesh has shading normals / uvs
+  std::vector<float4> vn0, vn1, vn2, vuv0, vuv1, vs0, vs1, vs2;  // only when some mesh has shading normals / uvs / tangents
   bool anyNormals = false;
   for (int k = 0; k < nT; ++k) {
     int ti = s->bvh.triOrder[k];
@@ -430,13 +430,15 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     int m = d->tri_material[ti];
     // tri_flags: bit0 reverseOrientation ^ transformSwapsHandedness, bit1 reverseOrientation, bit2 / bit3 "this triangle's
     // mesh has per-vertex normals / uvs" (default when tri_flags is NULL: every triangle uses the arrays that are given)
-    const uint8_t tf = d->tri_flags ? d->tri_flags[ti] : (uint8_t)((d->normals ? 4 : 0) | (d->uvs ? 8 : 0));
+    const uint8_t tf = d->tri_flags ? d->tri_flags[ti] : (uint8_t)((d->normals ? 4 : 0) | (d->uvs ? 8 : 0) | (d->tangents ? 16 : 0));
     uint32_t flags = (tf & 1 ? kTriFlagFlipNormal : 0u) | (tf & 2 ? kTriFlagReverse : 0u) |
                      ((tf & 4) && d->normals ? kTriFlagNormals : 0u) | ((tf & 8) && d->uvs ? kTriFlagUVs : 0u);
     // a triangle without a material carries the queue id of "medium boundary" as its type code
     if (m < 0) s->hasNullMat = true;
+    const bool hasTangents = (tf & 16) && d->tangents;  // TriangleMesh::s
     uint32_t w1 = m < 0 ? ((uint32_t)kQueueNull << kTriTypeShift) | (flags << kTriFlagShift)
                         : (uint32_t)m | ((uint32_t)d->materials[m].type << kTriTypeShift) | (flags << kTriFlagShift);
+    if (hasTangents) w1 |= kTriTangentBit;
     int32_t lid = d->tri_light ? d->tri_light[ti] : -1;
     v0[k] = make_float4(a[0], a[1], a[2], u2f((uint32_t)ti));
     v1[k] = make_float4(b[0], b[1], b[2], u2f(w1));
@@ -451,7 +453,6 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     triangle_frame(V3(a[0], a[1], a[2]), V3(b[0], b[1], b[2]), V3(c[0], c[1], c[2]), uv, (flags & kTriFlagFlipNormal) != 0, &n, &ss, &ts);
     if (flags & kTriFlagNormals) {
       anyNormals = true;
-      if (lid >= 0) return fail("pbrgpu_scene_create: an area light on a mesh with per-vertex shading normals is not supported");
       const float* n0 = d->normals + 3 * (size_t)d->indices[3 * (size_t)ti];
       const float* n1 = d->normals + 3 * (size_t)d->indices[3 * (size_t)ti + 1];
       const float* n2 = d->normals + 3 * (size_t)d->indices[3 * (size_t)ti + 2];
@@ -459,6 +460,13 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
       vn0[k] = make_float4(n0[0], n0[1], n0[2], 0.f);
       vn1[k] = make_float4(n1[0], n1[1], n1[2], 0.f);
       vn2[k] = make_float4(n2[0], n2[1], n2[2], 0.f);
+    }
+    if (hasTangents) {
+      if (vs0.empty()) { vs0.assign((size_t)nT, make_float4(0, 0, 0, 0)); vs1 = vs0; vs2 = vs0; }
+      for (int q = 0; q < 3; ++q) {
+        const float* sv = d->tangents + 3 * (size_t)d->indices[3 * (size_t)ti + q];
+        (q == 0 ? vs0 : (q == 1 ? vs1 : vs2))[k] = make_float4(sv[0], sv[1], sv[2], 0.f);
+      }
     }
     if (flags & kTriFlagUVs) {
       if (vuv0.empty()) { vuv0.assign((size_t)nT, make_float4(0, 0, 0, 0)); vuv1 = vuv0; }
@@ -472,6 +480,7 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   CK(s->tvN.upload(vN, st)); CK(s->tvS.upload(vS, st)); CK(s->tvT.upload(vT, st));
   if (anyNormals) { CK(s->tn0.upload(vn0, st)); CK(s->tn1.upload(vn1, st)); CK(s->tn2.upload(vn2, st)); }
   if (!vuv0.empty()) { CK(s->tuv0.upload(vuv0, st)); CK(s->tuv1.upload(vuv1, st)); }
+  if (!vs0.empty()) { CK(s->ts0.upload(vs0, st)); CK(s->ts1.upload(vs1, st)); CK(s->ts2.upload(vs2, st)); }
   {
     static_assert(sizeof(Bvh8Node) == 5 * sizeof(float4), "Bvh8Node is five 16-byte words");
     const size_t nN = s->bvh.nodes.size() * 5, nTv = (size_t)nT;
@@ -627,6 +636,12 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
         triangle_frame(p0, p1, p2, uvDefault, flip, &nI, &ss, &ts);
         l.light_to_world[0] = nS.x; l.light_to_world[1] = nS.y; l.light_to_world[2] = nS.z; l.light_to_world[3] = area;
         l.light_to_world[4] = nI.x; l.light_to_world[5] = nI.y; l.light_to_world[6] = nI.z;
+        //   [8..10] Normalize(Cross(p1 - p0, p2 - p0)) WITHOUT the orientation flip: Triangle::Sample of a mesh with shading
+        //   normals face-forwards this one to the interpolated normal instead (Triangle.cpp:371-377)
+        {
+          const V3 nU = normalize(cross(p1 - p0, p2 - p0));
+          l.light_to_world[8] = nU.x; l.light_to_world[9] = nU.y; l.light_to_world[10] = nU.z;
+        }
         l.tri = s->leafOf[l.tri];
         break;
       }
@@ -741,6 +756,7 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   CK(s->dlights.upload(s->lights, st));
 
   s->sc.tvN = s->tvN.p; s->sc.tvS = s->tvS.p; s->sc.tvT = s->tvT.p;
+  s->sc.ts0 = s->ts0.p; s->sc.ts1 = s->ts1.p; s->sc.ts2 = s->ts2.p;
   s->sc.tn0 = s->tn0.p; s->sc.tn1 = s->tn1.p; s->sc.tn2 = s->tn2.p; s->sc.tuv0 = s->tuv0.p; s->sc.tuv1 = s->tuv1.p;
   s->sc.mats = s->mats.p;
   s->sc.lights = s->dlights.p;

@@ -104,7 +104,7 @@ PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, f
   is->p = b0 * p0 + b1 * p1 + b2 * p2;
   const float4 n4 = __ldg(sc.tvN + tri);
   const uint32_t fl = t.w1 >> kTriFlagShift;
-  if (!(fl & kTriFlagNormals)) {
+  if (!(fl & kTriFlagNormals) && !(t.w1 & kTriTangentBit)) {
     // flat-shaded triangle: the whole frame is a per-triangle constant (host-precomputed, uvs included)
     const float4 s4 = __ldg(sc.tvS + tri), t4 = __ldg(sc.tvT + tri);
     is->n = V3(n4.x, n4.y, n4.z);
@@ -112,7 +112,8 @@ PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, f
     is->ss = V3(s4.x, s4.y, s4.z);
     is->ts = V3(t4.x, t4.y, t4.z);
   } else {
-    // per-vertex shading normals: Triangle.cpp:186-250 + SurfaceInteraction::SetShadingGeometry (Interaction.cpp:98-113)
+    // per-vertex shading normals and / or tangents (`mesh->n || mesh->s`): Triangle.cpp:186-250 +
+    // SurfaceInteraction::SetShadingGeometry (Interaction.cpp:98-113)
     float uv[6] = {0.f, 0.f, 1.f, 0.f, 1.f, 1.f};
     if (fl & kTriFlagUVs) {
       const float4 a = __ldg(sc.tuv0 + tri), b = __ldg(sc.tuv1 + tri);
@@ -120,11 +121,22 @@ PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, f
     }
     V3 n(n4.x, n4.y, n4.z);
     const V3 dpdu = triangle_dpdu(p0, p1, p2, uv[0], uv[1], uv[2], uv[3], uv[4], uv[5]);
-    const float4 a0 = __ldg(sc.tn0 + tri), a1 = __ldg(sc.tn1 + tri), a2 = __ldg(sc.tn2 + tri);
-    V3 ns = b0 * V3(a0.x, a0.y, a0.z) + b1 * V3(a1.x, a1.y, a1.z) + b2 * V3(a2.x, a2.y, a2.z);
-    if (length_sq(ns) > 0) ns = normalize(ns);
-    else ns = n;
-    V3 ss = normalize(dpdu);
+    V3 ns = n;
+    if (fl & kTriFlagNormals) {
+      const float4 a0 = __ldg(sc.tn0 + tri), a1 = __ldg(sc.tn1 + tri), a2 = __ldg(sc.tn2 + tri);
+      ns = b0 * V3(a0.x, a0.y, a0.z) + b1 * V3(a1.x, a1.y, a1.z) + b2 * V3(a2.x, a2.y, a2.z);
+      if (length_sq(ns) > 0) ns = normalize(ns);
+      else ns = n;
+    }
+    V3 ss;
+    if (t.w1 & kTriTangentBit) {  // mesh->s: interpolated tangent, Normalize(dpdu) when it vanishes (Triangle.cpp:204-213)
+      const float4 s0 = __ldg(sc.ts0 + tri), s1 = __ldg(sc.ts1 + tri), s2 = __ldg(sc.ts2 + tri);
+      ss = b0 * V3(s0.x, s0.y, s0.z) + b1 * V3(s1.x, s1.y, s1.z) + b2 * V3(s2.x, s2.y, s2.z);
+      if (length_sq(ss) > 0) ss = normalize(ss);
+      else ss = normalize(dpdu);
+    } else {
+      ss = normalize(dpdu);
+    }
     V3 ts = cross(ss, ns);
     if (length_sq(ts) > 0.f) {
       ts = normalize(ts);
@@ -349,6 +361,12 @@ PBR_D void sample_area_light(const SceneDev& sc, const pbrgpu_light& l, V3 refP,
   // n = Normalize(Cross(p1 - p0, p2 - p0)) (orientation flip applied) and Area() of Triangle::Sample
   // (Triangle.cpp:352-387) are per-light constants, precomputed on the host into the light record
   V3 n(l.light_to_world[0], l.light_to_world[1], l.light_to_world[2]);
+  if ((t.w1 >> kTriFlagShift) & kTriFlagNormals) {
+    // mesh->n: it.n = Faceforward(Normalize(Cross(p1 - p0, p2 - p0)), b0 n0 + b1 n1 + (1 - b0 - b1) n2)   (Triangle.cpp:372-377)
+    const float4 a0 = __ldg(sc.tn0 + l.tri), a1 = __ldg(sc.tn1 + l.tri), a2 = __ldg(sc.tn2 + l.tri);
+    const V3 ns = b0 * V3(a0.x, a0.y, a0.z) + b1 * V3(a1.x, a1.y, a1.z) + (1 - b0 - b1) * V3(a2.x, a2.y, a2.z);
+    n = faceforward(V3(l.light_to_world[8], l.light_to_world[9], l.light_to_world[10]), ns);
+  }
   V3 pAbsSum = vabs(b0 * t.p0) + vabs(b1 * t.p1) + vabs(b2 * t.p2);
   ls->pErr1 = gamma_f(6) * pAbsSum;
   float area = l.light_to_world[3];
@@ -375,6 +393,11 @@ PBR_D float area_light_pdf(const SceneDev& sc, const pbrgpu_light& l, V3 rayO, V
   if (!intersect_triangle(rp, kInfinity, t.p0, t.p1, t.p2, &th, &b0, &b1, &b2)) return 0;
   V3 pl = b0 * t.p0 + b1 * t.p1 + b2 * t.p2;
   V3 nl(l.light_to_world[4], l.light_to_world[5], l.light_to_world[6]);  // Triangle::Intersect's normal of the light
+  if (((t.w1 >> kTriFlagShift) & kTriFlagNormals) || (t.w1 & kTriTangentBit)) {  // isectLight.n after SetShadingGeometry
+    Isect il;
+    make_isect(sc, t, l.tri, b0, b1, b2, wi, &il);
+    nl = il.n;
+  }
   float area = l.light_to_world[3];
   float pdf = dist_sq(refP, pl) / (absdot(nl, -wi) * area);
   if (isinf(pdf)) pdf = 0.f;

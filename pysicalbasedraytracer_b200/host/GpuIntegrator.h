@@ -79,8 +79,8 @@ namespace PBR {
 namespace gpu_detail {
 
 struct Flat {
-  std::vector<float> verts, normals, uvs;  // normals / uvs: per emitted vertex, filled only if some mesh has them
-  bool anyNormals = false, anyUVs = false;
+  std::vector<float> verts, normals, uvs, tangents;  // normals / uvs / tangents: per emitted vertex, filled only if some mesh has them
+  bool anyNormals = false, anyUVs = false, anyTangents = false;
   std::vector<int32_t> indices, triMaterial, triLight;
   std::vector<uint8_t> triFlags;
   std::vector<pbrgpu_material> materials;
@@ -266,7 +266,6 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
     }
     auto* tri = dynamic_cast<const Triangle*>(gp->shape.get());
     if (!tri) { f->error = "shape is neither a Triangle nor an AnalyticSphere (the reference's Sphere is a stub, SURVEY Q4)"; return false; }
-    if (tri->mesh->s) { f->error = "per-vertex tangents (TriangleMesh::s) are not supported on the GPU path"; return false; }
     const size_t i = f->triMaterial.size();  // triangle index (analytic spheres are numbered separately)
     f->triMaterial.push_back(-1); f->triLight.push_back(-1); f->triFlags.push_back(0);
     f->triMediumIn.push_back(-1); f->triMediumOut.push_back(-1);
@@ -278,6 +277,7 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
       if (tri->mesh->n && !f->anyNormals) { f->anyNormals = true; f->normals.assign(n * 9, 0.f); }
       if (tri->mesh->uv && !f->anyUVs) { f->anyUVs = true; f->uvs.assign(n * 6, 0.f); }
     }
+    if (tri->mesh->s && !f->anyTangents) { f->anyTangents = true; f->tangents.assign(n * 9, 0.f); }
     for (int k = 0; k < 3; ++k) {
       const Point3f& p = tri->mesh->p[tri->v[k]];  // already world space (TriangleMesh ctor, Triangle.cpp:27-28)
       f->verts.push_back(p.x); f->verts.push_back(p.y); f->verts.push_back(p.z);
@@ -287,13 +287,18 @@ inline bool flattenScene(const Scene& scene, Flat* f) {
         float* d = &f->normals[9 * i + 3 * k];
         d[0] = nn.x; d[1] = nn.y; d[2] = nn.z;
       }
+      if (tri->mesh->s) {
+        const Vector3f& sv = tri->mesh->s[tri->v[k]];
+        float* d = &f->tangents[9 * i + 3 * k];
+        d[0] = sv.x; d[1] = sv.y; d[2] = sv.z;
+      }
       if (tri->mesh->uv) {
         const Point2f& t = tri->mesh->uv[tri->v[k]];
         f->uvs[6 * i + 2 * k] = t.x; f->uvs[6 * i + 2 * k + 1] = t.y;
       }
     }
     f->triFlags[i] = (uint8_t)(((tri->reverseOrientation ^ tri->transformSwapsHandedness) ? 1 : 0) | (tri->reverseOrientation ? 2 : 0) |
-                               (tri->mesh->n ? 4 : 0) | (tri->mesh->uv ? 8 : 0));
+                               (tri->mesh->n ? 4 : 0) | (tri->mesh->uv ? 8 : 0) | (tri->mesh->s ? 16 : 0));
     if (!materialOf(gp, &f->triMaterial[i])) return false;
     if (gp->areaLight) {
       auto li = lightId.find(gp->areaLight.get());
@@ -379,6 +384,7 @@ class GpuSamplerIntegrator : public Integrator {
       d.tri_material = f.triMaterial.data(); d.tri_light = f.triLight.data(); d.tri_flags = f.triFlags.data();
       d.normals = f.anyNormals ? f.normals.data() : nullptr;
       d.uvs = f.anyUVs ? f.uvs.data() : nullptr;
+      d.tangents = f.anyTangents ? f.tangents.data() : nullptr;
       d.n_materials = (int32_t)f.materials.size(); d.materials = f.materials.data();
       d.n_lights = (int32_t)f.lights.size(); d.lights = f.lights.data();
       d.env_width = f.envW; d.env_height = f.envH; d.env_texels = f.env.empty() ? nullptr : f.env.data();

@@ -49,6 +49,7 @@ class SceneData:
         self._verts = []
         self._normals = []
         self._uvs = []
+        self._tangents = []
         self._mesh_flags = []
         self._tris = []
         self._tri_mat = []
@@ -87,10 +88,10 @@ class SceneData:
         return len(self.media) - 1
 
     def add_mesh(self, verts, tris, material, emit=None, two_sided=False, n_samples=1, normals=None, uvs=None,
-                 reverse_orientation=False, medium_interface=None):
+                 reverse_orientation=False, medium_interface=None, tangents=None):
         """material: int id or per-triangle int array; None / -1 = no material (a pure medium boundary, VolPath only).
         emit: RGB Lemit -> one DiffuseAreaLight per triangle.
-        normals / uvs: optional per-vertex shading normals (world space) and uv (TriangleMesh::n / ::uv).
+        normals / uvs / tangents: optional per-vertex shading normals, uv and tangents (TriangleMesh::n / ::uv / ::s; world space).
         medium_interface: (inside, outside) medium ids or None each  (MediumInterface, Media/Medium.h:51-59)."""
         if material is None:
             material = -1
@@ -99,8 +100,9 @@ class SceneData:
         n = tris.shape[0]
         self._normals.append(np.zeros_like(verts) if normals is None else np.ascontiguousarray(normals, dtype=F).reshape(-1, 3))
         self._uvs.append(np.zeros((verts.shape[0], 2), dtype=F) if uvs is None else np.ascontiguousarray(uvs, dtype=F).reshape(-1, 2))
+        self._tangents.append(np.zeros_like(verts) if tangents is None else np.ascontiguousarray(tangents, dtype=F).reshape(-1, 3))
         self._mesh_flags.append(np.full(n, (3 if reverse_orientation else 0) | (4 if normals is not None else 0) |
-                                        (8 if uvs is not None else 0), dtype=np.uint8))
+                                        (8 if uvs is not None else 0) | (16 if tangents is not None else 0), dtype=np.uint8))
         mats = np.full(n, material, dtype=np.int32) if np.isscalar(material) else np.asarray(material, dtype=np.int32)
         lights = np.full(n, -1, dtype=np.int32)
         if emit is not None:
@@ -217,6 +219,10 @@ class SceneData:
             uv = np.ascontiguousarray(np.concatenate(self._uvs), dtype=F)
             d.uvs = uv.ctypes.data_as(C.POINTER(C.c_float))
             keep.append(uv)
+        if (fl & 16).any():
+            tg = np.ascontiguousarray(np.concatenate(self._tangents), dtype=F)
+            d.tangents = tg.ctypes.data_as(C.POINTER(C.c_float))
+            keep.append(tg)
         if self.env is not None:
             d.env_height, d.env_width = self.env.shape[0], self.env.shape[1]
             d.env_texels = self.env.ctypes.data_as(C.POINTER(C.c_float))

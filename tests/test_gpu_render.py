@@ -296,6 +296,51 @@ def test_smooth_shading_normals_and_uvs(api, ref, gpu_ctx):
     _direct_check(p, ref, max_depth=4, spp=2)
 
 
+def test_vertex_tangents_and_emissive_smooth_mesh(api, ref, gpu_ctx):
+    """TriangleMesh::s (Triangle.cpp:204-213: interpolated tangents feed the shading frame - visible through an anisotropic
+    Metal) with and without TriangleMesh::n, and a DiffuseAreaLight on a mesh WITH shading normals: Triangle::Sample
+    face-forwards the sampled normal to the interpolated one (Triangle.cpp:371-377), Shape::Pdf / SurfaceInteraction::Le see
+    the hit normal after SetShadingGeometry."""
+    s = scenes.SceneData()
+    white = s.add_material(scenes.matte([0.8, 0.8, 0.8]))
+    brushed = s.add_material(scenes.metal([0.2, 0.9, 1.1], [3.9, 2.4, 2.2], 0.04, 0.35, False))  # anisotropic: the frame matters
+    g = 4.0
+    P = np.array([[-g, -1, -g], [g, -1, -g], [g, -1, g], [-g, -1, g]], dtype=np.float32)
+    s.add_mesh(P, np.array([[0, 2, 1], [0, 3, 2]], dtype=np.int32), white)
+    rng = np.random.default_rng(21)
+    for k, (cx, with_n) in enumerate(((-1.2, True), (1.2, False))):
+        v, t = scenes.uv_sphere([cx, 0.0, 0.0], 1.0, 10, 20)
+        nrm = v - np.array([cx, 0.0, 0.0], dtype=np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        tang = np.cross(nrm, np.array([0.3, 1.0, 0.2])) + rng.normal(size=nrm.shape) * 0.05  # swirl around a tilted axis
+        tang[::17] = 0.0                                                                      # some vanish: Normalize(dpdu) fallback
+        s.add_mesh(v, t, brushed, normals=nrm if with_n else None, tangents=tang)
+    # emissive, smooth-shaded, one-sided dome above the scene: the shading normals lean away from the geometric ones
+    v, t = scenes.uv_sphere([0.0, 3.2, 0.0], 0.6, 6, 12)
+    nrm = v - np.array([0.0, 3.2, 0.0], dtype=np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = (nrm + np.array([0.0, -0.35, 0.0])).astype(np.float32)
+    s.add_mesh(v, t, white, emit=[6.0, 5.0, 4.0], normals=nrm)
+    p = Pair(api, ref, s, 96, 72, 2, eye=(0.0, 1.5, 5.0), look=(0.0, 0.4, 0.0))
+    _direct_check(p, ref, max_depth=1, spp=2)
+    _direct_check(p, ref, max_depth=4, spp=2, rr_threshold=0.8)
+    _direct_check(p, ref, max_depth=3, spp=2, integrator=A.INTEGRATOR_DIRECT_ALL)
+    # Light::Sample_Li / Pdf_Li of an emissive smooth triangle against the reference, through the parity hook
+    rows = np.zeros((2048, 16), dtype=np.float32)
+    rows[:, 0:3] = rng.uniform(-2, 2, (2048, 3)) + [0, 1.0, 0]
+    rows[:, 3:6] = 1e-6
+    rows[:, 6:9] = [0, 1, 0]
+    rows[:, 9:11] = rng.uniform(0, 1, (2048, 2))
+    lt = len(s.lights) // 2
+    tri = s.verts[s.indices[s.lights[lt].tri]]
+    q = tri.mean(0) - rows[:, 0:3] + rng.normal(size=(2048, 3)) * 0.02
+    rows[:, 11:14] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    want, got = p.rscene.light_eval(lt, rows), p.scene.light_eval(lt, rows)
+    assert np.array_equal(want[:, 0:3], got[:, 0:3])                                 # Li: emitting side decided identically
+    assert np.allclose(want[:, 3], got[:, 3], rtol=2e-5) and np.allclose(want[:, 13], got[:, 13], rtol=2e-5)
+    assert (want[:, 13] > 0).mean() > 0.2 and (want[:, 0] > 0).any() and (want[:, 0] == 0).any()
+
+
 def test_full_size_dragon_class_properties(api, ref, gpu_ctx):
     """BASELINE configs[1] at FULL size (872 368 triangles, 1920x1080): the oracle cannot render this in seconds, so the
     check is through size-independent properties plus a sampled comparison of ray queries with the reference:
