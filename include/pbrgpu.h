@@ -68,7 +68,7 @@ typedef struct pbrgpu_material {
 /* ---- image textures: ImageTexture<RGBSpectrum, Spectrum> (Texture/ImageTexture.h) = UVMapping2D + MIPMap (Texture/MIPMap.h) ---- */
 enum { PBRGPU_WRAP_REPEAT = 0, PBRGPU_WRAP_BLACK = 1, PBRGPU_WRAP_CLAMP = 2 }; /* ImageWrap */
 typedef struct pbrgpu_texture {
-  int32_t width, height;  /* powers of two (MIPMap Lanczos-resamples anything else, MIPMap.h:93-144) */
+  int32_t width, height;  /* any size: sides that are not powers of two are Lanczos-resampled up like MIPMap does (MIPMap.h:93-144) */
   const float* texels;    /* width*height*3 RGB, row-major, as the MIPMap receives them, i.e. after ImageTexture::convertIn
                              (scale, optional inverse gamma) and after the loader's vertical flip (ImageTexture.cpp:16) */
   int32_t do_trilinear;   /* MIPMap::doTrilinear: trilinear filter instead of EWA */
@@ -141,7 +141,8 @@ typedef struct pbrgpu_scene_desc {
   int32_t n_lights;
   const pbrgpu_material* materials;
   const pbrgpu_light* lights;
-  int32_t env_width;  /* env map for INFINITE / SKYBOX lights (power-of-two sizes) */
+  int32_t env_width;  /* env map for INFINITE / SKYBOX lights; INFINITE: sides that are not powers of two are Lanczos-resampled
+                         up like InfiniteAreaLight's MIPMap does; SKYBOX reads the raw image at any size */
   int32_t env_height;
   const float* env_texels; /* env_width*env_height*3 RGB, row-major, raw (unscaled) */
   /* participating media (GeometricPrimitive::mediumInterface, Core/Primitive.h:43): all optional */
@@ -346,6 +347,11 @@ int pbrgpu_load_3d(const char* path, float scale, float** out_verts, int32_t* ou
 int pbrgpu_load_hdr(const char* path, int flip_vertically, float** out_rgb, int32_t* out_width, int32_t* out_height);
 void pbrgpu_free(void* p);
 
+/* Host-only helper: the level-0 image MIPMap builds from an image whose sides are not powers of two (separable 4-tap Lanczos
+ * up to RoundUpPow2, Texture/MIPMap.h:45-64,93-144) - what pbrgpu_scene_create applies to such textures / env maps.
+ * out_size receives the resampled width, height; out (may be NULL) width*height*3 floats. */
+int pbrgpu_resample_pow2(const float* rgb, int32_t width, int32_t height, int32_t wrap, float* out, int64_t out_floats,
+                         int32_t out_size[2]);
 /* Host-only helper: the sample sub-range rank `rank` of `world` renders for [s0,s1) (contiguous, balanced; what
  * pbrgpu_render applies on a multi-GPU context). */
 int pbrgpu_shard_samples(int64_t s0, int64_t s1, int rank, int world, int64_t out2[2]);

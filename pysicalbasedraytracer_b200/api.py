@@ -61,6 +61,7 @@ def lib():
         L.pbrgpu_load_hdr.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.pbrgpu_free.argtypes = [vp]
         L.pbrgpu_light_eval.argtypes = [vp, C.c_int, vp, C.c_int64, vp]
+        L.pbrgpu_resample_pow2.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int64, C.POINTER(C.c_int32)]
         L.pbrgpu_init_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
         L.pbrgpu_comm_unique_id.argtypes = [vp]
         L.pbrgpu_comm_attach.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -129,6 +130,16 @@ def comm_unique_id():
     buf = (C.c_ubyte * 128)()
     _check(lib().pbrgpu_comm_unique_id(buf))
     return bytes(buf)
+
+
+def resample_pow2(img, wrap=A.WRAP_REPEAT):
+    """MIPMap's level 0 for an RGB image [H,W,3] whose sides are not powers of two (host-only helper; Lanczos, MIPMap.h:93-144)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    size = (C.c_int32 * 2)()
+    _check(lib().pbrgpu_resample_pow2(img.ctypes.data, img.shape[1], img.shape[0], wrap, None, 0, size))
+    out = np.zeros((size[1], size[0], 3), dtype=np.float32)
+    _check(lib().pbrgpu_resample_pow2(img.ctypes.data, img.shape[1], img.shape[0], wrap, out.ctypes.data, out.size, size))
+    return out
 
 
 def shard_samples(s0, s1, rank, world):

@@ -125,5 +125,82 @@ inline float roughness_to_alpha(float roughness) {
   return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
+// MIPMap's resampling of an image whose sides are not powers of two (Texture/MIPMap.h:45-64,93-144): separable 4-tap Lanczos
+// (tau = 2, Texture/Texture.cpp:16-24) up to RoundUpPow2 in s, then in t, texels fetched through the wrap mode, result clamped
+// to [0, inf).  RGB texels; the float operations and their order are the reference's, std::sin is the host libm on both sides.
+// wrap: 0 = Repeat, 1 = Black, 2 = Clamp (PBRGPU_WRAP_*).
+inline float lanczos(float x, float tau = 2.f) {
+  x = std::abs(x);
+  if (x < 1e-5f) return 1;
+  if (x > 1.f) return 0;
+  x *= 3.14159265358979323846f;
+  float s = std::sin(x * tau) / (x * tau);
+  float lz = std::sin(x) / x;
+  return s * lz;
+}
+struct ResampleWeight {
+  int firstTexel;
+  float weight[4];
+};
+inline std::vector<ResampleWeight> resample_weights(int oldRes, int newRes) {
+  std::vector<ResampleWeight> wt((size_t)newRes);
+  const float filterwidth = 2.f;
+  for (int i = 0; i < newRes; ++i) {
+    float center = (i + .5f) * oldRes / newRes;
+    wt[i].firstTexel = (int)std::floor((center - filterwidth) + 0.5f);
+    for (int j = 0; j < 4; ++j) {
+      float pos = wt[i].firstTexel + j + .5f;
+      wt[i].weight[j] = lanczos((pos - center) / filterwidth);
+    }
+    float invSumWts = 1 / (wt[i].weight[0] + wt[i].weight[1] + wt[i].weight[2] + wt[i].weight[3]);
+    for (int j = 0; j < 4; ++j) wt[i].weight[j] *= invSumWts;
+  }
+  return wt;
+}
+inline int round_up_pow2(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int wrap_index(int i, int n, int wrap) {  // -1 = outside (contributes nothing)
+  if (wrap == 0) { int r = i - (i / n) * n; i = r < 0 ? r + n : r; }
+  else if (wrap == 2) i = std::max(0, std::min(n - 1, i));
+  return (i >= 0 && i < n) ? i : -1;
+}
+// in: w*h*3 floats -> out: (*W2)*(*H2)*3 floats
+inline std::vector<float> resample_to_pow2(const float* img, int w, int h, int wrap, int* W2, int* H2) {
+  const int w2 = round_up_pow2(w), h2 = round_up_pow2(h);
+  *W2 = w2; *H2 = h2;
+  std::vector<float> res((size_t)w2 * h2 * 3, 0.f);
+  const std::vector<ResampleWeight> sW = resample_weights(w, w2);
+  for (int t = 0; t < h; ++t)
+    for (int s = 0; s < w2; ++s) {
+      float* dst = &res[3 * ((size_t)t * w2 + s)];
+      dst[0] = dst[1] = dst[2] = 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const int o = wrap_index(sW[s].firstTexel + j, w, wrap);
+        if (o >= 0)
+          for (int c = 0; c < 3; ++c) dst[c] += sW[s].weight[j] * img[3 * ((size_t)t * w + o) + c];
+      }
+    }
+  const std::vector<ResampleWeight> tW = resample_weights(h, h2);
+  std::vector<float> work((size_t)h2 * 3);
+  for (int s = 0; s < w2; ++s) {
+    for (int t = 0; t < h2; ++t) {
+      float* wd = &work[3 * (size_t)t];
+      wd[0] = wd[1] = wd[2] = 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const int o = wrap_index(tW[t].firstTexel + j, h, wrap);
+        if (o >= 0)
+          for (int c = 0; c < 3; ++c) wd[c] += tW[t].weight[j] * res[3 * ((size_t)o * w2 + s) + c];
+      }
+    }
+    for (int t = 0; t < h2; ++t)
+      for (int c = 0; c < 3; ++c) res[3 * ((size_t)t * w2 + s) + c] = std::max(0.f, work[3 * (size_t)t + c]);  // Clamp(v, 0, Infinity)
+  }
+  return res;
+}
+
 }  // namespace host
 }  // namespace pbr

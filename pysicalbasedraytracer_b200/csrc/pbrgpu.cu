@@ -542,18 +542,19 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     s->texPyramids.resize((size_t)d->n_textures);
     for (int ti = 0; ti < d->n_textures; ++ti) {
       const pbrgpu_texture& t = d->textures[ti];
-      const int W = t.width, H = t.height;
-      if (W <= 0 || H <= 0 || !t.texels || (W & (W - 1)) || (H & (H - 1)) || W > 32768 || H > 32768)
-        return fail("pbrgpu_scene_create: texture sizes must be powers of two (MIPMap would Lanczos-resample otherwise)");
+      int W = t.width, H = t.height;
+      if (W <= 0 || H <= 0 || !t.texels || W > 32768 || H > 32768) return fail("pbrgpu_scene_create: bad texture size");
       if (t.wrap < PBRGPU_WRAP_REPEAT || t.wrap > PBRGPU_WRAP_CLAMP) return fail("pbrgpu_scene_create: bad texture wrap mode");
       TexDev& td = table[(size_t)ti];
+      std::vector<float> prev(t.texels, t.texels + (size_t)W * H * 3), cur;
+      if (!host::is_pow2(W) || !host::is_pow2(H))  // MIPMap ctor: Lanczos resampling up to powers of two (MIPMap.h:93-144)
+        prev = host::resample_to_pow2(t.texels, t.width, t.height, t.wrap, &W, &H);
       td.width = W; td.height = H; td.doTrilinear = t.do_trilinear ? 1 : 0; td.wrap = t.wrap; td.maxAnisotropy = t.max_anisotropy;
       td.su = t.su; td.sv = t.sv; td.du = t.du; td.dv = t.dv;
       int nLevels = 1;
       for (int m = std::max(W, H); m > 1; m >>= 1) ++nLevels;  // 1 + Log2Int(max(w, h))
       td.nLevels = nLevels;
       std::vector<float4> all;
-      std::vector<float> prev(t.texels, t.texels + (size_t)W * H * 3), cur;
       int pw = W, ph = H;
       for (int lv = 0; lv < nLevels; ++lv) {
         if (lv > 0) {
@@ -669,17 +670,23 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     }
   }
   if (envUser >= 0) {
-    const int W = d->env_width, H = d->env_height;
+    int W = d->env_width, H = d->env_height;
     if (!d->env_texels || W <= 0 || H <= 0) return fail("pbrgpu_scene_create: environment light without env_texels");
-    if ((W & (W - 1)) || (H & (H - 1)))
-      return fail("pbrgpu_scene_create: env map sizes must be powers of two (MIPMap would Lanczos-resample otherwise)");
     const pbrgpu_light& l = s->lights[envUser];
     std::vector<float> tex(d->env_texels, d->env_texels + (size_t)W * H * 3);
-    s->sc.env.width = W;
-    s->sc.env.height = H;
     if (l.type == PBRGPU_LIGHT_INFINITE) {
       for (size_t k = 0; k < (size_t)W * H; ++k)
         for (int c = 0; c < 3; ++c) tex[3 * k + c] = l.L[c] * tex[3 * k + c];  // InfiniteAreaLight.cpp:20-31
+      // Lmap = MIPMap(resolution, texels): a map whose sides are not powers of two is Lanczos-resampled (Repeat wrap) and the
+      // sampling distribution is built over the RESAMPLED size (InfiniteAreaLight.cpp:40-59).  SkyBoxLight reads its raw image.
+      if (!host::is_pow2(W) || !host::is_pow2(H)) {
+        std::vector<float> rs = host::resample_to_pow2(tex.data(), W, H, PBRGPU_WRAP_REPEAT, &W, &H);
+        tex.swap(rs);
+      }
+    }
+    s->sc.env.width = W;
+    s->sc.env.height = H;
+    if (l.type == PBRGPU_LIGHT_INFINITE) {
       // sampling image (InfiniteAreaLight.cpp:44-59) and Distribution2D (Sampling.cpp:121-133)
       std::vector<float> img((size_t)W * H);
       for (int v = 0; v < H; ++v) {
@@ -1519,6 +1526,21 @@ int pbrgpu_comm_attach(pbrgpu_ctx* c, int nranks, int rank, const void* unique_i
   if (r) { c->comm = nullptr; return nccl_fail(api, "ncclCommInitRank", r); }
   c->nranks = nranks;
   c->rank = rank;
+  return 0;
+}
+
+int pbrgpu_resample_pow2(const float* rgb, int32_t width, int32_t height, int32_t wrap, float* out, int64_t out_floats, int32_t out_size[2]) {
+  if (!rgb || !out_size || width <= 0 || height <= 0 || wrap < PBRGPU_WRAP_REPEAT || wrap > PBRGPU_WRAP_CLAMP)
+    return fail("pbrgpu_resample_pow2: bad argument");
+  int W = width, H = height;
+  std::vector<float> r;
+  if (host::is_pow2(W) && host::is_pow2(H)) r.assign(rgb, rgb + (size_t)W * H * 3);
+  else r = host::resample_to_pow2(rgb, width, height, wrap, &W, &H);
+  out_size[0] = W; out_size[1] = H;
+  if (out) {
+    if (out_floats < (int64_t)r.size()) return fail("pbrgpu_resample_pow2: output too small");
+    memcpy(out, r.data(), r.size() * sizeof(float));
+  }
   return 0;
 }
 

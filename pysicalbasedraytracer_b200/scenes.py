@@ -74,7 +74,7 @@ class SceneData:
 
     def add_texture(self, texels, do_trilinear=False, max_anisotropy=8.0, wrap=A.WRAP_REPEAT, su=1.0, sv=1.0, du=0.0, dv=0.0):
         """ImageTexture<RGBSpectrum, Spectrum>(UVMapping2D(su, sv, du, dv), ..., doTrilinear, maxAniso, wrap) over the RGB
-        image `texels` [H,W,3] (power-of-two sizes; the values the MIPMap receives, Texture/ImageTexture.cpp:88-95) -> id."""
+        image `texels` [H,W,3] (any size; the values the MIPMap receives, Texture/ImageTexture.cpp:88-95) -> id."""
         tx = np.ascontiguousarray(texels, dtype=F)
         assert tx.ndim == 3 and tx.shape[2] == 3
         t = A.Texture(width=tx.shape[1], height=tx.shape[0], texels=tx.ctypes.data_as(C.POINTER(C.c_float)),

@@ -73,6 +73,29 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("wrap", [A.WRAP_REPEAT, A.WRAP_BLACK, A.WRAP_CLAMP])
+def test_lanczos_resampling_bit_exact_vs_reference_mipmap(api, ref, wrap):
+    """Images whose sides are not powers of two: the library's host resampler (what pbrgpu_scene_create applies) against level 0
+    of the reference's own MIPMap (Texture/MIPMap.h:93-144), read back through ImageTexture::Evaluate at the texel centres with a
+    zero footprint (bilinear weights 1, 0, 0, 0 -> the texel itself)."""
+    rng = np.random.default_rng(17)
+    for (h, w) in [(24, 50), (5, 3), (33, 64), (100, 37)]:
+        img = rng.uniform(0.0, 2.0, (h, w, 3)).astype(np.float32)
+        got = api.resample_pow2(img, wrap)
+        H2, W2 = got.shape[:2]
+        assert (W2 & (W2 - 1)) == 0 and (H2 & (H2 - 1)) == 0 and W2 >= w and H2 >= h and W2 < 2 * w and H2 < 2 * h
+        tex = A.Texture(width=w, height=h, texels=img.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)),
+                        do_trilinear=0, max_anisotropy=8.0, wrap=wrap, su=1.0, sv=1.0, du=0.0, dv=0.0)
+        rows = np.zeros((H2 * W2, 8), dtype=np.float32)
+        uu, vv = np.meshgrid((np.arange(W2, dtype=np.float32) + np.float32(0.5)) / np.float32(W2),
+                             (np.arange(H2, dtype=np.float32) + np.float32(0.5)) / np.float32(H2))
+        rows[:, 0], rows[:, 1] = uu.reshape(-1), vv.reshape(-1)
+        want = ref.texture_kat((tex, img), rows).reshape(H2, W2, 3)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (h, w, wrap)
+    same = api.resample_pow2(np.ones((8, 16, 3), dtype=np.float32))
+    assert same.shape == (8, 16, 3)
+
+
 def test_shard_samples_partition_properties(api):
     """pbrgpu_shard_samples (the split pbrgpu_render applies on a multi-GPU context): the shards tile [s0, s1) without gaps
     or overlap, in rank order, sizes differ by at most one; ranks beyond the sample count get empty ranges."""
