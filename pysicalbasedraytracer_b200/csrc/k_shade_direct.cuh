@@ -132,8 +132,15 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
         } else {  // UniformSampleAll: two sample arrays per light per recursion depth
           int arr = 2 * sc.nLights * depth;
           const int nArrays = (P.arrayEndDim - 5) / 2;
+          // sample k of pixel-sample s of an array lives at GetIndexForSample(s * n + k) (GlobalSampler::StartPixel, Sampler.cpp:97-120)
+          const bool sobol = sc.hp.type == PBRGPU_SAMPLER_SOBOL;
           const int64_t stride = sc.hp.sampleStride;
-          const int64_t s = (cur.index - P.pixelOffsetOf(cur.index)) / stride;  // pixel-sample number
+          int px, py;
+          long long sNum;
+          uint32_t pix;
+          slot_to_pixel(P, slot, &px, &py, &sNum, &pix);
+          const int64_t pixelOffset = sobol ? 0 : P.pixelOffsetOf(cur.index);
+          const int64_t s = sobol ? (int64_t)sNum : (cur.index - pixelOffset) / stride;  // pixel-sample number
           for (int j = 0; j < sc.nLights; ++j) {
             int nS = sc.lights[j].n_samples;
             if (arr + 1 >= nArrays) {  // arrays exhausted: one plain sample (Integrator.cpp:29-33)
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
             } else {
               int dimL = 5 + 2 * arr, dimS = 5 + 2 * (arr + 1);
               for (int k = 0; k < nS; ++k) {
-                int64_t idx = P.pixelOffsetOf(cur.index) + (s * nS + k) * stride;  // GetIndexForSample(s*n+k)
+                const int64_t idx = sobol ? sobol_index_for_sample(px, py, s * nS + k, sc.hp) : pixelOffset + (s * nS + k) * stride;
                 float uL0 = halton_sample_dimension(idx, dimL, sc.hp), uL1 = halton_sample_dimension(idx, dimL + 1, sc.hp);
                 float uS0 = halton_sample_dimension(idx, dimS, sc.hp), uS1 = halton_sample_dimension(idx, dimS + 1, sc.hp);
                 estimate_direct<MAT>(P, bsdf, is, j, uL0, uL1, uS0, uS1, beta, (float)nS, slot);

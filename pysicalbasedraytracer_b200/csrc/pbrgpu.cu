@@ -946,8 +946,6 @@ static int check_render_args(pbrgpu_scene* s, const pbrgpu_render_desc* rd) {
     return fail("pbrgpu_render: the scene has triangles without a material (medium boundaries); only the VolPath integrator renders them");
   if (rd->integrator == PBRGPU_INTEGRATOR_VOLPATH && rd->max_depth > (int)kMetaBounceMask - 1)
     return fail("pbrgpu_render: VolPath max_depth > 126");
-  if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL && s->sc.hp.type == PBRGPU_SAMPLER_SOBOL)
-    return fail("pbrgpu_render: UniformSampleAll sample arrays are implemented for the Halton sampler only");
   if (s->bvh.maxDepth >= kSmemStack + kLocalStack) return fail("pbrgpu_render: BVH deeper than the traversal stack");
   return 0;
 }

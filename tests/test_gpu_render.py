@@ -196,6 +196,16 @@ def test_sobol_path_render_vs_reference_with_cpu_twin(api, ref, gpu_ctx):
     _direct_check(p, ref, max_depth=5, spp=4, rr_threshold=0.8)
 
 
+def test_sobol_uniform_sample_all_arrays(api, ref, gpu_ctx):
+    """DirectLighting / UniformSampleAll with the Sobol sampler: the 2D sample arrays of GlobalSampler::StartPixel
+    (Sampler.cpp:97-120: sample k of pixel-sample s sits at GetIndexForSample(s * n + k)) through the Sobol index mapping."""
+    data = scenes.cornell(sphere_tess=12, floor_mirror=True)
+    data.add_point_light([0.5, 1.5, 0.5], [20.0, 18.0, 15.0])
+    p = Pair(api, ref, data, 64, 64, 4, eye=(0.3, 0.2, 5.0), look=(0.1, -0.2, 0.0), sampler_type=A.SAMPLER_SOBOL)
+    _direct_check(p, ref, max_depth=3, spp=2, integrator=A.INTEGRATOR_DIRECT_ALL)
+    _direct_check(p, ref, max_depth=3, spp=2, integrator=A.INTEGRATOR_DIRECT_ONE)
+
+
 def test_power_strategy_with_infinite_light(api, ref, gpu_ctx):
     """PowerLightDistribution with an InfiniteAreaLight among several lights: Power() needs the trilinear MIP lookup
     (InfiniteAreaLight.cpp:63-67), rebuilt on the host; SkyBoxLight::Power() is 0 and is never picked."""
@@ -598,7 +608,7 @@ def test_non_power_of_two_textures_and_env_map(api, ref, gpu_ctx, wrap):
     uu, vv = np.meshgrid((np.arange(64) + 0.5) / 64, (np.arange(32) + 0.5) / 32)
     rows[:, 0] = ((uu.reshape(-1) - (-0.2)) / 1.6).astype(np.float32)
     rows[:, 1] = ((vv.reshape(-1) - 0.1) / 1.3).astype(np.float32)
-    got_t, want_t = p.scene.texture_eval(0, rows), ref.texture_kat(s.textures[0][0], rows)
+    got_t, want_t = p.scene.texture_eval(0, rows), ref.texture_kat(s.textures[0], rows)
     assert np.abs(got_t - want_t).max() <= 2e-6 * max(1.0, np.abs(want_t).max())
     _direct_check(p, ref, max_depth=1, spp=2)
     _direct_check(p, ref, max_depth=4, spp=2, rr_threshold=0.8)
