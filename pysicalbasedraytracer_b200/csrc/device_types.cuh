@@ -171,6 +171,9 @@ struct RenderParams {
   int volShadowAnyHit;    // VolPath, scene without material-less surfaces: a shadow ray ends at ANY surface it finds
   int storeHitT;          // parity hooks: k_trace also stores the hit distance of path rays (rayO.w), like the VOL build
   int atomicL;            // several shadow / MIS rays per path and bounce (Whitted / DirectLighting): atomics on L
+  int deferShadow;        // VolPath tail (pbrgpu.cu): 1 = the shadow queue is left alone and keeps growing (k_trace skips it, k_classify
+                          // does not reset it); 2 = the flush launch: k_trace serves ONLY the shadow queue and leaves each ray's
+                          // contribution x transmittance in shC (0 when blocked) for k_shadow_add
   // Halton offset of the pixel a global index belongs to: index = offset(pixel) + sample * stride, offset < stride
   PBR_D int64_t pixelOffsetOf(int64_t index) const { return index % sc.hp.sampleStride; }
   float* accum;           // [h*w] RGBA sums (A = sample count)

@@ -36,7 +36,11 @@ constexpr int kNodeStepsPerIter = PBR_NODE_STEPS;
 constexpr int kMaxShadowCrossings = 256;
 PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T, const HitRec& hit, int* hops) {
   const SceneDev& sc = P.sc;
-  if (hit.tri >= 0 && ((hit.w1 >> kTriTypeShift) & 0xfu) != (uint32_t)kQueueNull) return false;  // opaque surface: Tr = 0
+  const bool toRecord = P.deferShadow == 2;
+  if (hit.tri >= 0 && ((hit.w1 >> kTriTypeShift) & 0xfu) != (uint32_t)kQueueNull) {  // opaque surface: Tr = 0
+    if (toRecord) P.ws.shC[ray] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return false;
+  }
   float4 c = P.ws.shC[ray];
   const float4 p1m = P.ws.shP1[ray], dd = P.ws.shD[ray];
   const int med = __float_as_int(p1m.w);
@@ -46,11 +50,16 @@ PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T,
     c.x *= tr.r; c.y *= tr.g; c.z *= tr.b;
   }
   if (hit.tri < 0) {
+    if (toRecord) { P.ws.shC[ray] = c; return false; }
     const uint32_t slot = __float_as_uint(dd.w);
     atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
     return false;
   }
-  if (++*hops > kMaxShadowCrossings) { atomicAdd(&P.ws.ctr->volCapHits, 1u); return false; }
+  if (++*hops > kMaxShadowCrossings) {
+    atomicAdd(&P.ws.ctr->volCapHits, 1u);
+    if (toRecord) P.ws.shC[ray] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return false;
+  }
   if (P.countStats) atomicMax(&P.ws.ctr->volMaxHops, (uint32_t)*hops);
   // ray = isect.SpawnRayTo(p1)   (Interaction.h:38-43; isect.mediumInterface from GeometricPrimitive::Intersect)
   const TriData tri = load_tri(sc, hit.tri);
@@ -84,13 +93,15 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   uint2* sstack = &sstk[warp][0][lane];
   uint2* tq = &stri[warp][0][lane];
   Counters* C = P.ws.ctr;
-  const uint32_t nPath = C->nCur, nShadow = C->nShadow, nMis = C->nMis;
+  // VolPath tail (RenderParams::deferShadow): 1 = leave the shadow queue alone, 2 = the shadow queue only
+  const uint32_t nPath = (VOL && P.deferShadow == 2) ? 0u : C->nCur, nShadow = (VOL && P.deferShadow == 1) ? 0u : C->nShadow;
+  const uint32_t nMis = (VOL && P.deferShadow == 2) ? 0u : C->nMis;
   const uint32_t n = nPath + nShadow + nMis;
   Trav T;
   TravSpill S;
   T.ngroup = make_uint2(0u, 0u); T.tgroup = make_uint2(0u, 0u); T.sp = 0;
   int nt = 0;  // parked triangle groups
-  bool busy = false, exhausted = false;
+  bool busy = false, pend = false, exhausted = false;  // pend: traversal finished, result not yet written
   int mode = TRACE_PATH;
   uint32_t ray = 0;  // index in the queue of `mode`: PATH = position in ws.cur, SHADOW / MIS = position in that ray queue
   int hops = 0;      // VOL: medium boundaries this shadow ray has crossed
@@ -98,28 +109,60 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   unsigned nodes = 0, tris = 0;
   unsigned rayWork0 = 0;  // COUNT: nodes + tris at the start of the current ray (-> Counters::maxRayWork)
   while (true) {
-    // ---- fetch: idle lanes take new rays with one warp-aggregated atomicAdd ----
+    // ---- completion + fetch, batched: a lane whose ray has finished parks (pend) until at least P.fetchMinIdle lanes of the
+    // warp are without traversal work; then the finished rays write their results together and the free lanes take new
+    // rays with one warp-aggregated atomicAdd.  (Writing each result the moment its ray finished ran that code - for VolPath
+    // the whole of VisibilityTester::Tr's next-segment set-up - with 1-4 active lanes.)
     // (a per-warp reserve of 128 rays per atomicAdd was measured: no faster - the cursor is not a bottleneck)
     const unsigned idle = __ballot_sync(full, !busy);
-    if (idle != 0u && !exhausted && (idle == full || __popc(idle) >= P.fetchMinIdle)) {
-      const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&C->cursor[0], (uint32_t)nIdle);
-      base = __shfl_sync(full, base, leader);
-      exhausted = base + (uint32_t)nIdle >= n;
-      if (!busy) {
-        uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
-        if (i < n) {
-          float4 ro, rd;
-          if (i < nPath) { mode = TRACE_PATH; ray = i; ro = P.ws.cur[i].o; rd = P.ws.cur[i].d; }  // coalesced: records are in queue order
-          else if (i < nPath + nShadow) { mode = TRACE_SHADOW; ray = i - nPath; ro = P.ws.shO[ray]; rd = P.ws.shD[ray]; }
-          else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
-          trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, P.sc.f32one);
-          nt = 0;
-          hops = 0;
-          busy = true;
-          hit.tri = -1;
-          if (COUNT) rayWork0 = nodes + tris;
+    if (idle != 0u && (exhausted || idle == full || __popc(idle) >= P.fetchMinIdle)) {
+      if (pend) {
+        pend = false;
+        if (COUNT) { atomicMax(&C->maxRayWork, nodes + tris - rayWork0); rayWork0 = nodes + tris; }
+        if (mode == TRACE_PATH) {
+          P.ws.hit[ray] = make_float4(__int_as_float(hit.tri), hit.b0, hit.b1, hit.b2);
+          // hit record and shading-queue id at the path's queue position
+          P.ws.qType[ray] = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
+          if (VOL || P.storeHitT) P.ws.cur[ray].o.w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
+        } else if (mode == TRACE_MIS) {
+          P.ws.miO[ray].w = __int_as_float(hit.tri);
+        } else if (VOL) {
+          segs++;
+          hit.t = T.tMax;
+          busy = vol_shadow_next_segment(P, ray, T, hit, &hops);  // true: next segment, same lane
+          if (busy) { hit.tri = -1; nt = 0; }
+        } else if (hit.tri < 0) {  // unoccluded: add the light-sampling contribution
+          const uint32_t slot = __float_as_uint(P.ws.shD[ray].w);
+          const float4 c = P.ws.shC[ray];
+          if (P.atomicL) {
+            atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
+          } else {
+            float4 L = P.ws.L[slot];
+            P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
+          }
+        }
+      }
+      const unsigned want = VOL ? __ballot_sync(full, !busy) : idle;  // VOL: a shadow ray continuing behind a boundary keeps its lane
+      if (!exhausted && want != 0u) {
+        const int nWant = __popc(want), leader = __ffs(want) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&C->cursor[0], (uint32_t)nWant);
+        base = __shfl_sync(full, base, leader);
+        exhausted = base + (uint32_t)nWant >= n;
+        if (!busy) {
+          uint32_t i = base + __popc(want & ((1u << lane) - 1u));
+          if (i < n) {
+            float4 ro, rd;
+            if (i < nPath) { mode = TRACE_PATH; ray = i; ro = P.ws.cur[i].o; rd = P.ws.cur[i].d; }  // coalesced: records are in queue order
+            else if (i < nPath + nShadow) { mode = TRACE_SHADOW; ray = i - nPath; ro = P.ws.shO[ray]; rd = P.ws.shD[ray]; }
+            else { mode = TRACE_MIS; ray = i - nPath - nShadow; ro = P.ws.miO[ray]; rd = P.ws.miD[ray]; }
+            trav_init(T, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, P.sc.f32one);
+            nt = 0;
+            hops = 0;
+            busy = true;
+            hit.tri = -1;
+            if (COUNT) rayWork0 = nodes + tris;
+          }
         }
       }
     }
@@ -157,34 +200,8 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         // (unless the scene has no such boundary at all: then the first surface found ends the ray either way)
         if (cw_tri_step<SPH>(P.sc, T, &hit) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
       }
-      // ---- ray finished?  (checked in the same iteration, so the lane is idle for the next fetch) ----
-      if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) {
-        bool again = false;
-        if (COUNT) { atomicMax(&C->maxRayWork, nodes + tris - rayWork0); rayWork0 = nodes + tris; }
-        if (mode == TRACE_PATH) {
-          P.ws.hit[ray] = make_float4(__int_as_float(hit.tri), hit.b0, hit.b1, hit.b2);
-          // hit record and shading-queue id at the path's queue position
-          P.ws.qType[ray] = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
-          if (VOL || P.storeHitT) P.ws.cur[ray].o.w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
-        } else if (mode == TRACE_MIS) {
-          P.ws.miO[ray].w = __int_as_float(hit.tri);
-        } else if (VOL) {
-          segs++;
-          hit.t = T.tMax;
-          again = vol_shadow_next_segment(P, ray, T, hit, &hops);  // true: next segment, same lane
-          if (again) hit.tri = -1;
-        } else if (hit.tri < 0) {  // unoccluded: add the light-sampling contribution
-          const uint32_t slot = __float_as_uint(P.ws.shD[ray].w);
-          const float4 c = P.ws.shC[ray];
-          if (P.atomicL) {
-            atomicAdd(&P.ws.L[slot].x, c.x); atomicAdd(&P.ws.L[slot].y, c.y); atomicAdd(&P.ws.L[slot].z, c.z);
-          } else {
-            float4 L = P.ws.L[slot];
-            P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
-          }
-        }
-        busy = again;
-      }
+      // ---- ray finished?  (checked in the same iteration, so the lane counts as idle at the next loop head) ----
+      if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) { busy = false; pend = true; }
     }
   }
   if (COUNT) {

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kBlock) k_classify(const __grid_constant__ Ren
   __shared__ uint32_t cnt[kNumQueues], basePos[kNumQueues];
   const uint32_t n = P.ws.ctr->nCur;
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // the shadow / MIS queues of the previous bounce are consumed
-    P.ws.ctr->nShadow = 0;
+    if (P.deferShadow != 1) P.ws.ctr->nShadow = 0;
     P.ws.ctr->nMis = 0;
     P.ws.ctr->cursor[0] = 0;
   }
@@ -369,6 +369,20 @@ __global__ void k_next_bounce(Counters* c) {
   c->nNext = 0;
   for (int k = 0; k < 8; ++k) c->nMat[k] = 0;
   for (int k = 0; k < 4; ++k) c->cursor[k] = 0;
+}
+
+// VolPath tail: the shadow rays that the tail iterations emitted were traced together by one k_trace launch
+// (RenderParams::deferShadow == 2), which left `contribution x transmittance` in shC.  Add them to their paths, one launch
+// per iteration's range of the queue: a path has at most one shadow ray per iteration, so the plain read-modify-write is
+// race-free and a path's sum is formed in iteration order (deterministic).
+__global__ void __launch_bounds__(kBlock) k_shadow_add(const __grid_constant__ RenderParams P, uint32_t begin, uint32_t end, int resetCount) {
+  for (uint32_t e = begin + blockIdx.x * blockDim.x + threadIdx.x; e < end; e += gridDim.x * blockDim.x) {
+    const uint32_t slot = __float_as_uint(P.ws.shD[e].w);
+    const float4 c = P.ws.shC[e];
+    float4 L = P.ws.L[slot];
+    P.ws.L[slot] = make_float4(L.x + c.x, L.y + c.y, L.z + c.z, 0.f);
+  }
+  if (resetCount && blockIdx.x == 0 && threadIdx.x == 0) { P.ws.ctr->nShadow = 0; P.ws.ctr->cursor[0] = 0; }
 }
 
 // wave end: per pixel, add the wave's per-path radiance in sample order (deterministic).

@@ -1084,8 +1084,43 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
         // VolPathIntegrator::Li: the bounce count is path state (crossing a medium boundary repeats the bounce), so the
         // number of iterations is not known up front: max_depth + 1 iterations are launched blind, then the live-path
         // and pending-ray counters are read back after every iteration until the wave has drained.
+        //
+        // Tail: from the first read-back on, the shadow rays that shading emits are NOT traced by the
+        // next iteration's k_trace.  They stay in the shadow queue, which keeps growing (RenderParams::deferShadow = 1),
+        // and ONE launch traces all of them when the paths have drained (deferShadow = 2) - a shadow ray marches through
+        // up to dozens of medium boundaries inside its lane, and with a few thousand live paths every iteration waited
+        // for its longest such chain (1-3 ms, 100+ times).  k_shadow_add then adds the contributions per iteration range.
         const int kMaxExtraIters = 4096;
         const bool volLog = getenv("PBRGPU_VOL_LOG") != nullptr;  // development aid: per-iteration queue sizes + wall time
+        const bool deferOk = getenv("PBRGPU_VOL_NO_DEFER") == nullptr;
+        const size_t shadowCap = (size_t)s->capacity;  // entries of the shadow-ray arrays this wave may use (raysPerHit == 1)
+        // Scenes WITH material-less medium boundaries defer from the first iteration on (one 16-byte read-back per iteration;
+        // the queue is flushed whenever the next iteration might overflow it): their shadow rays are the expensive, serial
+        // ones, and traced on their own - every lane in the same mode, one longest chain per flush instead of one per
+        // iteration - they cost about half.  Other scenes keep the blind launches: their shadow rays are single any-hit segments.
+        const int firstRead = (deferOk && s->hasNullMat) ? 0 : rd->max_depth;
+        std::vector<uint32_t> ranges;  // deferred shadow queue: start of each iteration's range, then the end
+        auto flush_deferred = [&]() -> int {
+          if (ranges.empty()) return 0;
+          if (ranges.back() > ranges.front()) {
+            P.deferShadow = 2;
+            CK(tl.mark(T_CLOSEST));
+            launch_trace(count, true, gt, st, P);
+            launches++;
+            CK(tl.mark(T_SHADE));
+            for (size_t k = 0; k + 1 < ranges.size(); ++k) {
+              const uint32_t b = ranges[k], e = ranges[k + 1];
+              const bool last = k + 2 == ranges.size();
+              if (e > b || last) {
+                k_shadow_add<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)(e - b) + kBlock - 1) / kBlock, (uint64_t)c->smCount * 8)), kBlock, 0, st>>>(P, b, e, last ? 1 : 0);
+                launches++;
+              }
+            }
+          }
+          ranges.clear();
+          P.deferShadow = 0;
+          return 0;
+        };
         for (int iter = 0;; ++iter) {
           std::chrono::steady_clock::time_point t0;
           if (volLog) {
@@ -1105,9 +1140,9 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
             CK(cudaMemcpy(&hc, s->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost));
             if (iter == 0) prev = Counters{};
             const double rays = (double)(hc.raysClosest - prev.raysClosest);
-            fprintf(stderr, "vol iter %d: paths %u shadow %u mis %u  k_trace %.3f ms  segments %.0f nodes/seg %.2f tris/seg %.2f  max work of one ray %u\n", iter,
+            fprintf(stderr, "vol iter %d: paths %u shadow %u mis %u  k_trace %.3f ms  segments %.0f nodes/seg %.2f tris/seg %.2f  max work of one ray %u%s\n", iter,
                     s->hNCur[0], s->hNCur[2], s->hNCur[3], ms, rays, (hc.nodesVisited - prev.nodesVisited) / std::max(rays, 1.0),
-                    (hc.trisTested - prev.trisTested) / std::max(rays, 1.0), hc.maxRayWork);
+                    (hc.trisTested - prev.trisTested) / std::max(rays, 1.0), hc.maxRayWork, P.deferShadow ? "  (shadow queue deferred)" : "");
             prev = hc;
             CK(cudaMemset(&s->ctr.p->maxRayWork, 0, sizeof(uint32_t)));
           }
@@ -1128,12 +1163,25 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
           k_next_bounce<<<1, 1, 0, st>>>(s->ctr.p);
           launches += 3;
           std::swap(P.ws.cur, P.ws.nxt);
-          if (iter >= rd->max_depth) {
+          if (iter >= firstRead) {
             CK(cudaMemcpyAsync(s->hNCur, s->ctr.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));  // nCur, nNext, nShadow, nMis
             CK(cudaStreamSynchronize(st));
-            if (s->hNCur[0] + s->hNCur[2] + s->hNCur[3] == 0 || iter >= rd->max_depth + kMaxExtraIters) break;
+            const uint32_t nLive = s->hNCur[0], nSh = s->hNCur[2], nMi = s->hNCur[3];
+            if (deferOk) {
+              if (ranges.empty()) ranges.push_back(0u);  // deferral starts: the rays just emitted are its first range
+              ranges.push_back(nSh);
+              const bool drained = nLive + nMi == 0;
+              // the next iteration appends at most one shadow ray per live path
+              if (drained || (size_t)nSh + nLive > shadowCap || iter >= rd->max_depth + kMaxExtraIters) {
+                if (flush_deferred()) return 1;
+                if (drained || iter >= rd->max_depth + kMaxExtraIters) break;
+                ranges.push_back(0u);
+              }
+              P.deferShadow = 1;
+            } else if (nLive + nSh + nMi == 0 || iter >= rd->max_depth + kMaxExtraIters) break;
           }
         }
+        P.deferShadow = 0;
       }
       const int lastBounce = volInteg ? -1 : (pathInteg ? rd->max_depth : std::max(rd->max_depth - 1, 0));
       for (int bounce = 0; bounce <= lastBounce; ++bounce) {
