@@ -77,25 +77,29 @@ PBR_HD void triangle_frame(V3 p0, V3 p1, V3 p2, const float uv[6], bool flip, V3
 
 // SurfaceInteraction of a hit on an analytic sphere (host/AnalyticSphere.h::Intersect); kept out of line: scenes without
 // spheres never call it and the shading kernels stay as compact as before.
-static __device__ __noinline__ void make_isect_sphere(const TriData& t, V3 rayO, V3 rayD, float tHit, Isect* is) {
-  const uint32_t fl = t.w1 >> kTriFlagShift;
-  const SphereHit h = sphere_hit(t.p0, t.p1.x, (fl & kTriFlagFlipNormal) != 0, rayO, rayD, tHit);
-  is->p = h.p;
-  is->pError = h.pError;
-  is->n = h.n;
-  is->ns = h.n;
-  is->ss = normalize(h.dpdu);   // BSDF ctor (Reflection.h:105-110): ss = Normalize(shading.dpdu), ts = Cross(ns, ss)
-  is->ts = cross(h.n, is->ss);
-  is->wo = normalize(-rayD);
-  is->matId = (int)(t.w1 & kTriMatMask);
-  is->matType = (int)((t.w1 >> kTriTypeShift) & 0xf);
-  is->lightId = (int)t.w2;
+// (Everything goes in and comes out BY VALUE: a pointer or reference to the caller's Isect / TriData handed to an out-of-line
+// function forces those structs into local memory in every shading kernel - 185 local loads / stores per shaded hit.)
+static __device__ __noinline__ Isect make_isect_sphere(V3 center, float radius, uint32_t w1, uint32_t w2, V3 rayO, V3 rayD, float tHit) {
+  Isect is;
+  const uint32_t fl = w1 >> kTriFlagShift;
+  const SphereHit h = sphere_hit(center, radius, (fl & kTriFlagFlipNormal) != 0, rayO, rayD, tHit);
+  is.p = h.p;
+  is.pError = h.pError;
+  is.n = h.n;
+  is.ns = h.n;
+  is.ss = normalize(h.dpdu);   // BSDF ctor (Reflection.h:105-110): ss = Normalize(shading.dpdu), ts = Cross(ns, ss)
+  is.ts = cross(h.n, is.ss);
+  is.wo = normalize(-rayD);
+  is.matId = (int)(w1 & kTriMatMask);
+  is.matType = (int)((w1 >> kTriTypeShift) & 0xf);
+  is.lightId = (int)w2;
+  return is;
 }
 
 // rayO: origin of the ray that produced the hit; read for analytic spheres only (their hit record is the ray parameter in b0)
 PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, float b1, float b2, V3 rayD, Isect* is,
                       V3 rayO = V3(0.f, 0.f, 0.f)) {
-  if (t.w1 & kPrimSphereBit) { make_isect_sphere(t, rayO, rayD, b0, is); return; }
+  if (t.w1 & kPrimSphereBit) { const Isect sph = make_isect_sphere(t.p0, t.p1.x, t.w1, t.w2, rayO, rayD, b0); *is = sph; return; }
   const V3 p0 = t.p0, p1 = t.p1, p2 = t.p2;
   float xAbsSum = (fabsf(b0 * p0.x) + fabsf(b1 * p1.x) + fabsf(b2 * p2.x));
   float yAbsSum = (fabsf(b0 * p0.y) + fabsf(b1 * p1.y) + fabsf(b2 * p2.y));
@@ -406,7 +410,10 @@ PBR_D float area_light_pdf(const SceneDev& sc, const pbrgpu_light& l, V3 rayO, V
 
 // DiffuseAreaLight over an analytic sphere: AnalyticSphere::Sample(ref, u) (uniform cone outside the sphere, uniform area
 // inside) and ::Pdf(ref, wi).  Out of line for the same reason as make_isect_sphere.
-static __device__ __noinline__ void sample_sphere_light(const pbrgpu_light& l, V3 refP, V3 refPError, V3 refN, float u0, float u1, LightSample* ls) {
+static __device__ __noinline__ LightSample sample_sphere_light(const pbrgpu_light& l, V3 refP, V3 refPError, V3 refN, float u0, float u1) {
+  LightSample out;
+  LightSample* ls = &out;
+  out.Li = Spec(0.f); out.wi = V3(0.f, 0.f, 0.f); out.pdf = 0.f;
   const V3 pCenter(l.pos[0], l.pos[1], l.pos[2]);
   const float radius = l.world_radius;
   const bool reverse = l.light_to_world[0] != 0.f;
@@ -462,10 +469,11 @@ static __device__ __noinline__ void sample_sphere_light(const pbrgpu_light& l, V
   }
   ls->p1 = p; ls->n1 = n; ls->pErr1 = pErr;
   // DiffuseAreaLight::Sample_Li (DiffuseLight.cpp:25-38)
-  if (pdf == 0 || length_sq(p - refP) == 0) { ls->pdf = 0; ls->Li = Spec(0.f); return; }
+  if (pdf == 0 || length_sq(p - refP) == 0) { ls->pdf = 0; ls->Li = Spec(0.f); return out; }
   ls->wi = normalize(p - refP);
   ls->pdf = pdf;
   ls->Li = area_light_L(l, n, -ls->wi);
+  return out;
 }
 static __device__ __noinline__ float sphere_light_pdf(const pbrgpu_light& l, V3 spawnO, V3 refP, V3 refPError, V3 refN, V3 wi) {
   const V3 pCenter(l.pos[0], l.pos[1], l.pos[2]);
@@ -502,7 +510,7 @@ PBR_D void sample_light(const SceneDev& sc, const pbrgpu_light& l, V3 refP, floa
       break;
     }
     case PBRGPU_LIGHT_AREA_TRI: sample_area_light(sc, l, refP, u0, u1, ls); break;
-    case PBRGPU_LIGHT_AREA_SPHERE: sample_sphere_light(l, refP, refPError, refN, u0, u1, ls); break;
+    case PBRGPU_LIGHT_AREA_SPHERE: { const LightSample sph = sample_sphere_light(l, refP, refPError, refN, u0, u1); *ls = sph; break; }
     case PBRGPU_LIGHT_INFINITE: {
       const EnvDev& e = sc.env;
       float pdf1, pdf0;
