@@ -4,6 +4,9 @@
 
 namespace pbr {
 
+#ifndef PBR_SHADE_STAGE_SMEM
+#define PBR_SHADE_STAGE_SMEM 1
+#endif
 #ifndef PBR_SHADE_MIN_BLOCKS
 #define PBR_SHADE_MIN_BLOCKS 6
 #endif
@@ -16,6 +19,13 @@ template <int MAT, bool VOL = false, bool TEX = false>
 __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderParams P, int bounce) {
   __shared__ uint32_t sCount, sBase;
   __shared__ uint32_t sCount3[3], sBase3[3];
+#if PBR_SHADE_STAGE_SMEM
+  // The rays a hit emits (shadow, MIS, continuation: 9-12 float4) wait for the block-wide queue push at the end of the
+  // iteration.  Kept in registers they were spilled (80-register budget): local stores are written through to L2.  Staged
+  // in shared memory, one 16-byte column per thread and field, they cost neither registers nor L2 traffic.
+  __shared__ float4 sStage[VOL ? 12 : 9][kShadeBlock];
+#define PBR_OUT(k) sStage[k][threadIdx.x]
+#endif
   const uint32_t n = P.ws.ctr->nMat[MAT];
   const SceneDev& sc = P.sc;
   const uint32_t* queue = P.ws.qMat + (size_t)MAT * P.ws.capacity;
@@ -24,8 +34,14 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
     bool active = i < n;
     bool pushShadow = false, pushMis = false, pushNext = false;
     uint32_t slot = 0;
+#if PBR_SHADE_STAGE_SMEM
+    float4 &shO = PBR_OUT(0), &shD = PBR_OUT(1), &shC = PBR_OUT(2), &miO = PBR_OUT(3), &miD = PBR_OUT(4), &miC = PBR_OUT(5);
+    float4 &nxO = PBR_OUT(6), &nxD = PBR_OUT(7), &nxB = PBR_OUT(8);
+    float4 &shP1 = PBR_OUT(VOL ? 9 : 0), &shE1 = PBR_OUT(VOL ? 10 : 0), &shN1 = PBR_OUT(VOL ? 11 : 0);
+#else
     float4 shO, shD, shC, miO, miD, miC, shP1, shE1, shN1;
     float4 nxO, nxD, nxB;              // the continuation ray's record, written at its compacted position after the queue push
+#endif
     uint32_t nxMeta = 0, idxLo = 0, idxHi = 0;
     if (active) {
       const uint32_t pos = queue[i];   // position of this path in ws.cur
