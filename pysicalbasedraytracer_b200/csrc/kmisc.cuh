@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kBlock) k_medium_presample(const __grid_consta
     const PathRegs r = load_path(rec);
     const float4 rd4 = r.d;
     const int med = __float_as_int(rd4.w);
-    SamplerCursor cur = load_cursor(P, r);
+    SamplerCursorX4 cur(load_cursor(P, r));
+    cur.prefetch(P.sc.hp, 2);
     const float u0 = cur.get1D(P.sc.hp);
     const float u1 = cur.get1D(P.sc.hp);
     rec->o.w = medium_sample_distance(P.sc.media[med], u0, u1, length(V3(rd4.x, rd4.y, rd4.z)));
@@ -189,13 +190,16 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_const
         const V3 zero(0, 0, 0);
         Spec beta(be4.x, be4.y, be4.z);
         const float etaScale = be4.w;
-        SamplerCursor cur = load_cursor(P, rec);
+        SamplerCursorX4 cur(load_cursor(P, rec));
+        // sampler dimensions in groups with interleaved digit loops: light pick + light sample, then phase sample + Sample_p
+        if (sc.nLights > 0) cur.prefetch(sc.hp, 3);
         if (sc.nLights > 0) {
           float pickPdf;
           const int lightNum = sample_discrete(sc.lightFunc, sc.lightCdf, sc.lightFuncInt, sc.nLights, cur.get1D(sc.hp), &pickPdf);
           if (pickPdf != 0) {
             float uL0, uL1, uS0, uS1;
             cur.get2D(sc.hp, &uL0, &uL1);
+            cur.prefetch(sc.hp, 4);  // uS0, uS1 and Sample_p's u0, u1
             cur.get2D(sc.hp, &uS0, &uS1);
             const pbrgpu_light& light = sc.lights[lightNum];
             LightSample ls;
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade_medium(const __grid_const
         }
         // mi.phase->Sample_p(wo, &wi, sampler.Get2D()); ray = mi.SpawnRay(wi); specularBounce = false
         float u0, u1;
+        cur.ensure(sc.hp, 2);
         cur.get2D(sc.hp, &u0, &u1);
         V3 wi;
         hg_sample_p(wo, &wi, u0, u1, g);
