@@ -110,6 +110,9 @@ struct Counters {
   unsigned long long raysClosest, raysShadow, nodesVisited, trisTested, raysPath;
   uint32_t maxRayWork;              // COUNT: most node steps + triangle tests spent on one ray (segment)
   uint32_t volMaxHops, volCapHits;  // VolPath shadow rays: most medium boundaries crossed by one ray / rays stopped at the cap
+  // COUNT build of k_trace, lane-activity profile (PBRGPU_LANE_LOG): warp loop iterations, and summed over them the lanes that
+  // were busy / did a node step / did a triangle test / had a triangle pass; fetch events and lanes fetched
+  unsigned long long laneProf[8];
 };
 
 // One live path of the current bounce: a 64-byte record = two full 32-byte sectors.  Records live in QUEUE ORDER: position i

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   unsigned segs = 0; // VOL: shadow-ray segments traced by this lane (each is one Scene::Intersect of VisibilityTester::Tr)
   unsigned nodes = 0, tris = 0;
   unsigned rayWork0 = 0;  // COUNT: nodes + tris at the start of the current ray (-> Counters::maxRayWork)
+  unsigned long long lp[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // COUNT: lane-activity profile (Counters::laneProf), kept by lane 0
   while (true) {
     // ---- completion + fetch, batched: a lane whose ray has finished parks (pend) until at least P.fetchMinIdle lanes of the
     // warp are without traversal work; then the finished rays write their results together and the free lanes take new
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         if (lane == leader) base = atomicAdd(&C->cursor[0], (uint32_t)nWant);
         base = __shfl_sync(full, base, leader);
         exhausted = base + (uint32_t)nWant >= n;
+        if (COUNT) { lp[5]++; lp[6] += (unsigned)nWant; }
         if (!busy) {
           uint32_t i = base + __popc(want & ((1u << lane) - 1u));
           if (i < n) {
@@ -167,6 +169,8 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
       }
     }
     if (exhausted && __ballot_sync(full, busy) == 0u) break;
+    bool didNode = false, didTri = false, triHit = false;
+    if (COUNT) { lp[0]++; lp[1] += __popc(__ballot_sync(full, busy)); }
     // ---- node phase: kNodeStepsPerIter x (pop if the node group is exhausted, then one node step).  More than one
     // node step per triangle round was measured (2: +4 % time, 3: +19 %): the extra speculative node visits cost more
     // than the fuller triangle rounds save, so kNodeStepsPerIter = 1 ----
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         if (T.ngroup.y > 0x00FFFFFFu && (T.tgroup.y == 0u || nt < kTriQueue)) {
           if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }  // park the unfinished triangle group
           cw_node_step(P.sc.nodes8, T, sstack, S);
-          if (COUNT) nodes++;
+          if (COUNT) { nodes++; didNode = true; }
         }
       }
     }
@@ -195,18 +199,27 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
     if (busy) {
       if (triRound && (T.tgroup.y != 0u || nt > 0)) {
         if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
-        if (COUNT) tris++;
+        if (COUNT) { tris++; didTri = true; }
         // any-hit exit for shadow rays; VolPath shadow rays need the CLOSEST surface (it may be a medium boundary)
         // (unless the scene has no such boundary at all: then the first surface found ends the ray either way)
-        if (cw_tri_step<SPH>(P.sc, T, &hit) && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
+        const bool th = cw_tri_step<SPH>(P.sc, T, &hit);
+        if (COUNT) triHit = th;
+        if (th && mode == TRACE_SHADOW && (!VOL || P.volShadowAnyHit)) { T.tgroup.y = 0u; nt = 0; T.ngroup.y = 0u; T.sp = 0; }
       }
       // ---- ray finished?  (checked in the same iteration, so the lane counts as idle at the next loop head) ----
       if (T.ngroup.y <= 0x00FFFFFFu && T.sp == 0 && T.tgroup.y == 0u && nt == 0) { busy = false; pend = true; }
+    }
+    if (COUNT) {
+      const unsigned mN = __ballot_sync(full, didNode), mT = __ballot_sync(full, didTri), mH = __ballot_sync(full, triHit);
+      lp[2] += __popc(mN); lp[3] += __popc(mT); lp[4] += __popc(mH);
+      lp[7] += (mT != 0u);  // iterations in which the triangle test ran at all
     }
   }
   if (COUNT) {
     atomicAdd(&C->nodesVisited, (unsigned long long)nodes);
     atomicAdd(&C->trisTested, (unsigned long long)tris);
+    if (lane == 0)
+      for (int k = 0; k < 8; ++k) atomicAdd(&C->laneProf[k], lp[k]);
   }
   if (VOL) {  // VolPath has no IntersectP queries: every shadow segment is a closest-hit query
     segs = __reduce_add_sync(full, segs);

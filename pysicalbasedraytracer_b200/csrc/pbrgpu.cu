@@ -966,6 +966,11 @@ static int fetch_stats(pbrgpu_scene* s, cudaStream_t st, pbrgpu_stats* stats) {
   stats->kernel_launches = s->last.launches;
   stats->ms_total = ms;
   stats->rays_path = hc.raysPath;
+  if (getenv("PBRGPU_LANE_LOG") && hc.laneProf[0])  // development aid (COUNT build of k_trace): where the lanes of a warp go
+    fprintf(stderr, "k_trace lanes: %llu warp iterations; per iteration busy %.2f, node step %.2f, triangle test %.2f (ran in %.1f %% of iterations), "
+            "triangle hit %.3f; %llu fetches of %.2f rays\n", hc.laneProf[0], (double)hc.laneProf[1] / hc.laneProf[0], (double)hc.laneProf[2] / hc.laneProf[0],
+            (double)hc.laneProf[3] / hc.laneProf[0], 100.0 * hc.laneProf[7] / hc.laneProf[0], (double)hc.laneProf[4] / hc.laneProf[0], hc.laneProf[5],
+            (double)hc.laneProf[6] / std::max<unsigned long long>(hc.laneProf[5], 1));
   if (getenv("PBRGPU_VOL_LOG")) fprintf(stderr, "vol shadow rays: max hops %u, stopped at the cap %u\n", hc.volMaxHops, hc.volCapHits);
   Timeline& tl = s->last.tl;
   if (tl.on) {
