@@ -177,6 +177,8 @@ struct RenderParams {
   int deferShadow;        // VolPath tail (pbrgpu.cu): 1 = the shadow queue is left alone and keeps growing (k_trace skips it, k_classify
                           // does not reset it); 2 = the flush launch: k_trace serves ONLY the shadow queue and leaves each ray's
                           // contribution x transmittance in shC (0 when blocked) for k_shadow_add
+  int volInLane;          // VolPath: k_trace applies Medium::Sample's weight and continues paths across material-less medium
+                          // boundaries in the lane (k_trace.cuh vol_path_next_segment); 0 = the separate kernels do it
   // Halton offset of the pixel a global index belongs to: index = offset(pixel) + sample * stride, offset < stride
   PBR_D int64_t pixelOffsetOf(int64_t index) const { return index % sc.hp.sampleStride; }
   float* accum;           // [h*w] RGBA sums (A = sample count)

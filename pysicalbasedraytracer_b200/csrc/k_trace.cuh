@@ -82,6 +82,61 @@ PBR_D bool vol_shadow_next_segment(const RenderParams& P, uint32_t ray, Trav& T,
   return true;
 }
 
+// VolPathIntegrator::Li's loop for a path ray whose segment has just been traced, in the lane that traced it:
+//   * `beta *= ray.medium->Sample(ray, sampler, &mi)` (VolPathIntegrator.cpp:35-36): the weight of the segment (the distance
+//     was drawn before the trace, media.cuh) - what k_medium_sample does as a separate pass when this is switched off;
+//   * closest hit on a surface WITHOUT a material, i.e. a medium boundary (:65-70): `ray = isect.SpawnRay(ray.d); bounces--;
+//     continue;` including the free-flight sample of the next segment (k_shade_null + k_medium_presample).
+// A path that crosses the ripples of a boundary mesh dozens of times stays in its lane instead of costing one wavefront
+// iteration (trace + classify + shade launches and a host read-back) per crossing.  Same arithmetic, same sampler
+// dimensions, same order as the separate kernels.  *q = shading queue of the path when it leaves the lane; returns true when
+// the lane continues with the re-spawned ray (*no, *nTMax; the direction is unchanged).
+PBR_D bool vol_path_next_segment(const RenderParams& P, uint32_t ray, float tEnd, const HitRec& hit, uint32_t* q, V3* no, float* nTMax) {
+  const SceneDev& sc = P.sc;
+  PathRec* rec = P.ws.cur + ray;
+  uint32_t meta = rec->meta;
+  const float4 rd4 = rec->d;
+  const V3 rayD(rd4.x, rd4.y, rd4.z);
+  const int med = __float_as_int(rd4.w);
+  if ((meta >> kMetaInMediumBit) & 1u) {
+    const bool sampled = hit.tri < 0 && tEnd < kInfinity;  // t < ray.tMax: scattering event before any surface
+    const Spec w = medium_sample_weight(sc.media[med], tEnd, sampled, length(rayD));
+    const float4 be4 = rec->beta;
+    const Spec beta = Spec(be4.x, be4.y, be4.z) * w;
+    if (beta.is_black()) { *q = kQueueDead; return false; }
+    rec->beta = make_float4(beta.r, beta.g, beta.b, be4.w);
+    if (sampled) *q = (uint32_t)kQueueMedium;  // mi.p = ray(t): t goes to rayO.w with the hit record
+  }
+  if (*q != (uint32_t)kQueueNull) return false;
+  const TriData td = load_tri(sc, hit.tri);
+  if ((int)td.w2 >= 0) return false;  // an emissive boundary: k_shade_null applies the emission rule
+  const int bounce = (int)((meta >> kMetaBounceShift) & kMetaBounceMask);
+  if (bounce >= P.maxDepth) { *q = kQueueDead; return false; }  // :60 `if (bounces >= maxDepth) break;`
+  const float4 ro4 = rec->o;
+  Isect is;
+  make_isect(sc, td, hit.tri, hit.b0, hit.b1, hit.b2, rayD, &is, V3(ro4.x, ro4.y, ro4.z));
+  int mIn, mOut;
+  isect_media(sc, hit.tri, med, &mIn, &mOut);
+  const V3 o = offset_ray_origin(is.p, is.pError, is.n, rayD);
+  const int nextMedium = dot(rayD, is.n) > 0 ? mOut : mIn;
+  float tMax = kInfinity;
+  meta &= ~(1u << kMetaInMediumBit);
+  if (nextMedium >= 0) {  // Medium::Sample's two sampler values for the next segment, drawn before it is traced
+    const int64_t index = (int64_t)(((uint64_t)rec->idxHi << 32) | rec->idxLo);
+    int dim = (int)(meta & 0xffffu);
+    if (dim >= 5 && dim < P.arrayEndDim) dim = P.arrayEndDim;
+    const float u0 = sample_dimension_outofline(index, dim, &sc.hp);
+    const float u1 = sample_dimension_outofline(index, dim + 1, &sc.hp);
+    tMax = medium_sample_distance(sc.media[nextMedium], u0, u1, length(rayD));
+    meta = (meta & ~0xffffu) | (uint32_t)(dim + 2) | (1u << kMetaInMediumBit);
+  }
+  rec->o = make_float4(o.x, o.y, o.z, tMax);
+  rec->d.w = __int_as_float(nextMedium);
+  rec->meta = meta;
+  *no = o; *nTMax = tMax;
+  return true;
+}
+
 template <bool COUNT, bool VOL = false, bool SPH = false>
 __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
   __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
@@ -106,6 +161,7 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   uint32_t ray = 0;  // index in the queue of `mode`: PATH = position in ws.cur, SHADOW / MIS = position in that ray queue
   int hops = 0;      // VOL: medium boundaries this shadow ray has crossed
   unsigned segs = 0; // VOL: shadow-ray segments traced by this lane (each is one Scene::Intersect of VisibilityTester::Tr)
+  unsigned psegs = 0; // VOL: path segments continued in this lane behind a medium boundary (each is one Scene::Intersect of Li's loop)
   unsigned nodes = 0, tris = 0;
   unsigned rayWork0 = 0;  // COUNT: nodes + tris at the start of the current ray (-> Counters::maxRayWork)
   unsigned long long lp[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // COUNT: lane-activity profile (Counters::laneProf), kept by lane 0
@@ -121,10 +177,23 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
         pend = false;
         if (COUNT) { atomicMax(&C->maxRayWork, nodes + tris - rayWork0); rayWork0 = nodes + tris; }
         if (mode == TRACE_PATH) {
-          P.ws.hit[ray] = make_float4(__int_as_float(hit.tri), hit.b0, hit.b1, hit.b2);
-          // hit record and shading-queue id at the path's queue position
-          P.ws.qType[ray] = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
-          if (VOL || P.storeHitT) P.ws.cur[ray].o.w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
+          uint32_t q = hit.tri >= 0 ? ((hit.w1 >> kTriTypeShift) & 0xfu) : (uint32_t)kQueueMiss;
+          if (VOL && P.volInLane) {
+            V3 no;
+            float nTMax;
+            if (vol_path_next_segment(P, ray, T.tMax, hit, &q, &no, &nTMax)) {  // crossed a medium boundary: next segment, same lane
+              const float4 rd = P.ws.cur[ray].d;
+              trav_init(T, no, V3(rd.x, rd.y, rd.z), nTMax, P.sc.f32one);
+              busy = true; hit.tri = -1; nt = 0;
+              psegs++;
+            }
+          }
+          if (!busy) {
+            P.ws.hit[ray] = make_float4(__int_as_float(hit.tri), hit.b0, hit.b1, hit.b2);
+            // hit record and shading-queue id at the path's queue position
+            P.ws.qType[ray] = q;
+            if (VOL || P.storeHitT) P.ws.cur[ray].o.w = T.tMax;  // ray.tMax after Scene::Intersect (hit distance, else unchanged), read by Medium::Sample
+          }
         } else if (mode == TRACE_MIS) {
           P.ws.miO[ray].w = __int_as_float(hit.tri);
         } else if (VOL) {
@@ -223,7 +292,9 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
   }
   if (VOL) {  // VolPath has no IntersectP queries: every shadow segment is a closest-hit query
     segs = __reduce_add_sync(full, segs);
-    if (lane == 0 && segs) atomicAdd(&C->raysClosest, (unsigned long long)segs);
+    psegs = __reduce_add_sync(full, psegs);
+    if (lane == 0 && segs + psegs) atomicAdd(&C->raysClosest, (unsigned long long)(segs + psegs));
+    if (lane == 0 && psegs) atomicAdd(&C->raysPath, (unsigned long long)psegs);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (!VOL) atomicAdd(&C->raysShadow, (unsigned long long)nShadow);

@@ -1038,6 +1038,13 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
   if (rd->integrator == PBRGPU_INTEGRATOR_DIRECT_ALL) P.arrayEndDim = 5 + 2 * (2 * (int)s->lights.size() * rd->max_depth);
   P.atomicL = (pathInteg || volInteg) ? 0 : 1;
   P.volShadowAnyHit = s->hasNullMat ? 0 : 1;
+  // VolPath tail: once fewer than volInLaneBelow paths are alive, k_trace continues a path across
+  // material-less medium boundaries inside its lane (k_trace.cuh vol_path_next_segment).  With millions of live paths the
+  // separate full-width kernels are faster (measured on the dragon-class smoke volume: in-lane from the first iteration
+  // 150 ms, never 143 ms); in the tail every crossing otherwise costs a whole wavefront iteration for a handful of paths.
+  uint32_t volInLaneBelow = 2u << 20;
+  if (const char* e = getenv("PBRGPU_VOL_INLANE_BELOW")) volInLaneBelow = (uint32_t)std::max(0ll, std::min(atoll(e), 0xffffffffll));
+  P.volInLane = (volInteg && volInLaneBelow == 0xffffffffu) ? 1 : 0;
   P.diffScale = 1 / std::sqrt((float)s->spp);
   P.countStats = count ? 1 : 0;
   P.fetchMinIdle = s->fetchMinIdle;
@@ -1154,7 +1161,7 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
           CK(tl.mark(T_MIS));
           if (iter > 0) { k_resolve_mis<<<g, kBlock, 0, st>>>(P); launches++; }
           CK(tl.mark(T_SHADE));
-          if (s->sc.nMedia > 0) { k_medium_sample<<<g, kBlock, 0, st>>>(P); launches++; }
+          if (s->sc.nMedia > 0 && !P.volInLane) { k_medium_sample<<<g, kBlock, 0, st>>>(P); launches++; }
           k_classify<<<gc, kBlock, 0, st>>>(P);
           for (int M = 0; M < PBRGPU_MAT_COUNT; ++M)
             if (s->hasMat[M]) {
@@ -1172,6 +1179,7 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
             CK(cudaMemcpyAsync(s->hNCur, s->ctr.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));  // nCur, nNext, nShadow, nMis
             CK(cudaStreamSynchronize(st));
             const uint32_t nLive = s->hNCur[0], nSh = s->hNCur[2], nMi = s->hNCur[3];
+            P.volInLane = nLive < volInLaneBelow ? 1 : 0;
             if (deferOk) {
               if (ranges.empty()) ranges.push_back(0u);  // deferral starts: the rays just emitted are its first range
               ranges.push_back(nSh);
