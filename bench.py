@@ -37,13 +37,13 @@ SPP_TOTAL = 1024
 MAX_DEPTH = 8
 RR_THRESHOLD = 1.0
 TESS = 467
-SPP_PER_STEP = 16
+SPP_PER_STEP = 32  # two 16-spp waves of the frame, kept in flight together by the library (two wave sets, two streams)
 EYE, LOOK, UP = (0.0, 0.0, 5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)
 def config_dict():
     """Identical on both arms (the driver compares it): the workload, not how an arm runs it."""
     return {"workload": WORKLOAD, "sampler": "Halton", "max_depth": MAX_DEPTH, "rr_threshold": RR_THRESHOLD, "resolution": [W, H],
             "spp_job": SPP_TOTAL,
-            "l2_policy": "GPU arm: the working set of a step (wave state 7.5 GB + 54 MB scene) exceeds the 126 MB L2, no explicit "
+            "l2_policy": "GPU arm: the working set of a step (wave state 2 x 9.8 GB + 54 MB scene) exceeds the 126 MB L2, no explicit "
                          "flush; reference arm: host caches, not applicable"}
 
 
@@ -414,7 +414,7 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(),
-            "run": {"spp_per_step_per_gpu": SPP_PER_STEP,
+            "run": {"spp_per_step_per_gpu": SPP_PER_STEP, "waves_per_step": 2, "waves_in_flight": int(os.environ.get("PBRGPU_WAVES_IN_FLIGHT", "2")),
                     "sharding": f"sample-range x{world} inside pbrgpu_render_device (pbrgpu_comm_attach) + ncclReduce to rank 0"},
             "mrays_per_s": mrays,
             "rays_per_s_per_sm": mrays * 1e6 / (sm_count * world),

@@ -117,6 +117,29 @@ def test_sample_range_sharding_is_additive(api, ref, gpu_ctx):
     assert np.array_equal(again, whole)  # wave size does not change the result
 
 
+def test_two_waves_in_flight_equal_waves_in_sequence(api, ref, gpu_ctx, monkeypatch):
+    # consecutive waves alternate between two wave sets / two streams (csrc/pbrgpu.cu render_device_single); the film takes
+    # them in order, so the image and the ray counts are those of the same waves run one after the other
+    kw = dict(max_depth=4, rr_threshold=0.8, s0=0, s1=10, samples_per_wave=3)
+    for integ in (A.INTEGRATOR_PATH, A.INTEGRATOR_WHITTED, A.INTEGRATOR_DIRECT_ALL):
+        p2 = Pair(api, None, scenes.cornell(sphere_tess=8), 96, 64, 10)
+        two, _, st2 = p2.scene.render(integrator=integ, **kw)
+        monkeypatch.setenv("PBRGPU_WAVES_IN_FLIGHT", "1")  # read by a scene's first render
+        p1 = Pair(api, None, scenes.cornell(sphere_tess=8), 96, 64, 10)
+        one, _, st1 = p1.scene.render(integrator=integ, **kw)
+        monkeypatch.delenv("PBRGPU_WAVES_IN_FLIGHT")
+        if integ == A.INTEGRATOR_PATH:
+            assert np.array_equal(two, one)
+        else:  # several shadow rays per hit add their contributions with float atomics: equal up to summation order
+            np.testing.assert_allclose(two, one, rtol=2e-5, atol=1e-5)
+        assert (st2.rays_closest, st2.rays_shadow, st2.camera_samples) == (st1.rays_closest, st1.rays_shadow, st1.camera_samples)
+        # a second render on the same scene reuses both wave sets
+        again, _, _ = p2.scene.render(integrator=integ, **kw)
+        np.testing.assert_allclose(again, two, rtol=2e-5, atol=1e-5)
+        if integ == A.INTEGRATOR_PATH:
+            assert np.array_equal(again, two)
+
+
 def test_film_resolve_8bit(api, ref, gpu_ctx):
     p = Pair(api, ref, scenes.cornell(sphere_tess=8), 64, 64, 4)
     rgb_sum, rgba8, _ = p.scene.render(max_depth=2, want_rgba8=True)
