@@ -168,8 +168,6 @@ struct RenderParams {
   int arrayEndDim;        // GlobalSampler::arrayEndDim (5 unless UniformSampleAll)
   int countStats;
   int fetchMinIdle;       // idle lanes of a warp that trigger a ray fetch
-  int triMinLanes;        // k_trace: lanes with a candidate triangle that trigger a triangle round (1 = every iteration)
-  int stallMin;           // k_trace: ... or this many lanes that cannot progress without a triangle round
   float diffScale;        // 1 / sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials of the render loop (image textures)
   int volShadowAnyHit;    // VolPath, scene without material-less surfaces: a shadow ray ends at ANY surface it finds
   int storeHitT;          // parity hooks: k_trace also stores the hit distance of path rays (rayO.w), like the VOL build

@@ -139,14 +139,16 @@ PBR_D bool vol_path_next_segment(const RenderParams& P, uint32_t ray, float tEnd
 
 template <bool COUNT, bool VOL = false, bool SPH = false>
 __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(const __grid_constant__ RenderParams P) {
-  __shared__ uint2 sstk[kTraceBlock / 32][kSmemStack][32];
-  __shared__ uint2 stri[kTraceBlock / 32][kTriQueue][32];
+  // traversal stack (first kSmemStack levels) and parked triangle groups of every lane: ONE [slot][thread] array, so that a
+  // single per-thread base register addresses all of it with immediate offsets (two separate [warp][slot][lane] arrays had
+  // the compiler re-derive two base addresses from threadIdx in every loop iteration: ~5 % of the kernel's instructions)
+  __shared__ uint2 slane[kSmemStack + kTriQueue][kTraceBlock];
   __shared__ HitRec shit[kTraceBlock];  // closest hit so far of each lane's ray (see cw_tri_step)
   HitRec& hit = shit[threadIdx.x];
   const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint2* sstack = &sstk[warp][0][lane];
-  uint2* tq = &stri[warp][0][lane];
+  const int lane = threadIdx.x & 31;
+  uint2* sstack = &slane[0][threadIdx.x];
+  uint2* tq = sstack + kSmemStack * kTraceBlock;
   Counters* C = P.ws.ctr;
   // VolPath tail (RenderParams::deferShadow): 1 = leave the shadow queue alone, 2 = the shadow queue only
   const uint32_t nPath = (VOL && P.deferShadow == 2) ? 0u : C->nCur, nShadow = (VOL && P.deferShadow == 1) ? 0u : C->nShadow;
@@ -246,28 +248,20 @@ __global__ void __launch_bounds__(kTraceBlock, PBR_TRACE_MIN_BLOCKS) k_trace(con
     if (busy) {
 #pragma unroll 1
       for (int rep = 0; rep < kNodeStepsPerIter; ++rep) {
-        if (T.ngroup.y <= 0x00FFFFFFu && T.sp > 0) T.ngroup = trav_pop(T, sstack, S);
+        if (T.ngroup.y <= 0x00FFFFFFu && T.sp > 0) T.ngroup = trav_pop<kTraceBlock>(T, sstack, S);
         if (T.ngroup.y > 0x00FFFFFFu && (T.tgroup.y == 0u || nt < kTriQueue)) {
-          if (T.tgroup.y != 0u) { tq[nt * 32] = T.tgroup; nt++; }  // park the unfinished triangle group
-          cw_node_step(P.sc.nodes8, T, sstack, S);
+          if (T.tgroup.y != 0u) { tq[nt * kTraceBlock] = T.tgroup; nt++; }  // park the unfinished triangle group
+          cw_node_step<kTraceBlock>(P.sc.nodes8, T, sstack, S);
           if (COUNT) { nodes++; didNode = true; }
         }
       }
     }
-    // ---- triangle round: ONE candidate triangle per lane.  The round is SKIPPED while fewer than P.triMinLanes lanes have a
-    // candidate, unless P.stallMin lanes cannot make progress without it (traversal finished with candidates pending, or the
-    // parked-group list is full) or no lane has node work left: the long watertight test then runs with fuller warps ----
-    bool triRound = true;
-    if (P.triMinLanes > 1) {
-      const bool wantTri = busy && (T.tgroup.y != 0u || nt > 0);
-      const bool canNode = busy && (T.ngroup.y > 0x00FFFFFFu || T.sp > 0) && (T.tgroup.y == 0u || nt < kTriQueue);
-      const unsigned mWant = __ballot_sync(full, wantTri), mStall = __ballot_sync(full, wantTri && !canNode);
-      const unsigned mNode = __ballot_sync(full, canNode);
-      triRound = __popc(mWant) >= P.triMinLanes || __popc(mStall) >= P.stallMin || mNode == 0u;
-    }
+    // ---- triangle round: ONE candidate triangle per lane, every iteration.  (Skipping the round while fewer than N lanes have
+    // a candidate - with and without a "stalled lanes" override - was measured for N = 6 .. 14: never faster, the lanes always
+    // have a backlog.) ----
     if (busy) {
-      if (triRound && (T.tgroup.y != 0u || nt > 0)) {
-        if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * 32]; }
+      if (T.tgroup.y != 0u || nt > 0) {
+        if (T.tgroup.y == 0u) { nt--; T.tgroup = tq[nt * kTraceBlock]; }
         if (COUNT) { tris++; didTri = true; }
         // any-hit exit for shadow rays; VolPath shadow rays need the CLOSEST surface (it may be a medium boundary)
         // (unless the scene has no such boundary at all: then the first surface found ends the ray either way)

@@ -145,7 +145,6 @@ struct pbrgpu_scene {
   int lightStrategyBuilt = -1;
   int traceBlocksPerSm = 0;
   int fetchMinIdle = 8;
-  int triMinLanes = 1, stallMin = 32;
   int waveLog2 = 25;
   bool hasMat[PBRGPU_MAT_COUNT] = {};  // material types present in the scene (absent ones: no shade launch)
   bool hasNullMat = false;             // some triangle has no material (medium boundary): VolPath only
@@ -1061,8 +1060,6 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
     s->traceBlocksPerSm = std::max(1, nb);
     if (const char* e = getenv("PBRGPU_FETCH_MIN_IDLE")) s->fetchMinIdle = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("PBRGPU_WAVE_LOG2")) s->waveLog2 = std::max(14, std::min(25, atoi(e)));
-    if (const char* e = getenv("PBRGPU_TRI_MIN_LANES")) s->triMinLanes = std::max(1, std::min(32, atoi(e)));
-    if (const char* e = getenv("PBRGPU_STALL_MIN")) s->stallMin = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("PBRGPU_WAVES_IN_FLIGHT")) s->wavesInFlight = std::max(1, std::min(2, atoi(e)));
   }
 
@@ -1130,8 +1127,6 @@ static int render_device_single(pbrgpu_scene* s, const pbrgpu_render_desc* rd, f
   P.diffScale = 1 / std::sqrt((float)s->spp);
   P.countStats = count ? 1 : 0;
   P.fetchMinIdle = s->fetchMinIdle;
-  P.triMinLanes = s->triMinLanes;
-  P.stallMin = s->stallMin;
 
   // traversal data persists in L2 for the duration of the render (window = the geometry slab; when the slab is larger than
   // the carve-out, hitRatio keeps a random carve-out-sized fraction of its lines persisting instead of thrashing)
@@ -1814,8 +1809,6 @@ int pbrgpu_debug_dump(pbrgpu_scene* s, const pbrgpu_dump_desc* dd, void* out, si
     P.x0 = dd->x0; P.y0 = dd->y0; P.w = W; P.h = H; P.sBegin = dd->s0; P.nsWave = (int)ns;
     P.arrayEndDim = 5;
     P.fetchMinIdle = s->fetchMinIdle;
-    P.triMinLanes = s->triMinLanes;
-    P.stallMin = s->stallMin;
     P.storeHitT = 1;
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(s->ctr.p, 0, sizeof(Counters), st));
@@ -1854,8 +1847,6 @@ int pbrgpu_trace_rays(pbrgpu_scene* s, const float* rays, int64_t n, int any_hit
     if (s->traceBlocksPerSm <= 0) s->traceBlocksPerSm = std::max(1, trace_blocks_per_sm());
     fill_wave(s, &P.ws);
     P.fetchMinIdle = s->fetchMinIdle;
-    P.triMinLanes = s->triMinLanes;
-    P.stallMin = s->stallMin;
     P.storeHitT = 1;
     DevBuf<int> dis;
     CK(dis.alloc(1));

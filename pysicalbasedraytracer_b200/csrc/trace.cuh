@@ -158,14 +158,18 @@ PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax, unsigned f32one) {
   T.hit.w1 = 0u;
 }
 
+// STRIDE: distance (in uint2) between two levels of a lane's column: 32 for a [warp][level][lane] array, the block size for
+// a [level][thread] one
+template <int STRIDE = 32>
 PBR_D void trav_push(Trav& T, uint2* sstack, TravSpill& S, uint2 v) {
-  if (T.sp < kSmemStack) sstack[T.sp * 32] = v;
+  if (T.sp < kSmemStack) sstack[T.sp * STRIDE] = v;
   else S.lstack[T.sp - kSmemStack] = v;
   T.sp++;
 }
+template <int STRIDE = 32>
 PBR_D uint2 trav_pop(Trav& T, const uint2* sstack, const TravSpill& S) {
   T.sp--;
-  return (T.sp < kSmemStack) ? sstack[T.sp * 32] : S.lstack[T.sp - kSmemStack];
+  return (T.sp < kSmemStack) ? sstack[T.sp * STRIDE] : S.lstack[T.sp - kSmemStack];
 }
 
 // byte J of `w` -> float in [1,2): 1 + byte / 32768   (one PRMT, no int->float conversion).  `one` holds
@@ -178,11 +182,12 @@ PBR_D float q2f(unsigned w, unsigned one) { return __uint_as_float(__byte_perm(w
 // 80-byte node with five 16-byte loads, slab-test the 8 quantised child boxes, emit a new node group
 // and triangle group.  The slab test is conservative: the rounding error of the fused evaluation is
 // bounded per axis and folded into the offsets (Bn = B - err, Bf = B + err).
+template <int STRIDE = 32>
 PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack, TravSpill& S) {
   const unsigned hits = T.ngroup.y;
   const int bit = 31 - __clz(hits);
   T.ngroup.y &= ~(1u << bit);
-  if (T.ngroup.y > 0x00FFFFFFu) trav_push(T, sstack, S, T.ngroup);
+  if (T.ngroup.y > 0x00FFFFFFu) trav_push<STRIDE>(T, sstack, S, T.ngroup);
   const unsigned slot = (unsigned)(bit - 24) ^ (T.octinv4 & 0xffu);
   const unsigned rel = __popc(hits & ~(0xFFFFFFFFu << slot));
   const float4* np = nodes + 5 * (size_t)(T.ngroup.x + rel);
