@@ -78,22 +78,24 @@ PBR_D bool intersect_triangle(const RayPrep& rp, float tMax, V3 p0, V3 p1, V3 p2
   float invDet = 1 / det;
   float b0 = e0 * invDet, b1 = e1 * invDet, b2 = e2 * invDet;
   float t = tScaled * invDet;
-  // conservative bound on the error of t (Triangle.cpp:133-145)
-  float maxZt = max_component(vabs(V3(p0t.z, p1t.z, p2t.z)));
+  // conservative bound on the error of t (Triangle.cpp:133-145).  MaxComponent(Abs(v)) as hardware max of magnitudes: the same
+  // value as the reference's compare-and-select for every non-NaN input (the arguments are magnitudes, so no -0 either), and a
+  // NaN here means t is NaN, which fails `t <= deltaT` whatever deltaT is
+  float maxZt = fmaxf(fmaxf(fabsf(p0t.z), fabsf(p1t.z)), fabsf(p2t.z));
   float deltaZ = gamma_f(3) * maxZt;
-  float maxXt = max_component(vabs(V3(p0t.x, p1t.x, p2t.x)));
-  float maxYt = max_component(vabs(V3(p0t.y, p1t.y, p2t.y)));
+  float maxXt = fmaxf(fmaxf(fabsf(p0t.x), fabsf(p1t.x)), fabsf(p2t.x));
+  float maxYt = fmaxf(fmaxf(fabsf(p0t.y), fabsf(p1t.y)), fabsf(p2t.y));
   float deltaX = gamma_f(5) * (maxXt + maxZt);
   float deltaY = gamma_f(5) * (maxYt + maxZt);
   float deltaE = 2 * (gamma_f(2) * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
-  float maxE = max_component(vabs(V3(e0, e1, e2)));
+  float maxE = fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fabsf(e2));
   float deltaT = 3 * (gamma_f(3) * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * fabsf(invDet);
   if (t <= deltaT) return false;
   *tOut = t; *b0Out = b0; *b1Out = b1; *b2Out = b2;
   return true;
 }
 
-struct HitRec {
+struct alignas(8) HitRec {
   int tri;  // leaf-order triangle index, -1 = miss
   float t, b0, b1, b2;
   uint32_t w1;  // tv1.w of the hit triangle (material id | type | flags), free with the vertex load
@@ -136,10 +138,17 @@ struct TravSpill {
 };
 
 PBR_D float safe_rcp(float d) {
-  // |1/d| capped at 1e24: an axis-parallel ray gets +-huge slab distances instead of inf/NaN
-  float r = 1.f / fmaxf(fabsf(d), 1e-24f);
+  // |1/d| capped at 1e24: an axis-parallel ray gets +-huge slab distances instead of inf/NaN.  The reciprocal only feeds the
+  // conservative box test, so the one-instruction approximation (relative error <= 2^-23, PTX ISA rcp.approx.f32) replaces the
+  // IEEE division (14 instructions each, three per ray); kSlabErr below accounts for it.
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(fabsf(d), 1e-24f)));
   return d < 0.f ? -r : r;
 }
+// Rounding-error bound of the slab distances, relative to |B| + |A| (cw_node_step).  With u = 2^-24: the reciprocal carries
+// 2u, B = fl(fl(origin - o) * idx) two more roundings (4u on |B| in all), fl(B - A) and fl(. -+ err) one each on |B| + |A|,
+// the final FMA u on |t| <= |B| + |A|: at most 7u|B| + 3u|A| = 4.2e-7 |B| + 1.8e-7 |A|.
+constexpr float kSlabErr = 5e-7f;
 
 PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax, unsigned f32one) {
   T.o = o;
@@ -200,7 +209,7 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
   const float Ay = __uint_as_float((((ei >> 8) & 0xffu) + 15u) << 23) * T.idy;
   const float Az = __uint_as_float((((ei >> 16) & 0xffu) + 15u) << 23) * T.idz;
   const float Bx = (n0.x - T.o.x) * T.idx, By = (n0.y - T.o.y) * T.idy, Bz = (n0.z - T.o.z) * T.idz;
-  const float ex = 4e-7f * (fabsf(Bx) + fabsf(Ax)), ey = 4e-7f * (fabsf(By) + fabsf(Ay)), ez = 4e-7f * (fabsf(Bz) + fabsf(Az));
+  const float ex = kSlabErr * (fabsf(Bx) + fabsf(Ax)), ey = kSlabErr * (fabsf(By) + fabsf(Ay)), ez = kSlabErr * (fabsf(Bz) + fabsf(Az));
   const float Bnx = (Bx - Ax) - ex, Bfx = (Bx - Ax) + ex;
   const float Bny = (By - Ay) - ey, Bfy = (By - Ay) + ey;
   const float Bnz = (Bz - Az) - ez, Bfz = (Bz - Az) + ez;
