@@ -12,6 +12,8 @@
 
 namespace pbr {
 
+constexpr int kSobolMatrixSize = 52;
+
 struct HaltonParams {
   int32_t baseScales[2];
   int32_t baseExponents[2];
@@ -34,8 +36,6 @@ struct HaltonParams {
   const uint64_t* sobolVdc;         // VdCSobolMatrices[log2Resolution-1][52]
   const uint64_t* sobolVdcInv;      // VdCSobolMatricesInv[log2Resolution-1][52]
 };
-constexpr int kSobolMatrixSize = 52;
-
 // SobolIntervalToIndex / SobolSampleFloat: see host/SobolSampler.h (same integer arithmetic)
 PBR_D int64_t sobol_index_for_sample(int px, int py, int64_t sampleNum, const HaltonParams& hp) {
   const uint32_t m = (uint32_t)hp.log2Resolution;
@@ -52,11 +52,15 @@ PBR_D int64_t sobol_index_for_sample(int px, int py, int64_t sampleNum, const Ha
 }
 PBR_D float sobol_sample(int64_t index, int dim, const HaltonParams& hp) {
   if (dim >= hp.sobolDims) return 0.f;
+  // v = XOR of the matrix columns selected by the set bits of the index (SobolSampleFloat's loop visits every bit up to the
+  // highest one and branches on it; XOR does not care about the order, so only the set bits are visited here: about half the
+  // iterations, no data-dependent branch inside, independent loads)
   uint32_t v = 0;
-  uint64_t a = (uint64_t)index;
+  uint32_t lo = (uint32_t)(uint64_t)index, hi = (uint32_t)((uint64_t)index >> 32);
   const uint32_t* row = hp.sobolMatrices32 + dim * kSobolMatrixSize;
-  for (int i = 0; a != 0; a >>= 1, ++i)
-    if (a & 1) v ^= __ldg(row + i);
+  while (lo) { v ^= __ldg(row + (__ffs((int)lo) - 1)); lo &= lo - 1u; }
+  hi &= (1u << (kSobolMatrixSize - 32)) - 1u;  // an index has at most kSobolMatrixSize bits
+  while (hi) { v ^= __ldg(row + 32 + (__ffs((int)hi) - 1)); hi &= hi - 1u; }
   return stdmin((float)v * 2.3283064365386963e-10f, kOneMinusEpsilon);
 }
 // dims 0 / 1 are remapped to the pixel (needs the pixel coordinate of that dimension)
