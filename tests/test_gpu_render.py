@@ -140,6 +140,34 @@ def test_two_waves_in_flight_equal_waves_in_sequence(api, ref, gpu_ctx, monkeypa
             assert np.array_equal(again, two)
 
 
+def test_paths_deeper_than_the_halton_prime_table(api, gpu_ctx):
+    """Sampler dimensions >= 1000: the reference indexes Primes[] / PrimeSums[] (1000 entries) out of bounds there
+    (LowDiscrepancy.cpp:2279-2316 guards at 1024) - undefined on the CPU, an illegal address or an endless digit loop on a GPU.
+    The device sampler returns 0 for every dimension beyond the tables (csrc/sampler.cuh).  Paths locked inside a closed shell
+    with Russian roulette off reach those dimensions: 7 per diffuse bounce (> 1000 after 143 bounces), 2 per mirror bounce."""
+    for mat, depth, dims_per_bounce in ((scenes.matte([0.97, 0.97, 0.97]), 200, 7), (scenes.mirror([0.99, 0.99, 0.99]), 600, 2)):
+        data = scenes.SceneData()
+        m = data.add_material(mat)
+        v, t = scenes.uv_sphere([0.0, 0.0, 0.0], 3.0, 16, 32)
+        data.add_mesh(v, t, m)                       # closed shell around the camera: nothing escapes
+        data.add_point_light([0.3, 0.5, -0.2], [5.0, 4.0, 3.0])
+        p = Pair(api, None, data, 32, 32, 2, eye=(0.0, 0.0, 1.0), look=(0.0, 0.0, 0.0))
+        kw = dict(integrator=A.INTEGRATOR_PATH, max_depth=depth, rr_threshold=0.0)
+        a, _, st = p.scene.render(**kw)
+        b, _, _ = p.scene.render(**kw)
+        assert 5 + dims_per_bounce * depth > 1000
+        assert np.isfinite(a).all() and a.min() >= 0
+        assert a.max() > 0 or dims_per_bounce == 2  # (a point light never shows in a shell of perfect mirrors)
+        assert np.array_equal(a, b)
+        # every path reaches the table's end (5 + 7 * 142 < 1000): a diffuse path then draws u = (0, 0), the cosine-hemisphere
+        # sample degenerates (pdf 0) and the path ends; a mirror path ignores u and runs to max_depth
+        n_cam = 32 * 32 * 2
+        print("segments per path", st.rays_path / n_cam)
+        assert 142 * n_cam <= st.rays_path <= (depth + 1) * n_cam
+        if dims_per_bounce == 2:
+            assert st.rays_path >= 0.98 * (depth + 1) * n_cam
+
+
 def test_film_resolve_8bit(api, ref, gpu_ctx):
     p = Pair(api, ref, scenes.cornell(sphere_tess=8), 64, 64, 4)
     rgb_sum, rgba8, _ = p.scene.render(max_depth=2, want_rgba8=True)
