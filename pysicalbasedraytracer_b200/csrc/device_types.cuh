@@ -20,12 +20,13 @@ constexpr int kMetaBounceShift = 17;
 constexpr uint32_t kMetaBounceMask = 0x7fu;
 constexpr int kMetaInMediumBit = 24;  // VolPath: Ray::medium != nullptr (lets the medium kernels skip a path after one 4-byte read)
 
-// ---- triangle record (leaf order): three float4 = three 16-byte loads ----
-//   tv0 = p0.xyz | caller's triangle index        tv1 = p1.xyz | material id (bits 0-21), tangents (22), sphere (23), material type (24-27), flags (28-31)
-//   tv2 = p2.xyz | area-light id or -1
+// ---- triangle record (leaf order): three float4 = three 16-byte loads from ONE 48-byte record (tv[3 * i + 0..2]: two
+// sectors, usually one cache line; three separate arrays cost three sectors in three lines per triangle) ----
+//   word 0 = p0.xyz | caller's triangle index     word 1 = p1.xyz | material id (bits 0-21), tangents (22), sphere (23), material type (24-27), flags (28-31)
+//   word 2 = p2.xyz | area-light id or -1
 constexpr uint32_t kTriMatMask = 0x003fffffu;
 constexpr uint32_t kTriTangentBit = 0x00400000u;  // the triangle's mesh has per-vertex tangents (TriangleMesh::s)
-constexpr uint32_t kPrimSphereBit = 0x00800000u;  // the record is an analytic sphere (sphere.cuh): tv0 = centre | id, tv1.x = radius
+constexpr uint32_t kPrimSphereBit = 0x00800000u;  // the record is an analytic sphere (sphere.cuh): word 0 = centre | id, word 1 .x = radius
 constexpr int kTriTypeShift = 24;
 constexpr int kTriFlagShift = 28;
 constexpr uint32_t kTriFlagFlipNormal = 1u;  // reverseOrientation ^ transformSwapsHandedness
@@ -63,15 +64,12 @@ struct TexDev {
 };
 
 struct SceneDev {
-  const float4* tv0;
-  const float4* tv1;
-  const float4* tv2;
+  const float4* tv;    // [3 * nTris] triangle records (above)
   // per-triangle shading frame, host-precomputed with the reference's own operation order (bit-identical to
   // what Triangle::Intersect / the BSDF ctor would compute per hit): removes two fp64 cross products, two
   // normalisations and ~30 conversions per shaded hit (the shading kernels were XU-pipe bound on them)
-  const float4* tvN;   // geometric normal of Triangle::Intersect (Triangle.cpp:182-184), orientation flip applied
-  const float4* tvS;   // ss = Normalize(dpdu)            (Reflection.h:105-110)
-  const float4* tvT;   // ts = Cross(ns, ss)
+  const float4* tf;    // [3 * nTris] frame records: word 0 = geometric normal of Triangle::Intersect (Triangle.cpp:182-184),
+                       // orientation flip applied; word 1 = ss = Normalize(dpdu) (Reflection.h:105-110); word 2 = ts = Cross(ns, ss)
   // optional per-vertex shading data (NULL when no mesh has it): smooth normals are interpolated per hit
   const float4* tn0;   // normal of vertex 0 | -          (triangles of meshes with TriangleMesh::n)
   const float4* tn1;

@@ -322,14 +322,14 @@ __global__ void __launch_bounds__(kBlock) k_resolve_mis(const __grid_constant__ 
     const pbrgpu_light& light = P.sc.lights[lightId];
     Spec Li(0.f);
     if (tri >= 0) {
-      if (__float_as_int(__ldg(&P.sc.tv2[tri].w)) == lightId) {
+      if (__float_as_int(__ldg(&P.sc.tv[3 * tri + 2].w)) == lightId) {
         if (light.type == PBRGPU_LIGHT_AREA_SPHERE) {  // the hit normal of the analytic sphere along this ray
           const V3 c(light.pos[0], light.pos[1], light.pos[2]), ro(o.x, o.y, o.z);
           float t;
           if (sphere_solve(ro - c, wi, light.world_radius, kInfinity, &t))
             Li = area_light_L(light, sphere_hit(c, light.world_radius, light.light_to_world[0] != 0.f, ro, wi, t).n, -wi);
         } else {
-          const float4 n4 = __ldg(P.sc.tvN + tri);
+          const float4 n4 = __ldg(P.sc.tf + 3 * tri);
           V3 nh(n4.x, n4.y, n4.z);
           const TriData td = load_tri(P.sc, tri);
           if (((td.w1 >> kTriFlagShift) & kTriFlagNormals) || (td.w1 & kTriTangentBit)) {
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kBlock) k_dump_primary(const __grid_constant__
       unsigned a = 0, b = 0;
       traverse<false, false, true>(P.sc, o, d, kInfinity, &h, sstack, &a, &b);
       int* q = outHits + 4 * i;
-      q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
+      q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv[3 * h.tri].w)) : -1;
       q[1] = __float_as_int(h.t);
       q[2] = h.tri >= 0 ? __float_as_int(h.b0) : 0;
       q[3] = h.tri >= 0 ? __float_as_int(h.b1) : 0;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_user(const __grid_constant__ R
     } else {
       traverse<false, false, true>(P.sc, o, d, r[3], &h, sstack, &a, &b);
       int* q = out + 4 * i;
-      q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[h.tri].w)) : -1;
+      q[0] = h.tri >= 0 ? __float_as_int(__ldg(&P.sc.tv[3 * h.tri].w)) : -1;
       q[1] = __float_as_int(h.t);
       q[2] = h.tri >= 0 ? __float_as_int(h.b0) : 0;
       q[3] = h.tri >= 0 ? __float_as_int(h.b1) : 0;
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kBlock) k_collect_wave_hits(const __grid_const
     const float4 h = P.ws.hit[slot];
     const int tri = __float_as_int(h.x);
     int* q = out + 4 * ((size_t)p * ns + j);
-    q[0] = tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[tri].w)) : -1;
+    q[0] = tri >= 0 ? __float_as_int(__ldg(&P.sc.tv[3 * tri].w)) : -1;
     q[1] = __float_as_int(P.ws.cur[slot].o.w);  // k_trace stored the hit distance (RenderParams::storeHitT), tMax on a miss
     q[2] = tri >= 0 ? __float_as_int(h.y) : 0;
     q[3] = tri >= 0 ? __float_as_int(h.z) : 0;
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kBlock) k_collect_rays(const __grid_constant__
     const int tri = __float_as_int(h.x);
     if (__float_as_int(P.ws.miO[i].w) != tri) atomicAdd(nDisagree, 1);  // the MIS queue must find the same triangle
     int* q = out + 4 * (size_t)i;
-    q[0] = tri >= 0 ? __float_as_int(__ldg(&P.sc.tv0[tri].w)) : -1;
+    q[0] = tri >= 0 ? __float_as_int(__ldg(&P.sc.tv[3 * tri].w)) : -1;
     q[1] = __float_as_int(P.ws.cur[i].o.w);
     q[2] = tri >= 0 ? __float_as_int(h.y) : 0;
     q[3] = tri >= 0 ? __float_as_int(h.z) : 0;

@@ -131,8 +131,8 @@ struct pbrgpu_scene {
   bool haveCamera = false, haveSampler = false;
   int64_t spp = 0;
   // device buffers
-  DevBuf<float4> tvN, tvS, tvT, tn0, tn1, tn2, ts0, ts1, ts2, tuv0, tuv1;
-  DevBuf<float4> geom;  // ONE slab: Bvh8Node[] | tv0 | tv1 | tv2 - everything k_trace reads, covered by one L2 access-policy window
+  DevBuf<float4> tfr, tn0, tn1, tn2, ts0, ts1, ts2, tuv0, tuv1;  // tfr: per-triangle frame records (SceneDev::tf)
+  DevBuf<float4> geom;  // ONE slab: Bvh8Node[] | triangle records - everything k_trace reads, covered by one L2 access-policy window
   DevBuf<pbrgpu_material> mats;
   DevBuf<pbrgpu_light> dlights;
   DevBuf<float> lightFunc, lightCdf;
@@ -466,20 +466,20 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     build_bvh8(d->verts, d->indices, nTriangles, maxLeaf, &s->bvh, sb.data(), d->n_spheres);
   }
   s->leafOf.assign((size_t)nT, -1);
-  std::vector<float4> v0((size_t)nT), v1((size_t)nT), v2((size_t)nT), vN((size_t)nT), vS((size_t)nT), vT((size_t)nT);
+  std::vector<float4> vrec((size_t)nT * 3), vfr((size_t)nT * 3);  // 48-byte triangle / frame records, leaf order
   std::vector<float4> vn0, vn1, vn2, vuv0, vuv1, vs0, vs1, vs2;  // only when some mesh has shading normals / uvs / tangents
   bool anyNormals = false;
   for (int k = 0; k < nT; ++k) {
     int ti = s->bvh.triOrder[k];
     s->leafOf[ti] = k;
-    if (ti >= nTriangles) {  // analytic sphere (sphere.cuh): tv0 = centre | id, tv1 = radius | material word, tv2 = - | light
+    if (ti >= nTriangles) {  // analytic sphere (sphere.cuh): word 0 = centre | id, word 1 = radius | material word, word 2 = - | light
       const pbrgpu_sphere& sp = d->spheres[ti - nTriangles];
       const uint32_t flags = sp.reverse_orientation ? (kTriFlagFlipNormal | kTriFlagReverse) : 0u;
       const uint32_t w1 = (uint32_t)sp.material | kPrimSphereBit | ((uint32_t)d->materials[sp.material].type << kTriTypeShift) | (flags << kTriFlagShift);
-      v0[k] = make_float4(sp.center[0], sp.center[1], sp.center[2], u2f((uint32_t)ti));
-      v1[k] = make_float4(sp.radius, 0.f, 0.f, u2f(w1));
-      v2[k] = make_float4(0.f, 0.f, 0.f, u2f((uint32_t)sp.light));
-      vN[k] = vS[k] = vT[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vrec[3 * (size_t)k] = make_float4(sp.center[0], sp.center[1], sp.center[2], u2f((uint32_t)ti));
+      vrec[3 * (size_t)k + 1] = make_float4(sp.radius, 0.f, 0.f, u2f(w1));
+      vrec[3 * (size_t)k + 2] = make_float4(0.f, 0.f, 0.f, u2f((uint32_t)sp.light));
+      vfr[3 * (size_t)k] = vfr[3 * (size_t)k + 1] = vfr[3 * (size_t)k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
       continue;
     }
     const float* a = d->verts + 3 * (size_t)d->indices[3 * (size_t)ti];
@@ -498,9 +498,9 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
                         : (uint32_t)m | ((uint32_t)d->materials[m].type << kTriTypeShift) | (flags << kTriFlagShift);
     if (hasTangents) w1 |= kTriTangentBit;
     int32_t lid = d->tri_light ? d->tri_light[ti] : -1;
-    v0[k] = make_float4(a[0], a[1], a[2], u2f((uint32_t)ti));
-    v1[k] = make_float4(b[0], b[1], b[2], u2f(w1));
-    v2[k] = make_float4(c[0], c[1], c[2], u2f((uint32_t)lid));
+    vrec[3 * (size_t)k] = make_float4(a[0], a[1], a[2], u2f((uint32_t)ti));
+    vrec[3 * (size_t)k + 1] = make_float4(b[0], b[1], b[2], u2f(w1));
+    vrec[3 * (size_t)k + 2] = make_float4(c[0], c[1], c[2], u2f((uint32_t)lid));
     V3 n, ss, ts;
     float uv[6] = {0.f, 0.f, 1.f, 0.f, 1.f, 1.f};  // Triangle::GetUVs default (Triangle.h:50-54)
     if (flags & kTriFlagUVs)
@@ -531,11 +531,11 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
       vuv0[k] = make_float4(uv[0], uv[1], uv[2], uv[3]);
       vuv1[k] = make_float4(uv[4], uv[5], 0.f, 0.f);
     }
-    vN[k] = make_float4(n.x, n.y, n.z, 0.f);
-    vS[k] = make_float4(ss.x, ss.y, ss.z, 0.f);
-    vT[k] = make_float4(ts.x, ts.y, ts.z, 0.f);
+    vfr[3 * (size_t)k] = make_float4(n.x, n.y, n.z, 0.f);
+    vfr[3 * (size_t)k + 1] = make_float4(ss.x, ss.y, ss.z, 0.f);
+    vfr[3 * (size_t)k + 2] = make_float4(ts.x, ts.y, ts.z, 0.f);
   }
-  CK(s->tvN.upload(vN, st)); CK(s->tvS.upload(vS, st)); CK(s->tvT.upload(vT, st));
+  CK(s->tfr.upload(vfr, st));
   if (anyNormals) { CK(s->tn0.upload(vn0, st)); CK(s->tn1.upload(vn1, st)); CK(s->tn2.upload(vn2, st)); }
   if (!vuv0.empty()) { CK(s->tuv0.upload(vuv0, st)); CK(s->tuv1.upload(vuv1, st)); }
   if (!vs0.empty()) { CK(s->ts0.upload(vs0, st)); CK(s->ts1.upload(vs1, st)); CK(s->ts2.upload(vs2, st)); }
@@ -544,12 +544,10 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     const size_t nN = s->bvh.nodes.size() * 5, nTv = (size_t)nT;
     CK(s->geom.alloc(nN + 3 * nTv));
     CK(cudaMemcpyAsync(s->geom.p, s->bvh.nodes.data(), nN * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->geom.p + nN, v0.data(), nTv * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->geom.p + nN + nTv, v1.data(), nTv * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->geom.p + nN + 2 * nTv, v2.data(), nTv * sizeof(float4), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // v0..v2 are locals
+    CK(cudaMemcpyAsync(s->geom.p + nN, vrec.data(), 3 * nTv * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // vrec is a local
     s->sc.nodes8 = s->geom.p;
-    s->sc.tv0 = s->geom.p + nN; s->sc.tv1 = s->geom.p + nN + nTv; s->sc.tv2 = s->geom.p + nN + 2 * nTv;
+    s->sc.tv = s->geom.p + nN;
   }
   // participating media + per-triangle MediumInterface (leaf order)
   if (d->n_media > 0) {
@@ -820,7 +818,7 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   }
   CK(s->dlights.upload(s->lights, st));
 
-  s->sc.tvN = s->tvN.p; s->sc.tvS = s->tvS.p; s->sc.tvT = s->tvT.p;
+  s->sc.tf = s->tfr.p;
   s->sc.ts0 = s->ts0.p; s->sc.ts1 = s->ts1.p; s->sc.ts2 = s->ts2.p;
   s->sc.tn0 = s->tn0.p; s->sc.tn1 = s->tn1.p; s->sc.tn2 = s->tn2.p; s->sc.tuv0 = s->tuv0.p; s->sc.tuv1 = s->tuv1.p;
   s->sc.mats = s->mats.p;

@@ -27,7 +27,8 @@ struct TriData {
   uint32_t w0, w1, w2;
 };
 PBR_D TriData load_tri(const SceneDev& sc, int ti) {
-  float4 a = __ldg(sc.tv0 + ti), b = __ldg(sc.tv1 + ti), c = __ldg(sc.tv2 + ti);
+  const float4* rec = sc.tv + 3 * (size_t)ti;
+  float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
   TriData t;
   t.p0 = V3(a.x, a.y, a.z); t.p1 = V3(b.x, b.y, b.z); t.p2 = V3(c.x, c.y, c.z);
   t.w0 = __float_as_uint(a.w); t.w1 = __float_as_uint(b.w); t.w2 = __float_as_uint(c.w);
@@ -106,11 +107,12 @@ PBR_D void make_isect(const SceneDev& sc, const TriData& t, int tri, float b0, f
   float zAbsSum = (fabsf(b0 * p0.z) + fabsf(b1 * p1.z) + fabsf(b2 * p2.z));
   is->pError = gamma_f(7) * V3(xAbsSum, yAbsSum, zAbsSum);
   is->p = b0 * p0 + b1 * p1 + b2 * p2;
-  const float4 n4 = __ldg(sc.tvN + tri);
+  const float4* frame = sc.tf + 3 * (size_t)tri;
+  const float4 n4 = __ldg(frame);
   const uint32_t fl = t.w1 >> kTriFlagShift;
   if (!(fl & kTriFlagNormals) && !(t.w1 & kTriTangentBit)) {
     // flat-shaded triangle: the whole frame is a per-triangle constant (host-precomputed, uvs included)
-    const float4 s4 = __ldg(sc.tvS + tri), t4 = __ldg(sc.tvT + tri);
+    const float4 s4 = __ldg(frame + 1), t4 = __ldg(frame + 2);
     is->n = V3(n4.x, n4.y, n4.z);
     is->ns = is->n;
     is->ss = V3(s4.x, s4.y, s4.z);

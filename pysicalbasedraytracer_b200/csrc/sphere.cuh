@@ -2,7 +2,7 @@
 // arithmetic here is that of the CPU twin host/AnalyticSphere.h (a subclass of the reference's Shape that implements what
 // Shape/README.md section 3 documents), operation for operation.  PARITY UNPINNED by the reference; pins: twin == GPU.
 // A sphere lives in the triangle arrays of the BVH leaf order as
-//   tv0 = centre.xyz | caller's primitive id     tv1 = radius, -, - | material word with kPrimSphereBit     tv2 = -,-,- | area-light id
+//   word 0 = centre.xyz | caller's primitive id     word 1 = radius, -, - | material word with kPrimSphereBit     word 2 = -,-,- | area-light id
 #pragma once
 #include "device_types.cuh"
 

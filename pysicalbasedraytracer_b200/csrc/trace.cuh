@@ -98,7 +98,7 @@ PBR_D bool intersect_triangle(const RayPrep& rp, float tMax, V3 p0, V3 p1, V3 p2
 struct alignas(8) HitRec {
   int tri;  // leaf-order triangle index, -1 = miss
   float t, b0, b1, b2;
-  uint32_t w1;  // tv1.w of the hit triangle (material id | type | flags), free with the vertex load
+  uint32_t w1;  // word 1 .w of the hit triangle's record (material id | type | flags), free with the vertex load
 };
 
 PBR_D V3 ld3(const float4* p, int i) {
@@ -256,9 +256,10 @@ PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T, HitRec* store = nullptr) {
   const int bit = 31 - __clz(T.tgroup.y);
   T.tgroup.y &= ~(1u << bit);
   const int ti = (int)T.tgroup.x + bit;
-  const float4 v1 = __ldg(sc.tv1 + ti);
+  const float4* rec = sc.tv + 3 * (size_t)ti;  // one 48-byte record
+  const float4 v1 = __ldg(rec + 1);
   if (SPH && (__float_as_uint(v1.w) & kPrimSphereBit)) {
-    const V3 center = ld3(sc.tv0, ti);
+    const V3 center = ld3(rec, 0);
     float ts;
     if (!sphere_solve(T.rp.o - center, T.dir, v1.x, T.tMax, &ts)) return false;
     T.tMax = ts;
@@ -267,7 +268,7 @@ PBR_D bool cw_tri_step(const SceneDev& sc, Trav& T, HitRec* store = nullptr) {
     h.w1 = __float_as_uint(v1.w);
     return true;
   }
-  V3 p0 = ld3(sc.tv0, ti), p1(v1.x, v1.y, v1.z), p2 = ld3(sc.tv2, ti);
+  V3 p0 = ld3(rec, 0), p1(v1.x, v1.y, v1.z), p2 = ld3(rec, 2);
   float t, b0, b1, b2;
   if (intersect_triangle(T.rp, T.tMax, p0, p1, p2, &t, &b0, &b1, &b2)) {
     T.tMax = t;
