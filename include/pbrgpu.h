@@ -360,7 +360,9 @@ int pbrgpu_shard_samples(int64_t s0, int64_t s1, int rank, int world, int64_t ou
  * the traversal kernel's node / triangle fetches; bytes >> L2: HBM read bandwidth. */
 int pbrgpu_measure_read_bandwidth(pbrgpu_ctx* ctx, size_t bytes, int iters, double* out_gb_per_s);
 
-/* BVH statistics: out[0]=n_nodes, out[1]=n_leaves, out[2]=max_leaf_size, out[3]=bytes_nodes, out[4]=bytes_tris */
+/* BVH statistics: out[0]=n_nodes, out[1]=n_leaves, out[2]=max_leaf_size, out[3]=bytes_nodes, out[4]=bytes_tris, out[5]=depth of
+ * the wide tree, out[6]=hash of the built nodes + leaf order (the host build is multi-threaded - PBRGPU_BUILD_THREADS, default
+ * min(16, cores) - and its result does not depend on the thread count) */
 int pbrgpu_scene_info(pbrgpu_scene* scene, int64_t out[8]);
 
 #ifdef __cplusplus

@@ -322,7 +322,7 @@ class Scene:
         out = (C.c_int64 * 8)()
         _check(lib().pbrgpu_scene_info(self.h, out))
         return dict(n_nodes=out[0], n_leaves=out[1], max_leaf=out[2], bytes_nodes=out[3], bytes_tris=out[4],
-                    max_depth=out[5])
+                    max_depth=out[5], bvh_hash=out[6])
 
     def set_camera(self, camera):
         d = camera.desc() if hasattr(camera, "desc") else camera

@@ -6,10 +6,15 @@
 #include "bvh.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <limits>
+#include <thread>
+#include <vector>
 
 namespace pbr {
 namespace {
@@ -48,8 +53,117 @@ constexpr float kIsectCost = 1.2f;
 
 namespace {
 struct BinaryStats { int maxLeafSize = 0; int64_t nLeaves = 0; int maxDepth = 0; };
+struct BuildTask { int32_t node, first, count, depth; };
 
-// Binned-SAH binary tree over triangle bounds; `order` = leaf-order permutation of triangle ids.
+// Binned-SAH top-down build of the subtree `root` into `tmp` (root.node must exist).  A node's split depends only on its
+// primitive range, so subtrees are independent: with `deferred` given, every subtree of at most `cutoff` primitives is NOT
+// descended into but recorded there (its node exists, empty) for another thread to build.  All three axes are binned in one
+// pass over the range (same per-bin boxes and counts as three passes).
+void build_range(const std::vector<Aabb>& tb, const std::vector<float>& cen, int maxLeaf, std::vector<TmpNode>& tmp, int32_t* order,
+                 BuildTask root, int64_t cutoff, std::vector<BuildTask>* deferred, BinaryStats* out) {
+  std::vector<BuildTask> stack;
+  stack.push_back(root);
+  while (!stack.empty()) {
+    BuildTask t = stack.back();
+    stack.pop_back();
+    if (deferred && t.count <= cutoff && t.node != root.node) { deferred->push_back(t); continue; }
+    Aabb box = empty_box(), cb = empty_box();
+    for (int32_t i = t.first; i < t.first + t.count; ++i) {
+      int32_t id = order[i];
+      grow(box, tb[id]);
+      for (int k = 0; k < 3; ++k) {
+        cb.lo[k] = std::min(cb.lo[k], cen[3 * id + k]);
+        cb.hi[k] = std::max(cb.hi[k], cen[3 * id + k]);
+      }
+    }
+    tmp[t.node].box = box;
+    tmp[t.node].first = t.first;   // every node records its (contiguous) triangle range
+    tmp[t.node].count = t.count;
+    out->maxDepth = std::max(out->maxDepth, (int)t.depth);
+    auto make_leaf = [&]() {
+      tmp[t.node].first = t.first;
+      tmp[t.node].count = t.count;
+      out->maxLeafSize = std::max(out->maxLeafSize, (int)t.count);
+      out->nLeaves++;
+    };
+    if (t.count <= 1) { make_leaf(); continue; }
+    // pick split: binned SAH, all three axes evaluated
+    int bestAxis = -1, bestBin = -1;
+    float bestCost = std::numeric_limits<float>::infinity();
+    float parentArea = half_area(box);
+    Aabb bb[3][kBins];
+    int bc[3][kBins];
+    float scale[3];
+    bool valid[3];
+    for (int axis = 0; axis < 3; ++axis) {
+      valid[axis] = cb.hi[axis] > cb.lo[axis];
+      scale[axis] = valid[axis] ? kBins / (cb.hi[axis] - cb.lo[axis]) : 0.f;
+      for (int b = 0; b < kBins; ++b) { bb[axis][b] = empty_box(); bc[axis][b] = 0; }
+    }
+    for (int32_t i = t.first; i < t.first + t.count; ++i) {
+      int32_t id = order[i];
+      for (int axis = 0; axis < 3; ++axis) {
+        if (!valid[axis]) continue;
+        int b = (int)((cen[3 * id + axis] - cb.lo[axis]) * scale[axis]);
+        b = std::max(0, std::min(kBins - 1, b));
+        bc[axis][b]++;
+        grow(bb[axis][b], tb[id]);
+      }
+    }
+    for (int axis = 0; axis < 3; ++axis) {
+      if (!valid[axis]) continue;
+      float rightArea[kBins];
+      int rightCount[kBins];
+      Aabb acc = empty_box();
+      int cnt = 0;
+      for (int b = kBins - 1; b > 0; --b) {
+        grow(acc, bb[axis][b]);
+        cnt += bc[axis][b];
+        rightArea[b] = half_area(acc);
+        rightCount[b] = cnt;
+      }
+      acc = empty_box();
+      cnt = 0;
+      for (int b = 0; b < kBins - 1; ++b) {
+        grow(acc, bb[axis][b]);
+        cnt += bc[axis][b];
+        if (cnt == 0 || rightCount[b + 1] == 0) continue;
+        float cost = kTravCost + kIsectCost * (cnt * half_area(acc) + rightCount[b + 1] * rightArea[b + 1]) /
+                                     std::max(parentArea, 1e-30f);
+        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+      }
+    }
+    float leafCost = kIsectCost * t.count;
+    if (t.count <= maxLeaf && (bestAxis < 0 || leafCost <= bestCost)) { make_leaf(); continue; }
+    int32_t mid;
+    if (bestAxis >= 0) {
+      float lo = cb.lo[bestAxis];
+      float sc = scale[bestAxis];
+      int32_t* b0 = order + t.first;
+      int32_t* m = std::stable_partition(b0, b0 + t.count, [&](int32_t id) {
+        int b = (int)((cen[3 * id + bestAxis] - lo) * sc);
+        b = std::max(0, std::min(kBins - 1, b));
+        return b <= bestBin;
+      });
+      mid = (int32_t)(m - order);
+    } else {
+      mid = t.first + t.count / 2;  // all centroids coincide: split by index
+    }
+    if (mid == t.first || mid == t.first + t.count) mid = t.first + t.count / 2;
+    int32_t l = (int32_t)tmp.size();
+    tmp.emplace_back();
+    tmp.emplace_back();
+    tmp[t.node].left = l;
+    tmp[t.node].right = l + 1;
+    stack.push_back({l + 1, mid, t.first + t.count - mid, t.depth + 1});
+    stack.push_back({l, t.first, mid - t.first, t.depth + 1});
+  }
+}
+
+// Binned-SAH binary tree over triangle bounds; `order` = leaf-order permutation of triangle ids.  The top of the tree is built
+// by the calling thread down to subtrees of <= nTris / (8 * threads) primitives; those are built by a pool of threads into
+// private node arrays and appended in a fixed order, so the tree (and everything derived from it) does not depend on the
+// number of threads or on their timing.  Children always get larger indices than their parent (compute_widening relies on it).
 void build_binary(const float* verts, const int32_t* indices, int64_t nTriangles, const Aabb* extra, int64_t nExtra, int maxLeaf,
                   std::vector<TmpNode>& tmp, std::vector<int32_t>& order, BinaryStats* out) {
   const int64_t nTris = nTriangles + nExtra;  // primitives: triangles, then the caller's extra boxes
@@ -74,101 +188,50 @@ void build_binary(const float* verts, const int32_t* indices, int64_t nTriangles
   order.resize((size_t)nTris);
   for (int64_t i = 0; i < nTris; ++i) order[i] = (int32_t)i;
 
+  int nThreads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = std::getenv("PBRGPU_BUILD_THREADS")) nThreads = std::max(1, std::min(64, std::atoi(e)));
+  if (nTris < (1 << 15)) nThreads = 1;
+
   tmp.clear();
   tmp.reserve((size_t)std::max<int64_t>(2 * nTris, 2));
-  struct Task { int32_t node, first, count, depth; };
-  std::vector<Task> stack;
   tmp.emplace_back();
-  stack.push_back({0, 0, (int32_t)nTris, 0});
-  out->maxLeafSize = 0;
-  out->nLeaves = 0;
-  out->maxDepth = 0;
-  while (!stack.empty()) {
-    Task t = stack.back();
-    stack.pop_back();
-    Aabb box = empty_box(), cb = empty_box();
-    for (int32_t i = t.first; i < t.first + t.count; ++i) {
-      int32_t id = order[i];
-      grow(box, tb[id]);
-      for (int k = 0; k < 3; ++k) {
-        cb.lo[k] = std::min(cb.lo[k], cen[3 * id + k]);
-        cb.hi[k] = std::max(cb.hi[k], cen[3 * id + k]);
-      }
+  *out = BinaryStats{};
+  std::vector<BuildTask> deferred;
+  build_range(tb, cen, maxLeaf, tmp, order.data(), {0, 0, (int32_t)nTris, 0}, nThreads > 1 ? nTris / (8 * (int64_t)nThreads) : 0,
+              nThreads > 1 ? &deferred : nullptr, out);
+  if (deferred.empty()) return;
+
+  std::vector<std::vector<TmpNode>> local(deferred.size());
+  std::vector<BinaryStats> stats(deferred.size());
+  std::vector<size_t> bySize(deferred.size());
+  for (size_t k = 0; k < bySize.size(); ++k) bySize[k] = k;
+  std::stable_sort(bySize.begin(), bySize.end(), [&](size_t a, size_t b) { return deferred[a].count > deferred[b].count; });  // big subtrees first
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    for (size_t q = next.fetch_add(1); q < bySize.size(); q = next.fetch_add(1)) {
+      const size_t k = bySize[q];
+      const BuildTask& d = deferred[k];
+      local[k].reserve((size_t)2 * d.count);
+      local[k].emplace_back();
+      build_range(tb, cen, maxLeaf, local[k], order.data(), {0, d.first, d.count, d.depth}, 0, nullptr, &stats[k]);
     }
-    tmp[t.node].box = box;
-    tmp[t.node].first = t.first;   // every node records its (contiguous) triangle range
-    tmp[t.node].count = t.count;
-    out->maxDepth = std::max(out->maxDepth, (int)t.depth);
-    auto make_leaf = [&]() {
-      tmp[t.node].first = t.first;
-      tmp[t.node].count = t.count;
-      out->maxLeafSize = std::max(out->maxLeafSize, (int)t.count);
-      out->nLeaves++;
-    };
-    if (t.count <= 1) { make_leaf(); continue; }
-    // pick split: binned SAH over the widest centroid axis first, all three axes evaluated
-    int bestAxis = -1, bestBin = -1;
-    float bestCost = std::numeric_limits<float>::infinity();
-    float parentArea = half_area(box);
-    for (int axis = 0; axis < 3; ++axis) {
-      float lo = cb.lo[axis], hi = cb.hi[axis];
-      if (!(hi > lo)) continue;
-      float scale = kBins / (hi - lo);
-      Aabb bb[kBins];
-      int bc[kBins];
-      for (int b = 0; b < kBins; ++b) { bb[b] = empty_box(); bc[b] = 0; }
-      for (int32_t i = t.first; i < t.first + t.count; ++i) {
-        int32_t id = order[i];
-        int b = (int)((cen[3 * id + axis] - lo) * scale);
-        b = std::max(0, std::min(kBins - 1, b));
-        bc[b]++;
-        grow(bb[b], tb[id]);
-      }
-      float rightArea[kBins];
-      int rightCount[kBins];
-      Aabb acc = empty_box();
-      int cnt = 0;
-      for (int b = kBins - 1; b > 0; --b) {
-        grow(acc, bb[b]);
-        cnt += bc[b];
-        rightArea[b] = half_area(acc);
-        rightCount[b] = cnt;
-      }
-      acc = empty_box();
-      cnt = 0;
-      for (int b = 0; b < kBins - 1; ++b) {
-        grow(acc, bb[b]);
-        cnt += bc[b];
-        if (cnt == 0 || rightCount[b + 1] == 0) continue;
-        float cost = kTravCost + kIsectCost * (cnt * half_area(acc) + rightCount[b + 1] * rightArea[b + 1]) /
-                                     std::max(parentArea, 1e-30f);
-        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
-      }
-    }
-    float leafCost = kIsectCost * t.count;
-    if (t.count <= maxLeaf && (bestAxis < 0 || leafCost <= bestCost)) { make_leaf(); continue; }
-    int32_t mid;
-    if (bestAxis >= 0) {
-      float lo = cb.lo[bestAxis], hi = cb.hi[bestAxis];
-      float scale = kBins / (hi - lo);
-      int32_t* b0 = order.data() + t.first;
-      int32_t* m = std::stable_partition(b0, b0 + t.count, [&](int32_t id) {
-        int b = (int)((cen[3 * id + bestAxis] - lo) * scale);
-        b = std::max(0, std::min(kBins - 1, b));
-        return b <= bestBin;
-      });
-      mid = (int32_t)(m - order.data());
-    } else {
-      mid = t.first + t.count / 2;  // all centroids coincide: split by index
-    }
-    if (mid == t.first || mid == t.first + t.count) mid = t.first + t.count / 2;
-    int32_t l = (int32_t)tmp.size();
-    tmp.emplace_back();
-    tmp.emplace_back();
-    tmp[t.node].left = l;
-    tmp[t.node].right = l + 1;
-    stack.push_back({l + 1, mid, t.first + t.count - mid, t.depth + 1});
-    stack.push_back({l, t.first, mid - t.first, t.depth + 1});
+  };
+  std::vector<std::thread> pool;
+  for (int th = 1; th < nThreads; ++th) pool.emplace_back(worker);
+  worker();
+  for (std::thread& th : pool) th.join();
+  // splice: subtree k's root is the node the top build left empty, its other nodes follow in the order of `deferred`
+  for (size_t k = 0; k < deferred.size(); ++k) {
+    const int32_t off = (int32_t)tmp.size() - 1;  // local id j >= 1 -> tmp id off + j
+    std::vector<TmpNode>& loc = local[k];
+    for (TmpNode& nd : loc)
+      if (nd.left >= 0) { nd.left += off; nd.right += off; }
+    tmp[deferred[k].node] = loc[0];
+    tmp.insert(tmp.end(), loc.begin() + 1, loc.end());
+    out->maxLeafSize = std::max(out->maxLeafSize, stats[k].maxLeafSize);
+    out->nLeaves += stats[k].nLeaves;
+    out->maxDepth = std::max(out->maxDepth, stats[k].maxDepth);
+    std::vector<TmpNode>().swap(loc);
   }
 }
 }  // namespace
@@ -255,10 +318,16 @@ void build_bvh8(const float* verts, const int32_t* indices, int64_t nTriangles, 
   std::vector<int32_t> order;
   BinaryStats bs;
   const int64_t nTris = nTriangles + nExtra;
+  const bool buildLog = std::getenv("PBRGPU_BUILD_LOG") != nullptr;  // development aid: phase times on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   build_binary(verts, indices, nTriangles, extra, nExtra, 1, tmp, order, &bs);  // one triangle per binary leaf: the widening forms the leaves
+  const auto t1 = now();
   Widening wd;
   if (const char* e = std::getenv("PBRGPU_PRIM_COST")) kPrimCost = (float)std::atof(e);
   compute_widening(tmp, maxLeaf, &wd);
+  const auto t2 = now();
   out->bounds = tmp[0].box;
   out->maxLeafSize = 0;
   out->nLeaves = 0;
@@ -368,6 +437,9 @@ void build_bvh8(const float* verts, const int32_t* indices, int64_t nTriangles, 
     }
     out->nodes[w.wide] = nd;
   }
+  if (buildLog)
+    fprintf(stderr, "build_bvh8: binary SAH tree %.1f ms (%zu nodes), widening %.1f ms, 8-wide layout + quantisation %.1f ms\n", ms(t0, t1), tmp.size(),
+            ms(t1, t2), ms(t2, now()));
 }
 
 }  // namespace pbr

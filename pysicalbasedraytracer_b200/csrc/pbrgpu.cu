@@ -988,6 +988,15 @@ int pbrgpu_scene_info(pbrgpu_scene* s, int64_t out[8]) {
   out[3] = (int64_t)(s->bvh.nodes.size() * sizeof(Bvh8Node));
   out[4] = (int64_t)s->sc.nTris * 48;
   out[5] = s->bvh.maxDepth;
+  // FNV-1a over the built nodes and the leaf order: the build is deterministic and independent of its thread count
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  };
+  mix(s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(Bvh8Node));
+  mix(s->bvh.triOrder.data(), s->bvh.triOrder.size() * sizeof(int32_t));
+  out[6] = (int64_t)(h >> 1);
   return 0;
 }
 

@@ -181,3 +181,19 @@ def test_c_abi_error_behaviour(api, gpu_ctx):
     d = A.SamplerDesc(type=A.SAMPLER_SOBOL, samples_per_pixel=4)
     with pytest.raises(api.PbrGpuError, match="Sobol needs"):
         sc.set_sampler(d)
+
+
+def test_bvh_build_is_independent_of_the_thread_count(api, gpu_ctx, monkeypatch):
+    """The host builder (csrc/bvh_build.cpp) builds the top of the binary SAH tree on the calling thread and the subtrees below
+    on a pool of threads; nodes, leaf order - and therefore every ray query - must not depend on how many threads there were."""
+    data = scenes.dragon_class(tess=96)  # 36 k triangles: above the builder's single-thread threshold
+    rays = _random_rays(20000, 3)
+    got = []
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("PBRGPU_BUILD_THREADS", threads)
+        sc = api.Scene(data, gpu_ctx)
+        got.append((sc.info(), sc.trace(rays)))
+        sc.close()
+    for info, hits in got[1:]:
+        assert info == got[0][0] and info["bvh_hash"] != 0
+        assert np.array_equal(hits, got[0][1])
