@@ -5,6 +5,7 @@
 //   BVH with a conservative slab test; the reference's slab test Geometry.h:1437-1468 has no gamma
 //   widening, ours is widened, so the set of triangles we test is a superset of what the reference tests).
 #pragma once
+#include <cuda_fp16.h>
 #include "device_types.cuh"
 #include "sphere.cuh"
 
@@ -113,11 +114,19 @@ PBR_D V3 ld3(const float4* p, int i) {
 // (and postponed triangle groups); its first kSmemStack levels live in shared memory, one column per
 // lane ([level][lane] -> conflict-free), deeper levels spill to a small local array.
 // ---------------------------------------------------------------------------------------------
+#ifndef PBR_NODE_HALF2
+#define PBR_NODE_HALF2 1
+#endif
+#ifndef PBR_H2_RATIO
+#define PBR_H2_RATIO 2048.f
+#endif
 #ifndef PBR_SMEM_STACK
 #define PBR_SMEM_STACK 8
 #endif
 constexpr int kSmemStack = PBR_SMEM_STACK;
 constexpr int kLocalStack = 36;
+
+constexpr unsigned kTravWideRange = 0x80000000u;  // flag in Trav::octinv4 (bit 31 is masked out wherever the octant bytes are used)
 
 struct Trav {
   V3 dir;                     // ray direction: read by the analytic-sphere test only (dead in every other instantiation)
@@ -156,6 +165,12 @@ PBR_D void trav_init(Trav& T, V3 o, V3 d, float tMax, unsigned f32one) {
   T.f32one = f32one;
   T.idx = safe_rcp(d.x); T.idy = safe_rcp(d.y); T.idz = safe_rcp(d.z);
   T.octinv4 = ((d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u)) * 0x01010101u;
+#if PBR_NODE_HALF2
+  {  // kTravWideRange: a direction with a component below 2^-11 of its largest one takes the fp32 box test (cw_node_test_h2)
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    if (!(fminf(fminf(ax, ay), az) * PBR_H2_RATIO >= fmaxf(fmaxf(ax, ay), az))) T.octinv4 |= kTravWideRange;
+  }
+#endif
   T.rp = prep_ray(o, d);
   T.tMax = tMax;
   T.ngroup = make_uint2(0u, 0x80000000u);
@@ -187,23 +202,11 @@ PBR_D uint2 trav_pop(Trav& T, const uint2* sstack, const TravSpill& S) {
 template <int J>
 PBR_D float q2f(unsigned w, unsigned one) { return __uint_as_float(__byte_perm(w, one, 0x7604u | (J << 4))); }
 
-// One node step: pick the next inner child of the node group (front-to-back by octant), fetch its
-// 80-byte node with five 16-byte loads, slab-test the 8 quantised child boxes, emit a new node group
-// and triangle group.  The slab test is conservative: the rounding error of the fused evaluation is
-// bounded per axis and folded into the offsets (Bn = B - err, Bf = B + err).
-template <int STRIDE = 32>
-PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack, TravSpill& S) {
-  const unsigned hits = T.ngroup.y;
-  const int bit = 31 - __clz(hits);
-  T.ngroup.y &= ~(1u << bit);
-  if (T.ngroup.y > 0x00FFFFFFu) trav_push<STRIDE>(T, sstack, S, T.ngroup);
-  const unsigned slot = (unsigned)(bit - 24) ^ (T.octinv4 & 0xffu);
-  const unsigned rel = __popc(hits & ~(0xFFFFFFFFu << slot));
-  const float4* np = nodes + 5 * (size_t)(T.ngroup.x + rel);
-  const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+// The slab test of one node's 8 quantised child boxes in fp32: returns the hit mask (inner children in [31:24] in traversal
+// order, triangles in [23:0]).  Conservative: the rounding error of the fused evaluation is bounded per axis and folded into the
+// offsets (Bn = B - err, Bf = B + err).
+PBR_D unsigned cw_node_test_f32(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const Trav& T) {
   const unsigned ei = __float_as_uint(n0.w);
-  T.ngroup.x = __float_as_uint(n1.x);
-  T.tgroup.x = __float_as_uint(n1.y);
   // A = 32768 * 2^e / d (exact scalings of 1/d: the factor 2^15 is added to the exponent byte), B = (origin - o) / d
   const float Ax = __uint_as_float(((ei & 0xffu) + 15u) << 23) * T.idx;
   const float Ay = __uint_as_float((((ei >> 8) & 0xffu) + 15u) << 23) * T.idy;
@@ -243,7 +246,121 @@ PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack
     PBR_CW_CHILD(0) PBR_CW_CHILD(1) PBR_CW_CHILD(2) PBR_CW_CHILD(3)
 #undef PBR_CW_CHILD
   }
-  T.ngroup.y = (hitmask & 0xFF000000u) | (ei >> 24);
+  return hitmask;
+}
+
+#if PBR_NODE_HALF2
+// The same test with the 48 slab distances evaluated two children at a time in half precision (HFMA2 / HMNMX2 / HSET2.LE):
+// k_trace is bound by the ALU pipe (PRMT, FMNMX, SEL, LOP3, SHF: one warp instruction per two cycles - scripts/ubench/pipes.cu),
+// and the fp32 test spends 88 ALU instructions per node on byte unpacking and min / max; this one 52.
+//   * Pivot.  Distances are taken relative to tref, the distance at which the ray enters the node's own box (fp32), and scaled
+//     by a power of two sg chosen per node so that the steepest axis' distance per grid unit is in [2^-10, 2^-9): every value
+//     that decides the test is then O(1) or smaller, and the values of the other axes keep 11 significant bits down to 2^-14.
+//   * A byte pair becomes two half DENORMALS q * 2^-24 with ONE PRMT (bytes b0,0,b1,0); the factor 2^24 goes into the slope.
+//   * Conservative.  With u = 2^-11 the half stage commits at most 2u(1+u)(|q a| + |b|) + 3 * 2^-25 (rounding of the slope, of
+//     the offset and of the fused result, each relative or - in the denormal range - absolute); kH = 2.3u and kAbs = 2^-23
+//     cover it (and the fp32 roundings of this function, relative 2^-24 each), on top of the fp32 bound kSlabErr on the
+//     un-pivoted distances.  Offsets that overflow become +-inf (never NaN: slopes and bytes are finite), which compare correctly.
+//     A false positive costs a node visit; a false negative cannot happen.
+//   * Range.  An axis whose distances are more than ~2^12 times smaller than the steepest one's sinks into the absolute error:
+//     the test stays conservative but stops culling along that axis.  Rays with such directions (kTravWideRange, set by
+//     trav_init: 0.15 % of uniformly distributed directions; every ray of an orthographic camera) take the fp32 test.
+// Node exponents are e in [-100, 100] (bvh_build.cpp) and 1/d in [~0.01, 1e24], so the exponent arithmetic below stays in range.
+PBR_D unsigned h2_as_u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
+PBR_D __half2 u_as_h2(unsigned u) { return *reinterpret_cast<__half2*>(&u); }
+PBR_D unsigned h2_le_mask(__half2 a, __half2 b) {  // 0xFFFF per half where a <= b
+  unsigned m;
+  asm("set.le.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(h2_as_u(a)), "r"(h2_as_u(b)));
+  return m;
+}
+PBR_D unsigned cw_node_test_h2(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, const Trav& T) {
+  constexpr float kH = 2.3f * 4.8828125e-4f;   // 2.3 * 2^-11
+  constexpr float kAbs = 1.1920929e-7f;        // 2^-23
+  constexpr float kQ = 255.f * 5.9604645e-8f;  // largest byte as a half denormal: 255 * 2^-24
+  const unsigned ei = __float_as_uint(n0.w);
+  // a = 2^e / d: distance per grid unit;  b = (origin - o) / d: distance of the grid plane 0
+  const float ax = __uint_as_float((ei & 0xffu) << 23) * T.idx;
+  const float ay = __uint_as_float(((ei >> 8) & 0xffu) << 23) * T.idy;
+  const float az = __uint_as_float(((ei >> 16) & 0xffu) << 23) * T.idz;
+  const float bx = (n0.x - T.o.x) * T.idx, by = (n0.y - T.o.y) * T.idy, bz = (n0.z - T.o.z) * T.idz;
+  // pivot: entry distance of the node's own box [0, 255]^3, not below 0
+  const float tref = fmaxf(fmaxf(fminf(bx, fmaf(255.f, ax, bx)), fminf(by, fmaf(255.f, ay, by))), fmaxf(fminf(bz, fmaf(255.f, az, bz)), 0.f));
+  // scale: S = 2^(141 - E) for the steepest slope amax in [2^(E-127), 2^(E-126)), i.e. amax * S in [2^14, 2^15); sg = S * 2^-24
+  const unsigned Eb = __float_as_uint(fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fabsf(az))) & 0x7F800000u;
+  const float S = __uint_as_float(0x86000000u - Eb), sg = __uint_as_float(0x7A000000u - Eb);
+  const float tsg = tref * sg;
+  const float sax = ax * S, say = ay * S, saz = az * S;
+  const float sbx = fmaf(bx, sg, -tsg), sby = fmaf(by, sg, -tsg), sbz = fmaf(bz, sg, -tsg);
+  // error bound per axis: fp32 part kSlabErr (|b| + 512 |a|) sg, half part kH (255 |a| sg + |b'|) + kAbs
+  const float c32 = kSlabErr * sg, ca = (kH * kQ);
+  const float ex = fmaf(c32, fmaf(512.f, fabsf(ax), fabsf(bx)), fmaf(ca, fabsf(sax), fmaf(kH, fabsf(sbx), kAbs)));
+  const float ey = fmaf(c32, fmaf(512.f, fabsf(ay), fabsf(by)), fmaf(ca, fabsf(say), fmaf(kH, fabsf(sby), kAbs)));
+  const float ez = fmaf(c32, fmaf(512.f, fabsf(az), fabsf(bz)), fmaf(ca, fabsf(saz), fmaf(kH, fabsf(sbz), kAbs)));
+  // the ray's own interval [0, tMax] relative to the pivot, rounded outwards
+  const float z0 = fmaf(-tsg, 1.f + kH, -kAbs);
+  const float tm0 = fmaf(T.tMax, sg, -tsg), tm = fmaf(kH, fabsf(tm0), tm0) + kAbs;
+  const __half2 hA0 = __floats2half2_rn(sax, say), hA1 = __floats2half2_rn(saz, z0);
+  const __half2 hN0 = __floats2half2_rn(sbx - ex, sby - ey), hN1 = __floats2half2_rn(sbz - ez, tm);
+  const __half2 hF0 = __floats2half2_rn(sbx + ex, sby + ey), hF1 = __floats2half2_rn(sbz + ez, 0.f);
+  const __half2 AX = __low2half2(hA0), AY = __high2half2(hA0), AZ = __low2half2(hA1), Z0 = __high2half2(hA1);
+  const __half2 BNX = __low2half2(hN0), BNY = __high2half2(hN0), BNZ = __low2half2(hN1), TM = __high2half2(hN1);
+  const __half2 BFX = __low2half2(hF0), BFY = __high2half2(hF0), BFZ = __low2half2(hF1);
+  const bool px = T.idx >= 0.f, py = T.idy >= 0.f, pz = T.idz >= 0.f;
+  unsigned hitmask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const unsigned meta4 = __float_as_uint(h ? n1.w : n1.z);
+    const unsigned isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const unsigned innerMask4 = (isInner4 >> 4) * 0xffu;
+    const unsigned bitIndex4 = meta4 ^ (T.octinv4 & innerMask4);  // bits [4:0] of each byte; the shifts below ignore the rest
+    const unsigned lox = __float_as_uint(h ? n2.y : n2.x), loy = __float_as_uint(h ? n2.w : n2.z);
+    const unsigned loz = __float_as_uint(h ? n3.y : n3.x), hix = __float_as_uint(h ? n3.w : n3.z);
+    const unsigned hiy = __float_as_uint(h ? n4.y : n4.x), hiz = __float_as_uint(h ? n4.w : n4.z);
+    const unsigned nx = px ? lox : hix, fx = px ? hix : lox;
+    const unsigned ny = py ? loy : hiy, fy = py ? hiy : loy;
+    const unsigned nz = pz ? loz : hiz, fz = pz ? hiz : loz;
+    unsigned m[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {  // children (4h + 2p, 4h + 2p + 1)
+      const unsigned sel = p ? 0x4342u : 0x4140u;
+      const __half2 tnx = __hfma2(u_as_h2(__byte_perm(nx, 0u, sel)), AX, BNX), tny = __hfma2(u_as_h2(__byte_perm(ny, 0u, sel)), AY, BNY);
+      const __half2 tnz = __hfma2(u_as_h2(__byte_perm(nz, 0u, sel)), AZ, BNZ);
+      const __half2 tfx = __hfma2(u_as_h2(__byte_perm(fx, 0u, sel)), AX, BFX), tfy = __hfma2(u_as_h2(__byte_perm(fy, 0u, sel)), AY, BFY);
+      const __half2 tfz = __hfma2(u_as_h2(__byte_perm(fz, 0u, sel)), AZ, BFZ);
+      m[p] = h2_le_mask(__hmax2(__hmax2(tnx, tny), __hmax2(tnz, Z0)), __hmin2(__hmin2(tfx, tfy), __hmin2(tfz, TM)));
+    }
+    // 0xFF per hit child, then (childBits & hit) << bitIndex per child
+    const unsigned cb4 = (meta4 >> 5) & 0x07070707u & __byte_perm(m[0], m[1], 0x6420u);
+    // x << (s & 31) as a funnel shift: no masking of the shift amount, so byte J of bitIndex4 only has to be moved down
+#define PBR_CW_CHILD(J) hitmask |= __funnelshift_l(0u, __byte_perm(cb4, 0u, 0x4440u | J), bitIndex4 >> (8 * J));
+    PBR_CW_CHILD(0) PBR_CW_CHILD(1) PBR_CW_CHILD(2) PBR_CW_CHILD(3)
+#undef PBR_CW_CHILD
+  }
+  return hitmask;
+}
+#endif
+
+// One node step: pick the next inner child of the node group (front-to-back by octant), fetch its
+// 80-byte node with five 16-byte loads, slab-test the 8 quantised child boxes, emit a new node group
+// and triangle group.
+template <int STRIDE = 32>
+PBR_D void cw_node_step(const float4* __restrict__ nodes, Trav& T, uint2* sstack, TravSpill& S) {
+  const unsigned hits = T.ngroup.y;
+  const int bit = 31 - __clz(hits);
+  T.ngroup.y &= ~(1u << bit);
+  if (T.ngroup.y > 0x00FFFFFFu) trav_push<STRIDE>(T, sstack, S, T.ngroup);
+  const unsigned slot = (unsigned)(bit - 24) ^ (T.octinv4 & 0xffu);
+  const unsigned rel = __popc(hits & ~(0xFFFFFFFFu << slot));
+  const float4* np = nodes + 5 * (size_t)(T.ngroup.x + rel);
+  const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+  T.ngroup.x = __float_as_uint(n1.x);
+  T.tgroup.x = __float_as_uint(n1.y);
+#if PBR_NODE_HALF2
+  const unsigned hitmask = (T.octinv4 & kTravWideRange) ? cw_node_test_f32(n0, n1, n2, n3, n4, T) : cw_node_test_h2(n0, n1, n2, n3, n4, T);
+#else
+  const unsigned hitmask = cw_node_test_f32(n0, n1, n2, n3, n4, T);
+#endif
+  T.ngroup.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
   T.tgroup.y = hitmask & 0x00FFFFFFu;
 }
 

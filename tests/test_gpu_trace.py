@@ -106,6 +106,34 @@ def test_axis_aligned_and_degenerate_rays(cornell):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
+def test_near_axis_parallel_rays(api, ref, gpu_ctx, kernel):
+    """Directions whose smallest component is 2^-6 .. 2^-16 of the largest: the half-precision box test (trace.cuh
+    cw_node_test_h2) loses range there and hands over to the fp32 test at a ratio of 2^11; hits must not change on either
+    side of the switch, for rays from outside the mesh and for rays that start inside its bounds."""
+    p = Pair(api, ref, scenes.dragon_class(tess=96), 64, 64, 1)
+    rng = np.random.default_rng(11)
+    n = 60_000
+    rays = _random_rays(n, 5)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    small = rng.integers(0, 3, n)
+    ratio = np.exp2(-rng.uniform(6, 16, n)).astype(np.float32)
+    d[np.arange(n), small] = np.abs(d).max(axis=1) * ratio * rng.choice([-1.0, 1.0], n).astype(np.float32)
+    both = rng.random(n) < 0.3  # two small components: the ray runs along one axis
+    d[both, (small[both] + 1) % 3] = np.abs(d[both]).max(axis=1) * ratio[both] * 0.5
+    rays[:, 4:7] = d
+    rays[n // 2:, 0:3] *= 0.3  # origins inside the mesh's bounds
+    want = p.rscene.trace(rays)
+    got = p.scene.trace(rays, via_wave_kernel=kernel == "k_trace")
+    assert (want[:, 0] >= 0).mean() > 0.5
+    assert _compare_hits(got, want) < MAX_MISMATCH
+    rays[:, 3] = rng.uniform(0.05, 3.0, n).astype(np.float32)
+    occ = p.rscene.trace(rays, any_hit=True)
+    assert (occ != p.scene.trace(rays, any_hit=True, via_wave_kernel=kernel == "k_trace")).mean() < MAX_MISMATCH
+    assert 0.02 < occ.mean() < 0.98
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 def test_dragon_class_primary_hits(api, ref, gpu_ctx, kernel):
     # reduced tessellation of the BASELINE config-2 mesh (the full 872 k-triangle mesh: test_gpu_render.py::test_full_size_*)
     p = Pair(api, ref, scenes.dragon_class(tess=96), 192, 108, 2)
