@@ -78,6 +78,22 @@ constexpr int kMaxResolution = 128;  // Halton.cpp:7
 // a run-time prime, so for a < 2^31 (every index of a <= 4096-spp 4K render) the quotient comes from a
 // precomputed multiply-shift (Granlund-Montgomery: exact for all a < 2^31) instead of a hardware-less
 // integer division; larger indices take the plain 64-bit path.  Integer results are identical.
+// indices of 2^31 and more (beyond every BASELINE configuration: 4096 spp at 4K stay below 2^27): plain 64-bit division, out
+// of line - inlined, its division code was ~650 of k_shade<Matte>'s 10 400 instructions, in a kernel that already stalls on
+// instruction fetch
+static __device__ __noinline__ uint64_t reverse_digits_wide(uint64_t a, uint32_t base, float invBase, float* invBaseN, const uint16_t* perm) {
+  uint64_t rev = 0;
+  float ibn = 1;
+  while (a) {
+    uint64_t next = a / base;
+    uint64_t digit = a - next * base;
+    rev = rev * base + (perm ? (uint64_t)perm[digit] : digit);
+    ibn *= invBase;
+    a = next;
+  }
+  *invBaseN = ibn;
+  return rev;
+}
 PBR_D uint64_t reverse_digits(uint64_t a, uint32_t base, uint2 magic, float invBase, float* invBaseN, const uint16_t* perm) {
   uint64_t rev = 0;
   float ibn = 1;
@@ -99,13 +115,7 @@ PBR_D uint64_t reverse_digits(uint64_t a, uint32_t base, uint2 magic, float invB
       ibn *= invBase;
     }
   } else {
-    while (a) {
-      uint64_t next = a / base;
-      uint64_t digit = a - next * base;
-      rev = rev * base + (perm ? (uint64_t)perm[digit] : digit);
-      ibn *= invBase;
-      a = next;
-    }
+    return reverse_digits_wide(a, base, invBase, invBaseN, perm);
   }
   *invBaseN = ibn;
   return rev;
