@@ -402,6 +402,12 @@ def run_gpu(args):
                      "warp_inst_per_ray": ctrs["warp_inst_per_ray"], "thread_inst_per_ray": ctrs["thread_inst_per_ray"],
                      "sm_mhz": sm_hz / 1e6, "source": "instructions per ray: profiles/r02_k_trace_counters.json (ncu, commit "
                      + str(ctrs.get("commit")) + "); rays/s: this run"}
+            if ctrs.get("alu_warp_inst_per_ray"):
+                # the ALU pipe (PRMT, FMNMX, SEL, LOP3, SHF, HMNMX2, HSET2 ...) accepts one warp instruction per TWO cycles per
+                # scheduler (measured: scripts/ubench/pipes.cu), so its ceiling is half the issue rate
+                issue["alu_pipe_util"] = ctrs["alu_warp_inst_per_ray"] * trace_rays_per_s / (sm_hz * sm_count * 4 * 0.5)
+                issue["alu_warp_inst_per_ray"] = ctrs["alu_warp_inst_per_ray"]
+                issue["fma_warp_inst_per_ray"] = ctrs.get("fma_warp_inst_per_ray")
             traffic = ctrs["dram_bytes_per_ray"] * rays_per_launch
             dram_gbs = ctrs["dram_bytes_per_ray"] * trace_rays_per_s / 1e9
             dram = {"achieved_gbs": dram_gbs, "peak_gbs": peak, "frac": dram_gbs / peak}
@@ -435,7 +441,7 @@ def run_gpu(args):
                          "dram": dram, "hbm_read_gbs_measured": hbm_read,
                          "bytes_per_ray": b_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_ms,
-                         "note": "achieved/peak/frac: algorithmic bytes per ray (SURVEY 8(d)) x rays/s against the HBM peak, as the contract asks - but the kernel is NOT HBM bound: the scene (8.5 MB of 8-wide nodes + 42 MB of triangles) is L2-resident, DRAM carries only the ray / hit records, and ncu shows the issue slots as the limiter.  `issue` = warp instructions issued per scheduler cycle and the active lanes per instruction; `l2` = node + triangle bytes per second against the L2 bandwidth measured in this run; `dram` = measured DRAM bytes per ray x rays/s against the HBM peak."},
+                         "note": "achieved/peak/frac: algorithmic bytes per ray (SURVEY 8(d)) x rays/s against the HBM peak, as the contract asks - but the kernel is NOT HBM bound: the scene (8.5 MB of 8-wide nodes + 42 MB of triangles) is L2-resident, DRAM carries only the ray / hit records, and ncu shows the issue slots and, inside them, the half-rate ALU pipe as the limiter.  `issue` = warp instructions issued per scheduler cycle, the active lanes per instruction and the ALU pipe's share of its own ceiling (one warp instruction per two cycles); `l2` = node + triangle bytes per second against the L2 bandwidth measured in this run; `dram` = measured DRAM bytes per ray x rays/s against the HBM peak."},
             "kernel_ms_per_step": {k: tsum[k] / args.steps for k in ("raygen", "closest", "shade", "mis", "film", "total")},
             "bvh": info,
             "scene_build_s": scene_build_s,

@@ -13,7 +13,8 @@ import sys
 
 METRICS = ("smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
            "gpu__time_duration.sum,lts__t_sectors_lookup_hit.sum,lts__t_sectors_lookup_miss.sum,lts__t_bytes.sum,"
-           "l1tex__t_sectors_lookup_hit.sum,l1tex__t_sectors_lookup_miss.sum,smsp__cycles_active.sum,smsp__issue_active.sum")
+           "l1tex__t_sectors_lookup_hit.sum,l1tex__t_sectors_lookup_miss.sum,smsp__cycles_active.sum,smsp__issue_active.sum,"
+           "sm__inst_executed_pipe_alu.sum,sm__inst_executed_pipe_fma.sum,sm__inst_executed_pipe_lsu.sum,sm__inst_executed_pipe_xu.sum")
 
 
 def main():
@@ -49,6 +50,9 @@ def main():
         "warp_inst": g("smsp__inst_executed.sum"), "thread_inst": g("smsp__thread_inst_executed.sum"),
         "warp_inst_per_ray": g("smsp__inst_executed.sum") / rays, "thread_inst_per_ray": g("smsp__thread_inst_executed.sum") / rays,
         "lanes_per_inst": g("smsp__thread_inst_executed.sum") / max(g("smsp__inst_executed.sum"), 1),
+        # warp instructions per ray by execution pipe (the ALU pipe takes one warp instruction per TWO cycles: scripts/ubench/pipes.cu)
+        "alu_warp_inst_per_ray": g("sm__inst_executed_pipe_alu.sum") / rays, "fma_warp_inst_per_ray": g("sm__inst_executed_pipe_fma.sum") / rays,
+        "lsu_warp_inst_per_ray": g("sm__inst_executed_pipe_lsu.sum") / rays, "xu_warp_inst_per_ray": g("sm__inst_executed_pipe_xu.sum") / rays,
         "issue_active_per_cycle_under_ncu": g("smsp__issue_active.sum") / max(g("smsp__cycles_active.sum"), 1),
         "dram_bytes_read": g("dram__bytes_read.sum"), "dram_bytes_write": g("dram__bytes_write.sum"),
         "dram_bytes_per_ray": (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")) / rays,
