@@ -133,6 +133,37 @@ def test_near_axis_parallel_rays(api, ref, gpu_ctx, kernel):
     assert 0.02 < occ.mean() < 0.98
 
 
+@pytest.mark.parametrize("scale,shift", [(1e-3, (0.0, 0.0, 0.0)), (1e3, (0.0, 0.0, 0.0)), (1.0, (3000.0, -2000.0, 1500.0)),
+                                         (0.05, (40.0, 40.0, -40.0))])
+def test_scaled_and_translated_scenes(api, ref, gpu_ctx, scale, shift):
+    """The box test works relative to each node (pivot at the node entry, per-node power-of-two scale): hits must not depend on
+    the size of the scene's coordinates or on its distance from the origin (large |origin - o| / grid unit is where the fp32
+    part of the error bound matters).  A flat, strongly anisotropic mesh (node exponents far apart per axis) is included."""
+    rng = np.random.default_rng(21)
+    s = scenes.SceneData()
+    m = s.add_material(scenes.matte([0.5, 0.5, 0.5]))
+    sh = np.asarray(shift, dtype=np.float64)
+    verts, tris = scenes.uv_sphere((0.0, 0.0, 0.0), lambda T, P: 1.0 + 0.05 * np.sin(9 * T) * np.cos(7 * P), 96, 192)
+    s.add_mesh((verts.astype(np.float64) * scale + sh).astype(np.float32), tris, m)
+    # a 400 x 1 grid of thin quads: long in x, flat in y
+    gx = np.linspace(-2.0, 2.0, 401)
+    strip = np.stack([np.stack([gx, 0.001 * np.sin(40 * gx), np.full_like(gx, z)], axis=1) for z in (-1.6, -1.55)]).reshape(-1, 3)
+    idx = np.arange(400)
+    stris = np.concatenate([np.stack([idx, idx + 1, idx + 401], axis=1), np.stack([idx + 1, idx + 402, idx + 401], axis=1)]).astype(np.int32)
+    s.add_mesh((strip * scale + sh).astype(np.float32), stris, m)
+    s.add_point_light(list(sh + np.array([0.0, 3.0, 0.0]) * scale), [10, 10, 10])
+    p = Pair(api, ref, s, 32, 32, 1, eye=tuple(sh + np.array([0.0, 0.0, 4.0]) * scale), look=tuple(sh))
+    n = 60_000
+    rays = _random_rays(n, 31)
+    rays[:, 0:3] = (rays[:, 0:3].astype(np.float64) * scale + sh).astype(np.float32)
+    aim = (rng.normal(size=(n, 3)) * 0.6 * scale + sh) - rays[:, 0:3]  # aimed at the mesh, so that most rays hit
+    rays[:, 4:7] = (aim / np.linalg.norm(aim, axis=1, keepdims=True)).astype(np.float32)
+    want = p.rscene.trace(rays)
+    assert (want[:, 0] >= 0).mean() > 0.3
+    for via in (False, True):
+        assert _compare_hits(p.scene.trace(rays, via_wave_kernel=via), want) < MAX_MISMATCH
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_dragon_class_primary_hits(api, ref, gpu_ctx, kernel):
     # reduced tessellation of the BASELINE config-2 mesh (the full 872 k-triangle mesh: test_gpu_render.py::test_full_size_*)
