@@ -55,7 +55,8 @@ typedef struct pbrgpu_material {
   float kd[3];
   float v_rough;
   float kr[3];
-  float pad0;
+  int32_t ks_texture_plus1; /* Plastic: Ks comes from textures[ks_texture_plus1 - 1] instead of kr (Main/main.cpp:63-77 builds its
+                               Plastic with ONE ImageTexture as Kd and Ks); 0 = ConstantTexture(kr).  Was padding: zero-filled records keep their meaning */
   float kt[3];
   int32_t kd_texture_plus1; /* Matte / Plastic: Kd comes from textures[kd_texture_plus1 - 1] (an ImageTexture) instead of kd;
                                0 = ConstantTexture(kd) */
@@ -151,7 +152,7 @@ typedef struct pbrgpu_scene_desc {
   const pbrgpu_medium* media;
   const int32_t* tri_medium_inside;  /* n_tris: index into media or -1 (MediumInterface::inside);  NULL = none */
   const int32_t* tri_medium_outside; /* n_tris: index into media or -1 (MediumInterface::outside); NULL = none */
-  /* image textures referenced by pbrgpu_material::kd_texture_plus1 */
+  /* image textures referenced by pbrgpu_material::kd_texture_plus1 / ks_texture_plus1 */
   int32_t n_textures;
   int32_t pad1;
   const pbrgpu_texture* textures;

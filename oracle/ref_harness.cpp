@@ -148,6 +148,9 @@ std::shared_ptr<Texture<Spectrum>> makeImageTexture(const pbrgpu_texture& t) {
 std::shared_ptr<Material> makeMaterial(const pbrgpu_material& m, const pbrgpu_scene_desc* d) {
   auto bump = ftex(0.f);
   std::shared_ptr<Texture<Spectrum>> kd = m.kd_texture_plus1 > 0 ? makeImageTexture(d->textures[m.kd_texture_plus1 - 1]) : nullptr;
+  // Ks of a Plastic: the SAME texture object when it names the same texture (Main/main.cpp:63-77 passes one ImageTexture twice)
+  std::shared_ptr<Texture<Spectrum>> ks = m.ks_texture_plus1 > 0
+      ? (m.ks_texture_plus1 == m.kd_texture_plus1 ? kd : makeImageTexture(d->textures[m.ks_texture_plus1 - 1])) : nullptr;
   switch (m.type) {
     case PBRGPU_MAT_MATTE: return std::make_shared<MatteMaterial>(kd ? kd : ctex(m.kd), ftex(m.sigma), bump);
     case PBRGPU_MAT_MIRROR: return std::make_shared<MirrorMaterial>(ctex(m.kr), bump);
@@ -158,7 +161,7 @@ std::shared_ptr<Material> makeMaterial(const pbrgpu_material& m, const pbrgpu_sc
       return std::make_shared<MetalMaterial>(ctex(m.eta), ctex(m.k), ftex(m.u_rough), ftex(m.u_rough),
                                              ftex(m.v_rough), bump, m.remap_roughness != 0);
     case PBRGPU_MAT_PLASTIC:
-      return std::make_shared<PlasticMaterial>(kd ? kd : ctex(m.kd), ctex(m.kr), ftex(m.u_rough), bump,
+      return std::make_shared<PlasticMaterial>(kd ? kd : ctex(m.kd), ks ? ks : ctex(m.kr), ftex(m.u_rough), bump,
                                                m.remap_roughness != 0);
   }
   return nullptr;

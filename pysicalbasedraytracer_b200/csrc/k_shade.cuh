@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
       bool alive = bounce < P.maxDepth;
       if (alive) {
         Bsdf bsdf;
-        Spec kdTex;
-        bool haveKdTex = false;
+        Spec kdTex, ksTex;
+        bool haveKdTex = false, haveKsTex = false;
         if (TEX && (MAT == PBRGPU_MAT_MATTE || MAT == PBRGPU_MAT_PLASTIC)) {
           const pbrgpu_material& m = sc.mats[is.matId];
           if (m.kd_texture_plus1 > 0) {
@@ -79,12 +79,19 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
             // camera rays included.  The differential code stays reachable through PBRGPU_DUMP_HIT_DIFFERENTIALS, where it is
             // checked against the reference's ComputeDifferentials called on the real RayDifferential.
             const bool cameraRay = false;
-            kdTex = eval_kd_texture(P, m, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, cameraRay, slot, cur.index,
-                                    V3(ro4.x, ro4.y, ro4.z), rayD);
+            kdTex = eval_image_texture(P, m.kd_texture_plus1, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, cameraRay, slot, cur.index,
+                                       V3(ro4.x, ro4.y, ro4.z), rayD);
             haveKdTex = true;
           }
+          if (MAT == PBRGPU_MAT_PLASTIC && m.ks_texture_plus1 > 0) {  // Ks->Evaluate(*si): the same lookup when Kd and Ks share the texture
+            const float4 ro4 = rec.o;
+            ksTex = (haveKdTex && m.ks_texture_plus1 == m.kd_texture_plus1) ? kdTex
+                    : eval_image_texture(P, m.ks_texture_plus1, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index,
+                                         V3(ro4.x, ro4.y, ro4.z), rayD);
+            haveKsTex = true;
+          }
         }
-        make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf, haveKdTex ? &kdTex : nullptr);
+        make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf, haveKdTex ? &kdTex : nullptr, haveKsTex ? &ksTex : nullptr);
         const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
         if ((VOL || bsdf_num_components<MAT>(bsdf, nonSpec) > 0) && sc.nLights > 0) {
           // UniformSampleOneLight (Integrator.cpp:46-69)

@@ -98,16 +98,21 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
         if (!Le.is_black()) { atomicAdd(&P.ws.L[slot].x, Le.r); atomicAdd(&P.ws.L[slot].y, Le.g); atomicAdd(&P.ws.L[slot].z, Le.b); }
       }
       Bsdf bsdf;
-      Spec kdTex;
-      bool haveKdTex = false;
+      Spec kdTex, ksTex;
+      bool haveKdTex = false, haveKsTex = false;
       if (TEX && (MAT == PBRGPU_MAT_MATTE || MAT == PBRGPU_MAT_PLASTIC)) {
         const pbrgpu_material& m = sc.mats[is.matId];
         if (m.kd_texture_plus1 > 0) {  // zero derivatives, like every lookup of the reference (see k_shade)
-          kdTex = eval_kd_texture(P, m, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index, V3(0, 0, 0), rayD);
+          kdTex = eval_image_texture(P, m.kd_texture_plus1, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index, V3(0, 0, 0), rayD);
           haveKdTex = true;
         }
+        if (MAT == PBRGPU_MAT_PLASTIC && m.ks_texture_plus1 > 0) {
+          ksTex = (haveKdTex && m.ks_texture_plus1 == m.kd_texture_plus1) ? kdTex
+                  : eval_image_texture(P, m.ks_texture_plus1, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index, V3(0, 0, 0), rayD);
+          haveKsTex = true;
+        }
       }
-      make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/false, &bsdf, haveKdTex ? &kdTex : nullptr);
+      make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/false, &bsdf, haveKdTex ? &kdTex : nullptr, haveKsTex ? &ksTex : nullptr);
       if (P.integrator == PBRGPU_INTEGRATOR_WHITTED) {
         for (int j = 0; j < sc.nLights; ++j) {
           float u0, u1;

@@ -119,14 +119,15 @@ PBR_D void hit_uv_differentials(const RenderParams& P, const TriData& tri, int t
   }
 }
 
-PBR_D Spec eval_kd_texture(const RenderParams& P, const pbrgpu_material& m, const TriData& tri, int triId, float b0, float b1, float b2,
-                           const Isect& is, bool cameraRay, uint32_t slot, int64_t index, V3 rayO, V3 rayD) {
+// texPlus1: pbrgpu_material::kd_texture_plus1 or ::ks_texture_plus1 (> 0)
+PBR_D Spec eval_image_texture(const RenderParams& P, int texPlus1, const TriData& tri, int triId, float b0, float b1, float b2,
+                              const Isect& is, bool cameraRay, uint32_t slot, int64_t index, V3 rayO, V3 rayD) {
   int px, py; long long sIdx; uint32_t pix;
   slot_to_pixel(P, slot, &px, &py, &sIdx, &pix);
   float u, v;
   UvDiff dd;
   hit_uv_differentials(P, tri, triId, b0, b1, b2, is.p, is.n, cameraRay, px, py, index, rayO, rayD, &u, &v, &dd);
-  return tex_evaluate(P.sc.textures[m.kd_texture_plus1 - 1], P.sc.ewaLut, u, v, dd);
+  return tex_evaluate(P.sc.textures[texPlus1 - 1], P.sc.ewaLut, u, v, dd);
 }
 
 // warp-aggregated append: one atomicAdd per (warp, queue)

@@ -180,9 +180,11 @@ PBR_D Lobe make_lobe(int kind, int flags, Spec R) {
 
 // Material::ComputeScatteringFunctions for the five materials.  `mats[...]` roughness values were
 // already passed through RoughnessToAlpha on the host when remap_roughness was set (Microfacet.h:78-83).
-// kdTex: Kd->Evaluate(si) of an ImageTexture (Matte / Plastic), or NULL for the ConstantTexture in the material record.
+// kdTex / ksTex: Kd->Evaluate(si) (Matte / Plastic) / Ks->Evaluate(si) (Plastic) of an ImageTexture, or NULL for the ConstantTexture in
+// the material record.
 template <int MAT>
-PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobes, Bsdf* b, const Spec* kdTex = nullptr) {
+PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobes, Bsdf* b, const Spec* kdTex = nullptr,
+                     const Spec* ksTex = nullptr) {
   const pbrgpu_material& m = sc.mats[is.matId];
   b->eta = 1.f;
   b->ns = is.ns;
@@ -219,7 +221,7 @@ PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobe
       Spec T = spec_clamp0(Spec(m.kt[0], m.kt[1], m.kt[2]));
       b->eta = eta;
       if (R.is_black() && T.is_black()) break;
-      bool isSpecular = (m.pad0 != 0.f);  // host: original urough == 0 && vrough == 0 (before remapping)
+      bool isSpecular = (m.pad2 != 0.f);  // host: original urough == 0 && vrough == 0 (before remapping)
       if (isSpecular && allowMultipleLobes) {
         Lobe l = make_lobe(LOBE_FRESNEL_SPEC, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR, R);
         l.T = T; l.etaA = 1.f; l.etaB = eta;
@@ -254,7 +256,7 @@ PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobe
     case PBRGPU_MAT_PLASTIC: {
       Spec kd = spec_clamp0(kdTex ? *kdTex : Spec(m.kd[0], m.kd[1], m.kd[2]));
       if (!kd.is_black()) b->lobes[b->n++] = make_lobe(LOBE_LAMBERT, BSDF_REFLECTION | BSDF_DIFFUSE, kd);
-      Spec ks = spec_clamp0(Spec(m.kr[0], m.kr[1], m.kr[2]));
+      Spec ks = spec_clamp0(ksTex ? *ksTex : Spec(m.kr[0], m.kr[1], m.kr[2]));
       if (!ks.is_black()) {
         Lobe l = make_lobe(LOBE_MICRO_REFL, BSDF_REFLECTION | BSDF_GLOSSY, ks);
         l.fresnel = FR_DIELECTRIC; l.frEtaI = 1.5f; l.frEtaT = 1.f;

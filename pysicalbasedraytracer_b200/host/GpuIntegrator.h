@@ -114,9 +114,10 @@ inline bool constFloat(const std::shared_ptr<Texture<float>>& t, float* out, std
 
 // Kd of Matte / Plastic: a ConstantTexture, or an ImageTexture<RGBSpectrum, Spectrum> with a UVMapping2D whose MIPMap level 0
 // (already converted by ImageTexture::convertIn) becomes a pbrgpu_texture
-inline bool flattenKd(const std::shared_ptr<Texture<Spectrum>>& t, pbrgpu_material* o, Flat* f) {
+// A spectrum texture of a material: a ConstantTexture goes to `rgb`, an ImageTexture to the texture table and `*texPlus1`
+inline bool flattenSpectrumTexture(const std::shared_ptr<Texture<Spectrum>>& t, float rgb[3], int32_t* texPlus1, Flat* f) {
   auto* img = dynamic_cast<const ImageTexture<RGBSpectrum, Spectrum>*>(t.get());
-  if (!img) return constSpectrum(t, o->kd, &f->error);
+  if (!img) return constSpectrum(t, rgb, &f->error);
   auto it = f->textureId.find(img);
   if (it == f->textureId.end()) {
     auto* map = dynamic_cast<const UVMapping2D*>(img->mapping.get());
@@ -141,8 +142,11 @@ inline bool flattenKd(const std::shared_ptr<Texture<Spectrum>>& t, pbrgpu_materi
     it = f->textureId.emplace(img, (int)f->textures.size()).first;
     f->textures.push_back(pt);  // .texels is filled in once texelStore stops growing (flattenScene's caller)
   }
-  o->kd_texture_plus1 = it->second + 1;
+  *texPlus1 = it->second + 1;
   return true;
+}
+inline bool flattenKd(const std::shared_ptr<Texture<Spectrum>>& t, pbrgpu_material* o, Flat* f) {
+  return flattenSpectrumTexture(t, o->kd, &o->kd_texture_plus1, f);
 }
 
 inline bool flattenMaterial(const Material* m, pbrgpu_material* o, Flat* f) {
@@ -178,7 +182,7 @@ inline bool flattenMaterial(const Material* m, pbrgpu_material* o, Flat* f) {
   if (auto* p = dynamic_cast<const PlasticMaterial*>(m)) {
     o->type = PBRGPU_MAT_PLASTIC;
     o->remap_roughness = p->remapRoughness ? 1 : 0;
-    bool ok = flattenKd(p->Kd, o, f) && constSpectrum(p->Ks, o->kr, err) && constFloat(p->roughness, &o->u_rough, err);
+    bool ok = flattenKd(p->Kd, o, f) && flattenSpectrumTexture(p->Ks, o->kr, &o->ks_texture_plus1, f) && constFloat(p->roughness, &o->u_rough, err);
     o->v_rough = o->u_rough;
     return ok;
   }

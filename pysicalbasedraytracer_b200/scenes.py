@@ -37,9 +37,10 @@ def metal(eta, k, u_rough, v_rough, remap=False):
                       remap_roughness=int(remap))
 
 
-def plastic(kd, ks, rough, remap=True, kd_texture=None):
+def plastic(kd, ks, rough, remap=True, kd_texture=None, ks_texture=None):
     return A.Material(type=A.MAT_PLASTIC, kd=_f3(kd), kr=_f3(ks), u_rough=rough, v_rough=rough,
-                      remap_roughness=int(remap), kd_texture_plus1=0 if kd_texture is None else kd_texture + 1)
+                      remap_roughness=int(remap), kd_texture_plus1=0 if kd_texture is None else kd_texture + 1,
+                      ks_texture_plus1=0 if ks_texture is None else ks_texture + 1)
 
 
 class SceneData:

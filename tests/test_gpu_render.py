@@ -599,7 +599,9 @@ def _textured_scene(variant):
     white = s.add_material(scenes.matte([1, 1, 1], kd_texture=t0))
     red = s.add_material(scenes.matte([0.9, 0.1, 0.17]))
     blue = s.add_material(scenes.matte([0.14, 0.21, 0.87], sigma=20.0, kd_texture=t1))
-    plast = s.add_material(scenes.plastic([0.3, 0.3, 0.3], [0.5, 0.5, 0.5], 0.1, kd_texture=t1))
+    # Ks of the Plastic: the same ImageTexture as Kd (what Main/main.cpp:63-77 builds), a different one, or a constant
+    ks_tex = dict(ewa_repeat=t1, trilinear_clamp=t0, ewa_black=None)[variant]
+    plast = s.add_material(scenes.plastic([0.3, 0.3, 0.3], [0.5, 0.5, 0.5], 0.1, kd_texture=t1, ks_texture=ks_tex))
     mir = s.add_material(scenes.mirror([0.9, 0.9, 0.9]))
     lightmat = s.add_material(scenes.matte([1, 1, 1]))
     scenes.cornell_walls(s, white, red, blue)   # no mesh uvs: every triangle gets (0,0),(1,0),(1,1)  (Triangle.h:50-54)
@@ -680,6 +682,19 @@ def test_image_texture_error_behaviour(api, gpu_ctx):
     scenes.cornell_walls(bad3, m, m, m)
     with pytest.raises(api.PbrGpuError, match="Matte and Plastic"):
         api.Scene(bad3)
+    bad4 = scenes.SceneData()
+    t = bad4.add_texture(np.zeros((8, 8, 3), dtype=np.float32))
+    mm = scenes.matte([1, 1, 1])
+    mm.ks_texture_plus1 = t + 1
+    m = bad4.add_material(mm)
+    scenes.cornell_walls(bad4, m, m, m)
+    with pytest.raises(api.PbrGpuError, match="Ks image texture"):
+        api.Scene(bad4)
+    bad5 = scenes.SceneData()
+    m = bad5.add_material(scenes.plastic([1, 1, 1], [1, 1, 1], 0.1, ks_texture=2))
+    scenes.cornell_walls(bad5, m, m, m)
+    with pytest.raises(api.PbrGpuError, match="ks_texture"):
+        api.Scene(bad5)
 
 
 def test_hit_differentials(api, ref, gpu_ctx):
@@ -722,10 +737,12 @@ def test_texture_lookup_known_answers(api, ref, gpu_ctx, variant):
         assert np.isfinite(got).all() and (err <= 1e-4).mean() >= 0.999 and err.max() < 5e-2
 
 
-def test_cpp_dropin_with_image_textures(api, ref, gpu_ctx):
+@pytest.mark.parametrize("variant", ["ewa_black", "ewa_repeat"])
+def test_cpp_dropin_with_image_textures(api, ref, gpu_ctx, variant):
     """GpuPathIntegrator's flattener reads ImageTexture objects (MIPMap level 0, filter settings, UVMapping2D) out of the
-    reference's materials; the FrameBuffer matches the reference's own PathIntegrator::Render."""
-    data = _textured_scene("ewa_black")
+    reference's materials; the FrameBuffer matches the reference's own PathIntegrator::Render.  "ewa_repeat": the Plastic takes
+    ONE ImageTexture object as Kd and Ks, the way Main/main.cpp:63-77 builds its material (one entry in the texture table)."""
+    data = _textured_scene(variant)
     rsc = ref.RefScene(data)
     rc = ref.RefCamera(A.CAMERA_PERSPECTIVE, 64, 64, (0, 0, 5), (0, 0, 0), (0, 1, 0))
     rgba, _, sec = ref.gpu_dropin_render(rsc, rc, 2, 64, 64, 4, 0.8, "uniform")
