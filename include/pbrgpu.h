@@ -61,7 +61,10 @@ typedef struct pbrgpu_material {
   int32_t kd_texture_plus1; /* Matte / Plastic: Kd comes from textures[kd_texture_plus1 - 1] (an ImageTexture) instead of kd;
                                0 = ConstantTexture(kd) */
   float eta[3]; /* Metal eta (RGB); Glass index of refraction in eta[0] */
-  float pad2;
+  int32_t rough_texture_plus1; /* Plastic with remap_roughness == 0: roughness comes from the first channel of
+                                  textures[rough_texture_plus1 - 1] - an ImageTexture<float, float> (Shape/ModelLoad.cpp:147-164 builds its
+                                  Plastic that way); the caller passes the float texels of its MIPMap replicated in R, G, B.
+                                  0 = ConstantTexture(u_rough).  Was padding */
   float k[3]; /* Metal absorption */
   float pad3;
 } pbrgpu_material; /* 96 bytes */

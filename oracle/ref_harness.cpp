@@ -145,6 +145,21 @@ std::shared_ptr<Texture<Spectrum>> makeImageTexture(const pbrgpu_texture& t) {
   return tex;
 }
 
+// ImageTexture<float, float> over the first channel of the caller's texels (same construction)
+std::shared_ptr<Texture<float>> makeFloatImageTexture(const pbrgpu_texture& t) {
+  static std::atomic<int> counter{0};
+  std::unique_ptr<TextureMapping2D> map(new UVMapping2D(t.su, t.sv, t.du, t.dv));
+  const std::string name = "/nonexistent/pbr_ref_float_texture_" + std::to_string(counter++);
+  const ImageWrap wrap = t.wrap == PBRGPU_WRAP_CLAMP ? ImageWrap::Clamp : (t.wrap == PBRGPU_WRAP_BLACK ? ImageWrap::Black : ImageWrap::Repeat);
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  auto tex = std::make_shared<ImageTexture<float, float>>(std::move(map), name, t.do_trilinear != 0, t.max_anisotropy, wrap, 1.f, false);
+  std::cerr.rdbuf(old);
+  std::vector<float> texels((size_t)t.width * t.height);
+  for (size_t k = 0; k < texels.size(); ++k) texels[k] = t.texels[3 * k];
+  tex->mipmap = new MIPMap<float>(Point2i(t.width, t.height), texels.data(), t.do_trilinear != 0, t.max_anisotropy, wrap);
+  return tex;
+}
+
 std::shared_ptr<Material> makeMaterial(const pbrgpu_material& m, const pbrgpu_scene_desc* d) {
   auto bump = ftex(0.f);
   std::shared_ptr<Texture<Spectrum>> kd = m.kd_texture_plus1 > 0 ? makeImageTexture(d->textures[m.kd_texture_plus1 - 1]) : nullptr;
@@ -161,7 +176,8 @@ std::shared_ptr<Material> makeMaterial(const pbrgpu_material& m, const pbrgpu_sc
       return std::make_shared<MetalMaterial>(ctex(m.eta), ctex(m.k), ftex(m.u_rough), ftex(m.u_rough),
                                              ftex(m.v_rough), bump, m.remap_roughness != 0);
     case PBRGPU_MAT_PLASTIC:
-      return std::make_shared<PlasticMaterial>(kd ? kd : ctex(m.kd), ks ? ks : ctex(m.kr), ftex(m.u_rough), bump,
+      return std::make_shared<PlasticMaterial>(kd ? kd : ctex(m.kd), ks ? ks : ctex(m.kr),
+                                               m.rough_texture_plus1 > 0 ? makeFloatImageTexture(d->textures[m.rough_texture_plus1 - 1]) : ftex(m.u_rough), bump,
                                                m.remap_roughness != 0);
   }
   return nullptr;

@@ -19,7 +19,7 @@ f16 = C.c_float * 16
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("remap_roughness", C.c_int32), ("sigma", C.c_float), ("u_rough", C.c_float),
                 ("kd", f3), ("v_rough", C.c_float), ("kr", f3), ("ks_texture_plus1", C.c_int32), ("kt", f3), ("kd_texture_plus1", C.c_int32),
-                ("eta", f3), ("pad2", C.c_float), ("k", f3), ("pad3", C.c_float)]
+                ("eta", f3), ("rough_texture_plus1", C.c_int32), ("k", f3), ("pad3", C.c_float)]
 
 
 class Light(C.Structure):

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
       if (alive) {
         Bsdf bsdf;
         Spec kdTex, ksTex;
-        bool haveKdTex = false, haveKsTex = false;
+        float roughTex = 0.f;
+        bool haveKdTex = false, haveKsTex = false, haveRoughTex = false;
         if (TEX && (MAT == PBRGPU_MAT_MATTE || MAT == PBRGPU_MAT_PLASTIC)) {
           const pbrgpu_material& m = sc.mats[is.matId];
           if (m.kd_texture_plus1 > 0) {
@@ -90,8 +91,15 @@ __global__ void __launch_bounds__(kShadeBlock, PBR_SHADE_MIN_BLOCKS) k_shade(con
                                          V3(ro4.x, ro4.y, ro4.z), rayD);
             haveKsTex = true;
           }
+          if (MAT == PBRGPU_MAT_PLASTIC && m.rough_texture_plus1 > 0) {  // ImageTexture<float, float>: first channel
+            const float4 ro4 = rec.o;
+            roughTex = eval_image_texture(P, m.rough_texture_plus1, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index,
+                                          V3(ro4.x, ro4.y, ro4.z), rayD).r;
+            haveRoughTex = true;
+          }
         }
-        make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf, haveKdTex ? &kdTex : nullptr, haveKsTex ? &ksTex : nullptr);
+        make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/true, &bsdf, haveKdTex ? &kdTex : nullptr, haveKsTex ? &ksTex : nullptr,
+                       haveRoughTex ? &roughTex : nullptr);
         const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
         if ((VOL || bsdf_num_components<MAT>(bsdf, nonSpec) > 0) && sc.nLights > 0) {
           // UniformSampleOneLight (Integrator.cpp:46-69)

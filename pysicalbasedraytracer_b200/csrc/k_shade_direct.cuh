@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
       }
       Bsdf bsdf;
       Spec kdTex, ksTex;
-      bool haveKdTex = false, haveKsTex = false;
+      float roughTex = 0.f;
+      bool haveKdTex = false, haveKsTex = false, haveRoughTex = false;
       if (TEX && (MAT == PBRGPU_MAT_MATTE || MAT == PBRGPU_MAT_PLASTIC)) {
         const pbrgpu_material& m = sc.mats[is.matId];
         if (m.kd_texture_plus1 > 0) {  // zero derivatives, like every lookup of the reference (see k_shade)
@@ -111,8 +112,13 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct(const __grid_constant__
                   : eval_image_texture(P, m.ks_texture_plus1, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index, V3(0, 0, 0), rayD);
           haveKsTex = true;
         }
+        if (MAT == PBRGPU_MAT_PLASTIC && m.rough_texture_plus1 > 0) {
+          roughTex = eval_image_texture(P, m.rough_texture_plus1, tri, __float_as_int(h4.x), h4.y, h4.z, h4.w, is, false, slot, cur.index, V3(0, 0, 0), rayD).r;
+          haveRoughTex = true;
+        }
       }
-      make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/false, &bsdf, haveKdTex ? &kdTex : nullptr, haveKsTex ? &ksTex : nullptr);
+      make_bsdf<MAT>(sc, is, /*allowMultipleLobes=*/false, &bsdf, haveKdTex ? &kdTex : nullptr, haveKsTex ? &ksTex : nullptr,
+                     haveRoughTex ? &roughTex : nullptr);
       if (P.integrator == PBRGPU_INTEGRATOR_WHITTED) {
         for (int j = 0; j < sc.nLights; ++j) {
           float u0, u1;

@@ -427,7 +427,8 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     if (!(sp.radius > 0)) return fail("pbrgpu_scene_create: sphere radius must be positive");
     if (sp.material < 0 || sp.material >= d->n_materials) return fail("pbrgpu_scene_create: sphere material out of range");
     if (sp.light >= d->n_lights) return fail("pbrgpu_scene_create: sphere light out of range");
-    if (d->materials[sp.material].kd_texture_plus1 > 0 || d->materials[sp.material].ks_texture_plus1 > 0) return fail("pbrgpu_scene_create: image textures on analytic spheres are not supported");
+    if (d->materials[sp.material].kd_texture_plus1 > 0 || d->materials[sp.material].ks_texture_plus1 > 0 ||
+        d->materials[sp.material].rough_texture_plus1 > 0) return fail("pbrgpu_scene_create: image textures on analytic spheres are not supported");
   }
   if (d->n_tris >= (1 << 29)) return fail("pbrgpu_scene_create: too many triangles");
   if (d->n_materials < 0 || d->n_materials > (int)kTriMatMask || (d->n_materials > 0 && !d->materials))
@@ -576,7 +577,7 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
   for (auto& m : mats) {
     if (m.type < 0 || m.type >= PBRGPU_MAT_COUNT) return fail("pbrgpu_scene_create: unknown material type");
     s->hasMat[m.type] = true;
-    m.pad2 = (m.type == PBRGPU_MAT_GLASS && m.u_rough == 0 && m.v_rough == 0) ? 1.f : 0.f;  // isSpecular (device copy only)
+    m.pad3 = (m.type == PBRGPU_MAT_GLASS && m.u_rough == 0 && m.v_rough == 0) ? 1.f : 0.f;  // isSpecular (device copy only)
     if (m.remap_roughness && m.type != PBRGPU_MAT_MATTE && m.type != PBRGPU_MAT_MIRROR) {
       m.u_rough = host::roughness_to_alpha(m.u_rough);
       m.v_rough = host::roughness_to_alpha(m.v_rough);
@@ -595,6 +596,13 @@ static int scene_create_single(pbrgpu_ctx* ctx, const pbrgpu_scene_desc* d, cons
     if (m.ks_texture_plus1 < 0 || m.ks_texture_plus1 > d->n_textures) return fail("pbrgpu_scene_create: ks_texture_plus1 out of range");
     if (m.ks_texture_plus1 > 0) {
       if (m.type != PBRGPU_MAT_PLASTIC) return fail("pbrgpu_scene_create: a Ks image texture is supported for Plastic materials only");
+      s->hasTextures = true;
+    }
+    if (m.rough_texture_plus1 < 0 || m.rough_texture_plus1 > d->n_textures) return fail("pbrgpu_scene_create: rough_texture_plus1 out of range");
+    if (m.rough_texture_plus1 > 0) {
+      if (m.type != PBRGPU_MAT_PLASTIC) return fail("pbrgpu_scene_create: a roughness image texture is supported for Plastic materials only");
+      // RoughnessToAlpha of a constant is evaluated on the host with glibc's logf (above); per hit it would be the device's logf
+      if (m.remap_roughness) return fail("pbrgpu_scene_create: a roughness image texture needs remap_roughness == 0");
       s->hasTextures = true;
     }
   }

@@ -180,11 +180,11 @@ PBR_D Lobe make_lobe(int kind, int flags, Spec R) {
 
 // Material::ComputeScatteringFunctions for the five materials.  `mats[...]` roughness values were
 // already passed through RoughnessToAlpha on the host when remap_roughness was set (Microfacet.h:78-83).
-// kdTex / ksTex: Kd->Evaluate(si) (Matte / Plastic) / Ks->Evaluate(si) (Plastic) of an ImageTexture, or NULL for the ConstantTexture in
-// the material record.
+// kdTex / ksTex / roughTex: Kd->Evaluate(si) (Matte / Plastic), Ks->Evaluate(si) and roughness->Evaluate(si) (Plastic) of an
+// ImageTexture, or NULL for the ConstantTexture in the material record.
 template <int MAT>
 PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobes, Bsdf* b, const Spec* kdTex = nullptr,
-                     const Spec* ksTex = nullptr) {
+                     const Spec* ksTex = nullptr, const float* roughTex = nullptr) {
   const pbrgpu_material& m = sc.mats[is.matId];
   b->eta = 1.f;
   b->ns = is.ns;
@@ -221,7 +221,7 @@ PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobe
       Spec T = spec_clamp0(Spec(m.kt[0], m.kt[1], m.kt[2]));
       b->eta = eta;
       if (R.is_black() && T.is_black()) break;
-      bool isSpecular = (m.pad2 != 0.f);  // host: original urough == 0 && vrough == 0 (before remapping)
+      bool isSpecular = (m.pad3 != 0.f);  // host: original urough == 0 && vrough == 0 (before remapping)
       if (isSpecular && allowMultipleLobes) {
         Lobe l = make_lobe(LOBE_FRESNEL_SPEC, BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR, R);
         l.T = T; l.etaA = 1.f; l.etaB = eta;
@@ -260,7 +260,8 @@ PBR_D void make_bsdf(const SceneDev& sc, const Isect& is, bool allowMultipleLobe
       if (!ks.is_black()) {
         Lobe l = make_lobe(LOBE_MICRO_REFL, BSDF_REFLECTION | BSDF_GLOSSY, ks);
         l.fresnel = FR_DIELECTRIC; l.frEtaI = 1.5f; l.frEtaT = 1.f;
-        l.alphax = stdmax(0.001f, m.u_rough); l.alphay = stdmax(0.001f, m.u_rough);
+        const float rough = roughTex ? *roughTex : m.u_rough;  // roughness->Evaluate(*si) (PlasticMaterial.cpp:21; remap on the host)
+        l.alphax = stdmax(0.001f, rough); l.alphay = stdmax(0.001f, rough);
         b->lobes[b->n++] = l;
       }
       break;

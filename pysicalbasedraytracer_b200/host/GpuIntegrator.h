@@ -145,6 +145,37 @@ inline bool flattenSpectrumTexture(const std::shared_ptr<Texture<Spectrum>>& t, 
   *texPlus1 = it->second + 1;
   return true;
 }
+// A float texture of a material: a ConstantTexture goes to `*value`, an ImageTexture<float, float> to the texture table with its
+// float texels replicated in R, G, B (the device reads the first channel)
+inline bool flattenFloatTexture(const std::shared_ptr<Texture<float>>& t, float* value, int32_t* texPlus1, Flat* f) {
+  auto* img = dynamic_cast<const ImageTexture<float, float>*>(t.get());
+  if (!img) return constFloat(t, value, &f->error);
+  auto it = f->textureId.find(img);
+  if (it == f->textureId.end()) {
+    auto* map = dynamic_cast<const UVMapping2D*>(img->mapping.get());
+    if (!map) { f->error = "ImageTexture with a mapping other than UVMapping2D"; return false; }
+    const MIPMap<float>* mm = img->mipmap;
+    const auto& lvl0 = *mm->pyramid[0];
+    pbrgpu_texture pt;
+    std::memset(&pt, 0, sizeof(pt));
+    pt.width = lvl0.uSize(); pt.height = lvl0.vSize();
+    pt.do_trilinear = mm->doTrilinear ? 1 : 0;
+    pt.max_anisotropy = mm->maxAnisotropy;
+    pt.wrap = mm->wrapMode == ImageWrap::Clamp ? PBRGPU_WRAP_CLAMP : (mm->wrapMode == ImageWrap::Black ? PBRGPU_WRAP_BLACK : PBRGPU_WRAP_REPEAT);
+    pt.su = map->su; pt.sv = map->sv; pt.du = map->du; pt.dv = map->dv;
+    f->texelStore.emplace_back((size_t)pt.width * pt.height * 3);
+    std::vector<float>& tx = f->texelStore.back();
+    for (int v = 0; v < pt.height; ++v)
+      for (int u = 0; u < pt.width; ++u) {
+        float* d = &tx[3 * ((size_t)v * pt.width + u)];
+        d[0] = d[1] = d[2] = lvl0(u, v);
+      }
+    it = f->textureId.emplace(img, (int)f->textures.size()).first;
+    f->textures.push_back(pt);
+  }
+  *texPlus1 = it->second + 1;
+  return true;
+}
 inline bool flattenKd(const std::shared_ptr<Texture<Spectrum>>& t, pbrgpu_material* o, Flat* f) {
   return flattenSpectrumTexture(t, o->kd, &o->kd_texture_plus1, f);
 }
@@ -182,7 +213,9 @@ inline bool flattenMaterial(const Material* m, pbrgpu_material* o, Flat* f) {
   if (auto* p = dynamic_cast<const PlasticMaterial*>(m)) {
     o->type = PBRGPU_MAT_PLASTIC;
     o->remap_roughness = p->remapRoughness ? 1 : 0;
-    bool ok = flattenKd(p->Kd, o, f) && flattenSpectrumTexture(p->Ks, o->kr, &o->ks_texture_plus1, f) && constFloat(p->roughness, &o->u_rough, err);
+    bool ok = flattenKd(p->Kd, o, f) && flattenSpectrumTexture(p->Ks, o->kr, &o->ks_texture_plus1, f) &&
+              flattenFloatTexture(p->roughness, &o->u_rough, &o->rough_texture_plus1, f);
+    if (ok && o->rough_texture_plus1 > 0 && o->remap_roughness) { *err = "Plastic: a roughness ImageTexture with remapRoughness is not supported on the GPU path"; ok = false; }
     o->v_rough = o->u_rough;
     return ok;
   }

@@ -37,10 +37,11 @@ def metal(eta, k, u_rough, v_rough, remap=False):
                       remap_roughness=int(remap))
 
 
-def plastic(kd, ks, rough, remap=True, kd_texture=None, ks_texture=None):
+def plastic(kd, ks, rough, remap=True, kd_texture=None, ks_texture=None, rough_texture=None):
     return A.Material(type=A.MAT_PLASTIC, kd=_f3(kd), kr=_f3(ks), u_rough=rough, v_rough=rough,
                       remap_roughness=int(remap), kd_texture_plus1=0 if kd_texture is None else kd_texture + 1,
-                      ks_texture_plus1=0 if ks_texture is None else ks_texture + 1)
+                      ks_texture_plus1=0 if ks_texture is None else ks_texture + 1,
+                      rough_texture_plus1=0 if rough_texture is None else rough_texture + 1)
 
 
 class SceneData:
@@ -77,6 +78,8 @@ class SceneData:
         """ImageTexture<RGBSpectrum, Spectrum>(UVMapping2D(su, sv, du, dv), ..., doTrilinear, maxAniso, wrap) over the RGB
         image `texels` [H,W,3] (any size; the values the MIPMap receives, Texture/ImageTexture.cpp:88-95) -> id."""
         tx = np.ascontiguousarray(texels, dtype=F)
+        if tx.ndim == 2:  # an ImageTexture<float, float>: the float texels replicated in R, G, B
+            tx = np.ascontiguousarray(np.repeat(tx[:, :, None], 3, axis=2))
         assert tx.ndim == 3 and tx.shape[2] == 3
         t = A.Texture(width=tx.shape[1], height=tx.shape[0], texels=tx.ctypes.data_as(C.POINTER(C.c_float)),
                       do_trilinear=int(do_trilinear), max_anisotropy=max_anisotropy, wrap=wrap, su=su, sv=sv, du=du, dv=dv)

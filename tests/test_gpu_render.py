@@ -613,6 +613,13 @@ def _textured_scene(variant):
     s.add_mesh(v, t, plast, uvs=uv)
     v, t = scenes.uv_sphere([1.2, -1.7, 0.9], 0.8, n_lat, n_lon)
     s.add_mesh(v, t, mir)
+    # the material Shape/ModelLoad.cpp:118-164 builds: Plastic with image textures for Kd, Ks (another image) and an
+    # ImageTexture<float, float> roughness, remapRoughness = false
+    rough = (0.05 + 0.4 * ((xx // 4 + yy // 4) % 2) + rng.uniform(0, 0.05, (H, W))).astype(np.float32)
+    t2 = s.add_texture(rough, su=2.0, sv=2.0, **{k: v for k, v in kw.items() if k in ("wrap", "do_trilinear")})
+    plast2 = s.add_material(scenes.plastic([0.3, 0.3, 0.3], [0.5, 0.5, 0.5], 0.3, remap=False, kd_texture=t0, ks_texture=t1, rough_texture=t2))
+    v, t = scenes.uv_sphere([0.9, 0.6, -0.8], 0.7, n_lat, n_lon)
+    s.add_mesh(v, t, plast2, uvs=uv)
     return s
 
 
@@ -690,6 +697,12 @@ def test_image_texture_error_behaviour(api, gpu_ctx):
     scenes.cornell_walls(bad4, m, m, m)
     with pytest.raises(api.PbrGpuError, match="Ks image texture"):
         api.Scene(bad4)
+    bad6 = scenes.SceneData()
+    t = bad6.add_texture(np.zeros((8, 8), dtype=np.float32))
+    m = bad6.add_material(scenes.plastic([1, 1, 1], [1, 1, 1], 0.1, remap=True, rough_texture=t))
+    scenes.cornell_walls(bad6, m, m, m)
+    with pytest.raises(api.PbrGpuError, match="remap_roughness == 0"):
+        api.Scene(bad6)
     bad5 = scenes.SceneData()
     m = bad5.add_material(scenes.plastic([1, 1, 1], [1, 1, 1], 0.1, ks_texture=2))
     scenes.cornell_walls(bad5, m, m, m)
