@@ -1,4 +1,4 @@
-// Pipe microbenchmark (development aid): which sm_100a pipe do the candidate node-test instructions issue to, and at what rate?
+// Pipe microbenchmark (development aid; build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/ubench/pipes scripts/ubench/pipes.cu): which sm_100a pipe do the candidate node-test instructions issue to, and at what rate?
 // Each test runs N independent dependency chains of one or two opcodes in a loop; reports warp-instructions per cycle per SM sub-partition.
 #include <cstdio>
 #include <cuda_runtime.h>
