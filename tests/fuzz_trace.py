@@ -1,4 +1,5 @@
-"""One-off parity fuzz of the traversal kernels against the compiled reference (development aid; needs oracle/_ref and a GPU):
+"""One-off parity fuzz of the traversal kernels against the compiled reference (a checker, so it lives under tests/; not collected by
+pytest; needs oracle/_ref and a GPU; run from the repository root: python tests/fuzz_trace.py 30):
 N random closest-hit and any-hit rays on the full 872 k-triangle dragon-class mesh - uniform directions, near-axis-parallel
 directions (either side of the fp16 / fp32 box-test switch), origins outside and inside the mesh - through k_trace's queues and
 through the one-thread-per-ray helper loop.  usage: fuzz_trace.py [millions of rays]"""
