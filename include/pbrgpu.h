@@ -12,8 +12,8 @@
  *     VolPathIntegrator::Li               Integrator/VolPathIntegrator.cpp:21-107  (+ Media/HomogeneousMedium.cpp:10-45,
  *                                         Media/Medium.cpp:7-28, VisibilityTester::Tr Light/Light.cpp:31-47)
  *     UniformSampleOneLight/EstimateDirect Integrator/Integrator.cpp:46-177
- *     Material::ComputeScatteringFunctions + BSDF::{f,Pdf,Sample_f}   Material/*.cpp
- *     Light::{Sample_Li,Pdf_Li,Le,L}      Light/*.cpp
+ *     Material::ComputeScatteringFunctions + BSDF::{f,Pdf,Sample_f}   Material/ (all .cpp)
+ *     Light::{Sample_Li,Pdf_Li,Le,L}      Light/ (all .cpp)
  *     per-pixel mean + XYZ/sRGB/gamma/8-bit  Integrator/Integrator.cpp:313-344
  *
  * The reference has no FFI layer: its boundary is the C++ virtual above, whose inputs are object
